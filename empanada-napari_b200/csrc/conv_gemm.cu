@@ -1,0 +1,331 @@
+// Implicit-GEMM convolution kernel: TMA -> smem (128B swizzle) -> tcgen05.mma -> TMEM ->
+// fused epilogue (bias / residual / ReLU / SiLU) -> NHWC bf16 (and optional fp32) stores.
+// See conv_gemm.cuh for the layout contract and the reference call sites this replaces.
+#include "conv_gemm.cuh"
+#include "sm100_ptx.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace convgemm {
+using namespace sm100;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_SILU) return v / (1.0f + __expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                 const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a_bytes = TILE_M * KCHUNK * 2;          // 16 KiB
+  const int b_bytes = p.block_n * KCHUNK * 2;       // block_n * 128 B
+  const int stage_bytes = a_bytes + b_bytes;
+  const int stages = p.stages;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int taps = p.R * p.S;
+  const int num_kb = taps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int mt = tile / p.tiles_n;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tb = mt / p.tiles_y;
+        const int x_in = tx * p.TW * p.stride - p.pad;
+        const int y_in = ty * p.TH * p.stride - p.pad;
+        const int b0 = tb * p.TB;
+        const int n0 = nt * p.block_n;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_dst = smem + static_cast<size_t>(stage) * stage_bytes;
+            uint8_t* b_dst = a_dst + a_bytes;
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            tma_load_4d(a_dst, &tmap_a, &full_bar[stage], kc * KCHUNK, x_in + s * p.dil,
+                        y_in + r * p.dil, b0);
+            tma_load_2d(b_dst, &tmap_b, &full_bar[stage], tap * p.Cin + kc * KCHUNK, n0);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TILE_M, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * MAX_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_bytes);
+#pragma unroll
+          for (int k = 0; k < KCHUNK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row (encoded >> 4)
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int tw = m % p.TW;
+    const int th = (m / p.TW) % p.TH;
+    const int tbi = m / (p.TW * p.TH);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tb = mt / p.tiles_y;
+      const int x = tx * p.TW + tw, y = ty * p.TH + th, b = tb * p.TB + tbi;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+      const long long pix = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
+      const int n0 = nt * p.block_n;
+
+      mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MAX_N;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (valid && n < p.Cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr && n + j < p.Cout) f[j] += __ldg(p.bias + n + j);
+          }
+          const bool full16 = (n + 16 <= p.Cout);
+          if (p.residual != nullptr) {
+            const __nv_bfloat16* rp = p.residual + pix * p.res_ld + n;
+            if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+              const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+                f[2 * j] += __bfloat162float(h.x);
+                f[2 * j + 1] += __bfloat162float(h.y);
+              }
+            } else {
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) f[j] += __bfloat162float(rp[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act);
+          if (p.out != nullptr) {
+            __nv_bfloat16* op = p.out + pix * p.out_ld + p.out_coff + n;
+            if (full16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) op[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float* fp = p.out_f32 + pix * p.out_f32_ld + n;
+            for (int j = 0; j < 16 && n + j < p.Cout; ++j) fp[j] = f[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------- host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static void pick_tile_geometry(int B, int Ho, int Wo, int* TW, int* TH, int* TB) {
+  // minimise padded pixels; prefer wide rows on ties (longer contiguous TMA segments)
+  long long best = -1;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      const int tb = 128 / (tw * th);
+      if (tb > 1 && (th < Ho || tw < Wo)) continue;  // only batch-tile maps that fit one tile
+      const long long cost = 1LL * ((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th *
+                             ((B + tb - 1) / tb) * tb;
+      if (best < 0 || cost < best) {
+        best = cost; *TW = tw; *TH = th; *TB = tb;
+      }
+    }
+  }
+}
+
+// Describes one convolution call. Input: NHWC bf16 [B, Hi, Wi, >=Cin] with pixel stride in_ld.
+// Weights: [Cout][R*S*Cin] bf16. Output map: Ho x Wo.
+int conv_gemm_plan(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
+                   int Cin, const __nv_bfloat16* w, int Cout, int R, int S, int stride, int dil,
+                   int pad, int Ho, int Wo, __nv_bfloat16* out, long long out_ld, int out_coff,
+                   float* out_f32, long long out_f32_ld, const float* bias,
+                   const __nv_bfloat16* residual, long long res_ld, int act, int num_sms) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -1;
+  if (Cin % 8 != 0 || in_ld % 8 != 0) return -2;
+  if (R * S > 1 && Cin % KCHUNK != 0) return -3;
+  Params& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S;
+  p.stride = stride; p.dil = dil; p.pad = pad;
+  pick_tile_geometry(B, Ho, Wo, &p.TW, &p.TH, &p.TB);
+  if (p.TW * stride > 256 || p.TH * stride > 256) {
+    // TMA box limit: fall back to narrower rows
+    while (p.TW * stride > 256) { p.TW >>= 1; p.TH <<= 1; }
+  }
+  p.tiles_x = (Wo + p.TW - 1) / p.TW;
+  p.tiles_y = (Ho + p.TH - 1) / p.TH;
+  p.tiles_b = (B + p.TB - 1) / p.TB;
+  int bn = ((Cout + 15) / 16) * 16;
+  if (bn > MAX_N) bn = (Cout % 256 == 0) ? 256 : ((Cout % 192 == 0) ? 192 : ((Cout % 128 == 0) ? 128 : 256));
+  p.block_n = bn;
+  p.tiles_n = (Cout + bn - 1) / bn;
+  p.kchunks = (Cin + KCHUNK - 1) / KCHUNK;
+  const int stage_bytes = TILE_M * KCHUNK * 2 + bn * KCHUNK * 2;
+  int stages = (227 * 1024 - 1024 - 256) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -4;
+  p.stages = stages;
+  p.out = out; p.out_ld = out_ld; p.out_coff = out_coff;
+  p.out_f32 = out_f32; p.out_f32_ld = out_f32_ld;
+  p.bias = bias; p.residual = residual; p.res_ld = res_ld; p.act = act;
+  L->smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  const long long total = 1LL * p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  L->grid = static_cast<int>(total < num_sms ? total : num_sms);
+
+  {
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(Wi),
+                          static_cast<cuuint64_t>(Hi), static_cast<cuuint64_t>(B)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(in_ld) * 2,
+                          static_cast<cuuint64_t>(in_ld) * 2 * Wi,
+                          static_cast<cuuint64_t>(in_ld) * 2 * Wi * Hi};
+    cuuint32_t box[4] = {KCHUNK, static_cast<cuuint32_t>(p.TW * stride),
+                         static_cast<cuuint32_t>(p.TH * stride), static_cast<cuuint32_t>(p.TB)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+    CUresult r = enc(&L->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                     const_cast<__nv_bfloat16*>(in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -100 - static_cast<int>(r);
+  }
+  {
+    const long long ktot = 1LL * R * S * Cin;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(Cout)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ktot) * 2};
+    cuuint32_t box[2] = {KCHUNK, static_cast<cuuint32_t>(bn)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&L->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<__nv_bfloat16*>(w), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -200 - static_cast<int>(r);
+  }
+  return 0;
+}
+
+int conv_gemm_launch(const Launch* L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  conv_gemm_kernel<<<L->grid, NUM_THREADS, L->smem, stream>>>(L->tmap_a, L->tmap_b, L->p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace convgemm
