@@ -1,0 +1,247 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) through
+oracle/ref_shim.py in the build container. The fixtures travel to the GPU box; the reference
+does not. Run: `python -m oracle.make_golden` from the repo root.
+
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+import torch  # noqa: E402
+
+import empanada_napari_b200.synthetic as syn  # noqa: E402
+
+MODEL_CONFIG = {
+    "class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "model": "unused",
+    "model_quantized": None, "padding_factor": 16, "norms": {"mean": 0.57571, "std": 0.12765},
+}
+
+
+def noisy_heads(label_slice, pad_to, noise, rng):
+    sem, ctr, off = syn.analytic_heads(label_slice, pad_to=pad_to)
+    if noise > 0:
+        sem = sem + rng.normal(0, 2.5 * noise, size=sem.shape).astype(np.float32)
+        ctr = ctr + rng.normal(0, 0.05 * noise, size=ctr.shape).astype(np.float32)
+        off = off + rng.normal(0, 2.0 * noise, size=off.shape).astype(np.float32)
+    return sem.astype(np.float32), ctr.astype(np.float32), off.astype(np.float32)
+
+
+class FakeModel(torch.nn.Module):
+    """Stands in for the TorchScript network: returns precomputed heads slice by slice
+    (the engine calls the model exactly once per slice, in order)."""
+
+    def __init__(self, heads):
+        super().__init__()
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+        self.heads = heads
+        self.i = 0
+
+    def forward(self, x, render_steps: int = 2, interpolate_ins: bool = False):
+        sem, ctr, off = self.heads[self.i]
+        self.i += 1
+        assert tuple(x.shape[-2:]) == tuple(sem.shape[-2:]), (x.shape, sem.shape)
+        return {"sem_logits": torch.from_numpy(sem)[None], "ctr_hmp": torch.from_numpy(ctr)[None, None],
+                "offsets": torch.from_numpy(off)[None]}
+
+
+def slices_of(lab, axis):
+    return [np.take(lab, i, axis=axis) for i in range(lab.shape[axis])]
+
+
+def pack_instances(prefix, instances, out):
+    labels = np.array(list(instances.keys()), dtype=np.int64)
+    out[prefix + "labels"] = labels
+    out[prefix + "boxes"] = np.array([instances[k]["box"] for k in labels], dtype=np.int64).reshape(-1, 6)
+    lens = np.array([len(instances[k]["starts"]) for k in labels], dtype=np.int64)
+    out[prefix + "lens"] = lens
+    out[prefix + "starts"] = (np.concatenate([instances[k]["starts"] for k in labels])
+                              if len(labels) else np.zeros(0, np.int64)).astype(np.int64)
+    out[prefix + "runs"] = (np.concatenate([instances[k]["runs"] for k in labels])
+                            if len(labels) else np.zeros(0, np.int64)).astype(np.int64)
+
+
+def gen_post_cases():
+    """Per-slice post-processing vectors (pieces 2,3): reference engines/postprocess on heads."""
+    from empanada.inference.engines import PanopticDeepLabRenderEngine
+    from empanada.inference.postprocess import find_instance_center
+
+    rng = np.random.default_rng(7)
+    cases = []
+    shapes = [(64, 64), (48, 80), (128, 96), (16, 16)]
+    for ci in range(14):
+        H, W = shapes[ci % len(shapes)]
+        h4, w4 = H // 4, W // 4
+        kind = ci % 7
+        nms_kernel = [3, 7, 3, 5, 4, 3, 7][kind]
+        thr = 0.1
+        if kind == 0:      # analytic objects, few centres
+            lab = syn.label_volume((1, H, W), syn.make_ellipsoids((1, H, W), 3, seed=ci, scale=1.0)
+                                   * np.array([0, 1, 1, 1, 1, 1], np.float32) + np.array([0.4, 0, 0, 0, 0, 0], np.float32))[0]
+            sem, ctr, off = noisy_heads(lab, None, 0.3, rng)
+        elif kind == 1:    # random everything, many centres (> 20 -> chunked path)
+            sem = rng.normal(0, 3, (1, H, W)).astype(np.float32)
+            ctr = rng.uniform(0, 1, (h4, w4)).astype(np.float32)
+            off = rng.normal(0, 6, (2, h4, w4)).astype(np.float32)
+        elif kind == 2:    # no centres at all
+            sem = rng.normal(0, 3, (1, H, W)).astype(np.float32)
+            ctr = rng.uniform(0, 0.09, (h4, w4)).astype(np.float32)
+            off = rng.normal(0, 6, (2, h4, w4)).astype(np.float32)
+        elif kind == 3:    # plateaus + exact distance ties (integer offsets, quantised heat map)
+            sem = rng.normal(1, 3, (1, H, W)).astype(np.float32)
+            ctr = (rng.integers(0, 4, (h4, w4)) / 4.0).astype(np.float32)
+            off = rng.integers(-8, 9, (2, h4, w4)).astype(np.float32)
+        elif kind == 4:    # even NMS kernel
+            sem = rng.normal(0, 3, (1, H, W)).astype(np.float32)
+            ctr = rng.uniform(0, 1, (h4, w4)).astype(np.float32) ** 4
+            off = rng.normal(0, 3, (2, h4, w4)).astype(np.float32)
+        elif kind == 5:    # 1..20 centres (argmin path), zero offsets => symmetric ties
+            sem = np.full((1, H, W), 3.0, np.float32)
+            ctr = np.zeros((h4, w4), np.float32)
+            for _ in range(6):
+                ctr[rng.integers(0, h4), rng.integers(0, w4)] = 0.9
+            off = np.zeros((2, h4, w4), np.float32)
+        else:              # everything foreground, huge offsets (> 1e5 with K > 20 -> id 0)
+            sem = np.full((1, H, W), 3.0, np.float32)
+            ctr = rng.uniform(0, 1, (h4, w4)).astype(np.float32)
+            off = rng.normal(0, 6, (2, h4, w4)).astype(np.float32)
+            off[:, : h4 // 2] += 3e5
+        conf = 0.5
+        eng = PanopticDeepLabRenderEngine(
+            torch.nn.Conv2d(1, 1, 1), thing_list=[1], label_divisor=1000, stuff_area=64, void_label=0,
+            nms_threshold=thr, nms_kernel=nms_kernel, confidence_thr=conf, padding_factor=16,
+            coarse_boundaries=True)
+        prob = torch.sigmoid(torch.from_numpy(sem)[None])
+        centers = find_instance_center(torch.from_numpy(ctr.copy())[None, None], thr, nms_kernel).numpy()
+        cells = eng.get_instance_cells(torch.from_numpy(ctr.copy())[None, None], torch.from_numpy(off)[None], 1)
+        pan = eng.postprocess(prob, cells)
+        cases.append(dict(prob=prob[0].numpy(), ctr=ctr, off=off, nms_kernel=nms_kernel, thr=thr, conf=conf,
+                          centers=centers, cells=cells[0, 0].numpy(), pan=pan[0].numpy()))
+    out = {"n": len(cases)}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            out[f"c{i}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(GOLD, "post_cases.npz"), **out)
+    print("post_cases", len(cases))
+
+
+def gen_median():
+    from empanada.inference.engines import _MedianQueue
+
+    rng = np.random.default_rng(3)
+    out = {}
+    for ci, (ks, n) in enumerate([(3, 7), (5, 9), (1, 4), (7, 7), (3, 3)]):
+        q = _MedianQueue(ks)
+        x = rng.uniform(0, 1, (n, 1, 6, 5)).astype(np.float32)
+        emitted = []
+        for t in range(n):
+            q.enqueue({"sem": torch.from_numpy(x[t].copy())[None], "t": t})
+            o = q.get_next(keys=["sem"])
+            if o is not None:
+                emitted.append((o["t"], o["sem"][0].numpy().copy()))
+        for o in q.end():
+            emitted.append((o["t"], o["sem"][0].numpy().copy()))
+        out[f"m{ci}_ks"] = ks
+        out[f"m{ci}_x"] = x
+        out[f"m{ci}_t"] = np.array([e[0] for e in emitted])
+        out[f"m{ci}_y"] = np.stack([e[1] for e in emitted])
+    out["n"] = 5
+    np.savez_compressed(os.path.join(GOLD, "median_cases.npz"), **out)
+    print("median done")
+
+
+def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent, tag, pixel_vote_thr=2,
+                         allow_one_view=False):
+    """Engine3d.infer_on_axis x3 + tracker_consensus + stack_postprocessing, unmodified."""
+    import empanada_napari.inference as inf
+
+    vol, lab, ell = syn.make_volume(shape, seed=seed, n_objects=n_objects, scale=1.0)
+    out = {"shape": np.array(shape), "seed": seed, "noise": noise, "ks": ks, "n_objects": n_objects,
+           "min_size": min_size, "min_extent": min_extent, "pixel_vote_thr": pixel_vote_thr,
+           "allow_one_view": int(allow_one_view)}
+    rng = np.random.default_rng(seed + 100)
+    trackers = {}
+    orig_loader = inf.load_model_to_device
+    for axis_name, axis in (("xy", 0), ("xz", 1), ("yz", 2)):
+        heads = [noisy_heads(s, 16, noise, rng) for s in slices_of(lab, axis)]
+        out[f"{axis_name}_sem"] = np.stack([h[0] for h in heads]).astype(np.float16)  # +-4 +- noise: stored as f16
+        out[f"{axis_name}_ctr"] = np.stack([h[1] for h in heads]).astype(np.float32)
+        out[f"{axis_name}_off"] = np.stack([h[2] for h in heads]).astype(np.float32)
+        # the reference must see exactly what the fixture stores
+        heads = [(out[f"{axis_name}_sem"][i].astype(np.float32), h[1], h[2]) for i, h in enumerate(heads)]
+        fake = FakeModel(heads)
+        inf.load_model_to_device = lambda url, device: fake
+        eng = inf.Engine3d(MODEL_CONFIG, inference_scale=1, label_divisor=1000, median_kernel_size=ks,
+                           nms_threshold=0.1, nms_kernel=3, confidence_thr=0.5, min_size=min_size,
+                           min_extent=min_extent, use_gpu=False, save_panoptic=True)
+        stack, trs = eng.infer_on_axis(vol, axis_name)
+        trackers[axis_name] = trs
+        out[f"{axis_name}_stack"] = stack.astype(np.int32)
+        pack_instances(f"{axis_name}_tr_", trs[0].instances, out)
+    inf.load_model_to_device = orig_loader
+    for v, name, instances in inf.tracker_consensus(
+            trackers, None, MODEL_CONFIG, label_divisor=1000, pixel_vote_thr=pixel_vote_thr,
+            cluster_iou_thr=0.75, allow_one_view=allow_one_view, min_size=min_size,
+            min_extent=min_extent, dtype=np.int32):
+        out["consensus_vol"] = v.astype(np.int32)
+        pack_instances("consensus_", instances, out)
+    for v, name, instances in inf.stack_postprocessing(
+            {"xy": trackers["xy"]}, None, MODEL_CONFIG, label_divisor=1000, min_size=min_size,
+            min_extent=min_extent, dtype=np.int32):
+        out["stackpost_vol"] = v.astype(np.int32)
+        pack_instances("stackpost_", instances, out)
+    np.savez_compressed(os.path.join(GOLD, f"volume_{tag}.npz"), **out)
+    print("volume", tag, {k: len(trackers[k][0].instances) for k in trackers},
+          "consensus", len(out["consensus_labels"]))
+
+
+def gen_model_tiny():
+    """Reference PDL classes with the seeded weights of synthetic.make_pdl_state_dict(0)."""
+    import yaml
+    from empanada.models.quantization.panoptic_deeplab import QuantizablePanopticDeepLabPR
+
+    cfg = yaml.safe_load(open(os.path.join(ref_shim.REF_ROOT, "empanada_napari/training/pdl_model.yaml")))
+    cfg.pop("arch")
+    cfg["num_classes"] = 1
+    m = QuantizablePanopticDeepLabPR(**cfg, quantize=False).eval()
+    m.fuse_model()
+    sd = syn.make_pdl_state_dict(0)
+    m.load_state_dict(sd)
+    m = torch.jit.script(m)  # the deployed form
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (96, 80), dtype=np.uint8)
+    from empanada_napari.utils import Preprocessor
+    x = Preprocessor(**MODEL_CONFIG["norms"])(img)["image"].unsqueeze(0)
+    from empanada.inference.postprocess import factor_pad
+    x = factor_pad(x, 16)
+    with torch.no_grad():
+        o = m(x, 2, False)
+    np.savez_compressed(os.path.join(GOLD, "model_pdl_tiny.npz"), img=img, x=x.numpy(),
+                        sem_logits=o["sem_logits"].numpy(), ctr_hmp=o["ctr_hmp"].numpy(),
+                        offsets=o["offsets"].numpy())
+    print("model tiny", {k: tuple(v.shape) for k, v in o.items()})
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["post", "median", "model", "volumes"]
+    if "post" in which:
+        gen_post_cases()
+    if "median" in which:
+        gen_median()
+    if "model" in which:
+        gen_model_tiny()
+    if "volumes" in which:
+        run_reference_volume((24, 40, 48), seed=1, noise=0.0, ks=3, n_objects=10, min_size=50, min_extent=3, tag="clean")
+        run_reference_volume((32, 36, 44), seed=2, noise=0.6, ks=3, n_objects=14, min_size=20, min_extent=2, tag="noisy")
+        run_reference_volume((20, 33, 30), seed=3, noise=0.3, ks=5, n_objects=8, min_size=10, min_extent=2, tag="ks5_odd",
+                             pixel_vote_thr=1, allow_one_view=True)

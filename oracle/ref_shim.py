@@ -145,8 +145,8 @@ def install():
         ("dask", {}),
         ("joblib", dict(Parallel=_notimpl, delayed=_notimpl)),
         ("cztile", {}),
-        ("cztile.fixed_total_area_strategy", dict(AlmostEqualBorderFixedTotalAreaStrategy2D=_notimpl)),
-        ("cztile.tiling_strategy", dict(Rectangle=_notimpl)),
+        ("cztile.fixed_total_area_strategy_2d", dict(AlmostEqualBorderFixedTotalAreaStrategy2D=_notimpl)),
+        ("cztile.tiling_strategy", dict(Rectangle=_notimpl, Region2D=_notimpl)),
         ("requests", {}),
         ("napari", {}),
         ("napari.qt", {}),

@@ -1,0 +1,124 @@
+"""Pins the CPU oracle (oracle/) against (i) the reference's own known-answer tests
+(tests/test_array_utils.py:8-154 of the reference, re-stated here) and (ii) fixtures produced by
+running the unmodified reference in the build container (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_instances_equal, unpack_instances
+from oracle import consensus, pipeline, post, ranges, tracking
+
+MODEL_CONFIG = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 16,
+                "norms": {"mean": 0.57571, "std": 0.12765}}
+
+
+# ---- reference known-answer vectors (reference tests/test_array_utils.py) ----
+def test_box_iou_vectors():
+    pairs, ious, inters = ranges.box_iou_pairs(np.array([[0, 0, 20, 20]]), np.array([[5, 5, 25, 25]]))
+    assert pairs.tolist() == [[0, 0]] and ious[0] == pytest.approx(0.39, abs=0.02) and inters == [225]
+    pairs, ious, inters = ranges.box_iou_pairs(np.array([[0, 0, 20, 20]]), np.array([[30, 0, 50, 20]]))
+    assert len(pairs) == 0 and ious == [] and inters == []
+
+
+def test_intersection_from_ranges_vectors():
+    assert ranges.intersection_from_ranges(np.array([[0, 10], [7, 20]]), np.array([True])) == 3
+    assert ranges.intersection_from_ranges(np.array([[0, 10], [7, 20]]), np.array([False])) == 0
+
+
+def test_split_range_by_votes_vectors():
+    r = ranges.split_range_by_votes(np.array([0, 10]), np.array([2, 3, 3, 3, 1, 2, 2, 3, 3, 4]), 2)
+    assert [list(x) for x in r] == [[0, 4], [5, 10]]
+    r = ranges.split_range_by_votes(np.array([0, 10]), np.array([2, 3, 3, 3, 2, 2, 2, 3, 3, 4]), 2)
+    assert [list(x) for x in r] == [[0, 10]]
+
+
+def test_extend_range_vector():
+    r, v = ranges.extend_range(np.array([1, 10]), np.array([3, 10]), np.array([2, 4, 4, 4, 4, 2, 2, 2, 2, 2]))
+    assert list(r) == [1, 10] and list(v) == [2, 4, 5, 5, 5, 3, 3, 3, 3, 3]
+
+
+def test_rle_voting_vector_quirk():
+    r = ranges.rle_voting(np.array([(10, 20), (7, 26)]))
+    assert [list(x) for x in r] == [[10, 20], [23, 26]]
+
+
+def test_join_ranges_vectors():
+    assert np.array_equal(ranges._join_ranges(np.array([(0, 10), (6, 10)])), [[0, 10]])
+    assert np.array_equal(ranges._join_ranges(np.array([(0, 10), (11, 20)])), [[0, 10], [11, 20]])
+    assert np.array_equal(ranges._join_ranges(np.array([(0, 10), (10, 20)])), [[0, 20]])
+
+
+def test_invert_ranges_vector_quirk():
+    assert np.array_equal(ranges.invert_ranges(np.array([(2, 6), (4, 12)]), 15), [[0, 2], [6, 4], [12, 15]])
+
+
+# ---- fixtures generated from the reference ----
+def test_post_cases_match_reference():
+    z = np.load(os.path.join(GOLDEN, "post_cases.npz"))
+    for i in range(int(z["n"])):
+        ctr, off, prob = z[f"c{i}_ctr"], z[f"c{i}_off"], z[f"c{i}_prob"]
+        k, thr, conf = int(z[f"c{i}_nms_kernel"]), float(z[f"c{i}_thr"]), float(z[f"c{i}_conf"])
+        centers = post.find_instance_center(ctr, thr, k)
+        assert np.array_equal(centers, z[f"c{i}_centers"].reshape(-1, 2)), i
+        cells = post.get_instance_cells(ctr, off, thr, k, True, 1)
+        assert np.array_equal(cells, z[f"c{i}_cells"]), i
+        pan = post.get_panoptic_seg(post.harden_seg(prob, conf), cells, 1000, [1], 64, 0)
+        assert np.array_equal(pan, z[f"c{i}_pan"]), i
+
+
+def test_median_queue_matches_reference():
+    z = np.load(os.path.join(GOLDEN, "median_cases.npz"))
+    for i in range(int(z["n"])):
+        q = post.MedianQueue(int(z[f"m{i}_ks"]))
+        x = z[f"m{i}_x"]
+        ts, ys = [], []
+        for t in range(len(x)):
+            o = q.push({"sem": x[t].copy(), "t": t})
+            if o is not None:
+                ts.append(o["t"]); ys.append(o["sem"].copy())
+        for o in q.end():
+            ts.append(o["t"]); ys.append(o["sem"].copy())
+        assert ts == z[f"m{i}_t"].tolist()
+        assert np.array_equal(np.stack(ys), z[f"m{i}_y"])
+
+
+@pytest.mark.parametrize("tag", ["clean", "noisy", "ks5_odd"])
+def test_volume_pipeline_matches_reference(tag):
+    import empanada_napari_b200.synthetic as syn
+    z = np.load(os.path.join(GOLDEN, f"volume_{tag}.npz"))
+    shape = tuple(int(v) for v in z["shape"])
+    vol, lab, _ = syn.make_volume(shape, seed=int(z["seed"]), n_objects=int(z["n_objects"]), scale=1.0)
+    trackers = {}
+    for axis_name in ("xy", "xz", "yz"):
+        sem, ctr, off = z[f"{axis_name}_sem"].astype(np.float32), z[f"{axis_name}_ctr"], z[f"{axis_name}_off"]
+        stack, trs = pipeline.infer_on_axis(
+            vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), MODEL_CONFIG,
+            median_kernel_size=int(z["ks"]), nms_kernel=3, confidence_thr=0.5,
+            min_size=int(z["min_size"]), min_extent=int(z["min_extent"]))
+        assert_instances_equal(trs[0].instances, unpack_instances(z, f"{axis_name}_tr_"))
+        assert np.array_equal(stack, z[f"{axis_name}_stack"])
+        trackers[axis_name] = trs
+    for v, name, inst in consensus.tracker_consensus(
+            trackers, MODEL_CONFIG, pixel_vote_thr=int(z["pixel_vote_thr"]),
+            allow_one_view=bool(z["allow_one_view"]), min_size=int(z["min_size"]),
+            min_extent=int(z["min_extent"]), dtype=np.int32):
+        assert_instances_equal(inst, unpack_instances(z, "consensus_"))
+        assert np.array_equal(v, z["consensus_vol"])
+    for v, name, inst in consensus.stack_postprocessing(
+            {"xy": trackers["xy"]}, MODEL_CONFIG, min_size=int(z["min_size"]),
+            min_extent=int(z["min_extent"]), dtype=np.int32):
+        assert_instances_equal(inst, unpack_instances(z, "stackpost_"))
+        assert np.array_equal(v, z["stackpost_vol"])
+
+
+def test_model_restatement_matches_reference_fixture():
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from oracle import model
+    z = np.load(os.path.join(GOLDEN, "model_pdl_tiny.npz"))
+    x = post.factor_pad(post.normalize(z["img"], 0.57571, 0.12765), 16)[None, None]
+    assert np.array_equal(x, z["x"])
+    out = model.pdl_forward(syn.make_pdl_state_dict(0), torch.from_numpy(x), 2, False)
+    for k in ("sem_logits", "ctr_hmp", "offsets"):
+        assert np.allclose(out[k].numpy(), z[k], atol=2e-4, rtol=1e-4), k
