@@ -1,0 +1,424 @@
+// Connected components, per-component tables, adjacent-slice overlap tables, LUT relabel and
+// run-length extraction (pieces 5 and 6b of the hot path), batched over slices.
+// Restates on the GPU what the reference does per slice on the CPU in
+//   * connected_components / pan_seg_to_rle_seg (empanada/inference/rle.py:18-86):
+//       8-connected components of EQUAL-valued pixels inside one class range, numbered in
+//       raster order of their first pixel (skimage.measure.label semantics), bbox + area;
+//   * rle_intersection between consecutive slices (empanada/array_utils.py:375-407): here a
+//       sparse (cc_prev, cc_cur) -> overlapping-pixel-count table built in one pass;
+//   * rle_encode (array_utils.py:213-239): maximal runs of equal label over FLAT indices
+//       (runs may continue across row ends, exactly as the reference's flat-index encoding).
+// Bandwidth-bound integer kernels: 4-byte coalesced accesses, atomics only at run heads.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace cc {
+
+// ------------------------------------------------------------------ union-find labelling
+__device__ __forceinline__ int find_root(const int* L, int a) {
+  int p = L[a];
+  while (p != a) { a = p; p = L[a]; }
+  return a;
+}
+__device__ __forceinline__ void unite(int* L, int a, int b) {
+  while (true) {
+    a = find_root(L, a);
+    b = find_root(L, b);
+    if (a == b) return;
+    if (a > b) { const int t = a; a = b; b = t; }  // a < b: smaller index becomes the root
+    const int old = atomicMin(&L[b], a);
+    if (old == b) return;
+    b = old;
+  }
+}
+
+// value of pixel p restricted to the class range [lo, hi) (rle.py:60-66)
+__device__ __forceinline__ int cls_val(const int* pan, long long i, int lo, int hi) {
+  const int v = pan[i];
+  return (v >= lo && v < hi && v != 0) ? v : 0;
+}
+
+__global__ void cc_init_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w,
+                               int lo, int hi) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const long long base = static_cast<long long>(b) * h * w;
+  const int p = y * w + x;
+  L[base + p] = cls_val(pan, base + p, lo, hi) ? p : -1;
+}
+
+__global__ void cc_merge_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w,
+                                int lo, int hi) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const long long base = static_cast<long long>(b) * h * w;
+  const int p = y * w + x;
+  const int v = cls_val(pan, base + p, lo, hi);
+  if (!v) return;
+  int* Lb = L + base;
+  if (x > 0 && cls_val(pan, base + p - 1, lo, hi) == v) unite(Lb, p, p - 1);
+  if (y > 0) {
+    if (cls_val(pan, base + p - w, lo, hi) == v) unite(Lb, p, p - w);
+    if (x > 0 && cls_val(pan, base + p - w - 1, lo, hi) == v) unite(Lb, p, p - w - 1);
+    if (x + 1 < w && cls_val(pan, base + p - w + 1, lo, hi) == v) unite(Lb, p, p - w + 1);
+  }
+}
+
+__global__ void cc_compress_kernel(int* __restrict__ L, long long hw_total, int hw) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= hw_total) return;
+  const int v = L[i];
+  if (v < 0) return;
+  int* Lb = L + (i / hw) * hw;
+  L[i] = find_root(Lb, v);
+}
+
+// roots per 1024-pixel chunk (raster order) -> chunk_counts[b][chunk]
+constexpr int CHUNK = 1024;
+__global__ void __launch_bounds__(CHUNK)
+cc_count_roots_kernel(const int* __restrict__ L, int hw, int chunks, int* __restrict__ chunk_counts) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int p = ch * CHUNK + threadIdx.x;
+  const bool root = (p < hw) && (L[static_cast<long long>(b) * hw + p] == p);
+  const int n = __syncthreads_count(root);
+  if (threadIdx.x == 0) chunk_counts[b * chunks + ch] = n;
+}
+
+// one CTA per slice: exclusive scan of chunk counts (in place), total -> n_cc[b]
+__global__ void __launch_bounds__(1024)
+cc_scan_chunks_kernel(int* __restrict__ chunk_counts, int chunks, int* __restrict__ n_cc) {
+  typedef cub::BlockScan<int, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ int carry;
+  int* c = chunk_counts + static_cast<long long>(blockIdx.x) * chunks;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int s = 0; s < chunks; s += 1024) {
+    const int i = s + threadIdx.x;
+    const int v = (i < chunks) ? c[i] : 0;
+    int ex, total;
+    Scan(tmp).ExclusiveSum(v, ex, total);
+    if (i < chunks) c[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_cc[blockIdx.x] = carry;
+}
+
+// roots receive their raster-order id (1-based) in `out`
+__global__ void __launch_bounds__(CHUNK)
+cc_number_roots_kernel(const int* __restrict__ L, int hw, int chunks,
+                       const int* __restrict__ chunk_offsets, int* __restrict__ out) {
+  typedef cub::BlockScan<int, CHUNK> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int p = ch * CHUNK + threadIdx.x;
+  const long long base = static_cast<long long>(b) * hw;
+  const int root = (p < hw) && (L[base + p] == p);
+  int ex;
+  Scan(tmp).ExclusiveSum(root, ex);
+  if (root) out[base + p] = chunk_offsets[b * chunks + ch] + ex + 1;
+}
+
+__global__ void cc_apply_ids_kernel(const int* __restrict__ L, int* __restrict__ out,
+                                    long long hw_total, int hw) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= hw_total) return;
+  const int r = L[i];
+  if (r < 0) { out[i] = 0; return; }
+  const long long base = (i / hw) * hw;
+  if (base + r != i) out[i] = out[base + r];
+}
+
+// per-component area + bbox; one atomic group per horizontal run
+// table layout per slice: [cap][5] = area, y0, x0, y1, x1 (half-open); pre-initialised.
+__global__ void cc_table_init_kernel(int* __restrict__ table, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int f = static_cast<int>(i % 5);
+  table[i] = (f == 1 || f == 2) ? 0x7fffffff : 0;
+}
+__global__ void cc_stats_kernel(const int* __restrict__ ccimg, int h, int w, int cap,
+                                int* __restrict__ table) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const int* row = ccimg + (static_cast<long long>(b) * h + y) * w;
+  const int id = row[x];
+  if (id == 0 || id > cap) return;
+  if (x > 0 && row[x - 1] == id) return;  // not a run head
+  int e = x + 1;
+  while (e < w && row[e] == id) ++e;
+  int* t = table + (static_cast<long long>(b) * cap + (id - 1)) * 5;
+  atomicAdd(&t[0], e - x);
+  atomicMin(&t[1], y);
+  atomicMin(&t[2], x);
+  atomicMax(&t[3], y + 1);
+  atomicMax(&t[4], e);
+}
+
+// ------------------------------------------------------------------ adjacent-slice overlaps
+// open-addressing table: key = slice(24) | prev_cc(20) | cur_cc(20); val = pixel count
+constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+__device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+__device__ __forceinline__ bool hash_add(unsigned long long* keys, int* vals, unsigned long long cap_mask,
+                                         unsigned long long key, int count) {
+  unsigned long long slot = mix64(key) & cap_mask;
+  for (unsigned long long probe = 0; probe <= cap_mask; ++probe) {
+    const unsigned long long cur = keys[slot];
+    if (cur == key) { atomicAdd(&vals[slot], count); return true; }
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&keys[slot], EMPTY_KEY, key);
+      if (old == EMPTY_KEY || old == key) { atomicAdd(&vals[slot], count); return true; }
+    }
+    slot = (slot + 1) & cap_mask;
+  }
+  return false;
+}
+
+// ccimg: plane buffer [N][h][w]; processes slices [s0, s1), pairing slice s with s-1 (s >= 1)
+__global__ void pair_overlap_kernel(const int* __restrict__ ccimg, int h, int w, int s0,
+                                    unsigned long long* __restrict__ keys, int* __restrict__ vals,
+                                    unsigned long long cap_mask, int* __restrict__ overflow) {
+  const int s = s0 + blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w || s < 1) return;
+  const int* cur = ccimg + (static_cast<long long>(s) * h + y) * w;
+  const int* prv = cur - static_cast<long long>(h) * w;
+  const int c = cur[x], q = prv[x];
+  if (c == 0 || q == 0) return;
+  if (x > 0 && cur[x - 1] == c && prv[x - 1] == q) return;  // not the head of this pair run
+  int e = x + 1;
+  while (e < w && cur[e] == c && prv[e] == q) ++e;
+  const unsigned long long key = (static_cast<unsigned long long>(s) << 40) |
+                                 (static_cast<unsigned long long>(q) << 20) |
+                                 static_cast<unsigned long long>(c);
+  if (!hash_add(keys, vals, cap_mask, key, e - x)) atomicExch(overflow, 1);
+}
+
+// generic compaction of a (key, count) table into dense arrays (order unspecified)
+__global__ void hash_compact_kernel(const unsigned long long* __restrict__ keys,
+                                    const int* __restrict__ vals, unsigned long long cap,
+                                    unsigned long long* __restrict__ out_keys,
+                                    int* __restrict__ out_vals, int out_cap,
+                                    int* __restrict__ cursor) {
+  const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i >= cap) return;
+  const unsigned long long k = keys[i];
+  if (k == EMPTY_KEY) return;
+  const int pos = atomicAdd(cursor, 1);
+  if (pos < out_cap) { out_keys[pos] = k; out_vals[pos] = vals[i]; }
+}
+
+// ------------------------------------------------------------------ LUT relabel into a volume
+// src: cc image of slices [s0, s0+B) laid out [B][h][w]; lut: [N][lut_stride] (entry 0 unused);
+// dst: (D,H,W)-ordered volume; element (slice s, row y, col x) lands at
+//      s*stride_s + y*stride_y + x*stride_x  (xy: HW, W, 1 | xz: W, HW, 1 | yz: 1, HW, W)
+__global__ void relabel_kernel(const int* __restrict__ src, int h, int w, int s0,
+                               const int* __restrict__ lut, int lut_stride,
+                               int* __restrict__ dst, long long stride_s, long long stride_y,
+                               long long stride_x) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const int id = src[(static_cast<long long>(b) * h + y) * w + x];
+  const int s = s0 + b;
+  int v = 0;
+  if (id > 0 && id < lut_stride) v = lut[static_cast<long long>(s) * lut_stride + id];
+  dst[s * stride_s + y * stride_y + x * stride_x] = v;
+}
+
+// tiled transpose variant for the yz plane (stride_x == W, stride_s == 1): a 32x32 tile of
+// (slice, x) is staged through shared memory so both the read and the write are coalesced.
+__global__ void relabel_yz_kernel(const int* __restrict__ src, int h, int w, int s0, int nb,
+                                  const int* __restrict__ lut, int lut_stride,
+                                  int* __restrict__ dst, long long HW, int Wvol) {
+  __shared__ int tile[32][33];
+  const int y = blockIdx.y;                 // row of the slice = z of the volume
+  const int x0 = blockIdx.x * 32;           // col of the slice = y of the volume
+  const int b0 = blockIdx.z * 32;           // slice within the batch = x of the volume
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int b = b0 + j, x = x0 + threadIdx.x;
+    int v = 0;
+    if (b < nb && x < w) {
+      const int id = src[(static_cast<long long>(b) * h + y) * w + x];
+      if (id > 0 && id < lut_stride) v = lut[static_cast<long long>(s0 + b) * lut_stride + id];
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = x0 + j, b = b0 + threadIdx.x;
+    if (b < nb && x < w) dst[y * HW + static_cast<long long>(x) * Wvol + (s0 + b)] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------ run-length extraction
+// Runs of equal non-zero label over the FLAT index space of each segment (segment = one slice
+// for xy/xz trackers, the whole volume for yz / consensus). Two passes give raster order.
+__device__ __forceinline__ bool is_run_head(const int* img, long long i, long long seg_len) {
+  const int v = img[i];
+  if (v == 0) return false;
+  return (i % seg_len == 0) || (img[i - 1] != v);
+}
+__global__ void __launch_bounds__(CHUNK)
+runs_count_kernel(const int* __restrict__ img, long long n, long long seg_len,
+                  int* __restrict__ chunk_counts) {
+  const long long i = blockIdx.x * static_cast<long long>(CHUNK) + threadIdx.x;
+  const bool head = (i < n) && is_run_head(img, i, seg_len);
+  const int c = __syncthreads_count(head);
+  if (threadIdx.x == 0) chunk_counts[blockIdx.x] = c;
+}
+// out_label / out_start / out_len indexed by the global raster rank of the run
+__global__ void __launch_bounds__(CHUNK)
+runs_write_kernel(const int* __restrict__ img, long long n, long long seg_len,
+                  const long long* __restrict__ chunk_offsets, int* __restrict__ out_label,
+                  long long* __restrict__ out_start, int* __restrict__ out_len, long long out_cap) {
+  typedef cub::BlockScan<int, CHUNK> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  const long long i = blockIdx.x * static_cast<long long>(CHUNK) + threadIdx.x;
+  const int head = (i < n) && is_run_head(img, i, seg_len);
+  int ex;
+  Scan(tmp).ExclusiveSum(head, ex);
+  if (!head) return;
+  const long long pos = chunk_offsets[blockIdx.x] + ex;
+  if (pos >= out_cap) return;
+  const int v = img[i];
+  const long long seg_end = (i / seg_len + 1) * seg_len;
+  long long e = i + 1;
+  while (e < seg_end && img[e] == v) ++e;
+  out_label[pos] = v;
+  out_start[pos] = i;
+  out_len[pos] = static_cast<int>(e - i);
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, unsigned long long n) {
+  const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace cc
+
+// ------------------------------------------------------------------------------ launchers
+extern "C" {
+
+// workspace: L [B*h*w] int32, chunk_counts [B*chunks] int32
+int be_cc_label(const int* pan, int B, int h, int w, int lo, int hi, int* L, int* chunk_counts,
+                int* cc_out, int* n_cc, int cap, int* table, cudaStream_t stream) {
+  const int hw = h * w;
+  const long long total = static_cast<long long>(B) * hw;
+  dim3 grid((w + 255) / 256, h, B);
+  cc::cc_init_kernel<<<grid, 256, 0, stream>>>(pan, L, h, w, lo, hi);
+  cc::cc_merge_kernel<<<grid, 256, 0, stream>>>(pan, L, h, w, lo, hi);
+  const unsigned nb = static_cast<unsigned>((total + 255) / 256);
+  cc::cc_compress_kernel<<<nb, 256, 0, stream>>>(L, total, hw);
+  const int chunks = (hw + cc::CHUNK - 1) / cc::CHUNK;
+  cc::cc_count_roots_kernel<<<dim3(chunks, B), cc::CHUNK, 0, stream>>>(L, hw, chunks, chunk_counts);
+  cc::cc_scan_chunks_kernel<<<B, 1024, 0, stream>>>(chunk_counts, chunks, n_cc);
+  cc::cc_number_roots_kernel<<<dim3(chunks, B), cc::CHUNK, 0, stream>>>(L, hw, chunks, chunk_counts, cc_out);
+  cc::cc_apply_ids_kernel<<<nb, 256, 0, stream>>>(L, cc_out, total, hw);
+  if (table != nullptr) {
+    const long long tn = static_cast<long long>(B) * cap * 5;
+    cc::cc_table_init_kernel<<<static_cast<unsigned>((tn + 255) / 256), 256, 0, stream>>>(table, tn);
+    cc::cc_stats_kernel<<<grid, 256, 0, stream>>>(cc_out, h, w, cap, table);
+  }
+  return be_check_launch("cc_label kernels");
+}
+
+int be_hash_clear(unsigned long long* keys, int* vals, unsigned long long cap, cudaStream_t stream) {
+  cc::fill_u64_kernel<<<static_cast<unsigned>((cap + 255) / 256), 256, 0, stream>>>(keys, cc::EMPTY_KEY, cap);
+  cudaError_t e = cudaMemsetAsync(vals, 0, sizeof(int) * cap, stream);
+  if (e != cudaSuccess) return be_set_error(cudaGetErrorString(e));
+  return be_check_launch("hash_clear");
+}
+
+int be_pair_overlap(const int* cc_plane, int h, int w, int s0, int s1, unsigned long long* keys,
+                    int* vals, unsigned long long cap, int* overflow, cudaStream_t stream) {
+  if (cap & (cap - 1)) return be_set_error("hash capacity must be a power of two");
+  if (s1 <= s0) return 0;
+  dim3 grid((w + 255) / 256, h, s1 - s0);
+  cc::pair_overlap_kernel<<<grid, 256, 0, stream>>>(cc_plane, h, w, s0, keys, vals, cap - 1, overflow);
+  return be_check_launch("pair_overlap_kernel");
+}
+
+int be_hash_compact(const unsigned long long* keys, const int* vals, unsigned long long cap,
+                    unsigned long long* out_keys, int* out_vals, int out_cap, int* cursor,
+                    cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return be_set_error(cudaGetErrorString(e));
+  cc::hash_compact_kernel<<<static_cast<unsigned>((cap + 255) / 256), 256, 0, stream>>>(
+      keys, vals, cap, out_keys, out_vals, out_cap, cursor);
+  return be_check_launch("hash_compact_kernel");
+}
+
+int be_relabel(const int* cc_batch, int B, int h, int w, int s0, const int* lut, int lut_stride,
+               int* dst, long long stride_s, long long stride_y, long long stride_x,
+               cudaStream_t stream) {
+  if (stride_s == 1 && stride_x > 1) {
+    // yz plane: x of the slice is y of the volume (stride_x == W), slice index is x of the volume
+    dim3 grid((w + 31) / 32, h, (B + 31) / 32);
+    cc::relabel_yz_kernel<<<grid, dim3(32, 8), 0, stream>>>(cc_batch, h, w, s0, B, lut, lut_stride,
+                                                            dst, stride_y, static_cast<int>(stride_x));
+  } else {
+    dim3 grid((w + 255) / 256, h, B);
+    cc::relabel_kernel<<<grid, 256, 0, stream>>>(cc_batch, h, w, s0, lut, lut_stride, dst, stride_s,
+                                                 stride_y, stride_x);
+  }
+  return be_check_launch("relabel kernels");
+}
+
+// Pass 1 of run extraction: per-chunk counts (chunk = 1024 elements). The caller scans the
+// counts (be_scan_i32_to_i64) and then calls be_runs_write.
+int be_runs_count(const int* img, long long n, long long seg_len, int* chunk_counts,
+                  cudaStream_t stream) {
+  const unsigned chunks = static_cast<unsigned>((n + cc::CHUNK - 1) / cc::CHUNK);
+  cc::runs_count_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, chunk_counts);
+  return be_check_launch("runs_count_kernel");
+}
+
+// exclusive scan int32 counts -> int64 offsets (+ total at offsets[n]) using cub
+int be_scan_i32_to_i64(const int* counts, long long* offsets, long long n, void* temp,
+                       size_t temp_bytes, size_t* temp_needed, cudaStream_t stream) {
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, counts, offsets, static_cast<int>(n + 1), stream);
+  if (temp_needed) *temp_needed = need;
+  if (temp == nullptr) return 0;
+  if (temp_bytes < need) return be_set_error("scan temp storage too small");
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(temp, need, counts, offsets, static_cast<int>(n + 1), stream);
+  if (e != cudaSuccess) return be_set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+int be_runs_write(const int* img, long long n, long long seg_len, const long long* chunk_offsets,
+                  int* out_label, long long* out_start, int* out_len, long long out_cap,
+                  cudaStream_t stream) {
+  const unsigned chunks = static_cast<unsigned>((n + cc::CHUNK - 1) / cc::CHUNK);
+  cc::runs_write_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, chunk_offsets, out_label,
+                                                          out_start, out_len, out_cap);
+  return be_check_launch("runs_write_kernel");
+}
+
+// stable sort of runs by 64-bit key (label rank << 40 | sequence) carrying (start, len)
+int be_sort_runs(const unsigned long long* keys_in, unsigned long long* keys_out,
+                 const int* idx_in, int* idx_out, int n, void* temp, size_t temp_bytes,
+                 size_t* temp_needed, cudaStream_t stream) {
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, idx_in, idx_out, n, 0, 64, stream);
+  if (temp_needed) *temp_needed = need;
+  if (temp == nullptr) return 0;
+  if (temp_bytes < need) return be_set_error("sort temp storage too small");
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, need, keys_in, keys_out, idx_in, idx_out, n, 0, 64, stream);
+  if (e != cudaSuccess) return be_set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"
