@@ -1,0 +1,308 @@
+"""Drop-in orchestration engines: same constructor keywords, methods and return types as
+`empanada_napari.inference` (Engine2d :171, Engine3d :327, tracker_consensus :111,
+stack_postprocessing :56 of /root/reference/empanada_napari/inference.py), backed by the
+sm_100a kernels of this package. There is no CPU path: a CUDA device is required.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, consensus, tracking
+from .model import load_model
+from .postproc import PlanePost
+from .tracking import InstanceTracker
+
+__all__ = ["Engine2d", "Engine3d", "tracker_consensus", "stack_postprocessing"]
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.B200EmpanadaError("a CUDA device (B200) is required; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _unsupported(name):
+    raise NotImplementedError(
+        f"{name} is outside the hot path built so far (SURVEY.md section 8f 'next' rows)")
+
+
+class _VolumeCache:
+    """Keeps the uint8 volume resident in HBM across the xy/xz/yz passes."""
+
+    def __init__(self):
+        self.key = None
+        self.dev = None
+
+    def get(self, volume, device):
+        key = (id(volume), volume.shape, str(volume.dtype))
+        if self.key != key:
+            if not isinstance(volume, np.ndarray):
+                _unsupported("zarr / dask input volumes")
+            if np.issubdtype(volume.dtype, np.floating):
+                raise Exception("Input image cannot be float type!")
+            if volume.dtype != np.uint8:
+                _unsupported(f"{volume.dtype} volumes (uint8 only)")
+            self.dev = torch.from_numpy(np.ascontiguousarray(volume)).to(device, non_blocking=False)
+            self.key = key
+        return self.dev
+
+    def clear(self):
+        self.key, self.dev = None, None
+
+
+class Engine3d:
+    r"""Engine for 3D ortho-plane and stack inference (reference signature preserved)."""
+
+    def __init__(self, model_config, inference_scale=1, label_divisor=1000, median_kernel_size=5,
+                 stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3,
+                 force_connected=True, min_size=500, min_extent=4, fine_boundaries=False,
+                 semantic_only=False, use_gpu=True, use_quantized=False, store_url=None,
+                 chunk_size=(256, 256, 256), save_panoptic=False, label_erosion=0,
+                 label_dilation=0, fill_holes_in_segmentation=False, batch_size=8):
+        self.device = _require_cuda()
+        if not use_gpu:
+            raise _lib.B200EmpanadaError("use_gpu=False requested: this engine has no CPU path")
+        self.model_config = model_config
+        self.labels = model_config["labels"]
+        self.class_names = model_config["class_names"]
+        self.label_divisor = label_divisor
+        self.padding_factor = model_config["padding_factor"]
+        self.inference_scale = inference_scale
+        self.label_erosion = label_erosion
+        self.label_dilation = label_dilation
+        self.fill_holes_in_segmentation = fill_holes_in_segmentation
+        self.thing_list = [] if semantic_only else model_config["thing_list"]
+        self.median_kernel_size = median_kernel_size
+        self.stuff_area = stuff_area
+        self.void_label = void_label
+        self.nms_threshold = nms_threshold
+        self.nms_kernel = nms_kernel
+        self.confidence_thr = confidence_thr
+        self.axes = {"xy": 0, "xz": 1, "yz": 2}
+        self.merge_iou_thr = 0.25
+        self.merge_ioa_thr = 0.25
+        self.force_connected = force_connected
+        self.min_size = min_size
+        self.min_extent = min_extent
+        self.fine_boundaries = fine_boundaries
+        self.save_panoptic = save_panoptic
+        self.chunk_size = chunk_size
+        self.zarr_store = None
+        if store_url is not None:
+            _unsupported("zarr output stores")
+        self.dtype = np.int32
+        self.batch_size = batch_size
+        self.model = load_model(model_config["model"], self.device, model_config)
+        self.engine = self  # widgets call engine.engine.reset(); kept for attribute parity
+        self._cache = _VolumeCache()
+        self.last_stats = {}
+
+    # attribute parity with PanopticDeepLabRenderEngine3d (mutated by the widgets)
+    @property
+    def ks(self):
+        return self.median_kernel_size
+
+    @ks.setter
+    def ks(self, v):
+        self.median_kernel_size = v
+
+    def reset(self):
+        pass
+
+    def update_params(self, inference_scale, label_divisor, median_kernel_size, nms_threshold,
+                      nms_kernel, confidence_thr, min_size, min_extent, fine_boundaries,
+                      semantic_only, store_url, chunk_size, save_panoptic, label_erosion,
+                      label_dilation, fill_holes_in_segmentation):
+        self.label_divisor = label_divisor
+        self.inference_scale = inference_scale
+        self.min_size = min_size
+        self.min_extent = min_extent
+        self.fine_boundaries = fine_boundaries
+        self.median_kernel_size = median_kernel_size
+        self.nms_threshold = nms_threshold
+        self.nms_kernel = nms_kernel
+        self.confidence_thr = confidence_thr
+        self.label_erosion = label_erosion
+        self.label_dilation = label_dilation
+        self.fill_holes_in_segmentation = fill_holes_in_segmentation
+        self.thing_list = [] if semantic_only else self.model_config["thing_list"]
+        self.save_panoptic = save_panoptic
+        self.chunk_size = chunk_size
+        if store_url is not None:
+            _unsupported("zarr output stores")
+
+    def create_trackers(self, shape3d, axis_name):
+        return [InstanceTracker(label, self.label_divisor, shape3d, axis_name) for label in self.labels]
+
+    def _check_supported(self):
+        if self.inference_scale != 1:
+            _unsupported("inference_scale > 1")
+        if self.fine_boundaries:
+            _unsupported("fine_boundaries")
+        if self.label_erosion or self.label_dilation or self.fill_holes_in_segmentation:
+            _unsupported("tracker morphology (erode / dilate / fill holes)")
+        if len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
+            _unsupported("multi-class / semantic-only models")
+
+    def infer_on_axis(self, volume, axis_name):
+        self._check_supported()
+        axis = self.axes[axis_name]
+        dev = self.device
+        vol_d = self._cache.get(volume, dev)
+        shape3d = tuple(int(s) for s in volume.shape)
+        n = shape3d[axis]
+        h, w = [s for i, s in enumerate(shape3d) if i != axis]
+        pf = self.padding_factor
+        H = h + (pf - h % pf) % pf
+        W = w + (pf - w % pf) % pf
+        cls = self.thing_list[0]
+        post = PlanePost(n, h, w, H, W, ks=self.median_kernel_size, thing_class=cls,
+                         label_divisor=self.label_divisor, void_label=self.void_label,
+                         nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
+                         confidence_thr=self.confidence_thr, device=dev)
+        norms = self.model_config["norms"]
+        for s0 in range(0, n, self.batch_size):
+            s1 = min(n, s0 + self.batch_size)
+            sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            post.push_heads(sem, ctr, off, is_prob=False)
+        post.finish_heads()
+        post.run_cc()
+        lut, labels, sizes, boxes = post.replay(axis_name, self.merge_iou_thr, self.merge_ioa_thr)
+        # filters.remove_small_objects / remove_pancakes (inference.py:556-558), applied on tables
+        spans = boxes[:, 3:] - boxes[:, :3] if len(boxes) else np.zeros((0, 3), np.int32)
+        keep = (sizes >= self.min_size) & (spans >= self.min_extent).all(axis=1) if len(labels) else np.zeros(0, bool)
+        kept_labels = labels[keep]
+        max_label = int(lut.max()) if lut.size else 0
+        keep_lut = np.zeros(max_label + 1, dtype=np.int32)
+        keep_lut[kept_labels] = kept_labels
+        lut_f = keep_lut[lut]
+        dense = post.relabel(lut_f, axis_name, shape3d)
+        trackers = self.create_trackers(shape3d, axis_name)
+        tr = trackers[0]
+        tr.instances = post.tracker_instances(axis_name, shape3d, lut_f, kept_labels, boxes[keep], dense)
+        tr.finish()
+        tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
+        stack = dense.cpu().numpy() if self.save_panoptic else None
+        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0)}
+        return stack, trackers
+
+    def release(self):
+        self._cache.clear()
+
+
+class Engine2d:
+    r"""Engine for 2D inference (reference signature preserved; no tiling yet)."""
+
+    def __init__(self, model_config, inference_scale=1, label_divisor=1000, nms_threshold=0.1,
+                 nms_kernel=3, confidence_thr=0.3, semantic_only=False, fine_boundaries=False,
+                 tile_size=0, use_gpu=True, use_quantized=False):
+        self.device = _require_cuda()
+        if not use_gpu:
+            raise _lib.B200EmpanadaError("use_gpu=False requested: this engine has no CPU path")
+        self.model_config = model_config
+        self.thing_list = model_config["thing_list"]
+        self.labels = model_config["labels"]
+        self.class_names = model_config["class_names"]
+        self.label_divisor = label_divisor
+        self.padding_factor = model_config["padding_factor"]
+        self.inference_scale = inference_scale
+        self.fine_boundaries = fine_boundaries
+        self.semantic_only = semantic_only
+        self.tile_size = tile_size
+        self.nms_threshold = nms_threshold
+        self.nms_kernel = nms_kernel
+        self.confidence_thr = confidence_thr
+        self.model = load_model(model_config["model"], self.device, model_config)
+        self.engine = self
+
+    def update_params(self, inference_scale, label_divisor, nms_threshold, nms_kernel,
+                      confidence_thr, fine_boundaries, semantic_only=False, tile_size=0):
+        self.inference_scale = inference_scale
+        self.label_divisor = label_divisor
+        self.nms_threshold = nms_threshold
+        self.nms_kernel = nms_kernel
+        self.confidence_thr = confidence_thr
+        self.fine_boundaries = fine_boundaries
+        self.semantic_only = semantic_only
+        self.tile_size = tile_size
+
+    def infer_batch(self, images):
+        """images: uint8 array (n, h, w) -> int32 (n, h, w). One launch sequence for the batch."""
+        if self.inference_scale != 1:
+            _unsupported("inference_scale > 1")
+        if self.fine_boundaries:
+            _unsupported("fine_boundaries")
+        if self.semantic_only or len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
+            _unsupported("multi-class / semantic-only models")
+        if self.tile_size > 0 and any(s > self.tile_size for s in images.shape[1:]):
+            _unsupported("tiled 2-D inference")
+        if np.issubdtype(images.dtype, np.floating):
+            raise Exception("Input image cannot be float type!")
+        if images.dtype != np.uint8:
+            _unsupported(f"{images.dtype} images (uint8 only)")
+        dev = self.device
+        n, h, w = images.shape
+        pf = self.padding_factor
+        H = h + (pf - h % pf) % pf
+        W = w + (pf - w % pf) % pf
+        vol_d = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images)).to(dev)
+        cls = self.thing_list[0]
+        post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=self.label_divisor,
+                         void_label=0, nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
+                         confidence_thr=self.confidence_thr, device=dev)
+        sem, ctr, off = self.model.forward_slices(vol_d, 0, 0, n, self.model_config["norms"], pf)
+        post.push_heads(sem, ctr, off, is_prob=False)
+        post.finish_heads()
+        # force_connected (inference.py:263-279): pan <- class*div + component id
+        post.run_cc(batch=min(n, 16))
+        out = torch.where(post.cc > 0, post.cc + cls * self.label_divisor, torch.zeros_like(post.cc))
+        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0)}
+        return out
+
+    def infer(self, image):
+        if image.ndim != 2:
+            raise ValueError("Engine2d.infer expects a 2-D image")
+        return self.infer_batch(image[None])[0].cpu().numpy().astype(np.int32)
+
+
+def get_axis_trackers_by_class(trackers, class_id):
+    """patterns.py:154-166."""
+    return [t for axis_trackers in trackers.values() for t in axis_trackers if t.class_id == class_id]
+
+
+def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pixel_vote_thr=2,
+                      cluster_iou_thr=0.75, allow_one_view=False, min_size=200, min_extent=4,
+                      dtype=np.uint32, chunk_size=(256, 256, 256)):
+    r"""Orthoplane consensus (generator, as the reference): yields (volume, class_name, instances)."""
+    if store_url is not None:
+        _unsupported("zarr output stores")
+    thing_list = model_config["thing_list"]
+    for class_id, class_name in model_config["class_names"].items():
+        class_trackers = get_axis_trackers_by_class(trackers, class_id)
+        shape3d = class_trackers[0].shape3d
+        if class_id not in thing_list:
+            _unsupported("semantic (stuff) class consensus")
+        out = InstanceTracker(class_id, class_trackers[0].label_divisor, shape3d, "xy")
+        vol_d, instances = consensus.merge_objects_from_trackers(
+            class_trackers, pixel_vote_thr, cluster_iou_thr, allow_one_view, min_size, min_extent)
+        out.instances = instances
+        vol = vol_d.cpu().numpy().astype(dtype, copy=False)
+        yield vol, class_name, out.instances
+
+
+def stack_postprocessing(trackers, store_url, model_config, label_divisor=1000, min_size=200,
+                         min_extent=4, dtype=np.uint32, chunk_size=(256, 256, 256)):
+    r"""Relabel 1..n + filter + fill for single-plane stacks (generator, as the reference)."""
+    if store_url is not None:
+        _unsupported("zarr output stores")
+    thing_list = model_config["thing_list"]
+    for class_id, class_name in model_config["class_names"].items():
+        ct = get_axis_trackers_by_class(trackers, class_id)[0]
+        st = InstanceTracker(class_id, label_divisor, ct.shape3d, "xy")
+        st.instances = consensus.instance_relabel(ct)
+        if class_id in thing_list:
+            tracking.remove_small_objects(st, min_size=min_size)
+            tracking.remove_pancakes(st, min_span=min_extent)
+        vol = consensus.fill_volume_device(ct, st.instances, dtype)
+        yield vol, class_name, st.instances

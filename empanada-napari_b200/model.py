@@ -1,0 +1,72 @@
+"""Model boundary: `load_model` mirrors `empanada_napari.utils.load_model_to_device`
+(/root/reference/empanada_napari/utils.py:80-106): it takes the `model` entry of a model config
+(a local TorchScript archive exported by the reference, a plain state_dict file, or an
+already-constructed model object) and returns an object with
+
+    forward_slices(volume_u8 (D,H,W) cuda, axis, s0, s1, norms, padding_factor)
+        -> sem_logits (B,Hp,Wp) fp32, ctr_hmp (B,Hp/4,Wp/4) fp32, offsets (B,2,Hp/4,Wp/4) fp32
+
+i.e. `model(image, render_steps, interpolate_ins=False)` of engines.py:250 for a batch of slices,
+with slice extraction, normalisation and padding (volume_dataset.py:37-53, utils.py:170-201,
+postprocess.py:26-36) fused in front.
+"""
+import os
+
+import torch
+
+from . import _lib
+
+
+class SyntheticHeadsModel:
+    """Test/benchmark stand-in for the network: head maps come from a callable
+    `heads_fn(axis, s0, s1) -> (sem_logits, ctr_hmp, offsets)` (cuda tensors). Optionally runs a
+    real model first so that the forward pass is still executed and timed (bench.py)."""
+
+    def __init__(self, heads_fn, inner=None):
+        self.heads_fn = heads_fn
+        self.inner = inner
+        self.launches = 0
+
+    def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
+        if self.inner is not None:
+            self.inner.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            self.launches = self.inner.launches
+        return self.heads_fn(axis, s0, s1)
+
+
+def load_state_dict_any(path):
+    """state_dict of a TorchScript archive (the reference's deployment format) or a plain
+    `torch.save(state_dict)` file."""
+    try:
+        m = torch.jit.load(path, map_location="cpu")
+        return {k: v.detach() for k, v in m.state_dict().items()}
+    except Exception:
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        if not isinstance(sd, dict):
+            raise _lib.B200EmpanadaError(f"{path}: neither a TorchScript archive nor a state_dict")
+        return sd
+
+
+def load_model(model, device, model_config=None):
+    if hasattr(model, "forward_slices"):
+        return model
+    if isinstance(model, dict):
+        sd = model
+    elif isinstance(model, str):
+        path = model
+        if path.startswith("http://") or path.startswith("https://"):
+            # same cache location as the reference (utils.py:86-104); no download here
+            cached = os.path.join(os.path.expanduser("~"), ".empanada", os.path.basename(path).split("?")[0])
+            if not os.path.isfile(cached):
+                raise _lib.B200EmpanadaError(
+                    f"model URL {path} is not cached at {cached} and this build does not download")
+            path = cached
+        sd = load_state_dict_any(path)
+    else:
+        raise _lib.B200EmpanadaError(f"unsupported model specification: {type(model)}")
+    from .pdl import PDLModel, is_pdl_state_dict
+    if is_pdl_state_dict(sd):
+        return PDLModel(sd, device)
+    raise _lib.B200EmpanadaError(
+        "unsupported network: only the PanopticDeepLab-PointRend / ResNet-50 export is built so far "
+        "(PanopticBiFPN is the next model family)")

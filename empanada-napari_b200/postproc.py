@@ -1,0 +1,250 @@
+"""Per-plane GPU post-processing driver: median queue -> centres -> grouping -> merge ->
+connected components -> overlap tables -> (host matcher replay) -> relabel -> RLE runs.
+
+Everything between the model's head outputs and the tracker dictionaries of
+`Engine3d.infer_on_axis` (empanada_napari/inference.py:526-578) for ONE plane, batched over
+slices. torch is used for device buffers and trivial index plumbing; every per-pixel pass is
+one of the library's own kernels (csrc/post_kernels.cu, cc_kernels.cu).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+from . import tracking
+
+AXES = {"xy": 0, "xz": 1, "yz": 2}
+
+
+def _next_pow2(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+class PlanePost:
+    """State for one `infer_on_axis` pass over `n_slices` slices of size (h, w), padded (H, W)."""
+
+    def __init__(self, n_slices, h, w, H, W, *, ks, thing_class, label_divisor, void_label=0,
+                 nms_threshold=0.1, nms_kernel=3, confidence_thr=0.5, scale=4, device="cuda:0",
+                 center_cap=4096, cc_cap=4096, keep_prob=False):
+        if ks % 2 != 1:
+            raise AssertionError("Kernel size must be odd integer!")
+        if n_slices < ks:
+            raise ValueError(f"stack of {n_slices} slices is shorter than the median kernel ({ks})")
+        self.N, self.h, self.w, self.H, self.W = n_slices, h, w, H, W
+        self.ks, self.mid = ks, (ks - 1) // 2
+        self.cls, self.div, self.void = thing_class, label_divisor, void_label
+        self.thr, self.k, self.conf, self.scale = nms_threshold, nms_kernel, confidence_thr, scale
+        self.dev = torch.device(device)
+        self.h4, self.w4 = H // scale, W // scale
+        self.center_cap, self.cc_cap = center_cap, cc_cap
+        d = self.dev
+        self.hard = torch.zeros((n_slices, H, W), dtype=torch.uint8, device=d)
+        self.prob = torch.zeros((n_slices, H, W), dtype=torch.float32, device=d) if keep_prob else None
+        self.cells4 = torch.zeros((n_slices, self.h4, self.w4), dtype=torch.int32, device=d)
+        self.hist = torch.zeros((max(ks - 1, 1), H, W), dtype=torch.float32, device=d)
+        self.n_hist = 0
+        self.pushed = 0
+        self.centers = torch.zeros((n_slices, center_cap), dtype=torch.int32, device=d)
+        self.center_counts = torch.zeros(n_slices, dtype=torch.int32, device=d)
+        self.cc = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ stage 1: heads in
+    def push_heads(self, sem, ctr, off, is_prob=False):
+        """sem (B,H,W) fp32 logits (or probabilities), ctr (B,h4,w4), off (B,2,h4,w4)."""
+        B = sem.shape[0]
+        s0 = self.pushed
+        assert s0 + B <= self.N
+        st = stream_ptr()
+        call("be_median_push", ptr(sem), B, self.H, self.W, self.ks, ptr(self.hist), self.n_hist,
+             s0, float(self.conf), int(is_prob), ptr(self.hard), ptr(self.prob), st)
+        call("be_centers", ptr(ctr), B, self.h4, self.w4, float(self.thr), int(self.k),
+             ptr(self.centers[s0]), self.center_cap, ptr(self.center_counts[s0:]), st)
+        call("be_group_pixels", ptr(off), ptr(self.centers[s0]), self.center_cap,
+             ptr(self.center_counts[s0:]), B, self.h4, self.w4, float(self.scale),
+             ptr(self.cells4[s0]), st)
+        self.launches += 3
+        self.pushed += B
+        self.n_hist = min(self.n_hist + B, self.ks - 1)
+
+    def finish_heads(self):
+        assert self.pushed == self.N
+        if self.ks > 1:
+            call("be_median_flush", ptr(self.hist), self.n_hist, self.ks, self.H, self.W, self.N,
+                 float(self.conf), ptr(self.hard), ptr(self.prob), stream_ptr())
+            self.launches += 1
+        cmax = int(self.center_counts.max().item())
+        if cmax > self.center_cap:
+            raise _lib.B200EmpanadaError(
+                f"{cmax} centres in one slice exceed center_cap={self.center_cap}")
+
+    # ------------------------------------------------------------------ stage 2: pan -> cc
+    def pan_batch(self, s0, s1):
+        """pan_seg (B,h,w) int32 for emitted slices [s0, s1) (the per-slice engine output)."""
+        B = s1 - s0
+        pan = torch.empty((B, self.h, self.w), dtype=torch.int32, device=self.dev)
+        present = torch.empty((B, self.center_cap + 1), dtype=torch.int32, device=self.dev)
+        call("be_merge_pan", ptr(self.hard[s0]), ptr(self.cells4[s0]), B, self.H, self.W, self.h,
+             self.w, self.scale, self.center_cap, int(self.div), int(self.cls), int(self.void),
+             ptr(present), ptr(pan), stream_ptr())
+        self.launches += 4
+        return pan
+
+    def run_cc(self, batch=16):
+        """Connected components + tables for all slices; overlap table between neighbours."""
+        N, h, w, d = self.N, self.h, self.w, self.dev
+        while True:
+            self.cc = torch.empty((N, h, w), dtype=torch.int32, device=d)
+            self.n_cc = torch.zeros(N, dtype=torch.int32, device=d)
+            self.cc_table = torch.empty((N, self.cc_cap, 5), dtype=torch.int32, device=d)
+            chunks = (h * w + 1023) // 1024
+            L = torch.empty((batch, h, w), dtype=torch.int32, device=d)
+            chunk_counts = torch.empty((batch, chunks), dtype=torch.int32, device=d)
+            lo, hi = self.cls * self.div, (self.cls + 1) * self.div
+            for s0 in range(0, N, batch):
+                s1 = min(N, s0 + batch)
+                pan = self.pan_batch(s0, s1)
+                call("be_cc_label", ptr(pan), s1 - s0, h, w, lo, hi, ptr(L), ptr(chunk_counts),
+                     ptr(self.cc[s0]), ptr(self.n_cc[s0:]), self.cc_cap, ptr(self.cc_table[s0]),
+                     stream_ptr())
+                self.launches += 9
+            n_cc_max = int(self.n_cc.max().item())
+            if n_cc_max <= self.cc_cap and n_cc_max < (1 << 20):
+                break
+            if n_cc_max >= (1 << 20):
+                raise _lib.B200EmpanadaError("more than 2^20 components in one slice")
+            self.cc_cap = _next_pow2(n_cc_max + 1)
+        # overlap table (slice s vs s-1)
+        total_cc = int(self.n_cc.sum().item())
+        cap = _next_pow2(max(1 << 16, 8 * total_cc))
+        while True:
+            keys = torch.empty(cap, dtype=torch.int64, device=d)
+            vals = torch.empty(cap, dtype=torch.int32, device=d)
+            overflow = torch.zeros(1, dtype=torch.int32, device=d)
+            call("be_hash_clear", ptr(keys), ptr(vals), cap, stream_ptr())
+            call("be_pair_overlap", ptr(self.cc), h, w, 0, N, ptr(keys), ptr(vals), cap,
+                 ptr(overflow), stream_ptr())
+            self.launches += 3
+            if int(overflow.item()) == 0:
+                break
+            cap *= 4
+        out_keys = torch.empty(cap, dtype=torch.int64, device=d)
+        out_vals = torch.empty(cap, dtype=torch.int32, device=d)
+        cursor = torch.zeros(1, dtype=torch.int32, device=d)
+        call("be_hash_compact", ptr(keys), ptr(vals), cap, ptr(out_keys), ptr(out_vals), cap,
+             ptr(cursor), stream_ptr())
+        self.launches += 1
+        n_pairs = int(cursor.item())
+        self.pair_keys = out_keys[:n_pairs].cpu().numpy().view(np.uint64)
+        self.pair_vals = out_vals[:n_pairs].cpu().numpy()
+
+    # ------------------------------------------------------------------ stage 3: host replay
+    def replay(self, axis_name, iou_thr=0.25, ioa_thr=0.25):
+        n_cc = self.n_cc.cpu().numpy()
+        cap = max(1, int(n_cc.max()))
+        table = self.cc_table[:, :cap].contiguous().cpu().numpy()
+        return tracking.match_replay(n_cc, table, self.pair_keys, self.pair_vals, self.cls,
+                                     self.div, axis_name, iou_thr, ioa_thr)
+
+    # ------------------------------------------------------------------ stage 4: relabel + runs
+    def relabel(self, lut, axis_name, shape3d, batch=64):
+        """Paint final labels (lut [N, stride] int32, 0 = dropped) into a (D,H,W) device volume."""
+        D, Hv, Wv = shape3d
+        vol = torch.empty(shape3d, dtype=torch.int32, device=self.dev)
+        lut_d = torch.from_numpy(np.ascontiguousarray(lut)).to(self.dev)
+        strides = {"xy": (Hv * Wv, Wv, 1), "xz": (Wv, Hv * Wv, 1), "yz": (1, Hv * Wv, Wv)}[axis_name]
+        for s0 in range(0, self.N, batch):
+            s1 = min(self.N, s0 + batch)
+            call("be_relabel", ptr(self.cc[s0]), s1 - s0, self.h, self.w, s0, ptr(lut_d),
+                 lut_d.shape[1], ptr(vol), *strides, stream_ptr())
+            self.launches += 1
+        self._lut_d = lut_d
+        return vol
+
+    def extract_runs(self, img, seg_len):
+        """Maximal runs of equal non-zero label over flat indices, split at multiples of
+        seg_len. Returns device tensors (labels int32, starts int64, lens int32), raster order."""
+        n = img.numel()
+        chunks = (n + 1023) // 1024
+        counts = torch.zeros(chunks + 1, dtype=torch.int32, device=self.dev)
+        offsets = torch.empty(chunks + 1, dtype=torch.int64, device=self.dev)
+        st = stream_ptr()
+        call("be_runs_count", ptr(img), n, seg_len, ptr(counts), st)
+        torch.cumsum(counts[:-1], 0, out=offsets[1:])
+        offsets[0] = 0
+        total = int(offsets[-1].item())
+        labels = torch.empty(total, dtype=torch.int32, device=self.dev)
+        starts = torch.empty(total, dtype=torch.int64, device=self.dev)
+        lens = torch.empty(total, dtype=torch.int32, device=self.dev)
+        if total:
+            call("be_runs_write", ptr(img), n, seg_len, ptr(offsets), ptr(labels), ptr(starts),
+                 ptr(lens), total, st)
+        self.launches += 2
+        return labels, starts, lens
+
+    def tracker_instances(self, axis_name, shape3d, lut, labels, boxes, vol, batch=64):
+        """Builds the reference's `InstanceTracker.instances` dictionary (tracker.py:61-123):
+        per label, runs in arrival order (reverse slice order for xy/xz; sorted for yz)."""
+        D, Hv, Wv = shape3d
+        dev = self.dev
+        if len(labels) == 0:
+            return {}
+        if axis_name == "yz":
+            lab, st3, ln = self.extract_runs(vol, vol.numel())
+            seq = st3
+        else:
+            labs, sts, lns = [], [], []
+            tmp = torch.empty((batch, self.h, self.w), dtype=torch.int32, device=dev)
+            hw = self.h * self.w
+            for s0 in range(0, self.N, batch):
+                s1 = min(self.N, s0 + batch)
+                if axis_name == "xy":
+                    img = vol[s0:s1]
+                else:
+                    img = tmp[: s1 - s0]
+                    call("be_relabel", ptr(self.cc[s0]), s1 - s0, self.h, self.w, s0,
+                         ptr(self._lut_d), self._lut_d.shape[1], ptr(img[0]) - s0 * hw * 4,
+                         hw, self.w, 1, stream_ptr())
+                    self.launches += 1
+                l_, s_, n_ = self.extract_runs(img, hw)
+                labs.append(l_); sts.append(s_ + s0 * hw); lns.append(n_)
+            lab, stg, ln = torch.cat(labs), torch.cat(sts), torch.cat(lns)
+            sl = torch.div(stg, hw, rounding_mode="floor")
+            s2d = stg - sl * hw
+            seq = (self.N - 1 - sl) * hw + s2d
+            if axis_name == "xy":
+                st3 = stg
+            else:  # xz: (z, x) of slice `sl` -> (z, sl, x); run lengths kept (tracker.py:80-84)
+                z = torch.div(s2d, self.w, rounding_mode="floor")
+                st3 = (z * Hv + sl) * Wv + (s2d - z * self.w)
+        # rank of each label in tracker insertion order
+        max_label = int(max(int(labels.max()), int(lab.max().item()) if lab.numel() else 0))
+        rank_lut = torch.full((max_label + 1,), -1, dtype=torch.int64, device=dev)
+        rank_lut[torch.from_numpy(labels.astype(np.int64)).to(dev)] = torch.arange(len(labels), device=dev)
+        rank = rank_lut[lab.long()]
+        keys = (rank << 40) | seq
+        n = keys.numel()
+        idx = torch.arange(n, dtype=torch.int32, device=dev)
+        keys_out = torch.empty_like(keys)
+        idx_out = torch.empty_like(idx)
+        need = _lib.SZ(0)
+        _lib.lib().be_sort_runs(None, None, None, None, n, None, 0, need, None)
+        temp = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
+        call("be_sort_runs", ptr(keys), ptr(keys_out), ptr(idx), ptr(idx_out), n, ptr(temp),
+             temp.numel(), None, stream_ptr())
+        self.launches += 1
+        order = idx_out.long()
+        st_sorted = st3[order].cpu().numpy()
+        ln_sorted = ln[order].long().cpu().numpy()
+        rank_sorted = (keys_out >> 40)
+        counts = torch.bincount(rank_sorted, minlength=len(labels)).cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        instances = {}
+        for i, lab_i in enumerate(labels):
+            a, b = offs[i], offs[i + 1]
+            instances[int(lab_i)] = {"box": tuple(int(v) for v in boxes[i]),
+                                     "starts": st_sorted[a:b], "runs": ln_sorted[a:b]}
+        return instances

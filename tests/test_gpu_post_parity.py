@@ -1,0 +1,152 @@
+"""-m gpu: the CUDA post-processing / tracking / consensus path against the CPU oracle on the
+same seeded inputs, and against the golden fixtures generated from the reference itself.
+Bit-exact (integer label maps, RLE tables)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_instances_equal, unpack_instances
+
+pytestmark = pytest.mark.gpu
+
+MODEL_CONFIG = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 16,
+                "norms": {"mean": 0.57571, "std": 0.12765}, "model": None}
+
+
+def _engine(heads_by_axis, **kw):
+    import torch
+    from empanada_napari_b200.inference import Engine3d
+    from empanada_napari_b200.model import SyntheticHeadsModel
+
+    def heads_fn(axis, s0, s1):
+        sem, ctr, off = heads_by_axis[axis]
+        dev = torch.device("cuda:0")
+        return (torch.from_numpy(np.ascontiguousarray(sem[s0:s1, 0])).to(dev),
+                torch.from_numpy(np.ascontiguousarray(ctr[s0:s1])).to(dev),
+                torch.from_numpy(np.ascontiguousarray(off[s0:s1])).to(dev))
+
+    cfg = dict(MODEL_CONFIG)
+    cfg["model"] = SyntheticHeadsModel(heads_fn)
+    return Engine3d(cfg, **kw), cfg
+
+
+def test_post_cases_golden():
+    """per-slice kernels vs reference-generated vectors (centres, cells, pan_seg)."""
+    import torch
+    from empanada_napari_b200.postproc import PlanePost
+    z = np.load(os.path.join(GOLDEN, "post_cases.npz"))
+    dev = torch.device("cuda:0")
+    for i in range(int(z["n"])):
+        ctr, off, prob = z[f"c{i}_ctr"], z[f"c{i}_off"], z[f"c{i}_prob"]
+        H, W = prob.shape[-2:]
+        post = PlanePost(1, H, W, H, W, ks=1, thing_class=1, label_divisor=1000,
+                         nms_threshold=float(z[f"c{i}_thr"]), nms_kernel=int(z[f"c{i}_nms_kernel"]),
+                         confidence_thr=float(z[f"c{i}_conf"]), device=dev)
+        post.push_heads(torch.from_numpy(prob).to(dev), torch.from_numpy(ctr[None]).to(dev),
+                        torch.from_numpy(off[None]).to(dev), is_prob=True)
+        post.finish_heads()
+        k = int(post.center_counts[0].item())
+        packed = post.centers[0, :k].cpu().numpy()
+        centers = np.stack([packed >> 16, packed & 0xFFFF], axis=1).reshape(-1, 2)
+        assert np.array_equal(centers, z[f"c{i}_centers"].reshape(-1, 2)), i
+        cells4 = post.cells4[0].cpu().numpy()
+        assert np.array_equal(np.repeat(np.repeat(cells4, 4, 0), 4, 1), z[f"c{i}_cells"].astype(np.int32)), i
+        pan = post.pan_batch(0, 1)[0].cpu().numpy()
+        assert np.array_equal(pan, z[f"c{i}_pan"]), i
+
+
+def test_median_golden():
+    import torch
+    from empanada_napari_b200.postproc import PlanePost
+    z = np.load(os.path.join(GOLDEN, "median_cases.npz"))
+    dev = torch.device("cuda:0")
+    for i in range(int(z["n"])):
+        ks, x, ts, ys = int(z[f"m{i}_ks"]), z[f"m{i}_x"], z[f"m{i}_t"], z[f"m{i}_y"]
+        n, _, H, W = x.shape
+        if n < ks:
+            continue
+        for bs in (1, 2, n):
+            post = PlanePost(n, H, W, H, W, ks=ks, thing_class=1, label_divisor=1000, device=dev,
+                             keep_prob=True, scale=1)
+            for s0 in range(0, n, bs):
+                s1 = min(n, s0 + bs)
+                post.push_heads(torch.from_numpy(x[s0:s1, 0]).to(dev),
+                                torch.zeros((s1 - s0, H, W), device=dev),
+                                torch.zeros((s1 - s0, 2, H, W), device=dev), is_prob=True)
+            post.finish_heads()
+            got = post.prob.cpu().numpy()
+            assert ts.tolist() == list(range(n))
+            assert np.array_equal(got, ys[:, 0]), (i, bs)
+            assert np.array_equal(post.hard.cpu().numpy(), (ys[:, 0] >= np.float32(0.5)).astype(np.uint8))
+
+
+@pytest.mark.parametrize("tag", ["clean", "noisy", "ks5_odd"])
+def test_volume_golden(tag):
+    """Engine3d.infer_on_axis x3 + tracker_consensus + stack_postprocessing vs the reference."""
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import stack_postprocessing, tracker_consensus
+    z = np.load(os.path.join(GOLDEN, f"volume_{tag}.npz"))
+    shape = tuple(int(v) for v in z["shape"])
+    vol, _, _ = syn.make_volume(shape, seed=int(z["seed"]), n_objects=int(z["n_objects"]), scale=1.0)
+    heads = {a: (z[f"{n}_sem"].astype(np.float32), z[f"{n}_ctr"], z[f"{n}_off"])
+             for a, n in enumerate(("xy", "xz", "yz"))}
+    eng, cfg = _engine(heads, median_kernel_size=int(z["ks"]), nms_kernel=3, confidence_thr=0.5,
+                       min_size=int(z["min_size"]), min_extent=int(z["min_extent"]),
+                       save_panoptic=True, batch_size=5)
+    trackers = {}
+    for axis_name in ("xy", "xz", "yz"):
+        stack, trs = eng.infer_on_axis(vol, axis_name)
+        assert_instances_equal(trs[0].instances, unpack_instances(z, f"{axis_name}_tr_"))
+        assert stack.dtype == np.int32 and np.array_equal(stack, z[f"{axis_name}_stack"])
+        trackers[axis_name] = trs
+    for v, name, inst in tracker_consensus(
+            trackers, None, cfg, pixel_vote_thr=int(z["pixel_vote_thr"]),
+            allow_one_view=bool(z["allow_one_view"]), min_size=int(z["min_size"]),
+            min_extent=int(z["min_extent"]), dtype=np.int32):
+        assert_instances_equal(inst, unpack_instances(z, "consensus_"))
+        assert np.array_equal(v, z["consensus_vol"])
+    for v, name, inst in stack_postprocessing(
+            {"xy": trackers["xy"]}, None, cfg, min_size=int(z["min_size"]),
+            min_extent=int(z["min_extent"]), dtype=np.int32):
+        assert_instances_equal(inst, unpack_instances(z, "stackpost_"))
+        assert np.array_equal(v, z["stackpost_vol"])
+
+
+@pytest.mark.parametrize("seed,shape,noise,ks", [(11, (40, 64, 72), 0.0, 3), (12, (48, 56, 50), 0.5, 3),
+                                                 (13, (36, 70, 41), 0.8, 5), (14, (64, 64, 64), 0.3, 1)])
+def test_volume_vs_oracle(seed, shape, noise, ks):
+    """Larger random volumes: CUDA path vs the pinned CPU oracle, bit-exact."""
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import tracker_consensus
+    from oracle import consensus as ocons, pipeline
+    vol, lab, _ = syn.make_volume(shape, seed=seed, scale=1.0)
+    rng = np.random.default_rng(seed)
+    heads = {}
+    for axis in range(3):
+        hs = []
+        for i in range(shape[axis]):
+            sem, ctr, off = syn.analytic_heads(np.take(lab, i, axis=axis), pad_to=16)
+            sem = sem + rng.normal(0, 2.5 * noise, sem.shape).astype(np.float32)
+            ctr = ctr + rng.normal(0, 0.05 * noise, ctr.shape).astype(np.float32)
+            off = off + rng.normal(0, 2.0 * noise, off.shape).astype(np.float32)
+            hs.append((sem.astype(np.float32), ctr.astype(np.float32), off.astype(np.float32)))
+        heads[axis] = (np.stack([h[0] for h in hs]), np.stack([h[1] for h in hs]), np.stack([h[2] for h in hs]))
+    eng, cfg = _engine(heads, median_kernel_size=ks, nms_kernel=3, confidence_thr=0.5, min_size=30,
+                       min_extent=3, save_panoptic=True, batch_size=7)
+    got, want = {}, {}
+    for a, axis_name in enumerate(("xy", "xz", "yz")):
+        stack, trs = eng.infer_on_axis(vol, axis_name)
+        sem, ctr, off = heads[a]
+        ostack, otrs = pipeline.infer_on_axis(vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), cfg,
+                                              median_kernel_size=ks, nms_kernel=3, confidence_thr=0.5,
+                                              min_size=30, min_extent=3)
+        assert_instances_equal(trs[0].instances, otrs[0].instances)
+        assert np.array_equal(stack, ostack)
+        got[axis_name], want[axis_name] = trs, otrs
+    for (v, _, inst), (ov, _, oinst) in zip(
+            tracker_consensus(got, None, cfg, pixel_vote_thr=2, min_size=30, min_extent=3, dtype=np.int32),
+            ocons.tracker_consensus(want, cfg, pixel_vote_thr=2, min_size=30, min_extent=3, dtype=np.int32)):
+        assert_instances_equal(inst, oinst)
+        assert np.array_equal(v, ov)
+        assert len(inst) > 0
