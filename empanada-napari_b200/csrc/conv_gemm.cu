@@ -143,6 +143,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MAX_N;
+      const float* bias = p.bias ? p.bias + static_cast<long long>(b) * p.bias_img_stride : nullptr;
+      float hacc0 = 0.0f, hacc1 = 0.0f;
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + c0, v);
@@ -153,7 +155,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             f[j] = __uint_as_float(v[j]);
-            if (p.bias != nullptr && n + j < p.Cout) f[j] += __ldg(p.bias + n + j);
+            if (bias != nullptr && n + j < p.Cout) f[j] += __ldg(bias + n + j);
           }
           const bool full16 = (n + 16 <= p.Cout);
           if (p.residual != nullptr) {
@@ -190,10 +192,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
           if (p.out_f32 != nullptr) {
-            float* fp = p.out_f32 + pix * p.out_f32_ld + n;
-            for (int j = 0; j < 16 && n + j < p.Cout; ++j) fp[j] = f[j];
+            if (p.out_f32_planar) {
+              const long long hw = static_cast<long long>(p.Ho) * p.Wo;
+              float* fp = p.out_f32 + (static_cast<long long>(b) * p.Cout + n) * hw + (static_cast<long long>(y) * p.Wo + x);
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) fp[j * hw] = f[j];
+            } else {
+              float* fp = p.out_f32 + pix * p.out_f32_ld + n;
+              for (int j = 0; j < 16 && n + j < p.Cout; ++j) fp[j] = f[j];
+            }
+          }
+          if (p.head_n > 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n + j < p.Cout) {
+                hacc0 = fmaf(f[j], __ldg(p.head_w + n + j), hacc0);
+                if (p.head_n > 1) hacc1 = fmaf(f[j], __ldg(p.head_w + p.Cout + n + j), hacc1);
+              }
+            }
           }
         }
+      }
+      if (p.head_n > 0 && valid) {
+        const long long hw = static_cast<long long>(p.Ho) * p.Wo;
+        float* hp = p.head_out + static_cast<long long>(b) * p.head_n * hw + (static_cast<long long>(y) * p.Wo + x);
+        hp[0] = hacc0 + __ldg(p.head_b);
+        if (p.head_n > 1) hp[hw] = hacc1 + __ldg(p.head_b + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -246,6 +269,14 @@ static void pick_tile_geometry(int B, int Ho, int Wo, int* TW, int* TH, int* TB)
   }
 }
 
+int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
+                      int Cin, const __nv_bfloat16* w, int Cout, int R, int S, int stride, int dil,
+                      int pad, int Ho, int Wo, __nv_bfloat16* out, long long out_ld, int out_coff,
+                      float* out_f32, long long out_f32_ld, int out_f32_planar, const float* bias,
+                      long long bias_img_stride, const __nv_bfloat16* residual, long long res_ld,
+                      int act, const float* head_w, const float* head_b, float* head_out,
+                      int head_n, int num_sms);
+
 // Describes one convolution call. Input: NHWC bf16 [B, Hi, Wi, >=Cin] with pixel stride in_ld.
 // Weights: [Cout][R*S*Cin] bf16. Output map: Ho x Wo.
 int conv_gemm_plan(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
@@ -253,6 +284,18 @@ int conv_gemm_plan(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, i
                    int pad, int Ho, int Wo, __nv_bfloat16* out, long long out_ld, int out_coff,
                    float* out_f32, long long out_f32_ld, const float* bias,
                    const __nv_bfloat16* residual, long long res_ld, int act, int num_sms) {
+  return conv_gemm_plan_ex(L, in, in_ld, B, Hi, Wi, Cin, w, Cout, R, S, stride, dil, pad, Ho, Wo, out,
+                           out_ld, out_coff, out_f32, out_f32_ld, 0, bias, 0, residual, res_ld, act,
+                           nullptr, nullptr, nullptr, 0, num_sms);
+}
+
+int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
+                      int Cin, const __nv_bfloat16* w, int Cout, int R, int S, int stride, int dil,
+                      int pad, int Ho, int Wo, __nv_bfloat16* out, long long out_ld, int out_coff,
+                      float* out_f32, long long out_f32_ld, int out_f32_planar, const float* bias,
+                      long long bias_img_stride, const __nv_bfloat16* residual, long long res_ld,
+                      int act, const float* head_w, const float* head_b, float* head_out,
+                      int head_n, int num_sms) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return -1;
   if (Cin % 8 != 0 || in_ld % 8 != 0) return -2;
@@ -282,6 +325,9 @@ int conv_gemm_plan(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, i
   p.out = out; p.out_ld = out_ld; p.out_coff = out_coff;
   p.out_f32 = out_f32; p.out_f32_ld = out_f32_ld;
   p.bias = bias; p.residual = residual; p.res_ld = res_ld; p.act = act;
+  p.bias_img_stride = bias_img_stride; p.out_f32_planar = out_f32_planar;
+  p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_n = head_n;
+  if (head_n > 0 && (p.tiles_n != 1 || head_n > 2)) return -5;
   L->smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
   const long long total = 1LL * p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   L->grid = static_cast<int>(total < num_sms ? total : num_sms);

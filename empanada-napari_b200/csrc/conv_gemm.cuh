@@ -45,6 +45,14 @@ struct Params {
   float* out_f32;        // optional fp32 NHWC output (pixel stride out_f32_ld)
   long long out_f32_ld;
   const float* bias;     // [Cout] or nullptr (BN folded on the host)
+  long long bias_img_stride;  // 0: shared bias; else bias + b * stride (per-image bias)
+  int out_f32_planar;    // fp32 output as [B][Cout][Ho*Wo] instead of NHWC
+  // fused 1x1 "head" (Cout -> head_n <= 2) applied to the activated tile: the 256-channel
+  // intermediate never reaches HBM (requires tiles_n == 1)
+  const float* head_w;   // [head_n][Cout]
+  const float* head_b;   // [head_n]
+  float* head_out;       // [B][head_n][Ho*Wo] fp32
+  int head_n;
   const __nv_bfloat16* residual;  // optional NHWC addend (pixel stride res_ld)
   long long res_ld;
   int act;

@@ -1,0 +1,449 @@
+// Non-GEMM layers of the PanopticDeepLab forward pass (piece 1): everything around the tcgen05
+// implicit-GEMM convolutions. NHWC bf16 activations, fp32 math, 16-byte vector accesses.
+//   stem_kernel        slice gather + normalise + zero pad (volume_dataset.py:37-53,
+//                      utils.py:170-201, postprocess.py:26-36) fused into conv1 7x7/2 + BN + ReLU
+//                      (encoders/resnet.py:217-220)
+//   maxpool_kernel     MaxPool2d(3, 2, 1)                      (encoders/resnet.py:221)
+//   dwconv_kernel      depthwise k x k of SeparableConv2d      (blocks.py:15-35)
+//   bilinear_kernel    F.interpolate(bilinear, align_corners=True) into a concat slice
+//                      (decoders/panoptic_deeplab.py:76)
+//   aspp_pool_*        ASPPPooling branch folded into a per-image bias of the ASPP projection
+//                      (decoders/aspp.py:30-48,97-102)
+//   up2_kernel / topk_* / pr_* : PointRend refinement (point_rend.py:110-137,241-269)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace mk {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __bfloat162float(h[i].x); f[2 * i + 1] = __bfloat162float(h[i].y); }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// ------------------------------------------------------------------ stem
+// One thread = one output pixel x 64 channels. 16x16 output tile per CTA, 37x37 input patch.
+constexpr int ST = 16;
+constexpr int SP = 2 * ST + 5;
+__global__ void __launch_bounds__(ST * ST)
+stem_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long stride_y,
+            long long stride_x, int s0, int h, int w, int H, int W, float mean255, float den,
+            const float* __restrict__ wt /*[49][64]*/, const float* __restrict__ bias,
+            bf16* __restrict__ out) {
+  __shared__ float patch[SP][SP + 1];
+  __shared__ __align__(16) float ws[49 * 64];
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
+  const int Ho = H / 2, Wo = W / 2;
+  const uint8_t* src = vol + static_cast<long long>(s0 + b) * stride_s;
+  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) ws[i] = wt[i];
+  for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) {
+    const int py = i / SP, px = i - py * SP;
+    const int y = 2 * oy0 - 3 + py, x = 2 * ox0 - 3 + px;
+    float v = 0.0f;
+    if (y >= 0 && y < h && x >= 0 && x < w)
+      v = __fmul_rn(__fsub_rn(static_cast<float>(src[y * stride_y + x * stride_x]), mean255), den);
+    patch[py][px] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / ST, tx = threadIdx.x - ty * ST;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+  for (int r = 0; r < 7; ++r) {
+    for (int s = 0; s < 7; ++s) {
+      const float v = patch[2 * ty + r][2 * tx + s];
+      const float4* wv = reinterpret_cast<const float4*>(&ws[(r * 7 + s) * 64]);
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 wq = wv[c4];
+        acc[4 * c4] = fmaf(v, wq.x, acc[4 * c4]);
+        acc[4 * c4 + 1] = fmaf(v, wq.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(v, wq.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(v, wq.w, acc[4 * c4 + 3]);
+      }
+    }
+  }
+  if (oy < Ho && ox < Wo) {
+    bf16* op = out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(acc[8 * g + j] + bias[8 * g + j], 0.0f);
+      reinterpret_cast<uint4*>(op)[g] = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ maxpool 3x3 / 2, pad 1
+__global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int Wi, int C,
+                               bf16* __restrict__ out, int Ho, int Wo) {
+  const int cg = C / 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  long long pix = i / cg;
+  const int ox = static_cast<int>(pix % Wo); pix /= Wo;
+  const int oy = static_cast<int>(pix % Ho);
+  const int b = static_cast<int>(pix / Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int dy = 0; dy < 3; ++dy) {
+    const int y = 2 * oy - 1 + dy;
+    if (y < 0 || y >= Hi) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int x = 2 * ox - 1 + dx;
+      if (x < 0 || x >= Wi) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * Hi + y) * Wi + x) * C + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + g * 8) = pack8(m);
+}
+
+// ------------------------------------------------------------------ depthwise k x k, stride 1
+// weights [k*k][C] fp32 in shared memory; one thread = one pixel x 8 channels.
+__global__ void dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
+                              int C, int k, const float* __restrict__ wt, bf16* __restrict__ out,
+                              long long out_ld) {
+  extern __shared__ float wsm[];
+  for (int i = threadIdx.x; i < k * k * C; i += blockDim.x) wsm[i] = wt[i];
+  __syncthreads();
+  const int cg = C / 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * cg;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  long long pix = i / cg;
+  const int x = static_cast<int>(pix % W); pix /= W;
+  const int y = static_cast<int>(pix % H);
+  const int b = static_cast<int>(pix / H);
+  const int pad = (k - 1) / 2;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  for (int r = 0; r < k; ++r) {
+    const int yy = y - pad + r;
+    if (yy < 0 || yy >= H) continue;
+    for (int s = 0; s < k; ++s) {
+      const int xx = x - pad + s;
+      if (xx < 0 || xx >= W) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + yy) * W + xx) * in_ld + g * 8), f);
+      const float* wp = wsm + (r * k + s) * C + g * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wp[j], acc[j]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + g * 8) = pack8(acc);
+}
+
+// ------------------------------------------------------------------ bilinear, align_corners=True
+__global__ void bilinear_kernel(const bf16* __restrict__ in, long long in_ld, int B, int Hi, int Wi,
+                                int C, bf16* __restrict__ out, long long out_ld, int out_coff,
+                                int Ho, int Wo) {
+  const int cg = C / 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  long long pix = i / cg;
+  const int ox = static_cast<int>(pix % Wo); pix /= Wo;
+  const int oy = static_cast<int>(pix % Ho);
+  const int b = static_cast<int>(pix / Ho);
+  const float sy = (Ho > 1) ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.0f;
+  const float sx = (Wo > 1) ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.0f;
+  const float fy = sy * oy, fx = sx * ox;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const bf16* base = in + static_cast<long long>(b) * Hi * Wi * in_ld + g * 8;
+  float a[8], c[8], d[8], e[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x0) * in_ld), a);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x1) * in_ld), c);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x0) * in_ld), d);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x1) * in_ld), e);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
+  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * out_ld + out_coff + g * 8) = pack8(o);
+}
+
+// ------------------------------------------------------------------ ASPP image-pool branch
+// pooled[b][c] = mean over pixels (fp32)
+__global__ void avgpool_kernel(const bf16* __restrict__ in, int HW, int C, float* __restrict__ pooled) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel pair? keep simple
+  if (c >= C) return;
+  const bf16* p = in + static_cast<long long>(b) * HW * C + c;
+  float s = 0.0f;
+  for (int i = 0; i < HW; ++i) s += __bfloat162float(p[static_cast<long long>(i) * C]);
+  pooled[b * C + c] = s / static_cast<float>(HW);
+}
+// v[b][j] = relu(sum_c Wpool[j][c] * pooled[b][c]);  one warp per output
+__global__ void gemv_relu_kernel(const float* __restrict__ Wm, const float* __restrict__ x, int K,
+                                 int N, int relu, const float* __restrict__ bias0,
+                                 float* __restrict__ y) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= N) return;
+  float s = 0.0f;
+  for (int c = lane; c < K; c += 32) s = fmaf(Wm[static_cast<long long>(j) * K + c], x[b * K + c], s);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (bias0) s += bias0[j];
+    y[b * N + j] = relu ? fmaxf(s, 0.0f) : s;
+  }
+}
+
+// ------------------------------------------------------------------ PointRend
+// bilinear x2, align_corners=False (F.interpolate(scale_factor=2)) on (B,h,w) fp32
+__global__ void up2_kernel(const float* __restrict__ in, int B, int h, int w, float* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int Ho = 2 * h, Wo = 2 * w;
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  if (i >= total) return;
+  const int ox = static_cast<int>(i % Wo);
+  const int oy = static_cast<int>((i / Wo) % Ho);
+  const int b = static_cast<int>(i / (static_cast<long long>(Wo) * Ho));
+  float fy = (oy + 0.5f) * 0.5f - 0.5f; if (fy < 0.f) fy = 0.f;
+  float fx = (ox + 0.5f) * 0.5f - 0.5f; if (fx < 0.f) fx = 0.f;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float* p = in + static_cast<long long>(b) * h * w;
+  out[i] = (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) +
+           ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+}
+
+// top-k of uncertainty = -|x|  <=>  k smallest |x|. 3-pass radix select (11/11/10 bits) on the
+// fp32 bit pattern of |x|. state per image: [0]=prefix, [1]=remaining k, [2]=ties to take,
+// [3]=output cursor, [4]=tie cursor.
+__device__ __forceinline__ unsigned absbits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+__global__ void topk_hist_kernel(const float* __restrict__ x, int n, int pass,
+                                 const unsigned* __restrict__ state, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[2048];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const unsigned prefix = state[b * 8];
+  const int shift = (pass == 0) ? 21 : (pass == 1 ? 10 : 0);
+  const unsigned himask = (pass == 0) ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+  const unsigned dmask = (pass == 2) ? 0x3FFu : 0x7FFu;
+  const float* xb = x + static_cast<long long>(b) * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned k = absbits(xb[i]);
+    if ((k & himask) == (prefix & himask)) atomicAdd(&sh[(k >> shift) & dmask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[(b * 3 + pass) * 2048 + i], sh[i]);
+}
+__global__ void topk_pick_kernel(int pass, unsigned* __restrict__ state, const unsigned* __restrict__ hist) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  unsigned remaining = state[b * 8 + 1];
+  const unsigned* h = hist + (b * 3 + pass) * 2048;
+  const int shift = (pass == 0) ? 21 : (pass == 1 ? 10 : 0);
+  const int bins = (pass == 2) ? 1024 : 2048;
+  unsigned acc = 0;
+  int d = 0;
+  for (; d < bins; ++d) {
+    if (acc + h[d] >= remaining) break;
+    acc += h[d];
+  }
+  if (d == bins) d = bins - 1;
+  state[b * 8] |= static_cast<unsigned>(d) << shift;
+  state[b * 8 + 1] = remaining - acc;          // still to take inside the chosen bucket
+  if (pass == 2) state[b * 8 + 2] = remaining - acc;  // number of exact-threshold ties to take
+}
+__global__ void topk_select_kernel(const float* __restrict__ x, int n, int k, unsigned* __restrict__ state,
+                                   int* __restrict__ idx_out) {
+  const int b = blockIdx.y;
+  const unsigned thr = state[b * 8];
+  const unsigned ties = state[b * 8 + 2];
+  const float* xb = x + static_cast<long long>(b) * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned key = absbits(xb[i]);
+    bool take = key < thr;
+    if (key == thr) take = atomicAdd(&state[b * 8 + 4], 1u) < ties;
+    if (take) {
+      const unsigned pos = atomicAdd(&state[b * 8 + 3], 1u);
+      if (pos < static_cast<unsigned>(k)) idx_out[b * k + pos] = i;
+    }
+  }
+}
+__global__ void topk_init_kernel(unsigned* state, unsigned* hist, int B, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 3 * 2048) hist[i] = 0;
+  if (i < B * 8) state[i] = ((i & 7) == 1) ? static_cast<unsigned>(k) : 0u;
+}
+
+// grid_sample(bilinear, zeros padding, align_corners=False) of the /4 coarse logits and the /4
+// feature map at the selected fine-grid points. One warp per point: lanes cover 8 channels each.
+// P: [B*k][ldp] bf16 (cols 0..C-1 features, col C coarse, rest zero); also written to P2's
+// coarse column so every MLP layer sees the re-concatenated coarse prediction.
+__global__ void pr_sample_kernel(const int* __restrict__ idx, int k, int Hf, int Wf,
+                                 const float* __restrict__ coarse, const bf16* __restrict__ feat,
+                                 int h4, int w4, int C, bf16* __restrict__ P, bf16* __restrict__ P2,
+                                 int ldp, float* __restrict__ coarse_pts, int total_pts) {
+  const int pt = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pt >= total_pts) return;
+  const int b = pt / k;
+  const int id = idx[pt];
+  const float w_step = 1.0f / static_cast<float>(Wf), h_step = 1.0f / static_cast<float>(Hf);
+  const float cx = 0.5f * w_step + w_step * static_cast<float>(id % Wf);
+  const float cy = 0.5f * h_step + h_step * static_cast<float>(id / Wf);
+  const float gx = 2.0f * cx - 1.0f, gy = 2.0f * cy - 1.0f;
+  const float ix = ((gx + 1.0f) * w4 - 1.0f) * 0.5f, iy = ((gy + 1.0f) * h4 - 1.0f) * 0.5f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0), x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+  const bool vx0 = x0 >= 0 && x0 < w4, vx1 = x1 >= 0 && x1 < w4, vy0 = y0 >= 0 && y0 < h4, vy1 = y1 >= 0 && y1 < h4;
+  const float w00 = (vx0 && vy0) ? wx0 * wy0 : 0.f, w01 = (vx1 && vy0) ? wx1 * wy0 : 0.f;
+  const float w10 = (vx0 && vy1) ? wx0 * wy1 : 0.f, w11 = (vx1 && vy1) ? wx1 * wy1 : 0.f;
+  const int cx0 = min(max(x0, 0), w4 - 1), cx1 = min(max(x1, 0), w4 - 1);
+  const int cy0 = min(max(y0, 0), h4 - 1), cy1 = min(max(y1, 0), h4 - 1);
+  const long long pb = static_cast<long long>(b) * h4 * w4;
+  const long long o00 = pb + cy0 * w4 + cx0, o01 = pb + cy0 * w4 + cx1, o10 = pb + cy1 * w4 + cx0, o11 = pb + cy1 * w4 + cx1;
+  bf16* row = P + static_cast<long long>(pt) * ldp;
+  for (int g = lane; g < C / 8; g += 32) {
+    float a[8], c[8], d[8], e[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(feat + o00 * C + g * 8), a);
+    unpack8(*reinterpret_cast<const uint4*>(feat + o01 * C + g * 8), c);
+    unpack8(*reinterpret_cast<const uint4*>(feat + o10 * C + g * 8), d);
+    unpack8(*reinterpret_cast<const uint4*>(feat + o11 * C + g * 8), e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * c[j] + w10 * d[j] + w11 * e[j];
+    *reinterpret_cast<uint4*>(row + g * 8) = pack8(o);
+  }
+  if (lane == 0) {
+    const float cv = w00 * coarse[o00] + w01 * coarse[o01] + w10 * coarse[o10] + w11 * coarse[o11];
+    coarse_pts[pt] = cv;
+    bf16* row2 = P2 + static_cast<long long>(pt) * ldp;
+    row[C] = __float2bfloat16_rn(cv);
+    row2[C] = __float2bfloat16_rn(cv);
+    for (int j = C + 1; j < ldp; ++j) { row[j] = __float2bfloat16_rn(0.f); row2[j] = __float2bfloat16_rn(0.f); }
+  }
+}
+
+// predictor (Conv1d(C+1 -> 1)) on the last MLP activation + scatter into the fine logits
+__global__ void pr_predict_kernel(const bf16* __restrict__ X, int ldp, int C,
+                                  const float* __restrict__ coarse_pts, const float* __restrict__ wp,
+                                  float bias, const int* __restrict__ idx, int k, int HWf,
+                                  float* __restrict__ sem, int total_pts) {
+  const int pt = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pt >= total_pts) return;
+  const bf16* row = X + static_cast<long long>(pt) * ldp;
+  float s = 0.0f;
+  for (int g = lane; g < C / 8; g += 32) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + g * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s = fmaf(f[j], wp[g * 8 + j], s);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    s += wp[C] * coarse_pts[pt] + bias;
+    const int b = pt / k;
+    sem[static_cast<long long>(b) * HWf + idx[pt]] = s;
+  }
+}
+
+}  // namespace mk
+
+extern "C" {
+
+int be_stem(const uint8_t* vol, long long stride_s, long long stride_y, long long stride_x, int s0,
+            int B, int h, int w, int H, int W, float mean255, float den, const float* wt,
+            const float* bias, __nv_bfloat16* out, cudaStream_t st) {
+  dim3 grid((W / 2 + mk::ST - 1) / mk::ST, (H / 2 + mk::ST - 1) / mk::ST, B);
+  mk::stem_kernel<<<grid, mk::ST * mk::ST, 0, st>>>(vol, stride_s, stride_y, stride_x, s0, h, w, H, W,
+                                                   mean255, den, wt, bias, out);
+  return be_check_launch("stem_kernel");
+}
+int be_maxpool(const __nv_bfloat16* in, int B, int Hi, int Wi, int C, __nv_bfloat16* out, int Ho,
+               int Wo, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  mk::maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, B, Hi, Wi, C, out, Ho, Wo);
+  return be_check_launch("maxpool_kernel");
+}
+int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int C, int k,
+              const float* wt, __nv_bfloat16* out, long long out_ld, cudaStream_t st) {
+  if (C % 8) return be_set_error("dwconv: C must be a multiple of 8");
+  const long long total = static_cast<long long>(B) * H * W * (C / 8);
+  const size_t smem = sizeof(float) * k * k * C;
+  mk::dwconv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, smem, st>>>(in, in_ld, B, H, W, C, k, wt, out, out_ld);
+  return be_check_launch("dwconv_kernel");
+}
+int be_bilinear(const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi, int C,
+                __nv_bfloat16* out, long long out_ld, int out_coff, int Ho, int Wo, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  mk::bilinear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, in_ld, B, Hi, Wi, C, out, out_ld, out_coff, Ho, Wo);
+  return be_check_launch("bilinear_kernel");
+}
+// bias_out[b][n] = bias_proj[n] + sum_j Wproj_pool[n][j] * relu(sum_c Wpool[j][c] * mean_pix(in[b,:,c]))
+int be_aspp_pool_bias(const __nv_bfloat16* in, int B, int HW, int C, const float* w_pool, int Cmid,
+                      const float* w_proj_pool, const float* bias_proj, int N, float* pooled,
+                      float* mid, float* bias_out, cudaStream_t st) {
+  mk::avgpool_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(in, HW, C, pooled);
+  mk::gemv_relu_kernel<<<dim3((Cmid + 7) / 8, B), 256, 0, st>>>(w_pool, pooled, C, Cmid, 1, nullptr, mid);
+  mk::gemv_relu_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(w_proj_pool, mid, Cmid, N, 0, bias_proj, bias_out);
+  return be_check_launch("aspp_pool_bias kernels");
+}
+int be_up2(const float* in, int B, int h, int w, float* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * 4 * h * w;
+  mk::up2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, B, h, w, out);
+  return be_check_launch("up2_kernel");
+}
+// idx_out [B][k]; state [B][8] u32, hist [B][3][2048] u32 scratch
+int be_topk_uncertain(const float* x, int B, int n, int k, unsigned* state, unsigned* hist,
+                      int* idx_out, cudaStream_t st) {
+  if (k > n) return be_set_error("topk: k > n");
+  mk::topk_init_kernel<<<(B * 3 * 2048 + 255) / 256, 256, 0, st>>>(state, hist, B, k);
+  const int blocks = min(64, (n + 1023) / 1024);
+  for (int pass = 0; pass < 3; ++pass) {
+    mk::topk_hist_kernel<<<dim3(blocks, B), 1024, 0, st>>>(x, n, pass, state, hist);
+    mk::topk_pick_kernel<<<B, 32, 0, st>>>(pass, state, hist);
+  }
+  mk::topk_select_kernel<<<dim3(blocks, B), 1024, 0, st>>>(x, n, k, state, idx_out);
+  return be_check_launch("topk kernels");
+}
+int be_pr_sample(const int* idx, int B, int k, int Hf, int Wf, const float* coarse,
+                 const __nv_bfloat16* feat, int h4, int w4, int C, __nv_bfloat16* P,
+                 __nv_bfloat16* P2, int ldp, float* coarse_pts, cudaStream_t st) {
+  const int total = B * k;
+  mk::pr_sample_kernel<<<(total + 7) / 8, 256, 0, st>>>(idx, k, Hf, Wf, coarse, feat, h4, w4, C, P, P2, ldp, coarse_pts, total);
+  return be_check_launch("pr_sample_kernel");
+}
+int be_pr_predict(const __nv_bfloat16* X, int ldp, int C, const float* coarse_pts, const float* wp,
+                  float bias, const int* idx, int B, int k, int HWf, float* sem, cudaStream_t st) {
+  const int total = B * k;
+  mk::pr_predict_kernel<<<(total + 7) / 8, 256, 0, st>>>(X, ldp, C, coarse_pts, wp, bias, idx, k, HWf, sem, total);
+  return be_check_launch("pr_predict_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+// Launch lists: the forward pass of one network at one (batch, height, width) is recorded once
+// as a list of kernel launches with all pointers and tensor maps resolved, then replayed per
+// batch of slices with a single C call (no Python between kernels). Every `be_op_*` entry point
+// either records into a list (list != NULL) or launches immediately (list == NULL).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <functional>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+namespace convgemm {
+int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
+                      int Cin, const __nv_bfloat16* w, int Cout, int R, int S, int stride, int dil,
+                      int pad, int Ho, int Wo, __nv_bfloat16* out, long long out_ld, int out_coff,
+                      float* out_f32, long long out_f32_ld, int out_f32_planar, const float* bias,
+                      long long bias_img_stride, const __nv_bfloat16* residual, long long res_ld,
+                      int act, const float* head_w, const float* head_b, float* head_out,
+                      int head_n, int num_sms);
+int conv_gemm_launch(const Launch* L, cudaStream_t stream);
+}  // namespace convgemm
+
+extern "C" {
+int be_stem(const uint8_t*, long long, long long, long long, int, int, int, int, int, int, float,
+            float, const float*, const float*, __nv_bfloat16*, cudaStream_t);
+int be_maxpool(const __nv_bfloat16*, int, int, int, int, __nv_bfloat16*, int, int, cudaStream_t);
+int be_dwconv(const __nv_bfloat16*, long long, int, int, int, int, int, const float*,
+              __nv_bfloat16*, long long, cudaStream_t);
+int be_bilinear(const __nv_bfloat16*, long long, int, int, int, int, __nv_bfloat16*, long long, int,
+                int, int, cudaStream_t);
+int be_aspp_pool_bias(const __nv_bfloat16*, int, int, int, const float*, int, const float*,
+                      const float*, int, float*, float*, float*, cudaStream_t);
+int be_up2(const float*, int, int, int, float*, cudaStream_t);
+int be_topk_uncertain(const float*, int, int, int, unsigned*, unsigned*, int*, cudaStream_t);
+int be_pr_sample(const int*, int, int, int, int, const float*, const __nv_bfloat16*, int, int, int,
+                 __nv_bfloat16*, __nv_bfloat16*, int, float*, cudaStream_t);
+int be_pr_predict(const __nv_bfloat16*, int, int, const float*, const float*, float, const int*,
+                  int, int, int, float*, cudaStream_t);
+}
+
+namespace {
+
+struct RunArgs {  // per-replay parameters (the only things that change between batches)
+  const uint8_t* vol;
+  long long stride_s, stride_y, stride_x;
+  int s0;
+};
+
+struct OpList {
+  std::vector<std::function<int(cudaStream_t, const RunArgs&)>> ops;
+  int kernel_launches = 0;  // kernels per replay
+};
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <class F>
+int record_or_run(void* list, int launches, cudaStream_t st, F&& fn) {
+  if (list != nullptr) {
+    OpList* l = static_cast<OpList*>(list);
+    l->ops.emplace_back(std::forward<F>(fn));
+    l->kernel_launches += launches;
+    return 0;
+  }
+  RunArgs ra{};
+  return fn(st, ra);
+}
+
+}  // namespace
+
+extern "C" {
+
+int be_oplist_create(void** out) {
+  *out = new OpList();
+  return 0;
+}
+int be_oplist_destroy(void* list) {
+  delete static_cast<OpList*>(list);
+  return 0;
+}
+int be_oplist_launches(void* list) { return static_cast<OpList*>(list)->kernel_launches; }
+
+int be_oplist_run(void* list, const uint8_t* vol, long long stride_s, long long stride_y,
+                  long long stride_x, int s0, cudaStream_t st) {
+  OpList* l = static_cast<OpList*>(list);
+  RunArgs ra{vol, stride_s, stride_y, stride_x, s0};
+  for (auto& op : l->ops) {
+    const int rc = op(st, ra);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// ---- recorded ops ------------------------------------------------------------------------
+int be_op_conv(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int Cin,
+               const void* w, int Cout, int R, int S, int stride, int dil, int pad, int Ho, int Wo,
+               void* out, long long out_ld, int out_coff, float* out_f32, long long out_f32_ld,
+               int out_f32_planar, const float* bias, long long bias_img_stride,
+               const void* residual, long long res_ld, int act, const float* head_w,
+               const float* head_b, float* head_out, int head_n, cudaStream_t st) {
+  convgemm::Launch L;
+  const int rc = convgemm::conv_gemm_plan_ex(
+      &L, static_cast<const __nv_bfloat16*>(in), in_ld, B, Hi, Wi, Cin,
+      static_cast<const __nv_bfloat16*>(w), Cout, R, S, stride, dil, pad, Ho, Wo,
+      static_cast<__nv_bfloat16*>(out), out_ld, out_coff, out_f32, out_f32_ld, out_f32_planar, bias,
+      bias_img_stride, static_cast<const __nv_bfloat16*>(residual), res_ld, act, head_w, head_b,
+      head_out, head_n, num_sms());
+  if (rc != 0) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "conv_gemm_plan failed (%d): Cin=%d Cout=%d R=%d stride=%d", rc, Cin, Cout, R, stride);
+    return be_set_error(msg);
+  }
+  return record_or_run(list, 1, st, [L](cudaStream_t s, const RunArgs&) {
+    const int e = convgemm::conv_gemm_launch(&L, s);
+    return e == 0 ? 0 : be_set_error(cudaGetErrorString(static_cast<cudaError_t>(e)));
+  });
+}
+
+int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, float den,
+               const float* wt, const float* bias, void* out, const uint8_t* vol, long long stride_s,
+               long long stride_y, long long stride_x, int s0, cudaStream_t st) {
+  if (list == nullptr)
+    return be_stem(vol, stride_s, stride_y, stride_x, s0, B, h, w, H, W, mean255, den, wt, bias,
+                   static_cast<__nv_bfloat16*>(out), st);
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs& ra) {
+    return be_stem(ra.vol, ra.stride_s, ra.stride_y, ra.stride_x, ra.s0, B, h, w, H, W, mean255, den,
+                   wt, bias, static_cast<__nv_bfloat16*>(out), s);
+  });
+}
+
+int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void* out, int Ho, int Wo,
+                  cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_maxpool(static_cast<const __nv_bfloat16*>(in), B, Hi, Wi, C, static_cast<__nv_bfloat16*>(out), Ho, Wo, s);
+  });
+}
+
+int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int W, int C, int k,
+                 const float* wt, void* out, long long out_ld, cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_dwconv(static_cast<const __nv_bfloat16*>(in), in_ld, B, H, W, C, k, wt,
+                     static_cast<__nv_bfloat16*>(out), out_ld, s);
+  });
+}
+
+int be_op_bilinear(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int C,
+                   void* out, long long out_ld, int out_coff, int Ho, int Wo, cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_bilinear(static_cast<const __nv_bfloat16*>(in), in_ld, B, Hi, Wi, C,
+                       static_cast<__nv_bfloat16*>(out), out_ld, out_coff, Ho, Wo, s);
+  });
+}
+
+int be_op_aspp_pool_bias(void* list, const void* in, int B, int HW, int C, const float* w_pool,
+                         int Cmid, const float* w_proj_pool, const float* bias_proj, int N,
+                         float* pooled, float* mid, float* bias_out, cudaStream_t st) {
+  return record_or_run(list, 3, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_aspp_pool_bias(static_cast<const __nv_bfloat16*>(in), B, HW, C, w_pool, Cmid, w_proj_pool,
+                             bias_proj, N, pooled, mid, bias_out, s);
+  });
+}
+
+int be_op_up2(void* list, const float* in, int B, int h, int w, float* out, cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) { return be_up2(in, B, h, w, out, s); });
+}
+
+int be_op_topk(void* list, const float* x, int B, int n, int k, unsigned* state, unsigned* hist,
+               int* idx_out, cudaStream_t st) {
+  return record_or_run(list, 8, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_topk_uncertain(x, B, n, k, state, hist, idx_out, s);
+  });
+}
+
+int be_op_pr_sample(void* list, const int* idx, int B, int k, int Hf, int Wf, const float* coarse,
+                    const void* feat, int h4, int w4, int C, void* P, void* P2, int ldp,
+                    float* coarse_pts, cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_pr_sample(idx, B, k, Hf, Wf, coarse, static_cast<const __nv_bfloat16*>(feat), h4, w4, C,
+                        static_cast<__nv_bfloat16*>(P), static_cast<__nv_bfloat16*>(P2), ldp, coarse_pts, s);
+  });
+}
+
+int be_op_pr_predict(void* list, const void* X, int ldp, int C, const float* coarse_pts,
+                     const float* wp, float bias, const int* idx, int B, int k, int HWf, float* sem,
+                     cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_pr_predict(static_cast<const __nv_bfloat16*>(X), ldp, C, coarse_pts, wp, bias, idx, B, k, HWf, sem, s);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+"""PanopticDeepLab-PointRend (ResNet-50, output stride 16) on the sm_100a kernels: weight
+ingestion from the reference's fused TorchScript export and the recorded launch list.
+
+Network structure follows the reference (file:line under /root/reference/empanada/models):
+  encoder            encoders/resnet.py:143-229, quantization/encoders/resnet.py:45-77
+  ASPP + decoder     decoders/aspp.py:51-102, decoders/panoptic_deeplab.py:68-80
+  heads              heads.py:9-19
+  PointRend (eval)   point_rend.py:110-137,241-269
+  forward            quantization/panoptic_deeplab.py:194-250 (render_steps=2, interpolate_ins=False)
+
+Layout decisions: NHWC bf16 activations; conv weights [Cout][R*S*Cin] bf16 with
+BatchNorm folded in fp32 before rounding; every 1x1/3x3 convolution is the tcgen05 implicit GEMM
+(csrc/conv_gemm.cu) with bias/ReLU/residual in the epilogue; concat buffers are written in
+place by their producers; the ASPP image-pool branch is a per-image bias of the projection;
+the 256->1/2 head convolutions are fused into the epilogue of the preceding pointwise conv.
+"""
+import ctypes
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+P, I, LL, F = c_void_p, c_int, c_longlong, c_float
+_lib.declare("be_oplist_create", [ctypes.POINTER(c_void_p)])
+_lib.declare("be_oplist_destroy", [P])
+_lib.declare("be_oplist_launches", [P])
+_lib.declare("be_oplist_run", [P, P, LL, LL, LL, I, P])
+_lib.declare("be_op_conv", [P, P, LL, I, I, I, I, P, I, I, I, I, I, I, I, I, P, LL, I, P, LL, I, P, LL,
+                            P, LL, I, P, P, P, I, P])
+_lib.declare("be_op_stem", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, P])
+_lib.declare("be_op_maxpool", [P, P, I, I, I, I, P, I, I, P])
+_lib.declare("be_op_dwconv", [P, P, LL, I, I, I, I, I, P, P, LL, P])
+_lib.declare("be_op_bilinear", [P, P, LL, I, I, I, I, P, LL, I, I, I, P])
+_lib.declare("be_op_aspp_pool_bias", [P, P, I, I, I, P, I, P, P, I, P, P, P, P])
+_lib.declare("be_op_up2", [P, P, I, I, I, P, P])
+_lib.declare("be_op_topk", [P, P, I, I, I, P, P, P, P])
+_lib.declare("be_op_pr_sample", [P, P, I, I, I, I, P, P, I, I, I, P, P, I, P, P])
+_lib.declare("be_op_pr_predict", [P, P, I, I, P, P, F, P, I, I, I, P, P])
+
+ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+BN_EPS = 1e-5
+
+
+def is_pdl_state_dict(sd):
+    return ("encoder.layer4.2.conv3.weight" in sd and "semantic_decoder.aspp.project.0.0.weight" in sd
+            and "semantic_pr.point_head.predictor.weight" in sd)
+
+
+def _conv_w(w):
+    """[Cout, Cin, R, S] fp32 -> [Cout][R*S*Cin] bf16 (K-major rows, tap-major K)."""
+    return w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+class _Weights:
+    """Device-resident, kernel-layout weights built from the export's state_dict."""
+
+    def __init__(self, sd, device):
+        self.dev = device
+        self.t = {}
+        f32 = lambda x: x.detach().to(torch.float32)
+
+        def put(name, tensor):
+            self.t[name] = tensor.contiguous().to(device)
+
+        def conv(name, key):
+            put(name + ".w", _conv_w(f32(sd[key + ".weight"])))
+            if key + ".bias" in sd:
+                put(name + ".b", f32(sd[key + ".bias"]))
+
+        # stem
+        w = f32(sd["encoder.conv1.0.weight"])  # [64,1,7,7]
+        if w.shape[1] != 1 or tuple(w.shape[2:]) != (7, 7) or w.shape[0] != 64:
+            raise _lib.B200EmpanadaError(f"unsupported stem convolution {tuple(w.shape)}")
+        put("stem.w", w.reshape(64, 49).t())   # [49][64]
+        put("stem.b", f32(sd["encoder.conv1.0.bias"]))
+        # encoder
+        self.blocks = []
+        for li in range(1, 5):
+            b = 0
+            while f"encoder.layer{li}.{b}.conv1.0.weight" in sd:
+                p = f"encoder.layer{li}.{b}"
+                for c, k in (("c1", ".conv1.0"), ("c2", ".conv2.0"), ("c3", ".conv3")):
+                    conv(f"{p}.{c}", p + k)
+                has_ds = (p + ".downsample.0.weight") in sd
+                if has_ds:
+                    conv(p + ".ds", p + ".downsample.0")
+                self.blocks.append((li, b, has_ds, sd[p + ".conv1.0.weight"].shape[0]))
+                b += 1
+        if [sum(1 for x in self.blocks if x[0] == l) for l in (1, 2, 3, 4)] != [3, 4, 6, 3]:
+            raise _lib.B200EmpanadaError("encoder is not a ResNet-50 (unsupported export)")
+        # decoders
+        self.has_ins_decoder = "instance_decoder.aspp.project.0.0.weight" in sd
+        for dec in ("semantic_decoder", "instance_decoder") if self.has_ins_decoder else ("semantic_decoder",):
+            for i in range(4):
+                conv(f"{dec}.aspp{i}", f"{dec}.aspp.convs.{i}.0.0")
+            put(dec + ".pool.w", f32(sd[dec + ".aspp.convs.4.aspp_pooling.1.0.weight"]).reshape(-1, 2048))
+            wp = f32(sd[dec + ".aspp.project.0.0.weight"]).reshape(256, -1)  # [256, 1280]
+            n_main = wp.shape[1] - self.t[dec + ".pool.w"].shape[0]
+            put(dec + ".proj.w", wp[:, :n_main].to(torch.bfloat16))
+            put(dec + ".proj.wpool", wp[:, n_main:])
+            put(dec + ".proj.b", f32(sd[dec + ".aspp.project.0.0.bias"]))
+            conv(dec + ".low", dec + ".project.0.0.0")
+            self._sepconv(sd, dec + ".fuse", dec + ".fuse.0", put)
+        for head in ("semantic_head", "ins_center", "ins_xy"):
+            self._sepconv(sd, head + ".sep", head + ".head.0", put)
+            put(head + ".out.w", f32(sd[head + ".head.1.weight"]).reshape(sd[head + ".head.1.weight"].shape[0], -1))
+            put(head + ".out.b", f32(sd[head + ".head.1.bias"]))
+        if sd["semantic_head.head.1.weight"].shape[0] != 1:
+            raise _lib.B200EmpanadaError("multi-class semantic heads are not built yet")
+        # PointRend MLP: K padded 257 -> 264 (16-byte rows for TMA)
+        self.num_fc = 0
+        while f"semantic_pr.point_head.fc_layers.{self.num_fc}.0.0.weight" in sd:
+            w = f32(sd[f"semantic_pr.point_head.fc_layers.{self.num_fc}.0.0.weight"])[:, :, 0]  # [256, 257]
+            wpad = torch.zeros(w.shape[0], 264)
+            wpad[:, : w.shape[1]] = w
+            put(f"pr.fc{self.num_fc}.w", wpad.to(torch.bfloat16))
+            put(f"pr.fc{self.num_fc}.b", f32(sd[f"semantic_pr.point_head.fc_layers.{self.num_fc}.0.0.bias"]))
+            self.num_fc += 1
+        put("pr.pred.w", f32(sd["semantic_pr.point_head.predictor.weight"]).reshape(-1))  # [257]
+        self.pr_pred_b = float(sd["semantic_pr.point_head.predictor.bias"].reshape(-1)[0])
+
+    def _sepconv(self, sd, name, key, put):
+        """separable_conv_bn_act (blocks.py): depthwise k x k, pointwise 1x1, live BatchNorm
+        folded into the pointwise weights in fp32."""
+        f32 = lambda x: x.detach().to(torch.float32)
+        dw = f32(sd[key + ".0.sepconv.0.weight"])          # [C,1,k,k]
+        C, k = dw.shape[0], dw.shape[-1]
+        put(name + ".dw", dw.reshape(C, k * k).t())        # [k*k][C]
+        pw = f32(sd[key + ".0.sepconv.1.weight"]).reshape(-1, C)
+        scale = f32(sd[key + ".1.weight"]) / torch.sqrt(f32(sd[key + ".1.running_var"]) + BN_EPS)
+        put(name + ".pw.w", (pw * scale[:, None]).to(torch.bfloat16))
+        put(name + ".pw.b", f32(sd[key + ".1.bias"]) - f32(sd[key + ".1.running_mean"]) * scale)
+
+    def __getitem__(self, k):
+        return self.t[k]
+
+
+class _Plan:
+    """Recorded launch list + its activation buffers for one (B, h, w, H, W)."""
+
+    def __init__(self, W, B, h, w, H, Wd, mean255, den, render_steps=2, num_points=8192):
+        dev = W.dev
+        self.handle = c_void_p()
+        _lib.lib().be_oplist_create(ctypes.byref(self.handle))
+        self.bufs = []
+        L = self.handle
+        st = None
+        bf = torch.bfloat16
+
+        def buf(*shape, dtype=bf):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            self.bufs.append(t)
+            return t
+
+        def conv(x, Hi, Wi, Cin, wname, Cout, k=1, stride=1, dil=1, out=None, out_ld=None, coff=0,
+                 act=ACT_RELU, res=None, bias=None, bias_img_stride=0, in_ld=None, head=None,
+                 Bn=B):
+            pad = dil * (k - 1) // 2
+            Ho = (Hi + 2 * pad - dil * (k - 1) - 1) // stride + 1
+            Wo = (Wi + 2 * pad - dil * (k - 1) - 1) // stride + 1
+            if out is None and head is None:
+                out = buf(Bn, Ho, Wo, Cout)
+            if out_ld is None:
+                out_ld = Cout
+            if bias is None and (wname + ".b") in W.t:
+                bias = W[wname + ".b"]
+            hw_, hb_, ho_, hn_ = (None, None, None, 0) if head is None else head
+            call("be_op_conv", L, ptr(x), in_ld or Cin, Bn, Hi, Wi, Cin, ptr(W[wname + ".w"]), Cout, k, k,
+                 stride, dil, pad, Ho, Wo, ptr(out), out_ld, coff, None, 0, 0, ptr(bias),
+                 bias_img_stride, ptr(res), Cout if res is not None else 0, act, ptr(hw_), ptr(hb_),
+                 ptr(ho_), hn_, st)
+            return out, Ho, Wo
+
+        H2, W2, H4, W4 = H // 2, Wd // 2, H // 4, Wd // 4
+        stem = buf(B, H2, W2, 64)
+        call("be_op_stem", L, B, h, w, H, Wd, mean255, den, ptr(W["stem.w"]), ptr(W["stem.b"]),
+             ptr(stem), None, 0, 0, 0, 0, st)
+        x = buf(B, H4, W4, 64)
+        call("be_op_maxpool", L, ptr(stem), B, H2, W2, 64, ptr(x), H4, W4, st)
+        Hc, Wc, Cin = H4, W4, 64
+        p2 = None
+        for (li, b, has_ds, planes) in W.blocks:
+            pfx = f"encoder.layer{li}.{b}"
+            stride = 2 if (b == 0 and li in (2, 3)) else 1
+            dil = 2 if li == 4 else 1
+            t1, _, _ = conv(x, Hc, Wc, Cin, pfx + ".c1", planes)
+            t2, Ho, Wo = conv(t1, Hc, Wc, planes, pfx + ".c2", planes, k=3, stride=stride, dil=dil)
+            if has_ds:
+                idt, _, _ = conv(x, Hc, Wc, Cin, pfx + ".ds", planes * 4, stride=stride, act=ACT_NONE)
+            else:
+                idt = x
+            x, _, _ = conv(t2, Ho, Wo, planes, pfx + ".c3", planes * 4, res=idt)
+            Hc, Wc, Cin = Ho, Wo, planes * 4
+            if li == 1 and b == 2:
+                p2 = x
+        p5, H16, W16 = x, Hc, Wc
+        feats = {}
+        decs = ("semantic_decoder", "instance_decoder") if W.has_ins_decoder else ("semantic_decoder",)
+        for dec in decs:
+            cat = buf(B, H16, W16, 1024)
+            for i, r in enumerate((1, 2, 4, 6)):
+                conv(p5, H16, W16, 2048, f"{dec}.aspp{i}", 256, k=1 if i == 0 else 3, dil=1 if i == 0 else r,
+                     out=cat, out_ld=1024, coff=256 * i)
+            pooled, mid, pbias = buf(B, 2048, dtype=torch.float32), buf(B, 256, dtype=torch.float32), buf(B, 256, dtype=torch.float32)
+            call("be_op_aspp_pool_bias", L, ptr(p5), B, H16 * W16, 2048, ptr(W[dec + ".pool.w"]), 256,
+                 ptr(W[dec + ".proj.wpool"]), ptr(W[dec + ".proj.b"]), 256, ptr(pooled), ptr(mid), ptr(pbias), st)
+            aspp, _, _ = conv(cat, H16, W16, 1024, dec + ".proj", 256, bias=pbias, bias_img_stride=256)
+            clow = W[dec + ".low.w"].shape[0]
+            cf = 256 + clow
+            fcat = buf(B, H4, W4, cf)
+            conv(p2, H4, W4, 256, dec + ".low", clow, out=fcat, out_ld=cf, coff=256)
+            call("be_op_bilinear", L, ptr(aspp), 256, B, H16, W16, 256, ptr(fcat), cf, 0, H4, W4, st)
+            dw = buf(B, H4, W4, cf)
+            call("be_op_dwconv", L, ptr(fcat), cf, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf, st)
+            feats[dec], _, _ = conv(dw, H4, W4, cf, dec + ".fuse.pw", 256)
+        semantic_x = feats["semantic_decoder"]
+        instance_x = feats.get("instance_decoder", semantic_x)
+        self.coarse = buf(B, 1, H4, W4, dtype=torch.float32)
+        self.ctr = buf(B, H4, W4, dtype=torch.float32)
+        self.off = buf(B, 2, H4, W4, dtype=torch.float32)
+        for head, src, out, n in (("semantic_head", semantic_x, self.coarse, 1),
+                                  ("ins_center", instance_x, self.ctr, 1), ("ins_xy", instance_x, self.off, 2)):
+            dw = buf(B, H4, W4, 256)
+            call("be_op_dwconv", L, ptr(src), 256, B, H4, W4, 256, 5, ptr(W[head + ".sep.dw"]), ptr(dw), 256, st)
+            conv(dw, H4, W4, 256, head + ".sep.pw", 256, head=(W[head + ".out.w"], W[head + ".out.b"], out, n))
+        # PointRend
+        sem, Hs, Ws = self.coarse, H4, W4
+        ldp = 264
+        for step in range(render_steps):
+            up = buf(B, 2 * Hs, 2 * Ws, dtype=torch.float32)
+            call("be_op_up2", L, ptr(sem), B, Hs, Ws, ptr(up), st)
+            Hs, Ws = 2 * Hs, 2 * Ws
+            k = min(Hs * Ws, num_points)
+            state = buf(B, 8, dtype=torch.int32)
+            hist = buf(B, 3, 2048, dtype=torch.int32)
+            idx = buf(B, k, dtype=torch.int32)
+            call("be_op_topk", L, ptr(up), B, Hs * Ws, k, ptr(state), ptr(hist), ptr(idx), st)
+            Pa, Pb = buf(B * k, ldp), buf(B * k, ldp)
+            cpts = buf(B * k, dtype=torch.float32)
+            call("be_op_pr_sample", L, ptr(idx), B, k, Hs, Ws, ptr(self.coarse), ptr(semantic_x), H4, W4, 256,
+                 ptr(Pa), ptr(Pb), ldp, ptr(cpts), st)
+            src, dst = Pa, Pb
+            for l in range(W.num_fc):
+                conv(src, 1, B * k, ldp, f"pr.fc{l}", 256, out=dst, out_ld=ldp, in_ld=ldp, Bn=1)
+                src, dst = dst, src
+            call("be_op_pr_predict", L, ptr(src), ldp, 256, ptr(cpts), ptr(W["pr.pred.w"]), W.pr_pred_b,
+                 ptr(idx), B, k, Hs * Ws, ptr(up), st)
+            sem = up
+        self.sem = sem.view(B, Hs, Ws)
+        self.semantic_x, self.instance_x, self.p5, self.p2 = semantic_x, instance_x, p5, p2
+        self.launches = int(_lib.lib().be_oplist_launches(L))
+
+    def run(self, vol_d, strides, s0):
+        call("be_oplist_run", self.handle, ptr(vol_d), strides[0], strides[1], strides[2], s0, stream_ptr())
+
+    def __del__(self):
+        try:
+            _lib.lib().be_oplist_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class PDLModel:
+    def __init__(self, sd, device):
+        self.dev = device
+        with torch.cuda.device(device):
+            self.W = _Weights(sd, device)
+        self.plans = {}
+        self.launches = 0
+        self.render_steps = 2
+
+    def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
+        D, Hv, Wv = vol_d.shape
+        h, w = [(Hv, Wv), (D, Wv), (D, Hv)][axis]
+        strides = [(Hv * Wv, Wv, 1), (Wv, Hv * Wv, 1), (1, Hv * Wv, Wv)][axis]
+        H = h + (pf - h % pf) % pf
+        Wd = w + (pf - w % pf) % pf
+        if H % 16 or Wd % 16:
+            raise _lib.B200EmpanadaError("padded slice size must be a multiple of 16")
+        B = s1 - s0
+        mean255 = np.float32(np.float32(norms["mean"]) * np.float32(255))
+        den = np.reciprocal(np.float32(np.float32(norms["std"]) * np.float32(255)), dtype=np.float32)
+        key = (B, h, w, H, Wd, float(mean255), float(den))
+        plan = self.plans.get(key)
+        if plan is None:
+            with torch.cuda.device(self.dev):
+                plan = _Plan(self.W, B, h, w, H, Wd, float(mean255), float(den), self.render_steps)
+            self.plans[key] = plan
+        plan.run(vol_d, strides, s0)
+        self.launches += plan.launches
+        self.last_plan = plan
+        return plan.sem, plan.ctr, plan.off
