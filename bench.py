@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: MitoNet_v1-class (PanopticDeepLab-PointRend)
+3-D orthoplane inference + consensus on a synthetic 1024^3 uint8 volume. One "step" = the whole
+job: infer_on_axis for xy, xz, yz + tracker_consensus. Metric: input voxels / second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl reference]
+
+* value : volume and analytic head maps already resident in HBM, outputs left on the device.
+* e2e   : the public API with HOST buffers: numpy volume in (H2D inside the timed region),
+          numpy consensus volume + tracker dictionaries out (D2H inside the timed region).
+* roofline : live per-op CUDA-event times of the recorded launch list; dominant kernel =
+          conv_gemm_kernel (tensor bound); FLOPs = 2*MAC of every GEMM convolution it runs.
+* cpu_baseline / --impl reference : the CPU oracle port (oracle/, the reference restated and pinned
+          against the reference) on a bounded sample of the same workload, all host threads.
+Weights are seeded random (timing is weight independent); analytic head maps derived from the
+synthetic ground truth replace the network's own heads after the forward pass so that
+post-processing, tracking and consensus see realistic object counts.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NORMS = {"mean": 0.57571, "std": 0.12765}
+MODEL_CONFIG = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 16,
+                "norms": NORMS, "model": None}
+PDL_GFLOP_PER_PIXEL = 559.15e9 / (1024 * 1024)  # SURVEY.md section 8d (per plane)
+
+
+# ------------------------------------------------------------------------------ synthetic data
+def synth_on_device(S, dev, seed=0):
+    """EM-like uint8 volume + int32 ground-truth labels, rasterised on the GPU (setup, untimed)."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    ell = syn.make_ellipsoids((S, S, S), seed=seed)
+    lab = torch.zeros((S, S, S), dtype=torch.int32, device=dev)
+    ar = torch.arange(S, device=dev, dtype=torch.float32)
+    for i, (cz, cy, cx, rz, ry, rx) in enumerate(ell.tolist(), start=1):
+        z0, z1 = max(0, int(cz - rz)), min(S, int(cz + rz) + 2)
+        y0, y1 = max(0, int(cy - ry)), min(S, int(cy + ry) + 2)
+        x0, x1 = max(0, int(cx - rx)), min(S, int(cx + rx) + 2)
+        if z0 >= z1 or y0 >= y1 or x0 >= x1:
+            continue
+        dz = ((ar[z0:z1] - cz) / rz) ** 2
+        dy = ((ar[y0:y1] - cy) / ry) ** 2
+        dx = ((ar[x0:x1] - cx) / rx) ** 2
+        m = (dz[:, None, None] + dy[None, :, None] + dx[None, None, :]) <= 1.0
+        sub = lab[z0:z1, y0:y1, x0:x1]
+        sub[m] = i
+    g = torch.Generator(device=dev).manual_seed(seed + 1)
+    vol = torch.empty((S, S, S), dtype=torch.uint8, device=dev)
+    for z in range(0, S, 64):
+        blk = lab[z:z + 64]
+        img = torch.where(blk > 0, 70.0, 170.0) + torch.randn(blk.shape, generator=g, device=dev) * 8.0
+        vol[z:z + 64] = img.clamp_(0, 255).to(torch.uint8)
+    return vol, lab, len(ell)
+
+
+def analytic_heads_on_device(lab, axis, n_obj, pf=16, sigma=8.0):
+    """Per-plane head maps from the ground truth (setup, untimed): sem logits +-4, centre heat map
+    exp(-d^2/(2 sigma^2)) around each cross-section centroid, offsets to that centroid (both /4)."""
+    import torch
+    dev = lab.device
+    lab_p = lab.movedim(axis, 0)
+    N, h, w = lab_p.shape
+    H, W = h + (pf - h % pf) % pf, w + (pf - w % pf) % pf
+    sem = torch.full((N, H, W), -4.0, dtype=torch.float32, device=dev)
+    ctr = torch.zeros((N, H // 4, W // 4), dtype=torch.float32, device=dev)
+    off = torch.zeros((N, 2, H // 4, W // 4), dtype=torch.float32, device=dev)
+    yy = torch.arange(h, device=dev, dtype=torch.float32)[:, None].expand(h, w)
+    xx = torch.arange(w, device=dev, dtype=torch.float32)[None, :].expand(h, w)
+    y4 = (torch.arange(H // 4, device=dev, dtype=torch.float32) * 4)[:, None]
+    x4 = (torch.arange(W // 4, device=dev, dtype=torch.float32) * 4)[None, :]
+    for s in range(N):
+        l = lab_p[s].long()
+        sem[s, :h, :w] = torch.where(l > 0, 4.0, -4.0)
+        flat = l.reshape(-1)
+        cnt = torch.bincount(flat, minlength=n_obj + 1).float()
+        sy = torch.bincount(flat, weights=yy.reshape(-1), minlength=n_obj + 1)
+        sx = torch.bincount(flat, weights=xx.reshape(-1), minlength=n_obj + 1)
+        py = torch.round(sy / cnt.clamp(min=1) / 4) * 4
+        px = torch.round(sx / cnt.clamp(min=1) / 4) * 4
+        l4 = torch.zeros((H // 4, W // 4), dtype=torch.long, device=dev)
+        l4[: (h + 3) // 4, : (w + 3) // 4] = l[::4, ::4]
+        oy = py[l4] - y4
+        ox = px[l4] - x4
+        fg = l4 > 0
+        off[s, 0] = torch.where(fg, oy, torch.zeros_like(oy))
+        off[s, 1] = torch.where(fg, ox, torch.zeros_like(ox))
+        ctr[s] = torch.where(fg, torch.exp(-(oy * oy + ox * ox) / (2 * sigma * sigma)), torch.zeros_like(oy))
+    return sem, ctr, off
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index=0):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU oracle arm
+def cpu_oracle_voxels_per_s(S=96, seed=0):
+    """Full orthoplane pipeline of the CPU oracle (reference restated) on an S^3 cube."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from oracle import consensus as ocons, model as omodel, pipeline
+    torch.set_num_threads(os.cpu_count())
+    sd = syn.make_pdl_state_dict(0)
+    vol, lab, _ = syn.make_volume((S, S, S), seed=seed, scale=1.0)
+    cfg = dict(MODEL_CONFIG)
+
+    def make_heads_fn(axis):
+        def fn(i, x):
+            omodel.pdl_forward(sd, torch.from_numpy(x[None, None]), 2, False)  # the network (timed)
+            sem, ctr, off = syn.analytic_heads(np.take(lab, i, axis=axis), pad_to=16)
+            return sem, ctr, off
+        return fn
+
+    # warm numba / torch once on a toy stack
+    tiny, tl, _ = syn.make_volume((8, 32, 32), seed=1, n_objects=2, scale=1.0)
+    pipeline.infer_on_axis(tiny, "xy", lambda i, x: syn.analytic_heads(tl[i], pad_to=16), cfg, median_kernel_size=3,
+                           min_size=1, min_extent=1)
+    t0 = time.perf_counter()
+    trackers = {}
+    for a, name in enumerate(("xy", "xz", "yz")):
+        _, trackers[name] = pipeline.infer_on_axis(vol, name, make_heads_fn(a), cfg, median_kernel_size=3,
+                                                   nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5,
+                                                   save_panoptic=False)
+    for _ in ocons.tracker_consensus(trackers, cfg, pixel_vote_thr=2, min_size=500, min_extent=5, dtype=np.int32):
+        pass
+    dt = time.perf_counter() - t0
+    return S ** 3 / dt, dt
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-sample", type=int, default=96)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    S = args.size
+    workload = f"MitoNet_v1-class PDL 3D orthoplane (xy/xz/yz) consensus on {S}^3 uint8 volume"
+    config = {"workload": workload, "volume": [S, S, S], "median_kernel": 3, "nms_kernel": 3,
+              "pixel_vote_thr": 2, "min_size": 500, "min_extent": 5, "slice_batch": args.batch,
+              "l2": "inputs larger than L2 (1 GiB volume, >4 GiB of heads per plane)",
+              "parallelism": f"slice-range sharding x{world}" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            v, dt = cpu_oracle_voxels_per_s(args.cpu_sample)
+            vals.append(v)
+        v = float(np.mean(vals))
+        cores = os.cpu_count()
+        sample = f"{args.cpu_sample}^3 cube, full orthoplane pipeline + consensus on the CPU oracle port (torch fp32 + numpy/numba)"
+        print(json.dumps({
+            "impl": "reference", "metric": "3D orthoplane voxels/sec", "value": v, "unit": "voxels/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * args.cpu_sample ** 3 / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200 import multigpu
+    from empanada_napari_b200.inference import Engine3d, tracker_consensus
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    from empanada_napari_b200.pdl import PDLModel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    vol_d, lab_d, n_obj = synth_on_device(S, dev)
+    heads = {a: analytic_heads_on_device(lab_d, a, n_obj) for a in range(3)}
+    del lab_d
+    pdl = PDLModel(syn.make_pdl_state_dict(0), dev)
+
+    def heads_fn(axis, s0, s1):
+        sem, ctr, off = heads[axis]
+        return sem[s0:s1], ctr[s0:s1], off[s0:s1]
+
+    cfg = dict(MODEL_CONFIG)
+    cfg["model"] = SyntheticHeadsModel(heads_fn, inner=pdl)
+    kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5,
+              batch_size=args.batch)
+    eng = Engine3d(cfg, **kw) if world == 1 else multigpu.DistributedEngine3d(cfg, **kw)
+    vol_h = vol_d.cpu().numpy()
+    launches = {"n": 0}
+
+    def job(volume, to_host):
+        """The whole job. volume: cuda tensor (value arm) or numpy array (e2e arm)."""
+        trackers = {}
+        n_l = 0
+        for name in ("xy", "xz", "yz"):
+            _, trackers[name] = eng.infer_on_axis(volume, name)
+            n_l += eng.last_stats.get("kernel_launches", 0)
+        out = None
+        if rank == 0:
+            for vol, cname, inst in tracker_consensus(trackers, None, cfg, pixel_vote_thr=2, min_size=500,
+                                                      min_extent=5, dtype=np.int32, to_host=to_host):
+                out = (vol, inst)
+            n_l += getattr(tracker_consensus, "last_launches", 0)
+        launches["n"] = n_l
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    eng.set_device_volume(vol_d)
+    for _ in range(args.warmup):
+        out = job(vol_d, to_host=False)
+    with ClockSampler(local_rank) as clk:
+        ms_step = timed(lambda: job(vol_d, to_host=False), args.steps)
+    n_instances = len(out[1]) if out is not None else 0
+    gpu_launches = launches["n"] * args.steps
+    # end to end through the public API with host buffers
+    eng.release()
+    job(vol_h, to_host=True)
+    ms_e2e = timed(lambda: (eng.release(), job(vol_h, to_host=True)), max(1, min(args.steps, 2)))
+    d2h = int(S ** 3 * 4)
+
+    # live roofline of the dominant kernel (per-op CUDA events over one batch replay)
+    roof = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        plan = pdl.last_plan
+        B = args.batch
+        ms = plan.run_timed(vol_d, (S * S, S, 1), 0)
+        ms = plan.run_timed(vol_d, (S * S, S, 1), 0)
+        conv_ms = float(sum(t for (k, _), t in zip(plan.op_info, ms) if k == "conv"))
+        conv_fl = float(sum(f for (k, f) in plan.op_info if k == "conv"))
+        n_conv = sum(1 for (k, _) in plan.op_info if k == "conv")
+        achieved = conv_fl / (conv_ms * 1e-3) * 1e-12
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                "per_launch": {"launches_per_batch": n_conv, "avg_ms": conv_ms / n_conv,
+                               "flops_per_batch": conv_fl, "batch_slices": B},
+                "forward_ms_per_slice": float(ms.sum()) / B,
+                "share_of_forward": conv_ms / float(ms.sum())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, dt = cpu_oracle_voxels_per_s(args.cpu_sample)
+        cpu = {"value": v, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{args.cpu_sample}^3 cube, full orthoplane pipeline + consensus on the CPU oracle port, {dt:.1f} s"}
+
+    if rank == 0:
+        vox = float(S) ** 3
+        line = {
+            "metric": "3D orthoplane voxels/sec", "value": vox / (ms_step * 1e-3), "unit": "voxels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic volume; seeded random weights; analytic head maps substituted after the forward pass",
+            "config": config, "clocks": clk.summary(),
+            "e2e": {"value": vox / (ms_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(S ** 3), "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu,
+            "consensus_instances": n_instances,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@ from ._lib import call, ptr, stream_ptr
 
 MIN_OVERLAP = 100
 MIN_IOU = 1e-2
+LAST_LAUNCHES = 0  # kernels launched by the last merge_objects_from_trackers call
 
 
 def merge_boxes(box1, box2):
@@ -150,6 +151,8 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
                                 min_size=None, min_extent=None):
     """consensus.py:348-469 followed by the two tracker filters (inference.py:149-150).
     Returns (device int32 volume with the final ids painted, instances dict)."""
+    global LAST_LAUNCHES
+    LAST_LAUNCHES = 12  # hash clear/compact x2, pairs, vote stats, vote paint, hist, lut, runs x2
     dev = torch.device("cuda", torch.cuda.current_device())
     shape3d = tuple(int(s) for s in trackers[0].shape3d)
     n_vox = int(np.prod(shape3d))
@@ -229,8 +232,6 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     memb_off = np.zeros(n_nodes + 3, dtype=np.int32)
     memb_off[1:] = np.cumsum([len(m) for m in memb])
     memb_list = np.array([c for m in memb for c in m] or [0], dtype=np.int32)
-    if max(len(m) for m in memb) > 4:
-        raise _lib.B200EmpanadaError("an instance belongs to more than 4 consensus clusters")
     memb_off_d = torch.from_numpy(memb_off).to(dev)
     memb_list_d = torch.from_numpy(memb_list).to(dev)
 
@@ -243,7 +244,10 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         call("be_vote_stats", *vargs, n_vox, W, ptr(memb_off_d), ptr(memb_list_d),
              int(pixel_vote_thr), ptr(csize_d), ptr(keys), ptr(vals), cap2, ptr(overflow), stream_ptr())
-        if int(overflow.item()) == 0:
+        ov = int(overflow.item())
+        if ov == 2:
+            raise _lib.B200EmpanadaError("a voxel is claimed by more than 32 consensus clusters")
+        if ov == 0:
             break
         cap2 *= 4
     csize = csize_d.cpu().numpy().astype(np.int64)

@@ -75,25 +75,37 @@ __global__ void plane_pairs_kernel(const int* __restrict__ va, const int* __rest
 // memb_off[node] .. memb_off[node+1] indexes memb_list: the candidate output instances ("cids",
 // 1-based) the node is a member of (usually exactly one). A voxel is claimed by cid when at
 // least vote_thr of its (<= 3) nodes are members.
+__device__ __forceinline__ bool in_list(const int* __restrict__ memb_off, const int* __restrict__ memb_list,
+                                        int nd, int cid) {
+  if (nd == 0) return false;
+  for (int m = memb_off[nd]; m < memb_off[nd + 1]; ++m)
+    if (memb_list[m] == cid) return true;
+  return false;
+}
+constexpr int MAX_CLAIMS = 32;
+// returns the number of claiming cids written to claims[] (or -1 if more than MAX_CLAIMS claim)
 __device__ __forceinline__ int collect_claims(const Triple& t, const int* __restrict__ memb_off,
                                               const int* __restrict__ memb_list, int vote_thr,
-                                              int* claims, int max_claims) {
-  int cand[12], votes[12], nc = 0;
+                                              int* claims) {
   const int nodes[3] = {t.a, t.b, t.c};
+  int n = 0;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int nd = nodes[j];
     if (nd == 0) continue;
     for (int m = memb_off[nd]; m < memb_off[nd + 1]; ++m) {
       const int cid = memb_list[m];
-      int k = 0;
-      for (; k < nc; ++k) if (cand[k] == cid) { ++votes[k]; break; }
-      if (k == nc && nc < 12) { cand[nc] = cid; votes[nc] = 1; ++nc; }
+      bool seen = false;
+      for (int i = 0; i < j; ++i) seen |= in_list(memb_off, memb_list, nodes[i], cid);
+      if (seen) continue;  // counted at its first node
+      int votes = 1;
+      for (int i = j + 1; i < 3; ++i) votes += in_list(memb_off, memb_list, nodes[i], cid) ? 1 : 0;
+      if (votes >= vote_thr) {
+        if (n == MAX_CLAIMS) return -1;
+        claims[n++] = cid;
+      }
     }
   }
-  int n = 0;
-  for (int k = 0; k < nc; ++k)
-    if (votes[k] >= vote_thr && n < max_claims) claims[n++] = cand[k];
   return n;
 }
 
@@ -120,8 +132,9 @@ __global__ void vote_kernel(const int* __restrict__ va, const int* __restrict__ 
     if (x > 0 && same(t, load_triple(va, vb, vc, la, lb, lc, na, nb, nc, i - 1))) return;
     int len = 1;
     while (x + len < W && same(t, load_triple(va, vb, vc, la, lb, lc, na, nb, nc, i + len))) ++len;
-    int claims[8];
-    const int k = collect_claims(t, memb_off, memb_list, vote_thr, claims, 8);
+    int claims[MAX_CLAIMS];
+    const int k = collect_claims(t, memb_off, memb_list, vote_thr, claims);
+    if (k < 0) { atomicExch(overflow, 2); return; }
     bool ok = true;
     for (int u = 0; u < k; ++u) {
       atomicAdd(&sizes[claims[u]], len);
@@ -134,9 +147,9 @@ __global__ void vote_kernel(const int* __restrict__ va, const int* __restrict__ 
   } else {
     int best = 0;
     if ((t.a | t.b | t.c) != 0) {
-      int claims[8];
-      const int k = collect_claims(t, memb_off, memb_list, vote_thr, claims, 8);
-      int fin[8], nf = 0;
+      int claims[MAX_CLAIMS];
+      const int k = collect_claims(t, memb_off, memb_list, vote_thr, claims);  // >= 0: checked by the stats pass
+      int fin[MAX_CLAIMS], nf = 0;
       for (int u = 0; u < k; ++u) {
         const int f = cid_final[claims[u]];
         if (f == 0) continue;

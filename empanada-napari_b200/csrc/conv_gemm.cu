@@ -10,6 +10,10 @@
 namespace convgemm {
 using namespace sm100;
 
+constexpr int SBIAS_N = 2304;  // >= max Cout (2048) + one tile of zero padding
+// barriers + tmem ptr + s_bias + s_head + s_hpart
+constexpr int TAIL_BYTES = 256 + 16 + (SBIAS_N + 2 * MAX_N + 256) * 4;
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   if (act == ACT_SILU) return v / (1.0f + __expf(-v));
@@ -35,6 +39,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tfull_bar = empty_bar + stages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);   // [SBIAS_N]   bias, zero padded
+  float* s_head = s_bias + SBIAS_N;                         // [2][MAX_N]  fused head weights
+  float* s_hpart = s_head + 2 * MAX_N;                      // [128][2]    head partial sums
+  for (int i = threadIdx.x; i < SBIAS_N; i += blockDim.x)
+    s_bias[i] = (p.bias != nullptr && p.bias_img_stride == 0 && i < p.Cout) ? p.bias[i] : 0.0f;
+  for (int i = threadIdx.x; i < 2 * MAX_N; i += blockDim.x) {
+    const int r = i / MAX_N, c = i - r * MAX_N;
+    s_head[i] = (r < p.head_n && c < p.Cout) ? p.head_w[r * p.Cout + c] : 0.0f;
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -45,7 +58,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_mbar_init();
   }
@@ -121,12 +134,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    // epilogue: 8 warps. Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two
+    // warps of a lane quadrant split the tile's columns in halves.
+    const int ew = warp - 2;
     const int q = warp & 3;
+    const int half = ew >> 2;
     const int m = q * 32 + lane;
     const int tw = m % p.TW;
     const int th = (m / p.TW) % p.TH;
     const int tbi = m / (p.TW * p.TH);
+    const int cols_half = (((p.block_n >> 4) + 1) >> 1) << 4;
+    const int col_begin = half ? cols_half : 0;
+    const int col_end = half ? p.block_n : cols_half;
+    const long long hw = static_cast<long long>(p.Ho) * p.Wo;
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
@@ -139,13 +159,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
       const long long pix = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
       const int n0 = nt * p.block_n;
+      const float* gbias = (p.bias && p.bias_img_stride) ? p.bias + static_cast<long long>(b) * p.bias_img_stride : nullptr;
 
       mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MAX_N;
-      const float* bias = p.bias ? p.bias + static_cast<long long>(b) * p.bias_img_stride : nullptr;
       float hacc0 = 0.0f, hacc1 = 0.0f;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
@@ -153,9 +173,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (valid && n < p.Cout) {
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (bias != nullptr && n + j < p.Cout) f[j] += __ldg(bias + n + j);
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            if (gbias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) f[j] += __ldg(gbias + n + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += s_bias[n + j];  // padded with zeros past Cout
+            }
           }
           const bool full16 = (n + 16 <= p.Cout);
           if (p.residual != nullptr) {
@@ -166,12 +192,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-                f[2 * j] += __bfloat162float(h.x);
-                f[2 * j + 1] += __bfloat162float(h.y);
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+                f[2 * j] += __bfloat162float(h2.x);
+                f[2 * j + 1] += __bfloat162float(h2.y);
               }
             } else {
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) f[j] += __bfloat162float(rp[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) f[j] += __bfloat162float(rp[j]);
             }
           }
 #pragma unroll
@@ -182,41 +209,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               uint32_t pk[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
               }
               reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             } else {
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) op[j] = __float2bfloat16_rn(f[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) op[j] = __float2bfloat16_rn(f[j]);
             }
           }
           if (p.out_f32 != nullptr) {
             if (p.out_f32_planar) {
-              const long long hw = static_cast<long long>(p.Ho) * p.Wo;
               float* fp = p.out_f32 + (static_cast<long long>(b) * p.Cout + n) * hw + (static_cast<long long>(y) * p.Wo + x);
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) fp[j * hw] = f[j];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) fp[j * hw] = f[j];
             } else {
               float* fp = p.out_f32 + pix * p.out_f32_ld + n;
-              for (int j = 0; j < 16 && n + j < p.Cout; ++j) fp[j] = f[j];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) fp[j] = f[j];
             }
           }
           if (p.head_n > 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (n + j < p.Cout) {
-                hacc0 = fmaf(f[j], __ldg(p.head_w + n + j), hacc0);
-                if (p.head_n > 1) hacc1 = fmaf(f[j], __ldg(p.head_w + p.Cout + n + j), hacc1);
-              }
+              hacc0 = fmaf(f[j], s_head[n + j], hacc0);            // zero padded past Cout
+              hacc1 = fmaf(f[j], s_head[MAX_N + n + j], hacc1);
             }
           }
         }
       }
-      if (p.head_n > 0 && valid) {
-        const long long hw = static_cast<long long>(p.Ho) * p.Wo;
-        float* hp = p.head_out + static_cast<long long>(b) * p.head_n * hw + (static_cast<long long>(y) * p.Wo + x);
-        hp[0] = hacc0 + __ldg(p.head_b);
-        if (p.head_n > 1) hp[hw] = hacc1 + __ldg(p.head_b + 1);
+      if (p.head_n > 0) {
+        // combine the two column halves of each row through shared memory
+        if (half == 1) { s_hpart[2 * m] = hacc0; s_hpart[2 * m + 1] = hacc1; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          float* hp = p.head_out + static_cast<long long>(b) * p.head_n * hw + (static_cast<long long>(y) * p.Wo + x);
+          hp[0] = hacc0 + s_hpart[2 * m] + __ldg(p.head_b);
+          if (p.head_n > 1) hp[hw] = hacc1 + s_hpart[2 * m + 1] + __ldg(p.head_b + 1);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
@@ -318,7 +350,8 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   p.tiles_n = (Cout + bn - 1) / bn;
   p.kchunks = (Cin + KCHUNK - 1) / KCHUNK;
   const int stage_bytes = TILE_M * KCHUNK * 2 + bn * KCHUNK * 2;
-  int stages = (227 * 1024 - 1024 - 256) / stage_bytes;
+  if (Cout > SBIAS_N - 256) return -6;
+  int stages = (227 * 1024 - 1024 - TAIL_BYTES) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return -4;
   p.stages = stages;
@@ -327,8 +360,8 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   p.bias = bias; p.residual = residual; p.res_ld = res_ld; p.act = act;
   p.bias_img_stride = bias_img_stride; p.out_f32_planar = out_f32_planar;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_n = head_n;
-  if (head_n > 0 && (p.tiles_n != 1 || head_n > 2)) return -5;
-  L->smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  if (head_n > 0 && (p.tiles_n != 1 || head_n > 2 || Cout % 16 != 0)) return -5;
+  L->smem = static_cast<size_t>(stages) * stage_bytes + 1024 + TAIL_BYTES;
   const long long total = 1LL * p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   L->grid = static_cast<int>(total < num_sms ? total : num_sms);
 

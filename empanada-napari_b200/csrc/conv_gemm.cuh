@@ -22,7 +22,7 @@ namespace convgemm {
 constexpr int TILE_M = 128;   // output pixels per tile (UMMA M)
 constexpr int KCHUNK = 64;    // bf16 channels per pipeline stage (128 B swizzle row)
 constexpr int MAX_N = 256;    // UMMA N limit
-constexpr int NUM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int NUM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
 

@@ -120,40 +120,73 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int W
 }
 
 // ------------------------------------------------------------------ depthwise k x k, stride 1
-// weights [k*k][C] fp32 in shared memory; one thread = one pixel x 8 channels.
-__global__ void dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
-                              int C, int k, const float* __restrict__ wt, bf16* __restrict__ out,
-                              long long out_ld) {
-  extern __shared__ float wsm[];
-  for (int i = threadIdx.x; i < k * k * C; i += blockDim.x) wsm[i] = wt[i];
-  __syncthreads();
+// One thread = DW_PX consecutive output pixels along x times 8 channels: every loaded input
+// vector is reused by up to k taps x DW_PX outputs. Weights live in shared memory as
+// [tap][half][C/8][4] fp32 so that a warp's LDS.128 is conflict-free.
+constexpr int DW_PX = 4;
+template <int K>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W, int C,
+              const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld) {
+  extern __shared__ __align__(16) float wsm[];
   const int cg = C / 8;
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
+    const int tap = i / C, c = i - tap * C;
+    const int g = c >> 3, hf = (c >> 2) & 1, e = c & 3;
+    wsm[((tap * 2 + hf) * cg + g) * 4 + e] = wt[i];
+  }
+  __syncthreads();
+  const int wq = (W + DW_PX - 1) / DW_PX;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * cg;
+  const long long total = static_cast<long long>(B) * H * wq * cg;
   if (i >= total) return;
   const int g = static_cast<int>(i % cg);
-  long long pix = i / cg;
-  const int x = static_cast<int>(pix % W); pix /= W;
-  const int y = static_cast<int>(pix % H);
-  const int b = static_cast<int>(pix / H);
-  const int pad = (k - 1) / 2;
-  float acc[8];
+  long long r = i / cg;
+  const int xq = static_cast<int>(r % wq); r /= wq;
+  const int y = static_cast<int>(r % H);
+  const int b = static_cast<int>(r / H);
+  constexpr int PAD = (K - 1) / 2;
+  const int x0 = xq * DW_PX;
+  float acc[DW_PX][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-  for (int r = 0; r < k; ++r) {
-    const int yy = y - pad + r;
+  for (int px = 0; px < DW_PX; ++px)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[px][j] = 0.0f;
+  const float4* w4 = reinterpret_cast<const float4*>(wsm);
+#pragma unroll 1
+  for (int ry = 0; ry < K; ++ry) {
+    const int yy = y - PAD + ry;
     if (yy < 0 || yy >= H) continue;
-    for (int s = 0; s < k; ++s) {
-      const int xx = x - pad + s;
+    const bf16* rowp = in + (static_cast<long long>(b) * H + yy) * W * in_ld + g * 8;
+    float wr[K][8];  // this filter row's taps for the thread's 8 channels
+#pragma unroll
+    for (int sx = 0; sx < K; ++sx) {
+      const float4 wa = w4[((ry * K + sx) * 2 + 0) * cg + g];
+      const float4 wb = w4[((ry * K + sx) * 2 + 1) * cg + g];
+      wr[sx][0] = wa.x; wr[sx][1] = wa.y; wr[sx][2] = wa.z; wr[sx][3] = wa.w;
+      wr[sx][4] = wb.x; wr[sx][5] = wb.y; wr[sx][6] = wb.z; wr[sx][7] = wb.w;
+    }
+#pragma unroll
+    for (int c = 0; c < DW_PX + K - 1; ++c) {
+      const int xx = x0 - PAD + c;
       if (xx < 0 || xx >= W) continue;
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + yy) * W + xx) * in_ld + g * 8), f);
-      const float* wp = wsm + (r * k + s) * C + g * 8;
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(xx) * in_ld)), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wp[j], acc[j]);
+      for (int px = 0; px < DW_PX; ++px) {
+        const int sx = c - px;  // tap column for output px
+        if (sx < 0 || sx >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(f[j], wr[sx][j], acc[px][j]);
+      }
     }
   }
-  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + g * 8) = pack8(acc);
+#pragma unroll
+  for (int px = 0; px < DW_PX; ++px) {
+    const int x = x0 + px;
+    if (x < W)
+      *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + g * 8) = pack8(acc[px]);
+  }
 }
 
 // ------------------------------------------------------------------ bilinear, align_corners=True
@@ -394,9 +427,12 @@ int be_maxpool(const __nv_bfloat16* in, int B, int Hi, int Wi, int C, __nv_bfloa
 int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int C, int k,
               const float* wt, __nv_bfloat16* out, long long out_ld, cudaStream_t st) {
   if (C % 8) return be_set_error("dwconv: C must be a multiple of 8");
-  const long long total = static_cast<long long>(B) * H * W * (C / 8);
+  const long long total = static_cast<long long>(B) * H * ((W + mk::DW_PX - 1) / mk::DW_PX) * (C / 8);
   const size_t smem = sizeof(float) * k * k * C;
-  mk::dwconv_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, smem, st>>>(in, in_ld, B, H, W, C, k, wt, out, out_ld);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (k == 5) mk::dwconv_kernel<5><<<blocks, 256, smem, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
+  else if (k == 3) mk::dwconv_kernel<3><<<blocks, 256, smem, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
+  else return be_set_error("dwconv: only 3x3 and 5x5 kernels are built");
   return be_check_launch("dwconv_kernel");
 }
 int be_bilinear(const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi, int C,

@@ -199,3 +199,28 @@ int be_op_pr_predict(void* list, const void* X, int ldp, int C, const float* coa
 }
 
 }  // extern "C"
+
+// Replays the list with a CUDA event between consecutive ops; ms_out[i] = device time of op i.
+// Used by bench.py for the live per-kernel roofline figures (never inside the timed region).
+extern "C" int be_oplist_run_timed(void* list, const uint8_t* vol, long long stride_s,
+                                   long long stride_y, long long stride_x, int s0, float* ms_out,
+                                   int max_ops, cudaStream_t st) {
+  OpList* l = static_cast<OpList*>(list);
+  const int n = static_cast<int>(l->ops.size());
+  if (n > max_ops) return be_set_error("be_oplist_run_timed: ms_out too small");
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  RunArgs ra{vol, stride_s, stride_y, stride_x, s0};
+  cudaEventRecord(ev[0], st);
+  int rc = 0;
+  for (int i = 0; i < n && rc == 0; ++i) {
+    rc = l->ops[i](st, ra);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaStreamSynchronize(st);
+  if (rc == 0)
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+extern "C" int be_oplist_size(void* list) { return static_cast<int>(static_cast<OpList*>(list)->ops.size()); }

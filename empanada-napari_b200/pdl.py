@@ -28,6 +28,8 @@ _lib.declare("be_oplist_create", [ctypes.POINTER(c_void_p)])
 _lib.declare("be_oplist_destroy", [P])
 _lib.declare("be_oplist_launches", [P])
 _lib.declare("be_oplist_run", [P, P, LL, LL, LL, I, P])
+_lib.declare("be_oplist_run_timed", [P, P, LL, LL, LL, I, P, I, P])
+_lib.declare("be_oplist_size", [P])
 _lib.declare("be_op_conv", [P, P, LL, I, I, I, I, P, I, I, I, I, I, I, I, I, P, LL, I, P, LL, I, P, LL,
                             P, LL, I, P, P, P, I, P])
 _lib.declare("be_op_stem", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, P])
@@ -146,6 +148,7 @@ class _Plan:
         self.handle = c_void_p()
         _lib.lib().be_oplist_create(ctypes.byref(self.handle))
         self.bufs = []
+        self.op_info = []  # (kind, flops) per recorded op, same order as the launch list
         L = self.handle
         st = None
         bf = torch.bfloat16
@@ -157,7 +160,7 @@ class _Plan:
 
         def conv(x, Hi, Wi, Cin, wname, Cout, k=1, stride=1, dil=1, out=None, out_ld=None, coff=0,
                  act=ACT_RELU, res=None, bias=None, bias_img_stride=0, in_ld=None, head=None,
-                 Bn=B):
+                 Bn=B, alg_cin=None):
             pad = dil * (k - 1) // 2
             Ho = (Hi + 2 * pad - dil * (k - 1) - 1) // stride + 1
             Wo = (Wi + 2 * pad - dil * (k - 1) - 1) // stride + 1
@@ -172,14 +175,15 @@ class _Plan:
                  stride, dil, pad, Ho, Wo, ptr(out), out_ld, coff, None, 0, 0, ptr(bias),
                  bias_img_stride, ptr(res), Cout if res is not None else 0, act, ptr(hw_), ptr(hb_),
                  ptr(ho_), hn_, st)
+            self.op_info.append(("conv", 2.0 * Bn * Ho * Wo * Cout * k * k * (alg_cin or Cin)))
             return out, Ho, Wo
 
         H2, W2, H4, W4 = H // 2, Wd // 2, H // 4, Wd // 4
         stem = buf(B, H2, W2, 64)
-        call("be_op_stem", L, B, h, w, H, Wd, mean255, den, ptr(W["stem.w"]), ptr(W["stem.b"]),
+        self._rec("be_op_stem", L, B, h, w, H, Wd, mean255, den, ptr(W["stem.w"]), ptr(W["stem.b"]),
              ptr(stem), None, 0, 0, 0, 0, st)
         x = buf(B, H4, W4, 64)
-        call("be_op_maxpool", L, ptr(stem), B, H2, W2, 64, ptr(x), H4, W4, st)
+        self._rec("be_op_maxpool", L, ptr(stem), B, H2, W2, 64, ptr(x), H4, W4, st)
         Hc, Wc, Cin = H4, W4, 64
         p2 = None
         for (li, b, has_ds, planes) in W.blocks:
@@ -205,16 +209,16 @@ class _Plan:
                 conv(p5, H16, W16, 2048, f"{dec}.aspp{i}", 256, k=1 if i == 0 else 3, dil=1 if i == 0 else r,
                      out=cat, out_ld=1024, coff=256 * i)
             pooled, mid, pbias = buf(B, 2048, dtype=torch.float32), buf(B, 256, dtype=torch.float32), buf(B, 256, dtype=torch.float32)
-            call("be_op_aspp_pool_bias", L, ptr(p5), B, H16 * W16, 2048, ptr(W[dec + ".pool.w"]), 256,
+            self._rec("be_op_aspp_pool_bias", L, ptr(p5), B, H16 * W16, 2048, ptr(W[dec + ".pool.w"]), 256,
                  ptr(W[dec + ".proj.wpool"]), ptr(W[dec + ".proj.b"]), 256, ptr(pooled), ptr(mid), ptr(pbias), st)
             aspp, _, _ = conv(cat, H16, W16, 1024, dec + ".proj", 256, bias=pbias, bias_img_stride=256)
             clow = W[dec + ".low.w"].shape[0]
             cf = 256 + clow
             fcat = buf(B, H4, W4, cf)
             conv(p2, H4, W4, 256, dec + ".low", clow, out=fcat, out_ld=cf, coff=256)
-            call("be_op_bilinear", L, ptr(aspp), 256, B, H16, W16, 256, ptr(fcat), cf, 0, H4, W4, st)
+            self._rec("be_op_bilinear", L, ptr(aspp), 256, B, H16, W16, 256, ptr(fcat), cf, 0, H4, W4, st)
             dw = buf(B, H4, W4, cf)
-            call("be_op_dwconv", L, ptr(fcat), cf, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf, st)
+            self._rec("be_op_dwconv", L, ptr(fcat), cf, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf, st)
             feats[dec], _, _ = conv(dw, H4, W4, cf, dec + ".fuse.pw", 256)
         semantic_x = feats["semantic_decoder"]
         instance_x = feats.get("instance_decoder", semantic_x)
@@ -224,34 +228,47 @@ class _Plan:
         for head, src, out, n in (("semantic_head", semantic_x, self.coarse, 1),
                                   ("ins_center", instance_x, self.ctr, 1), ("ins_xy", instance_x, self.off, 2)):
             dw = buf(B, H4, W4, 256)
-            call("be_op_dwconv", L, ptr(src), 256, B, H4, W4, 256, 5, ptr(W[head + ".sep.dw"]), ptr(dw), 256, st)
+            self._rec("be_op_dwconv", L, ptr(src), 256, B, H4, W4, 256, 5, ptr(W[head + ".sep.dw"]), ptr(dw), 256, st)
             conv(dw, H4, W4, 256, head + ".sep.pw", 256, head=(W[head + ".out.w"], W[head + ".out.b"], out, n))
         # PointRend
         sem, Hs, Ws = self.coarse, H4, W4
         ldp = 264
         for step in range(render_steps):
             up = buf(B, 2 * Hs, 2 * Ws, dtype=torch.float32)
-            call("be_op_up2", L, ptr(sem), B, Hs, Ws, ptr(up), st)
+            self._rec("be_op_up2", L, ptr(sem), B, Hs, Ws, ptr(up), st)
             Hs, Ws = 2 * Hs, 2 * Ws
             k = min(Hs * Ws, num_points)
             state = buf(B, 8, dtype=torch.int32)
             hist = buf(B, 3, 2048, dtype=torch.int32)
             idx = buf(B, k, dtype=torch.int32)
-            call("be_op_topk", L, ptr(up), B, Hs * Ws, k, ptr(state), ptr(hist), ptr(idx), st)
+            self._rec("be_op_topk", L, ptr(up), B, Hs * Ws, k, ptr(state), ptr(hist), ptr(idx), st)
             Pa, Pb = buf(B * k, ldp), buf(B * k, ldp)
             cpts = buf(B * k, dtype=torch.float32)
-            call("be_op_pr_sample", L, ptr(idx), B, k, Hs, Ws, ptr(self.coarse), ptr(semantic_x), H4, W4, 256,
+            self._rec("be_op_pr_sample", L, ptr(idx), B, k, Hs, Ws, ptr(self.coarse), ptr(semantic_x), H4, W4, 256,
                  ptr(Pa), ptr(Pb), ldp, ptr(cpts), st)
             src, dst = Pa, Pb
             for l in range(W.num_fc):
-                conv(src, 1, B * k, ldp, f"pr.fc{l}", 256, out=dst, out_ld=ldp, in_ld=ldp, Bn=1)
+                conv(src, 1, B * k, ldp, f"pr.fc{l}", 256, out=dst, out_ld=ldp, in_ld=ldp, Bn=1, alg_cin=257)
                 src, dst = dst, src
-            call("be_op_pr_predict", L, ptr(src), ldp, 256, ptr(cpts), ptr(W["pr.pred.w"]), W.pr_pred_b,
+            self._rec("be_op_pr_predict", L, ptr(src), ldp, 256, ptr(cpts), ptr(W["pr.pred.w"]), W.pr_pred_b,
                  ptr(idx), B, k, Hs * Ws, ptr(up), st)
             sem = up
         self.sem = sem.view(B, Hs, Ws)
         self.semantic_x, self.instance_x, self.p5, self.p2 = semantic_x, instance_x, p5, p2
         self.launches = int(_lib.lib().be_oplist_launches(L))
+
+    def _rec(self, name, *args):
+        call(name, *args)
+        self.op_info.append((name[len("be_op_"):], 0.0))
+
+    def run_timed(self, vol_d, strides, s0):
+        """Per-op device times (ms) of one replay, measured with CUDA events between ops."""
+        n = int(_lib.lib().be_oplist_size(self.handle))
+        ms = np.zeros(n, dtype=np.float32)
+        call("be_oplist_run_timed", self.handle, ptr(vol_d), strides[0], strides[1], strides[2], s0,
+             ptr(ms), n, stream_ptr())
+        assert n == len(self.op_info)
+        return ms
 
     def run(self, vol_d, strides, s0):
         call("be_oplist_run", self.handle, ptr(vol_d), strides[0], strides[1], strides[2], s0, stream_ptr())
