@@ -20,6 +20,7 @@ from ._lib import call, ptr, stream_ptr
 
 MIN_OVERLAP = 100
 MIN_IOU = 1e-2
+LAST_PROFILE = {}
 LAST_LAUNCHES = 0  # kernels launched by the last merge_objects_from_trackers call
 
 
@@ -151,7 +152,18 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
                                 min_size=None, min_extent=None):
     """consensus.py:348-469 followed by the two tracker filters (inference.py:149-150).
     Returns (device int32 volume with the final ids painted, instances dict)."""
-    global LAST_LAUNCHES
+    global LAST_LAUNCHES, LAST_PROFILE
+    import os as _os, time as _time
+    _prof_on = _os.environ.get("B200_EMPANADA_PROFILE") == "1"
+    LAST_PROFILE = {}
+    _t0 = [_time.perf_counter()]
+
+    def _mark(name):
+        if _prof_on:
+            torch.cuda.synchronize()
+            t1 = _time.perf_counter()
+            LAST_PROFILE[name] = t1 - _t0[0]
+            _t0[0] = t1
     LAST_LAUNCHES = 12  # hash clear/compact x2, pairs, vote stats, vote paint, hist, lut, runs x2
     dev = torch.device("cuda", torch.cuda.current_device())
     shape3d = tuple(int(s) for s in trackers[0].shape3d)
@@ -196,6 +208,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             break
         cap *= 4
     pa, pb, inter = _hash_items(keys, vals, cap, dev)
+    _mark('plane pairs kernel')
     order = np.lexsort((pb, pa))
     graph = nx.Graph()
     for n in range(n_nodes):
@@ -221,6 +234,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             for m in cluster[1:]:
                 box = merge_boxes(box, node_boxes[m])
             cands.append((ci, cluster, box))
+    _mark('host graph clustering')
     if not cands:
         return empty_vol, {}
 
@@ -251,6 +265,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             break
         cap2 *= 4
     csize = csize_d.cpu().numpy().astype(np.int64)
+    _mark('vote stats kernel')
     ca, cb, cinter = _hash_items(keys, vals, cap2, dev)
     cpair = {(int(a), int(b)): int(v) for a, b, v in zip(ca, cb, cinter)}
 
@@ -302,6 +317,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
         if n_side <= side_cap:
             break
         side_cap = _next_pow2(n_side)
+    _mark('host merge_overlapping + paint kernel')
     hist = torch.zeros(n_final + 1, dtype=torch.int32, device=dev)
     call("be_label_hist", ptr(out), n_vox, W, n_final + 1, ptr(hist), stream_ptr())
     fsize = hist.cpu().numpy().astype(np.int64)
@@ -331,6 +347,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             flat.scatter_reduce_(0, side_vox, sid, reduce="amax", include_self=True)
 
     # instances: runs of the painted volume (+ hidden voxels of overlapped instances)
+    _mark('hist + filters')
     labels, starts, lens = extract_runs(out)
     order = torch.argsort(labels.long(), stable=True)
     lab_s = labels[order].cpu().numpy()
@@ -360,6 +377,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             joined = np.array(joined, dtype=np.int64)
             s, r = joined[:, 0], joined[:, 1] - joined[:, 0]
         instances[fid] = {"box": final_boxes[fid], "starts": s, "runs": r}
+    _mark('runs + instances dict')
     return out, instances
 
 

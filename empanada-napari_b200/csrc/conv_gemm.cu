@@ -10,14 +10,182 @@
 namespace convgemm {
 using namespace sm100;
 
+constexpr int MAX_RES_CHUNKS = MAX_N / 32;  // 16-column chunks per epilogue warp (half a tile)
 constexpr int SBIAS_N = 2304;  // >= max Cout (2048) + one tile of zero padding
 // barriers + tmem ptr + s_bias + s_head + s_hpart
-constexpr int TAIL_BYTES = 256 + 16 + (SBIAS_N + 2 * MAX_N + 256) * 4;
+constexpr int TAIL_BYTES = 256 + 32 + (SBIAS_N + 2 * MAX_N + 256) * 4;
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   if (act == ACT_SILU) return v / (1.0f + __expf(-v));
   return v;
+}
+
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Epilogue role (8 warps): TMEM -> registers -> bias / residual / activation -> bf16 NHWC stores
+// (or the fused 1x1 head). Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps
+// of a lane quadrant split the tile's columns in halves. The chunk loop stays rolled so that the
+// whole role fits the instruction cache; RES / HEAD are compile-time so unused paths vanish.
+template <bool RES, bool HEAD>
+__device__ __forceinline__ void epilogue_role(const Params& p, uint32_t s_bias, uint32_t s_head,
+                                              float* s_hpart, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t tmem_base, int warp,
+                                              int lane, int n_iter, int per_nt, bool wstat) {
+  const int ew = warp - 2;
+  const int q = warp & 3;
+  const int half = ew >> 2;
+  const int m = q * 32 + lane;
+  const int TW = p.TW, TH = p.TH, TB = p.TB, Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout;
+  const int tiles_x = p.tiles_x, tiles_y = p.tiles_y, tiles_n = p.tiles_n, block_n = p.block_n;
+  const int act = p.act;
+  __nv_bfloat16* const outp = p.out;
+  const long long out_ld = p.out_ld;
+  const int out_coff = p.out_coff;
+  const int tw = m % TW;
+  const int th = (m / TW) % TH;
+  const int tbi = m / (TW * TH);
+  const int cols_half = (((block_n >> 4) + 1) >> 1) << 4;
+  const int col_begin = half ? cols_half : 0;
+  const int col_end = half ? block_n : cols_half;
+  const long long hw = static_cast<long long>(Ho) * Wo;
+  const bool per_img_bias = (p.bias != nullptr) && (p.bias_img_stride != 0);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(outp) | (out_ld * 2) | (out_coff * 2)) & 15) == 0;
+  const bool res_vec_ok = RES && (((reinterpret_cast<uintptr_t>(p.residual) | (p.res_ld * 2)) & 15) == 0);
+  for (int t = 0; t < n_iter; ++t) {
+    const int buf = t & 1;
+    int nt, mt;
+    if (wstat) { nt = t / per_nt; mt = blockIdx.x + (t - nt * per_nt) * gridDim.x; }
+    else { const int tile_ = blockIdx.x + t * gridDim.x; nt = tile_ % tiles_n; mt = tile_ / tiles_n; }
+    const int tx = mt % tiles_x; mt /= tiles_x;
+    const int ty = mt % tiles_y;
+    const int tb = mt / tiles_y;
+    const int x = tx * TW + tw, y = ty * TH + th, b = tb * TB + tbi;
+    const bool valid = (x < Wo) && (y < Ho) && (b < Bn);
+    const long long pix = (static_cast<long long>(b) * Ho + y) * Wo + x;
+    const int n0 = nt * block_n;
+    const float* gbias = per_img_bias ? p.bias + static_cast<long long>(b) * p.bias_img_stride : nullptr;
+    const __nv_bfloat16* rrow = RES ? p.residual + pix * p.res_ld + n0 : nullptr;
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    if (RES && valid) {
+      // pull this thread's residual segment towards L2 while the MMAs of the tile run, and
+      // fetch the first chunk into registers
+      for (int c = col_begin; c < col_end && n0 + c < Cout; c += 64) prefetch_l2(rrow + c);
+      if (res_vec_ok && n0 + col_begin + 16 <= Cout) {
+        r0 = __ldg(reinterpret_cast<const uint4*>(rrow + col_begin));
+        r1 = __ldg(reinterpret_cast<const uint4*>(rrow + col_begin) + 1);
+      }
+    }
+    mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MAX_N;
+    float hacc0 = 0.0f, hacc1 = 0.0f;
+#pragma unroll 1
+    for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_32x16(taddr + c0, v);
+      // residual of the NEXT chunk is requested before this chunk's math
+      uint4 nr0 = make_uint4(0, 0, 0, 0), nr1 = nr0;
+      const int n = n0 + c0;
+      if (RES && valid && res_vec_ok && c0 + 16 < col_end && n + 32 <= Cout) {
+        nr0 = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 16));
+        nr1 = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 16) + 1);
+      }
+      tmem_ld_wait();
+      if (valid && n < Cout) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (per_img_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (n + j < Cout) f[j] += __ldg(gbias + n + j);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // zero padded past Cout
+            const float4 bb = lds_f32x4(s_bias + (n + 4 * g) * 4);
+            f[4 * g] += bb.x; f[4 * g + 1] += bb.y; f[4 * g + 2] += bb.z; f[4 * g + 3] += bb.w;
+          }
+        }
+        const bool full16 = (n + 16 <= Cout);
+        if (RES) {
+          if (res_vec_ok && full16) {
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+              f[2 * j] += __bfloat162float(h2.x);
+              f[2 * j + 1] += __bfloat162float(h2.y);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n + j < Cout) f[j] += __bfloat162float(rrow[c0 + j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], act);
+        if (outp != nullptr) {
+          __nv_bfloat16* op = outp + pix * out_ld + out_coff + n;
+          if (full16 && vec_ok && ((n & 7) == 0)) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n + j < Cout) op[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+        if (!RES && !HEAD && p.out_f32 != nullptr) {
+          if (p.out_f32_planar) {
+            float* fp = p.out_f32 + (static_cast<long long>(b) * Cout + n) * hw + (static_cast<long long>(y) * Wo + x);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n + j < Cout) fp[j * hw] = f[j];
+          } else {
+            float* fp = p.out_f32 + pix * p.out_f32_ld + n;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n + j < Cout) fp[j] = f[j];
+          }
+        }
+        if (HEAD) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // zero padded past Cout
+            const float4 w0 = lds_f32x4(s_head + (n + 4 * g) * 4);
+            const float4 w1 = lds_f32x4(s_head + (MAX_N + n + 4 * g) * 4);
+            hacc0 = fmaf(f[4 * g], w0.x, hacc0); hacc0 = fmaf(f[4 * g + 1], w0.y, hacc0);
+            hacc0 = fmaf(f[4 * g + 2], w0.z, hacc0); hacc0 = fmaf(f[4 * g + 3], w0.w, hacc0);
+            hacc1 = fmaf(f[4 * g], w1.x, hacc1); hacc1 = fmaf(f[4 * g + 1], w1.y, hacc1);
+            hacc1 = fmaf(f[4 * g + 2], w1.z, hacc1); hacc1 = fmaf(f[4 * g + 3], w1.w, hacc1);
+          }
+        }
+      }
+      r0 = nr0; r1 = nr1;
+    }
+    if (HEAD) {
+      // combine the two column halves of each row through shared memory
+      if (half == 1) { s_hpart[2 * m] = hacc0; s_hpart[2 * m + 1] = hacc1; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && valid) {
+        float* hp = p.head_out + static_cast<long long>(b) * p.head_n * hw + (static_cast<long long>(y) * Wo + x);
+        hp[0] = hacc0 + s_hpart[2 * m] + __ldg(p.head_b);
+        if (p.head_n > 1) hp[hw] = hacc1 + s_hpart[2 * m + 1] + __ldg(p.head_b + 1);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -31,14 +199,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int lane = threadIdx.x & 31;
   const int a_bytes = TILE_M * KCHUNK * 2;          // 16 KiB
   const int b_bytes = p.block_n * KCHUNK * 2;       // block_n * 128 B
-  const int stage_bytes = a_bytes + b_bytes;
+  const int taps = p.R * p.S;
+  const int num_kb = taps * p.kchunks;
+  // weight-stationary mode: all K blocks of the current N tile stay resident in shared memory
+  // and only the activation tiles stream through the pipeline stages
+  const bool wstat = p.b_stationary != 0;
+  const int stage_bytes = wstat ? a_bytes : a_bytes + b_bytes;
   const int stages = p.stages;
+  uint8_t* bres = smem;                                                    // [num_kb][b_bytes] (wstat)
+  uint8_t* stage_base = smem + (wstat ? static_cast<size_t>(num_kb) * b_bytes : 0);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bfull_bar = tempty_bar + 2;       // weights landed      (wstat)
+  uint64_t* bfree_bar = bfull_bar + 1;        // weights consumed    (wstat)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bfree_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);   // [SBIAS_N]   bias, zero padded
   float* s_head = s_bias + SBIAS_N;                         // [2][MAX_N]  fused head weights
   float* s_hpart = s_head + 2 * MAX_N;                      // [128][2]    head partial sums
@@ -60,6 +237,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    mbar_init(bfull_bar, 1);
+    mbar_init(bfree_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -73,16 +252,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = tiles_m * p.tiles_n;
-  const int taps = p.R * p.S;
-  const int num_kb = taps * p.kchunks;
+  // Work of this CTA, identical for the three roles. Streaming: tiles blockIdx.x + i*grid with N
+  // fastest. Weight-stationary: N tiles outermost, this CTA's M tiles (stride grid) innermost.
+  const int per_nt = (static_cast<int>(blockIdx.x) < tiles_m)
+                         ? (tiles_m - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+  const int n_iter = wstat ? per_nt * p.tiles_n
+                           : ((static_cast<int>(blockIdx.x) < total_tiles)
+                                  ? (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0);
+#define TILE_OF(it, nt, mt)                                                  \
+  int nt, mt;                                                                \
+  if (wstat) { nt = (it) / per_nt; mt = blockIdx.x + ((it) - nt * per_nt) * gridDim.x; } \
+  else { const int tile_ = blockIdx.x + (it) * gridDim.x; nt = tile_ % p.tiles_n; mt = tile_ / p.tiles_n; }
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int mt = tile / p.tiles_n;
+      for (int it = 0; it < n_iter; ++it) {
+        TILE_OF(it, nt, mt_)
+        int mt = mt_;
         const int tx = mt % p.tiles_x; mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
         const int tb = mt / p.tiles_y;
@@ -90,16 +278,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int y_in = ty * p.TH * p.stride - p.pad;
         const int b0 = tb * p.TB;
         const int n0 = nt * p.block_n;
+        if (wstat && (it % per_nt) == 0) {
+          // (re)load the resident weights of N tile nt once every MMA that read the previous
+          // ones has retired
+          mbar_wait(bfree_bar, (nt & 1) ^ 1);
+          mbar_expect_tx(bfull_bar, num_kb * b_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+            tma_load_2d(bres + static_cast<size_t>(kb) * b_bytes, &tmap_b, bfull_bar,
+                        tap * p.Cin + kc * KCHUNK, n0);
+          }
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / p.S, s = tap - r * p.S;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* a_dst = smem + static_cast<size_t>(stage) * stage_bytes;
-            uint8_t* b_dst = a_dst + a_bytes;
+            uint8_t* a_dst = stage_base + static_cast<size_t>(stage) * stage_bytes;
             mbar_expect_tx(&full_bar[stage], stage_bytes);
             tma_load_4d(a_dst, &tmap_a, &full_bar[stage], kc * KCHUNK, x_in + s * p.dil,
                         y_in + r * p.dil, b0);
-            tma_load_2d(b_dst, &tmap_b, &full_bar[stage], tap * p.Cin + kc * KCHUNK, n0);
+            if (!wstat)
+              tma_load_2d(a_dst + a_bytes, &tmap_b, &full_bar[stage], tap * p.Cin + kc * KCHUNK, n0);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -110,18 +309,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t idesc = make_idesc_bf16(TILE_M, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
-      int t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      for (int t = 0; t < n_iter; ++t) {
+        TILE_OF(t, nt, mt)
+        (void)mt;
         const int buf = t & 1;
+        if (wstat && (t % per_nt) == 0) {
+          mbar_wait(bfull_bar, nt & 1);
+          tc_fence_after();
+        }
         mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * MAX_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t b_addr = wstat ? smem_u32(bres + static_cast<size_t>(kb) * b_bytes) : a_addr + a_bytes;
           const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-          const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_bytes);
+          const uint64_t b_desc = make_sw128_kmajor_desc(b_addr);
 #pragma unroll
           for (int k = 0; k < KCHUNK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >> 4)
@@ -131,129 +336,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[buf]);
+        if (wstat && ((t + 1) % per_nt) == 0) umma_commit(bfree_bar);
       }
     }
   } else {
-    // epilogue: 8 warps. Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two
-    // warps of a lane quadrant split the tile's columns in halves.
-    const int ew = warp - 2;
-    const int q = warp & 3;
-    const int half = ew >> 2;
-    const int m = q * 32 + lane;
-    const int tw = m % p.TW;
-    const int th = (m / p.TW) % p.TH;
-    const int tbi = m / (p.TW * p.TH);
-    const int cols_half = (((p.block_n >> 4) + 1) >> 1) << 4;
-    const int col_begin = half ? cols_half : 0;
-    const int col_end = half ? p.block_n : cols_half;
-    const long long hw = static_cast<long long>(p.Ho) * p.Wo;
-    int t = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-      const int buf = t & 1;
-      const int nt = tile % p.tiles_n;
-      int mt = tile / p.tiles_n;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tb = mt / p.tiles_y;
-      const int x = tx * p.TW + tw, y = ty * p.TH + th, b = tb * p.TB + tbi;
-      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-      const long long pix = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
-      const int n0 = nt * p.block_n;
-      const float* gbias = (p.bias && p.bias_img_stride) ? p.bias + static_cast<long long>(b) * p.bias_img_stride : nullptr;
-
-      mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MAX_N;
-      float hacc0 = 0.0f, hacc1 = 0.0f;
-      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + c0, v);
-        tmem_ld_wait();
-        const int n = n0 + c0;
-        if (valid && n < p.Cout) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-            if (gbias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) f[j] += __ldg(gbias + n + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += s_bias[n + j];  // padded with zeros past Cout
-            }
-          }
-          const bool full16 = (n + 16 <= p.Cout);
-          if (p.residual != nullptr) {
-            const __nv_bfloat16* rp = p.residual + pix * p.res_ld + n;
-            if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-              const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-                f[2 * j] += __bfloat162float(h2.x);
-                f[2 * j + 1] += __bfloat162float(h2.y);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) f[j] += __bfloat162float(rp[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act);
-          if (p.out != nullptr) {
-            __nv_bfloat16* op = p.out + pix * p.out_ld + p.out_coff + n;
-            if (full16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) op[j] = __float2bfloat16_rn(f[j]);
-            }
-          }
-          if (p.out_f32 != nullptr) {
-            if (p.out_f32_planar) {
-              float* fp = p.out_f32 + (static_cast<long long>(b) * p.Cout + n) * hw + (static_cast<long long>(y) * p.Wo + x);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) fp[j * hw] = f[j];
-            } else {
-              float* fp = p.out_f32 + pix * p.out_f32_ld + n;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n + j < p.Cout) fp[j] = f[j];
-            }
-          }
-          if (p.head_n > 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              hacc0 = fmaf(f[j], s_head[n + j], hacc0);            // zero padded past Cout
-              hacc1 = fmaf(f[j], s_head[MAX_N + n + j], hacc1);
-            }
-          }
-        }
-      }
-      if (p.head_n > 0) {
-        // combine the two column halves of each row through shared memory
-        if (half == 1) { s_hpart[2 * m] = hacc0; s_hpart[2 * m + 1] = hacc1; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && valid) {
-          float* hp = p.head_out + static_cast<long long>(b) * p.head_n * hw + (static_cast<long long>(y) * p.Wo + x);
-          hp[0] = hacc0 + s_hpart[2 * m] + __ldg(p.head_b);
-          if (p.head_n > 1) hp[hw] = hacc1 + s_hpart[2 * m + 1] + __ldg(p.head_b + 1);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-    }
+    if (p.residual != nullptr) epilogue_role<true, false>(p, smem_u32(s_bias), smem_u32(s_head), s_hpart, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
+    else if (p.head_n > 0)     epilogue_role<false, true>(p, smem_u32(s_bias), smem_u32(s_head), s_hpart, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
+    else                       epilogue_role<false, false>(p, smem_u32(s_bias), smem_u32(s_head), s_hpart, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
   }
 
   tc_fence_before();
@@ -349,9 +438,16 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   p.block_n = bn;
   p.tiles_n = (Cout + bn - 1) / bn;
   p.kchunks = (Cin + KCHUNK - 1) / KCHUNK;
-  const int stage_bytes = TILE_M * KCHUNK * 2 + bn * KCHUNK * 2;
   if (Cout > SBIAS_N - 256) return -6;
-  int stages = (227 * 1024 - 1024 - TAIL_BYTES) / stage_bytes;
+  const int a_bytes_h = TILE_M * KCHUNK * 2, b_bytes_h = bn * KCHUNK * 2;
+  const long long num_kb_h = 1LL * R * S * p.kchunks;
+  const long long tiles_m_h = 1LL * p.tiles_x * p.tiles_y * p.tiles_b;
+  const long long smem_budget = 227 * 1024 - 1024 - TAIL_BYTES;
+  // weight-stationary when the whole K extent of one N tile fits beside >= 3 activation stages
+  // and every CTA reuses it for at least two M tiles
+  p.b_stationary = (num_kb_h * b_bytes_h + 3 * a_bytes_h <= smem_budget && tiles_m_h >= 2LL * num_sms) ? 1 : 0;
+  const int stage_bytes = p.b_stationary ? a_bytes_h : a_bytes_h + b_bytes_h;
+  int stages = static_cast<int>((smem_budget - (p.b_stationary ? num_kb_h * b_bytes_h : 0)) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return -4;
   p.stages = stages;
@@ -361,8 +457,8 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   p.bias_img_stride = bias_img_stride; p.out_f32_planar = out_f32_planar;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_n = head_n;
   if (head_n > 0 && (p.tiles_n != 1 || head_n > 2 || Cout % 16 != 0)) return -5;
-  L->smem = static_cast<size_t>(stages) * stage_bytes + 1024 + TAIL_BYTES;
-  const long long total = 1LL * p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  L->smem = static_cast<size_t>(stages) * stage_bytes + (p.b_stationary ? num_kb_h * b_bytes_h : 0) + 1024 + TAIL_BYTES;
+  const long long total = p.b_stationary ? tiles_m_h : tiles_m_h * p.tiles_n;
   L->grid = static_cast<int>(total < num_sms ? total : num_sms);
 
   {

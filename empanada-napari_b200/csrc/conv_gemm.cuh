@@ -38,6 +38,7 @@ struct Params {
   int block_n;           // channels per tile (multiple of 16, <= 256)
   int kchunks;           // ceil(Cin / 64)
   int stages;            // smem pipeline depth
+  int b_stationary;      // 1: weights of the current N tile stay resident in smem
   // epilogue
   __nv_bfloat16* out;    // NHWC, pixel stride out_ld, written at channel offset out_coff
   long long out_ld;

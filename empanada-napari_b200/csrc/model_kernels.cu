@@ -120,72 +120,82 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int W
 }
 
 // ------------------------------------------------------------------ depthwise k x k, stride 1
-// One thread = DW_PX consecutive output pixels along x times 8 channels: every loaded input
-// vector is reused by up to k taps x DW_PX outputs. Weights live in shared memory as
-// [tap][half][C/8][4] fp32 so that a warp's LDS.128 is conflict-free.
-constexpr int DW_PX = 4;
+// CTA = 8 rows x 32 pixels x 32 channels. The (8+K-1) x (32+K-1) input patch is staged once in
+// shared memory (halo re-read ~1.5x instead of K*K x from L2); a thread produces 4 consecutive
+// pixels x 8 channels with the current filter row's taps held in registers.
+constexpr int DW_TY = 8, DW_TX = 32, DW_PX = 4, DW_CG = 4;  // DW_CG groups of 8 channels
+constexpr int DW_PSTR = DW_CG + 1;                            // padded pixel stride (uint4 units)
 template <int K>
 __global__ void __launch_bounds__(256)
 dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W, int C,
               const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld) {
-  extern __shared__ __align__(16) float wsm[];
-  const int cg = C / 8;
-  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
-    const int tap = i / C, c = i - tap * C;
-    const int g = c >> 3, hf = (c >> 2) & 1, e = c & 3;
-    wsm[((tap * 2 + hf) * cg + g) * 4 + e] = wt[i];
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int PH = DW_TY + K - 1, PW = DW_TX + K - 1;
+  __shared__ uint4 patch[PH * PW * DW_PSTR];
+  __shared__ __align__(16) float wsm[K * K * 2 * DW_CG * 4];
+  const int cgs = C / 8;
+  const int cblocks = (cgs + DW_CG - 1) / DW_CG;
+  const int b = blockIdx.z / cblocks;
+  const int g0 = (blockIdx.z - b * cblocks) * DW_CG;
+  const int y0 = blockIdx.y * DW_TY, x0 = blockIdx.x * DW_TX;
+  for (int i = threadIdx.x; i < K * K * DW_CG * 8; i += blockDim.x) {
+    const int tap = i / (DW_CG * 8), c = i - tap * (DW_CG * 8);
+    const int gl = c >> 3, hf = (c >> 2) & 1, e = c & 3;
+    const int ch = g0 * 8 + c;
+    wsm[((tap * 2 + hf) * DW_CG + gl) * 4 + e] = (ch < C) ? wt[tap * C + ch] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
+    const int gl = i % DW_CG;
+    const int pix = i / DW_CG;
+    const int px = pix % PW, py = pix / PW;
+    const int y = y0 - PAD + py, x = x0 - PAD + px;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && x >= 0 && x < W && g0 + gl < cgs)
+      v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g0 + gl) * 8));
+    patch[pix * DW_PSTR + gl] = v;
   }
   __syncthreads();
-  const int wq = (W + DW_PX - 1) / DW_PX;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * wq * cg;
-  if (i >= total) return;
-  const int g = static_cast<int>(i % cg);
-  long long r = i / cg;
-  const int xq = static_cast<int>(r % wq); r /= wq;
-  const int y = static_cast<int>(r % H);
-  const int b = static_cast<int>(r / H);
-  constexpr int PAD = (K - 1) / 2;
-  const int x0 = xq * DW_PX;
+  const int ty = threadIdx.x >> 5;
+  const int xq = (threadIdx.x & 31) >> 2;
+  const int gl = threadIdx.x & 3;
   float acc[DW_PX][8];
 #pragma unroll
   for (int px = 0; px < DW_PX; ++px)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[px][j] = 0.0f;
   const float4* w4 = reinterpret_cast<const float4*>(wsm);
-#pragma unroll 1
+#pragma unroll
   for (int ry = 0; ry < K; ++ry) {
-    const int yy = y - PAD + ry;
-    if (yy < 0 || yy >= H) continue;
-    const bf16* rowp = in + (static_cast<long long>(b) * H + yy) * W * in_ld + g * 8;
-    float wr[K][8];  // this filter row's taps for the thread's 8 channels
+    float wr[K][8];
 #pragma unroll
     for (int sx = 0; sx < K; ++sx) {
-      const float4 wa = w4[((ry * K + sx) * 2 + 0) * cg + g];
-      const float4 wb = w4[((ry * K + sx) * 2 + 1) * cg + g];
+      const float4 wa = w4[((ry * K + sx) * 2 + 0) * DW_CG + gl];
+      const float4 wb = w4[((ry * K + sx) * 2 + 1) * DW_CG + gl];
       wr[sx][0] = wa.x; wr[sx][1] = wa.y; wr[sx][2] = wa.z; wr[sx][3] = wa.w;
       wr[sx][4] = wb.x; wr[sx][5] = wb.y; wr[sx][6] = wb.z; wr[sx][7] = wb.w;
     }
+    const uint4* prow = patch + ((ty + ry) * PW + xq * DW_PX) * DW_PSTR + gl;
 #pragma unroll
     for (int c = 0; c < DW_PX + K - 1; ++c) {
-      const int xx = x0 - PAD + c;
-      if (xx < 0 || xx >= W) continue;
       float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(xx) * in_ld)), f);
+      unpack8(prow[c * DW_PSTR], f);
 #pragma unroll
       for (int px = 0; px < DW_PX; ++px) {
-        const int sx = c - px;  // tap column for output px
+        const int sx = c - px;
         if (sx < 0 || sx >= K) continue;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(f[j], wr[sx][j], acc[px][j]);
       }
     }
   }
+  const int y = y0 + ty;
+  if (y < H && g0 + gl < cgs) {
 #pragma unroll
-  for (int px = 0; px < DW_PX; ++px) {
-    const int x = x0 + px;
-    if (x < W)
-      *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + g * 8) = pack8(acc[px]);
+    for (int px = 0; px < DW_PX; ++px) {
+      const int x = x0 + xq * DW_PX + px;
+      if (x < W)
+        *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + (g0 + gl) * 8) = pack8(acc[px]);
+    }
   }
 }
 
@@ -221,15 +231,27 @@ __global__ void bilinear_kernel(const bf16* __restrict__ in, long long in_ld, in
 }
 
 // ------------------------------------------------------------------ ASPP image-pool branch
-// pooled[b][c] = mean over pixels (fp32)
-__global__ void avgpool_kernel(const bf16* __restrict__ in, int HW, int C, float* __restrict__ pooled) {
+// pooled[b][c] += partial mean over a split of the pixels (fp32, pooled pre-zeroed)
+__global__ void avgpool_kernel(const bf16* __restrict__ in, int HW, int C, int splits,
+                               float* __restrict__ pooled) {
   const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel pair? keep simple
-  if (c >= C) return;
-  const bf16* p = in + static_cast<long long>(b) * HW * C + c;
-  float s = 0.0f;
-  for (int i = 0; i < HW; ++i) s += __bfloat162float(p[static_cast<long long>(i) * C]);
-  pooled[b * C + c] = s / static_cast<float>(HW);
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;  // 8-channel group
+  if (g * 8 >= C) return;
+  const int per = (HW + splits - 1) / splits;
+  const int p0 = blockIdx.z * per, p1 = min(HW, p0 + per);
+  const bf16* p = in + static_cast<long long>(b) * HW * C + g * 8;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.0f;
+  for (int i = p0; i < p1; ++i) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p + static_cast<long long>(i) * C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+  const float inv = 1.0f / static_cast<float>(HW);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&pooled[b * C + g * 8 + j], s[j] * inv);
 }
 // v[b][j] = relu(sum_c Wpool[j][c] * pooled[b][c]);  one warp per output
 __global__ void gemv_relu_kernel(const float* __restrict__ Wm, const float* __restrict__ x, int K,
@@ -284,31 +306,66 @@ __global__ void topk_hist_kernel(const float* __restrict__ x, int n, int pass,
   const unsigned himask = (pass == 0) ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
   const unsigned dmask = (pass == 2) ? 0x3FFu : 0x7FFu;
   const float* xb = x + static_cast<long long>(b) * n;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned k = absbits(xb[i]);
-    if ((k & himask) == (prefix & himask)) atomicAdd(&sh[(k >> shift) & dmask], 1u);
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;  // warp-uniform trip count
+    const unsigned k = (i < n) ? absbits(xb[i]) : 0u;
+    const bool hit = (i < n) && ((k & himask) == (prefix & himask));
+    const unsigned bin = (k >> shift) & dmask;
+    // warp-aggregated increment: lanes hitting the same bin elect one leader
+    const unsigned active = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const unsigned peers = __match_any_sync(active, bin);
+      if ((__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&sh[bin], __popc(peers));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
     if (sh[i]) atomicAdd(&hist[(b * 3 + pass) * 2048 + i], sh[i]);
 }
-__global__ void topk_pick_kernel(int pass, unsigned* __restrict__ state, const unsigned* __restrict__ hist) {
+__global__ void __launch_bounds__(1024)
+topk_pick_kernel(int pass, unsigned* __restrict__ state, const unsigned* __restrict__ hist) {
+  // one CTA per image: parallel inclusive scan over the 2048 bins, then the first bin whose
+  // cumulative count reaches `remaining` is the digit of the k-th smallest key
+  __shared__ unsigned cum[2048];
+  __shared__ unsigned warp_tot[32];
   const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  unsigned remaining = state[b * 8 + 1];
+  const unsigned remaining = state[b * 8 + 1];
   const unsigned* h = hist + (b * 3 + pass) * 2048;
   const int shift = (pass == 0) ? 21 : (pass == 1 ? 10 : 0);
   const int bins = (pass == 2) ? 1024 : 2048;
-  unsigned acc = 0;
-  int d = 0;
-  for (; d < bins; ++d) {
-    if (acc + h[d] >= remaining) break;
-    acc += h[d];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned a0 = (2 * t < bins) ? h[2 * t] : 0u, a1 = (2 * t + 1 < bins) ? h[2 * t + 1] : 0u;
+  unsigned v = a0 + a1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
   }
-  if (d == bins) d = bins - 1;
-  state[b * 8] |= static_cast<unsigned>(d) << shift;
-  state[b * 8 + 1] = remaining - acc;          // still to take inside the chosen bucket
-  if (pass == 2) state[b * 8 + 2] = remaining - acc;  // number of exact-threshold ties to take
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  const unsigned incl = v + (warp ? warp_tot[warp - 1] : 0u);  // inclusive over pairs
+  cum[2 * t] = incl - a1;
+  cum[2 * t + 1] = incl;
+  __syncthreads();
+  // bin d is the answer iff cum[d-1] < remaining <= cum[d]
+  for (int d = t; d < bins; d += blockDim.x) {
+    const unsigned before = d ? cum[d - 1] : 0u;
+    if (before < remaining && remaining <= cum[d]) {
+      state[b * 8] |= static_cast<unsigned>(d) << shift;
+      state[b * 8 + 1] = remaining - before;
+      if (pass == 2) state[b * 8 + 2] = remaining - before;
+    }
+  }
 }
 __global__ void topk_select_kernel(const float* __restrict__ x, int n, int k, unsigned* __restrict__ state,
                                    int* __restrict__ idx_out) {
@@ -427,11 +484,10 @@ int be_maxpool(const __nv_bfloat16* in, int B, int Hi, int Wi, int C, __nv_bfloa
 int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int C, int k,
               const float* wt, __nv_bfloat16* out, long long out_ld, cudaStream_t st) {
   if (C % 8) return be_set_error("dwconv: C must be a multiple of 8");
-  const long long total = static_cast<long long>(B) * H * ((W + mk::DW_PX - 1) / mk::DW_PX) * (C / 8);
-  const size_t smem = sizeof(float) * k * k * C;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (k == 5) mk::dwconv_kernel<5><<<blocks, 256, smem, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
-  else if (k == 3) mk::dwconv_kernel<3><<<blocks, 256, smem, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
+  const int cblocks = (C / 8 + mk::DW_CG - 1) / mk::DW_CG;
+  dim3 grid((W + mk::DW_TX - 1) / mk::DW_TX, (H + mk::DW_TY - 1) / mk::DW_TY, B * cblocks);
+  if (k == 5) mk::dwconv_kernel<5><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
+  else if (k == 3) mk::dwconv_kernel<3><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
   else return be_set_error("dwconv: only 3x3 and 5x5 kernels are built");
   return be_check_launch("dwconv_kernel");
 }
@@ -445,7 +501,9 @@ int be_bilinear(const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
 int be_aspp_pool_bias(const __nv_bfloat16* in, int B, int HW, int C, const float* w_pool, int Cmid,
                       const float* w_proj_pool, const float* bias_proj, int N, float* pooled,
                       float* mid, float* bias_out, cudaStream_t st) {
-  mk::avgpool_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(in, HW, C, pooled);
+  cudaMemsetAsync(pooled, 0, sizeof(float) * B * C, st);
+  const int splits = HW >= 1024 ? 32 : 1;
+  mk::avgpool_kernel<<<dim3((C / 8 + 63) / 64, B, splits), 64, 0, st>>>(in, HW, C, splits, pooled);
   mk::gemv_relu_kernel<<<dim3((Cmid + 7) / 8, B), 256, 0, st>>>(w_pool, pooled, C, Cmid, 1, nullptr, mid);
   mk::gemv_relu_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(w_proj_pool, mid, Cmid, N, 0, bias_proj, bias_out);
   return be_check_launch("aspp_pool_bias kernels");
@@ -463,7 +521,7 @@ int be_topk_uncertain(const float* x, int B, int n, int k, unsigned* state, unsi
   const int blocks = min(64, (n + 1023) / 1024);
   for (int pass = 0; pass < 3; ++pass) {
     mk::topk_hist_kernel<<<dim3(blocks, B), 1024, 0, st>>>(x, n, pass, state, hist);
-    mk::topk_pick_kernel<<<B, 32, 0, st>>>(pass, state, hist);
+    mk::topk_pick_kernel<<<B, 1024, 0, st>>>(pass, state, hist);
   }
   mk::topk_select_kernel<<<dim3(blocks, B), 1024, 0, st>>>(x, n, k, state, idx_out);
   return be_check_launch("topk kernels");

@@ -4,6 +4,8 @@ stack_postprocessing :56 of /root/reference/empanada_napari/inference.py), backe
 sm_100a kernels of this package. There is no CPU path: a CUDA device is required.
 """
 import math
+import os
+import time
 
 import numpy as np
 import torch
@@ -20,6 +22,23 @@ def _require_cuda():
     if not torch.cuda.is_available():
         raise _lib.B200EmpanadaError("a CUDA device (B200) is required; there is no CPU fallback")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+class _Phase:
+    """Optional wall-clock phase timer (B200_EMPANADA_PROFILE=1): synchronises between phases."""
+
+    def __init__(self, on):
+        self.on, self.t = on, {}
+        if on:
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            self.t[name] = self.t.get(name, 0.0) + (t1 - self.t0)
+            self.t0 = t1
 
 
 def _unsupported(name):
@@ -172,10 +191,14 @@ class Engine3d:
                          confidence_thr=self.confidence_thr, device=dev)
         norms = self.model_config["norms"]
         launches0 = getattr(self.model, "launches", 0)
+        prof = _Phase(os.environ.get("B200_EMPANADA_PROFILE") == "1")
         self._forward_all(post, vol_d, axis, n, norms, pf)
         post.finish_heads()
+        prof.mark("forward+median+centres+grouping")
         post.run_cc()
+        prof.mark("merge+cc+tables+overlaps")
         lut, labels, sizes, boxes = post.replay(axis_name, self.merge_iou_thr, self.merge_ioa_thr)
+        prof.mark("host matcher replay")
         # filters.remove_small_objects / remove_pancakes (inference.py:556-558), applied on tables
         spans = boxes[:, 3:] - boxes[:, :3] if len(boxes) else np.zeros((0, 3), np.int32)
         keep = (sizes >= self.min_size) & (spans >= self.min_extent).all(axis=1) if len(labels) else np.zeros(0, bool)
@@ -185,10 +208,13 @@ class Engine3d:
         keep_lut[kept_labels] = kept_labels
         lut_f = keep_lut[lut]
         dense = post.relabel(lut_f, axis_name, shape3d)
+        prof.mark("relabel")
         trackers = self.create_trackers(shape3d, axis_name)
         tr = trackers[0]
         tr.instances = post.tracker_instances(axis_name, shape3d, lut_f, kept_labels, boxes[keep], dense)
         tr.finish()
+        prof.mark("runs + tracker dict")
+        self.last_profile = prof.t
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
         stack = dense.cpu().numpy() if self.save_panoptic else None
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}

@@ -149,6 +149,7 @@ class _Plan:
         _lib.lib().be_oplist_create(ctypes.byref(self.handle))
         self.bufs = []
         self.op_info = []  # (kind, flops) per recorded op, same order as the launch list
+        self.op_desc = []
         L = self.handle
         st = None
         bf = torch.bfloat16
@@ -176,6 +177,8 @@ class _Plan:
                  bias_img_stride, ptr(res), Cout if res is not None else 0, act, ptr(hw_), ptr(hb_),
                  ptr(ho_), hn_, st)
             self.op_info.append(("conv", 2.0 * Bn * Ho * Wo * Cout * k * k * (alg_cin or Cin)))
+            nbytes = 2.0 * Bn * (Hi * Wi * Cin + (Ho * Wo * Cout if out is not None else 0) + (Ho * Wo * Cout if res is not None else 0)) + 2.0 * Cout * k * k * Cin
+            self.op_desc.append(f"{wname} {Cin}->{Cout} k{k} s{stride} d{dil} {Hi}x{Wi} bytes={nbytes/1e6:.0f}MB")
             return out, Ho, Wo
 
         H2, W2, H4, W4 = H // 2, Wd // 2, H // 4, Wd // 4
@@ -260,6 +263,7 @@ class _Plan:
     def _rec(self, name, *args):
         call(name, *args)
         self.op_info.append((name[len("be_op_"):], 0.0))
+        self.op_desc.append(name[len("be_op_"):])
 
     def run_timed(self, vol_d, strides, s0):
         """Per-op device times (ms) of one replay, measured with CUDA events between ops."""

@@ -30,8 +30,16 @@ print(f"B={B} {S}x{S}: forward {total:.3f} ms/batch = {total/B:.3f} ms/slice; su
 for k, (t, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"  {k:16s} n={n:3d} {t:8.3f} ms  {fl/1e9:9.1f} GF  {fl/t*1e-9 if t>0 else 0:8.1f} TF/s")
 convs = [(t, fl, i) for i, ((kind, fl), t) in enumerate(zip(plan.op_info, ms)) if kind == "conv"]
-print("slowest convs:")
-for t, fl, i in sorted(convs, reverse=True)[:25]:
-    print(f"   op{i:3d} {t:7.3f} ms {fl/1e9:8.1f} GF {fl/t*1e-9:8.1f} TF/s")
+print("all ops (ideal = max(bytes/6.5TB/s, flops/1400TF/s)):")
+gap = 0.0
+for i, ((kind, fl), t) in enumerate(zip(plan.op_info, ms)):
+    d = plan.op_desc[i]
+    ideal = 0.0
+    if kind == "conv":
+        mb = float(d.split("bytes=")[1][:-2])
+        ideal = max(mb * 1e6 / 6.5e12, fl / 1.4e15) * 1e3
+        gap += t - ideal
+    print(f"   op{i:3d} {t:7.3f} ms ideal {ideal:6.3f} {fl/1e9:8.1f} GF {fl/t*1e-9 if t > 0 else 0:8.1f} TF/s  {d}")
+print("conv gap to ideal (ms/batch):", gap)
 tot_fl = sum(fl for _, fl, _ in convs)
 print(f"conv total {sum(t for t,_,_ in convs):.3f} ms, {tot_fl/1e9:.1f} GF/batch = {tot_fl/B/1e9:.2f} GF/slice; whole-forward {tot_fl/total*1e-9:.1f} TF/s")
