@@ -279,8 +279,12 @@ def main():
     eng.set_device_volume(vol_d)
     for _ in range(args.warmup):
         out = job(vol_d, to_host=False)
+    if os.environ.get("BENCH_CUDA_PROFILER_API") == "1":  # `ncu --profile-from-start off` window
+        torch.cuda.profiler.start()
     with ClockSampler(local_rank) as clk:
         ms_step = timed(lambda: job(vol_d, to_host=False), args.steps)
+    if os.environ.get("BENCH_CUDA_PROFILER_API") == "1":
+        torch.cuda.profiler.stop()
     n_instances = len(out[1]) if out is not None else 0
     gpu_launches = launches["n"] * args.steps
     # end to end through the public API with host buffers

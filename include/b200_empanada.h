@@ -1,0 +1,135 @@
+/* C-ABI of libb200_empanada.so - the B200 (sm_100a) implementation of empanada's panoptic
+ * inference hot path. Plain pointers and sizes only; every device pointer is caller-owned; every
+ * GPU entry point takes the cudaStream_t to launch on (passed as void*); no hidden synchronisation.
+ * Convention: return 0 on success, negative on failure; be_last_error() returns the thread-local
+ * message. Each group cites the reference interface (paths under volume-em/empanada-napari) it
+ * replaces; the reference-side binding is shown in INTEGRATION.md.
+ */
+#ifndef B200_EMPANADA_H
+#define B200_EMPANADA_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* be_stream;  /* cudaStream_t */
+
+int be_version(void);
+const char* be_last_error(void);
+
+/* ---- piece (1): network forward. Replaces `self.model(image, render_steps, interpolate_ins)`
+ * (empanada/inference/engines.py:250) = QuantizablePanopticDeepLabPR.forward
+ * (empanada/models/quantization/panoptic_deeplab.py:238). The forward pass of one network at one
+ * (batch, H, W) is a launch list: be_op_* with list != NULL records, list == NULL launches now. */
+int be_oplist_create(void** list);
+int be_oplist_destroy(void* list);
+int be_oplist_launches(void* list);
+int be_oplist_size(void* list);
+int be_oplist_run(void* list, const uint8_t* volume_u8, long long stride_slice, long long stride_y,
+                  long long stride_x, int first_slice, be_stream st);
+int be_oplist_run_timed(void* list, const uint8_t* volume_u8, long long stride_slice,
+                        long long stride_y, long long stride_x, int first_slice, float* ms_per_op,
+                        int max_ops, be_stream st);
+/* implicit-GEMM convolution on tcgen05/TMEM fed by TMA (every nn.Conv2d / Conv1d with groups == 1:
+ * encoders/resnet.py:24-33, decoders/aspp.py:16-22,67-86, blocks.py conv_bn_act, point_rend.py:160-166);
+ * NHWC bf16 in/out, weights [Cout][R*S*Cin] bf16, fused bias / residual / ReLU|SiLU / 1x1 head */
+int be_op_conv(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int Cin,
+               const void* w, int Cout, int R, int S, int stride, int dil, int pad, int Ho, int Wo,
+               void* out, long long out_ld, int out_coff, float* out_f32, long long out_f32_ld,
+               int out_f32_planar, const float* bias, long long bias_img_stride,
+               const void* residual, long long res_ld, int act, const float* head_w,
+               const float* head_b, float* head_out, int head_n, be_stream st);
+/* slice gather + Preprocessor.normalize + factor_pad + conv1 7x7/2 + BN + ReLU
+ * (data/volume_dataset.py:37-53, empanada_napari/utils.py:170-201, inference/postprocess.py:26-36,
+ * encoders/resnet.py:217-220) */
+int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, float inv_std255,
+               const float* wt_49x64, const float* bias64, void* out, const uint8_t* vol,
+               long long stride_slice, long long stride_y, long long stride_x, int first_slice,
+               be_stream st);
+int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void* out, int Ho, int Wo,
+                  be_stream st);                                   /* encoders/resnet.py:221 */
+int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int W, int C, int k,
+                 const float* wt, void* out, long long out_ld, be_stream st); /* blocks.py:15-35 */
+int be_op_bilinear(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int C,
+                   void* out, long long out_ld, int out_coff, int Ho, int Wo,
+                   be_stream st);                                  /* decoders/panoptic_deeplab.py:76 */
+int be_op_aspp_pool_bias(void* list, const void* in, int B, int HW, int C, const float* w_pool,
+                         int Cmid, const float* w_proj_pool, const float* bias_proj, int N,
+                         float* pooled, float* mid, float* bias_out,
+                         be_stream st);                            /* decoders/aspp.py:30-48,97-102 */
+int be_op_up2(void* list, const float* in, int B, int h, int w, float* out, be_stream st);
+int be_op_topk(void* list, const float* x, int B, int n, int k, unsigned* state, unsigned* hist,
+               int* idx_out, be_stream st);                        /* point_rend.py:110-137 */
+int be_op_pr_sample(void* list, const int* idx, int B, int k, int Hf, int Wf, const float* coarse,
+                    const void* feat, int h4, int w4, int C, void* P, void* P2, int ldp,
+                    float* coarse_pts, be_stream st);              /* point_rend.py:24-59,255-258 */
+int be_op_pr_predict(void* list, const void* X, int ldp, int C, const float* coarse_pts,
+                     const float* wp, float bias, const int* idx, int B, int k, int HWf, float* sem,
+                     be_stream st);                                /* point_rend.py:181-188,260-267 */
+
+/* ---- piece (4): _MedianQueue + logits_to_prob + _harden_seg (engines.py:22-30,47-90,115-121,351-361) */
+int be_median_push(const float* logits, int B, int H, int W, int ks, float* hist, int n_hist,
+                   int slice0, float conf_thr, int is_prob, uint8_t* hard, float* prob_out,
+                   be_stream st);
+int be_median_flush(const float* hist, int n_hist, int ks, int H, int W, int n_slices_total,
+                    float conf_thr, uint8_t* hard, float* prob_out, be_stream st);
+/* ---- piece (2): find_instance_center (postprocess.py:39-76) */
+int be_centers(const float* ctr, int B, int h4, int w4, float thr, int k, int* centers, int cap,
+               int* counts, be_stream st);
+/* ---- piece (3): group_pixels / get_instance_cells (postprocess.py:79-169, engines.py:258-275) and
+ * get_panoptic_seg / merge_semantic_and_instance (engines.py:278-298, postprocess.py:224-296) */
+int be_group_pixels(const float* off, const int* centers, int cap, const int* counts, int B, int h4,
+                    int w4, float step, int* cells4, be_stream st);
+int be_merge_pan(const uint8_t* hard, const int* cells4, int B, int H, int W, int h, int w,
+                 int scale, int cap, int label_divisor, int class_id, int void_label, int* present,
+                 int* pan, be_stream st);
+/* ---- piece (5): connected_components / pan_seg_to_rle_seg (inference/rle.py:18-86), overlap
+ * tables standing for rle_intersection (array_utils.py:375-407), matcher + tracker replay
+ * (matcher.py:136-326, patterns.py:55-121, tracker.py:11-123), relabel, rle_encode
+ * (array_utils.py:213-239) */
+int be_cc_label(const int* pan, int B, int h, int w, int lo, int hi, int* L, int* chunk_counts,
+                int* cc_out, int* n_cc, int cap, int* table, be_stream st);
+int be_hash_clear(unsigned long long* keys, int* vals, unsigned long long cap, be_stream st);
+int be_pair_overlap(const int* cc_plane, int h, int w, int s0, int s1, unsigned long long* keys,
+                    int* vals, unsigned long long cap, int* overflow, be_stream st);
+int be_hash_compact(const unsigned long long* keys, const int* vals, unsigned long long cap,
+                    unsigned long long* out_keys, int* out_vals, int out_cap, int* cursor,
+                    be_stream st);
+int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
+                    const unsigned long long* pair_keys, const int* pair_vals, long long n_pairs,
+                    int class_id, int label_divisor, double iou_thr, double ioa_thr, int axis,
+                    int* lut, int lut_stride, int* inst_labels, long long* inst_sizes,
+                    int* inst_boxes, int max_inst, int* n_inst);            /* host function */
+int be_relabel(const int* cc_batch, int B, int h, int w, int s0, const int* lut, int lut_stride,
+               int* dst, long long stride_s, long long stride_y, long long stride_x, be_stream st);
+int be_runs_count(const int* img, long long n, long long seg_len, int* chunk_counts, be_stream st);
+int be_scan_i32_to_i64(const int* counts, long long* offsets, long long n, void* temp,
+                       size_t temp_bytes, size_t* temp_needed, be_stream st);
+int be_runs_write(const int* img, long long n, long long seg_len, const long long* chunk_offsets,
+                  int* out_label, long long* out_start, int* out_len, long long out_cap,
+                  be_stream st);
+int be_sort_runs(const unsigned long long* keys_in, unsigned long long* keys_out, const int* idx_in,
+                 int* idx_out, int n, void* temp, size_t temp_bytes, size_t* temp_needed,
+                 be_stream st);
+/* ---- piece (6): merge_objects_from_trackers (consensus.py:233-287,449-460), fill
+ * (array_utils.py:754-765), filters on the painted volume */
+int be_plane_pairs(const int* va, const int* vb, const int* vc, const int* la, const int* lb,
+                   const int* lc, int na, int nb, int nc, long long n, int W,
+                   unsigned long long* keys, int* vals, unsigned long long cap, int* overflow,
+                   be_stream st);
+int be_vote_stats(const int* va, const int* vb, const int* vc, const int* la, const int* lb,
+                  const int* lc, int na, int nb, int nc, long long n, int W, const int* memb_off,
+                  const int* memb_list, int vote_thr, int* sizes, unsigned long long* keys,
+                  int* vals, unsigned long long cap, int* overflow, be_stream st);
+int be_vote_paint(const int* va, const int* vb, const int* vc, const int* la, const int* lb,
+                  const int* lc, int na, int nb, int nc, long long n, int W, const int* memb_off,
+                  const int* memb_list, int vote_thr, const int* cid_final, int* out,
+                  long long* side_voxel, int* side_id, int side_cap, int* side_count, be_stream st);
+int be_label_hist(const int* vol, long long n, int W, int nbins, int* hist, be_stream st);
+int be_lut_inplace(int* vol, long long n, const int* lut, int nlut, be_stream st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
