@@ -27,6 +27,18 @@ def slice_ranges(n, world):
     return out
 
 
+def gather_slices_to_root(local, ranges, rank, world, group=None):
+    """Gathers per-rank slice blocks (first dim padded to the longest range) to rank 0 and returns
+    the list of per-rank blocks trimmed to their true length (None on other ranks). Works on any
+    backend (NCCL on GPUs, gloo in the CPU tests)."""
+    if rank == 0:
+        bufs = [torch.empty_like(local) for _ in range(world)]
+        dist.gather(local, bufs, dst=0, group=group)
+        return [bufs[r][: ranges[r][1] - ranges[r][0]] for r in range(world)]
+    dist.gather(local, None, dst=0, group=group)
+    return None
+
+
 class DistributedEngine3d(Engine3d):
     """Engine3d whose forward pass is sharded by slice range across the ranks of the default
     process group. `infer_on_axis` must be called by every rank; trackers are complete on rank 0
@@ -53,14 +65,7 @@ class DistributedEngine3d(Engine3d):
             sem[s0 - lo:s1 - lo].copy_(a)
             ctr[s0 - lo:s1 - lo].copy_(b)
             off[s0 - lo:s1 - lo].copy_(c)
-        gathered = []
-        for t in (sem, ctr, off):
-            if self.rank == 0:
-                bufs = [torch.empty_like(t) for _ in range(self.world)]
-                dist.gather(t, bufs, dst=0, group=self.group)
-                gathered.append(bufs)
-            else:
-                dist.gather(t, None, dst=0, group=self.group)
+        gathered = [gather_slices_to_root(t, ranges, self.rank, self.world, self.group) for t in (sem, ctr, off)]
         if self.rank == 0:
             for r, (a, b) in enumerate(ranges):
                 for s0 in range(a, b, 64):
