@@ -21,7 +21,7 @@ _SIGNATURES = {
     # post_kernels.cu
     "be_median_push": ([P, I, I, I, I, P, I, I, F, I, P, P, P], I),
     "be_median_flush": ([P, I, I, I, I, I, F, P, P, P], I),
-    "be_centers": ([P, I, I, I, F, I, P, I, P, P], I),
+    "be_centers": ([P, I, I, I, F, I, P, I, P, P, P], I),
     "be_group_pixels": ([P, P, I, P, I, I, I, F, P, P], I),
     "be_merge_pan": ([P, P, I, I, I, I, I, I, I, I, I, I, P, P, P], I),
     # cc_kernels.cu

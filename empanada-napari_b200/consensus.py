@@ -131,19 +131,20 @@ def extract_runs(vol):
     dev = vol.device
     n = vol.numel()
     chunks = (n + 1023) // 1024
-    counts = torch.zeros(chunks + 1, dtype=torch.int32, device=dev)
-    offsets = torch.empty(chunks + 1, dtype=torch.int64, device=dev)
+    counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=dev)
     st = stream_ptr()
     call("be_runs_count", ptr(vol), n, n, ptr(counts), st)
-    torch.cumsum(counts[:-1], 0, out=offsets[1:])
-    offsets[0] = 0
-    total = int(offsets[-1].item())
+    c2 = counts.view(2, chunks + 1)
+    offsets = torch.zeros((2, chunks + 1), dtype=torch.int64, device=dev)
+    torch.cumsum(c2[:, :-1], 1, out=offsets[:, 1:])
+    total = int(offsets[0, -1].item())
     labels = torch.empty(total, dtype=torch.int32, device=dev)
     starts = torch.empty(total, dtype=torch.int64, device=dev)
-    lens = torch.empty(total, dtype=torch.int32, device=dev)
+    ends = torch.empty(total, dtype=torch.int64, device=dev)
     if total:
-        call("be_runs_write", ptr(vol), n, n, ptr(offsets), ptr(labels), ptr(starts), ptr(lens),
+        call("be_runs_write", ptr(vol), n, n, ptr(offsets), ptr(labels), ptr(starts), ptr(ends),
              total, st)
+    lens = (ends - starts).to(torch.int32)
     return labels, starts, lens
 
 

@@ -41,16 +41,43 @@ __device__ __forceinline__ int cls_val(const int* pan, long long i, int lo, int 
   return (v >= lo && v < hi && v != 0) ? v : 0;
 }
 
-__global__ void cc_init_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w,
-                               int lo, int hi) {
+// Pass 1 (row runs): every pixel of a horizontal run of equal class value points at the run's
+// first pixel, computed with a segmented max-scan per 1024-pixel row chunk (no pointer chasing).
+// Runs are cut at chunk borders; pass 2 stitches them.
+constexpr int ROWCHUNK = 1024;
+__global__ void __launch_bounds__(ROWCHUNK)
+cc_init_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w, int lo, int hi) {
   const int b = blockIdx.z, y = blockIdx.y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= w) return;
+  const int x = blockIdx.x * ROWCHUNK + threadIdx.x;
   const long long base = static_cast<long long>(b) * h * w;
   const int p = y * w + x;
-  L[base + p] = cls_val(pan, base + p, lo, hi) ? p : -1;
+  const int v = (x < w) ? cls_val(pan, base + p, lo, hi) : 0;
+  const int vl = (x < w && threadIdx.x > 0) ? cls_val(pan, base + p - 1, lo, hi) : 0;
+  const bool head = v != 0 && (threadIdx.x == 0 || vl != v);
+  // start index of the run containing this pixel = max head position <= x
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const unsigned below = heads & (0xffffffffu >> (31 - lane));  // heads at lanes <= lane
+  int start = below ? (warp * 32 + 31 - __clz(below)) : -1;     // chunk-relative, -1: none in warp
+  __shared__ int warp_last[32];
+  if (lane == 31) warp_last[warp] = start;
+  __syncthreads();
+  if (warp == 0) {
+    int s = warp_last[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s = max(s, u);
+    }
+    warp_last[lane] = s;  // inclusive running max of "last head seen"
+  }
+  __syncthreads();
+  if (start < 0 && warp > 0) start = warp_last[warp - 1];
+  if (x < w) L[base + p] = v ? (y * w + blockIdx.x * ROWCHUNK + start) : -1;
 }
 
+// Pass 2: union run representatives across rows (8-connectivity) and across chunk borders.
+// Only the first pixel of a run that touches a given upper run issues the union.
 __global__ void cc_merge_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w,
                                 int lo, int hi) {
   const int b = blockIdx.z, y = blockIdx.y;
@@ -61,11 +88,23 @@ __global__ void cc_merge_kernel(const int* __restrict__ pan, int* __restrict__ L
   const int v = cls_val(pan, base + p, lo, hi);
   if (!v) return;
   int* Lb = L + base;
-  if (x > 0 && cls_val(pan, base + p - 1, lo, hi) == v) unite(Lb, p, p - 1);
+  const bool left_same = (x > 0) && (cls_val(pan, base + p - 1, lo, hi) == v);
+  const bool right_same = (x + 1 < w) && (cls_val(pan, base + p + 1, lo, hi) == v);
+  if (left_same && (x % ROWCHUNK) == 0) unite(Lb, p, p - 1);  // run cut at a chunk border
   if (y > 0) {
-    if (cls_val(pan, base + p - w, lo, hi) == v) unite(Lb, p, p - w);
-    if (x > 0 && cls_val(pan, base + p - w - 1, lo, hi) == v) unite(Lb, p, p - w - 1);
-    if (x + 1 < w && cls_val(pan, base + p - w + 1, lo, hi) == v) unite(Lb, p, p - w + 1);
+    const bool n_same = cls_val(pan, base + p - w, lo, hi) == v;
+    const bool nw_same = (x > 0) && (cls_val(pan, base + p - w - 1, lo, hi) == v);
+    const bool ne_same = (x + 1 < w) && (cls_val(pan, base + p - w + 1, lo, hi) == v);
+    if (n_same) {
+      // the pixel to the left already linked this pair of runs if it sits under the same upper run
+      if (!(left_same && nw_same)) unite(Lb, p, p - w);
+    } else {
+      if (nw_same && !left_same) unite(Lb, p, p - w - 1);
+      if (ne_same && !right_same) unite(Lb, p, p - w + 1);
+    }
+    // N equal and NE equal belong to the same upper run; N not equal but both diagonals equal are
+    // two different upper runs, each handled above
+    if (n_same == false && nw_same && left_same) { /* handled by the left pixel's N link */ }
   }
 }
 
@@ -270,35 +309,45 @@ __device__ __forceinline__ bool is_run_head(const int* img, long long i, long lo
   if (v == 0) return false;
   return (i % seg_len == 0) || (img[i - 1] != v);
 }
+__device__ __forceinline__ bool is_run_tail(const int* img, long long i, long long n, long long seg_len) {
+  const int v = img[i];
+  if (v == 0) return false;
+  return ((i + 1) % seg_len == 0) || (i + 1 >= n) || (img[i + 1] != v);
+}
+// chunk_counts[c] = heads in chunk c, chunk_counts[chunks + 1 + c] = tails in chunk c. The k-th
+// head and the k-th tail (global raster rank) delimit the same run, so no thread walks a run.
 __global__ void __launch_bounds__(CHUNK)
-runs_count_kernel(const int* __restrict__ img, long long n, long long seg_len,
+runs_count_kernel(const int* __restrict__ img, long long n, long long seg_len, int chunks,
                   int* __restrict__ chunk_counts) {
   const long long i = blockIdx.x * static_cast<long long>(CHUNK) + threadIdx.x;
   const bool head = (i < n) && is_run_head(img, i, seg_len);
-  const int c = __syncthreads_count(head);
-  if (threadIdx.x == 0) chunk_counts[blockIdx.x] = c;
+  const bool tail = (i < n) && is_run_tail(img, i, n, seg_len);
+  const int ch = __syncthreads_count(head);
+  const int ct = __syncthreads_count(tail);
+  if (threadIdx.x == 0) { chunk_counts[blockIdx.x] = ch; chunk_counts[chunks + 1 + blockIdx.x] = ct; }
 }
-// out_label / out_start / out_len indexed by the global raster rank of the run
+// out_label / out_start by head rank, out_len (= tail - start + 1) by tail rank
 __global__ void __launch_bounds__(CHUNK)
-runs_write_kernel(const int* __restrict__ img, long long n, long long seg_len,
+runs_write_kernel(const int* __restrict__ img, long long n, long long seg_len, int chunks,
                   const long long* __restrict__ chunk_offsets, int* __restrict__ out_label,
-                  long long* __restrict__ out_start, int* __restrict__ out_len, long long out_cap) {
+                  long long* __restrict__ out_start, long long* __restrict__ out_end, long long out_cap) {
   typedef cub::BlockScan<int, CHUNK> Scan;
   __shared__ typename Scan::TempStorage tmp;
   const long long i = blockIdx.x * static_cast<long long>(CHUNK) + threadIdx.x;
   const int head = (i < n) && is_run_head(img, i, seg_len);
-  int ex;
-  Scan(tmp).ExclusiveSum(head, ex);
-  if (!head) return;
-  const long long pos = chunk_offsets[blockIdx.x] + ex;
-  if (pos >= out_cap) return;
-  const int v = img[i];
-  const long long seg_end = (i / seg_len + 1) * seg_len;
-  long long e = i + 1;
-  while (e < seg_end && img[e] == v) ++e;
-  out_label[pos] = v;
-  out_start[pos] = i;
-  out_len[pos] = static_cast<int>(e - i);
+  const int tail = (i < n) && is_run_tail(img, i, n, seg_len);
+  int exh, ext;
+  Scan(tmp).ExclusiveSum(head, exh);
+  __syncthreads();
+  Scan(tmp).ExclusiveSum(tail, ext);
+  if (head) {
+    const long long pos = chunk_offsets[blockIdx.x] + exh;
+    if (pos < out_cap) { out_label[pos] = img[i]; out_start[pos] = i; }
+  }
+  if (tail) {
+    const long long pos = chunk_offsets[chunks + 1 + blockIdx.x] + ext;
+    if (pos < out_cap) out_end[pos] = i + 1;
+  }
 }
 
 __global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, unsigned long long n) {
@@ -317,7 +366,8 @@ int be_cc_label(const int* pan, int B, int h, int w, int lo, int hi, int* L, int
   const int hw = h * w;
   const long long total = static_cast<long long>(B) * hw;
   dim3 grid((w + 255) / 256, h, B);
-  cc::cc_init_kernel<<<grid, 256, 0, stream>>>(pan, L, h, w, lo, hi);
+  dim3 grid_rows((w + cc::ROWCHUNK - 1) / cc::ROWCHUNK, h, B);
+  cc::cc_init_kernel<<<grid_rows, cc::ROWCHUNK, 0, stream>>>(pan, L, h, w, lo, hi);
   cc::cc_merge_kernel<<<grid, 256, 0, stream>>>(pan, L, h, w, lo, hi);
   const unsigned nb = static_cast<unsigned>((total + 255) / 256);
   cc::cc_compress_kernel<<<nb, 256, 0, stream>>>(L, total, hw);
@@ -378,10 +428,11 @@ int be_relabel(const int* cc_batch, int B, int h, int w, int s0, const int* lut,
 
 // Pass 1 of run extraction: per-chunk counts (chunk = 1024 elements). The caller scans the
 // counts (be_scan_i32_to_i64) and then calls be_runs_write.
+// chunk_counts: [2 * (chunks + 1)] int32 (heads then tails; entry `chunks` of each half unused)
 int be_runs_count(const int* img, long long n, long long seg_len, int* chunk_counts,
                   cudaStream_t stream) {
   const unsigned chunks = static_cast<unsigned>((n + cc::CHUNK - 1) / cc::CHUNK);
-  cc::runs_count_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, chunk_counts);
+  cc::runs_count_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, static_cast<int>(chunks), chunk_counts);
   return be_check_launch("runs_count_kernel");
 }
 
@@ -398,12 +449,13 @@ int be_scan_i32_to_i64(const int* counts, long long* offsets, long long n, void*
   return 0;
 }
 
+// chunk_offsets: exclusive scans of the two halves of chunk_counts (same layout)
 int be_runs_write(const int* img, long long n, long long seg_len, const long long* chunk_offsets,
-                  int* out_label, long long* out_start, int* out_len, long long out_cap,
+                  int* out_label, long long* out_start, long long* out_end, long long out_cap,
                   cudaStream_t stream) {
   const unsigned chunks = static_cast<unsigned>((n + cc::CHUNK - 1) / cc::CHUNK);
-  cc::runs_write_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, chunk_offsets, out_label,
-                                                          out_start, out_len, out_cap);
+  cc::runs_write_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, static_cast<int>(chunks),
+                                                          chunk_offsets, out_label, out_start, out_end, out_cap);
   return be_check_launch("runs_write_kernel");
 }
 

@@ -123,12 +123,17 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int W
 // CTA = 8 rows x 32 pixels x 32 channels. The (8+K-1) x (32+K-1) input patch is staged once in
 // shared memory (halo re-read ~1.5x instead of K*K x from L2); a thread produces 4 consecutive
 // pixels x 8 channels with the current filter row's taps held in registers.
+// Optional fused producer: channels [0, Cup) of the input are the align_corners=True bilinear
+// upsampling of a low-resolution NHWC tensor `up` (the decoder's `F.interpolate` + `torch.cat`,
+// decoders/panoptic_deeplab.py:76-77), channels [Cup, C) come from `in`; the concatenated
+// tensor is never materialised.
 constexpr int DW_TY = 8, DW_TX = 32, DW_PX = 4, DW_CG = 4;  // DW_CG groups of 8 channels
 constexpr int DW_PSTR = DW_CG + 1;                            // padded pixel stride (uint4 units)
 template <int K>
 __global__ void __launch_bounds__(256)
 dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W, int C,
-              const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld) {
+              const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld,
+              const bf16* __restrict__ up, int Cup, int Hu, int Wu) {
   constexpr int PAD = (K - 1) / 2;
   constexpr int PH = DW_TY + K - 1, PW = DW_TX + K - 1;
   __shared__ uint4 patch[PH * PW * DW_PSTR];
@@ -144,14 +149,36 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
     const int ch = g0 * 8 + c;
     wsm[((tap * 2 + hf) * DW_CG + gl) * 4 + e] = (ch < C) ? wt[tap * C + ch] : 0.0f;
   }
+  const int cup_g = Cup / 8;
+  const float sy = (up != nullptr && H > 1) ? static_cast<float>(Hu - 1) / static_cast<float>(H - 1) : 0.0f;
+  const float sx = (up != nullptr && W > 1) ? static_cast<float>(Wu - 1) / static_cast<float>(W - 1) : 0.0f;
   for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
     const int gl = i % DW_CG;
     const int pix = i / DW_CG;
     const int px = pix % PW, py = pix / PW;
     const int y = y0 - PAD + py, x = x0 - PAD + px;
+    const int g = g0 + gl;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < H && x >= 0 && x < W && g0 + gl < cgs)
-      v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g0 + gl) * 8));
+    if (y >= 0 && y < H && x >= 0 && x < W && g < cgs) {
+      if (g < cup_g) {
+        const float fy = sy * y, fx = sx * x;
+        const int yy0 = static_cast<int>(fy), xx0 = static_cast<int>(fx);
+        const int yy1 = min(yy0 + 1, Hu - 1), xx1 = min(xx0 + 1, Wu - 1);
+        const float ly = fy - yy0, lx = fx - xx0;
+        const bf16* base = up + static_cast<long long>(b) * Hu * Wu * Cup + g * 8;
+        float a[8], c[8], d[8], e[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx0) * Cup)), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx1) * Cup)), c);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx0) * Cup)), d);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx1) * Cup)), e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
+        v = pack8(o);  // same bf16 rounding point as the materialised concat buffer
+      } else {
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g - cup_g) * 8));
+      }
+    }
     patch[pix * DW_PSTR + gl] = v;
   }
   __syncthreads();
@@ -168,11 +195,11 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
   for (int ry = 0; ry < K; ++ry) {
     float wr[K][8];
 #pragma unroll
-    for (int sx = 0; sx < K; ++sx) {
-      const float4 wa = w4[((ry * K + sx) * 2 + 0) * DW_CG + gl];
-      const float4 wb = w4[((ry * K + sx) * 2 + 1) * DW_CG + gl];
-      wr[sx][0] = wa.x; wr[sx][1] = wa.y; wr[sx][2] = wa.z; wr[sx][3] = wa.w;
-      wr[sx][4] = wb.x; wr[sx][5] = wb.y; wr[sx][6] = wb.z; wr[sx][7] = wb.w;
+    for (int sx2 = 0; sx2 < K; ++sx2) {
+      const float4 wa = w4[((ry * K + sx2) * 2 + 0) * DW_CG + gl];
+      const float4 wb = w4[((ry * K + sx2) * 2 + 1) * DW_CG + gl];
+      wr[sx2][0] = wa.x; wr[sx2][1] = wa.y; wr[sx2][2] = wa.z; wr[sx2][3] = wa.w;
+      wr[sx2][4] = wb.x; wr[sx2][5] = wb.y; wr[sx2][6] = wb.z; wr[sx2][7] = wb.w;
     }
     const uint4* prow = patch + ((ty + ry) * PW + xq * DW_PX) * DW_PSTR + gl;
 #pragma unroll
@@ -181,10 +208,10 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
       unpack8(prow[c * DW_PSTR], f);
 #pragma unroll
       for (int px = 0; px < DW_PX; ++px) {
-        const int sx = c - px;
-        if (sx < 0 || sx >= K) continue;
+        const int sx2 = c - px;
+        if (sx2 < 0 || sx2 >= K) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(f[j], wr[sx][j], acc[px][j]);
+        for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(f[j], wr[sx2][j], acc[px][j]);
       }
     }
   }
@@ -482,12 +509,13 @@ int be_maxpool(const __nv_bfloat16* in, int B, int Hi, int Wi, int C, __nv_bfloa
   return be_check_launch("maxpool_kernel");
 }
 int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int C, int k,
-              const float* wt, __nv_bfloat16* out, long long out_ld, cudaStream_t st) {
-  if (C % 8) return be_set_error("dwconv: C must be a multiple of 8");
+              const float* wt, __nv_bfloat16* out, long long out_ld, const __nv_bfloat16* up, int Cup,
+              int Hu, int Wu, cudaStream_t st) {
+  if (C % 8 || Cup % 8) return be_set_error("dwconv: C must be a multiple of 8");
   const int cblocks = (C / 8 + mk::DW_CG - 1) / mk::DW_CG;
   dim3 grid((W + mk::DW_TX - 1) / mk::DW_TX, (H + mk::DW_TY - 1) / mk::DW_TY, B * cblocks);
-  if (k == 5) mk::dwconv_kernel<5><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
-  else if (k == 3) mk::dwconv_kernel<3><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld);
+  if (k == 5) mk::dwconv_kernel<5><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
+  else if (k == 3) mk::dwconv_kernel<3><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
   else return be_set_error("dwconv: only 3x3 and 5x5 kernels are built");
   return be_check_launch("dwconv_kernel");
 }

@@ -27,7 +27,7 @@ int be_stem(const uint8_t*, long long, long long, long long, int, int, int, int,
             float, const float*, const float*, __nv_bfloat16*, cudaStream_t);
 int be_maxpool(const __nv_bfloat16*, int, int, int, int, __nv_bfloat16*, int, int, cudaStream_t);
 int be_dwconv(const __nv_bfloat16*, long long, int, int, int, int, int, const float*,
-              __nv_bfloat16*, long long, cudaStream_t);
+              __nv_bfloat16*, long long, const __nv_bfloat16*, int, int, int, cudaStream_t);
 int be_bilinear(const __nv_bfloat16*, long long, int, int, int, int, __nv_bfloat16*, long long, int,
                 int, int, cudaStream_t);
 int be_aspp_pool_bias(const __nv_bfloat16*, int, int, int, const float*, int, const float*,
@@ -146,10 +146,11 @@ int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void
 }
 
 int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int W, int C, int k,
-                 const float* wt, void* out, long long out_ld, cudaStream_t st) {
+                 const float* wt, void* out, long long out_ld, const void* up, int Cup, int Hu, int Wu,
+                 cudaStream_t st) {
   return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
     return be_dwconv(static_cast<const __nv_bfloat16*>(in), in_ld, B, H, W, C, k, wt,
-                     static_cast<__nv_bfloat16*>(out), out_ld, s);
+                     static_cast<__nv_bfloat16*>(out), out_ld, static_cast<const __nv_bfloat16*>(up), Cup, Hu, Wu, s);
   });
 }
 

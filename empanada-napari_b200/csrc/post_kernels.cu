@@ -98,68 +98,83 @@ __global__ void median_flush_kernel(const float* __restrict__ hist, int n_hist, 
 }
 
 // ------------------------------------------------------------------ centre NMS + ordered select
-// One CTA per slice; rows are scanned in raster order in chunks of blockDim.x pixels so the
-// compacted list is in torch.nonzero (row-major) order.
+// Two passes over 1024-pixel raster chunks (grid = chunks x slices): pass 0 counts the kept
+// pixels per chunk, pass 1 recomputes the flags and writes each kept pixel at
+// (kept pixels in earlier chunks) + (rank inside the chunk), i.e. torch.nonzero (row-major) order.
+__device__ __forceinline__ bool nms_keep(const float* __restrict__ c, int p, int n, int h4, int w4,
+                                         float thr, int k) {
+  if (p >= n) return false;
+  const int pad = k / 2;
+  const int y = p / w4, x = p - y * w4;
+  const float v0 = c[p];
+  const float t = (v0 > thr) ? v0 : -1.0f;
+  if (!(t > 0.0f)) return false;
+  // window [y-pad, y-pad+k) x [x-pad, x-pad+k): for even k this is the pooled output cell (y, x)
+  // of the (h+1, w+1) map whose last row/col the reference drops
+  float m = -INFINITY;
+  for (int dy = 0; dy < k; ++dy) {
+    const int yy = y - pad + dy;
+    if (yy < 0 || yy >= h4) continue;
+    for (int dx = 0; dx < k; ++dx) {
+      const int xx = x - pad + dx;
+      if (xx < 0 || xx >= w4) continue;
+      const float u = c[yy * w4 + xx];
+      m = fmaxf(m, (u > thr) ? u : -1.0f);
+    }
+  }
+  return t == m;
+}
+template <int PASS>
 __global__ void __launch_bounds__(1024)
 nms_centers_kernel(const float* __restrict__ ctr, int h4, int w4, float thr, int k,
-                   int* __restrict__ centers, int cap, int* __restrict__ counts) {
-  const int b = blockIdx.x;
-  const float* c = ctr + static_cast<long long>(b) * h4 * w4;
-  int* out = centers + static_cast<long long>(b) * cap;
+                   int* __restrict__ centers, int cap, int* __restrict__ counts,
+                   int* __restrict__ chunk_counts, int chunks) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int n = h4 * w4;
+  const int p = ch * 1024 + threadIdx.x;
+  const bool keep = nms_keep(ctr + static_cast<long long>(b) * n, p, n, h4, w4, thr, k);
+  if (PASS == 0) {
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) chunk_counts[b * chunks + ch] = c;
+    return;
+  }
   __shared__ int warp_sums[32];
   __shared__ int base;
-  if (threadIdx.x == 0) base = 0;
-  __syncthreads();
-  const int pad = k / 2;
-  const int n = h4 * w4;
-  for (int start = 0; start < n; start += blockDim.x) {
-    const int p = start + threadIdx.x;
-    bool keep = false;
-    if (p < n) {
-      const int y = p / w4, x = p - y * w4;
-      const float v0 = c[p];
-      const float t = (v0 > thr) ? v0 : -1.0f;
-      // window [y-pad, y-pad+k) x [x-pad, x-pad+k): for even k this is the pooled output cell
-      // (y, x) of the (h+1, w+1) map whose last row/col the reference drops
-      float m = -INFINITY;
-      for (int dy = 0; dy < k; ++dy) {
-        const int yy = y - pad + dy;
-        if (yy < 0 || yy >= h4) continue;
-        for (int dx = 0; dx < k; ++dx) {
-          const int xx = x - pad + dx;
-          if (xx < 0 || xx >= w4) continue;
-          const float u = c[yy * w4 + xx];
-          m = fmaxf(m, (u > thr) ? u : -1.0f);
-        }
-      }
-      keep = (t == m) && (t > 0.0f);
-    }
-    // ordered block compaction
-    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) warp_sums[warp] = __popc(ballot);
-    __syncthreads();
-    if (warp == 0) {
-      int v = warp_sums[lane];
+  // kept pixels of all earlier chunks of this slice (chunks <= a few thousand: one strided sum)
+  int part = 0;
+  for (int i = threadIdx.x; i < ch; i += 1024) part += chunk_counts[b * chunks + i];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-      }
-      warp_sums[lane] = v;  // inclusive
-    }
-    __syncthreads();
-    const int warp_off = (warp == 0) ? 0 : warp_sums[warp - 1];
-    const int pos = base + warp_off + __popc(ballot & ((1u << lane) - 1));
-    if (keep && pos < cap) {
-      const int y = p / w4, x = p - y * w4;
-      out[pos] = (y << 16) | x;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) base += warp_sums[31];
-    __syncthreads();
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < 32; ++i) s += warp_sums[i];
+    base = s;
   }
-  if (threadIdx.x == 0) counts[b] = base;  // may exceed cap: caller checks
+  __syncthreads();
+  const int chunk_base = base;
+  __syncthreads();
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_sums[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    int v = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    warp_sums[lane] = v;  // inclusive
+  }
+  __syncthreads();
+  const int pos = chunk_base + ((warp == 0) ? 0 : warp_sums[warp - 1]) + __popc(ballot & ((1u << lane) - 1));
+  if (keep && pos < cap) {
+    const int y = p / w4, x = p - y * w4;
+    centers[static_cast<long long>(b) * cap + pos] = (y << 16) | x;
+  }
+  if (ch == chunks - 1 && threadIdx.x == 0) counts[b] = chunk_base + warp_sums[31];  // may exceed cap
 }
 
 // ------------------------------------------------------------------ nearest-centre grouping
@@ -322,10 +337,13 @@ int be_median_flush(const float* hist, int n_hist, int ks, int H, int W, int n_s
   return be_check_launch("median_flush_kernel");
 }
 
+// chunk_counts: scratch [B * ceil(h4*w4/1024)] int32
 int be_centers(const float* ctr, int B, int h4, int w4, float thr, int k, int* centers, int cap,
-               int* counts, cudaStream_t stream) {
+               int* counts, int* chunk_counts, cudaStream_t stream) {
   if (h4 >= 65536 || w4 >= 65536) return be_set_error("head map too large for packed centres");
-  post::nms_centers_kernel<<<B, 1024, 0, stream>>>(ctr, h4, w4, thr, k, centers, cap, counts);
+  const int chunks = (h4 * w4 + 1023) / 1024;
+  post::nms_centers_kernel<0><<<dim3(chunks, B), 1024, 0, stream>>>(ctr, h4, w4, thr, k, centers, cap, counts, chunk_counts, chunks);
+  post::nms_centers_kernel<1><<<dim3(chunks, B), 1024, 0, stream>>>(ctr, h4, w4, thr, k, centers, cap, counts, chunk_counts, chunks);
   return be_check_launch("nms_centers_kernel");
 }
 

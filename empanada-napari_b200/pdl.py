@@ -34,7 +34,7 @@ _lib.declare("be_op_conv", [P, P, LL, I, I, I, I, P, I, I, I, I, I, I, I, I, P, 
                             P, LL, I, P, P, P, I, P])
 _lib.declare("be_op_stem", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, P])
 _lib.declare("be_op_maxpool", [P, P, I, I, I, I, P, I, I, P])
-_lib.declare("be_op_dwconv", [P, P, LL, I, I, I, I, I, P, P, LL, P])
+_lib.declare("be_op_dwconv", [P, P, LL, I, I, I, I, I, P, P, LL, P, I, I, I, P])
 _lib.declare("be_op_bilinear", [P, P, LL, I, I, I, I, P, LL, I, I, I, P])
 _lib.declare("be_op_aspp_pool_bias", [P, P, I, I, I, P, I, P, P, I, P, P, P, P])
 _lib.declare("be_op_up2", [P, P, I, I, I, P, P])
@@ -217,11 +217,11 @@ class _Plan:
             aspp, _, _ = conv(cat, H16, W16, 1024, dec + ".proj", 256, bias=pbias, bias_img_stride=256)
             clow = W[dec + ".low.w"].shape[0]
             cf = 256 + clow
-            fcat = buf(B, H4, W4, cf)
-            conv(p2, H4, W4, 256, dec + ".low", clow, out=fcat, out_ld=cf, coff=256)
-            self._rec("be_op_bilinear", L, ptr(aspp), 256, B, H16, W16, 256, ptr(fcat), cf, 0, H4, W4, st)
+            low, _, _ = conv(p2, H4, W4, 256, dec + ".low", clow)
             dw = buf(B, H4, W4, cf)
-            self._rec("be_op_dwconv", L, ptr(fcat), cf, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf, st)
+            # bilinear upsampling + concat fused into the depthwise producer
+            self._rec("be_op_dwconv", L, ptr(low), clow, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf,
+                      ptr(aspp), 256, H16, W16, st)
             feats[dec], _, _ = conv(dw, H4, W4, cf, dec + ".fuse.pw", 256)
         semantic_x = feats["semantic_decoder"]
         instance_x = feats.get("instance_decoder", semantic_x)
@@ -231,7 +231,8 @@ class _Plan:
         for head, src, out, n in (("semantic_head", semantic_x, self.coarse, 1),
                                   ("ins_center", instance_x, self.ctr, 1), ("ins_xy", instance_x, self.off, 2)):
             dw = buf(B, H4, W4, 256)
-            self._rec("be_op_dwconv", L, ptr(src), 256, B, H4, W4, 256, 5, ptr(W[head + ".sep.dw"]), ptr(dw), 256, st)
+            self._rec("be_op_dwconv", L, ptr(src), 256, B, H4, W4, 256, 5, ptr(W[head + ".sep.dw"]), ptr(dw), 256,
+                      None, 0, 0, 0, st)
             conv(dw, H4, W4, 256, head + ".sep.pw", 256, head=(W[head + ".out.w"], W[head + ".out.b"], out, n))
         # PointRend
         sem, Hs, Ws = self.coarse, H4, W4

@@ -61,12 +61,13 @@ class PlanePost:
         st = stream_ptr()
         call("be_median_push", ptr(sem), B, self.H, self.W, self.ks, ptr(self.hist), self.n_hist,
              s0, float(self.conf), int(is_prob), ptr(self.hard), ptr(self.prob), st)
+        scratch = torch.empty(B * ((self.h4 * self.w4 + 1023) // 1024), dtype=torch.int32, device=self.dev)
         call("be_centers", ptr(ctr), B, self.h4, self.w4, float(self.thr), int(self.k),
-             ptr(self.centers[s0]), self.center_cap, ptr(self.center_counts[s0:]), st)
+             ptr(self.centers[s0]), self.center_cap, ptr(self.center_counts[s0:]), ptr(scratch), st)
         call("be_group_pixels", ptr(off), ptr(self.centers[s0]), self.center_cap,
              ptr(self.center_counts[s0:]), B, self.h4, self.w4, float(self.scale),
              ptr(self.cells4[s0]), st)
-        self.launches += 3
+        self.launches += 4
         self.pushed += B
         self.n_hist = min(self.n_hist + B, self.ks - 1)
 
@@ -169,19 +170,20 @@ class PlanePost:
         seg_len. Returns device tensors (labels int32, starts int64, lens int32), raster order."""
         n = img.numel()
         chunks = (n + 1023) // 1024
-        counts = torch.zeros(chunks + 1, dtype=torch.int32, device=self.dev)
-        offsets = torch.empty(chunks + 1, dtype=torch.int64, device=self.dev)
+        counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=self.dev)
         st = stream_ptr()
         call("be_runs_count", ptr(img), n, seg_len, ptr(counts), st)
-        torch.cumsum(counts[:-1], 0, out=offsets[1:])
-        offsets[0] = 0
-        total = int(offsets[-1].item())
+        c2 = counts.view(2, chunks + 1)
+        offsets = torch.zeros((2, chunks + 1), dtype=torch.int64, device=self.dev)
+        torch.cumsum(c2[:, :-1], 1, out=offsets[:, 1:])
+        total = int(offsets[0, -1].item())
         labels = torch.empty(total, dtype=torch.int32, device=self.dev)
         starts = torch.empty(total, dtype=torch.int64, device=self.dev)
-        lens = torch.empty(total, dtype=torch.int32, device=self.dev)
+        ends = torch.empty(total, dtype=torch.int64, device=self.dev)
         if total:
             call("be_runs_write", ptr(img), n, seg_len, ptr(offsets), ptr(labels), ptr(starts),
-                 ptr(lens), total, st)
+                 ptr(ends), total, st)
+        lens = (ends - starts).to(torch.int32)
         self.launches += 2
         return labels, starts, lens
 

@@ -49,8 +49,11 @@ int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, flo
                be_stream st);
 int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void* out, int Ho, int Wo,
                   be_stream st);                                   /* encoders/resnet.py:221 */
+/* depthwise k x k (blocks.py:15-35); optional fused producer: channels [0,Cup) are the
+ * align_corners=True bilinear upsampling of `up` (decoders/panoptic_deeplab.py:76-77) */
 int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int W, int C, int k,
-                 const float* wt, void* out, long long out_ld, be_stream st); /* blocks.py:15-35 */
+                 const float* wt, void* out, long long out_ld, const void* up, int Cup, int Hu,
+                 int Wu, be_stream st);
 int be_op_bilinear(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int C,
                    void* out, long long out_ld, int out_coff, int Ho, int Wo,
                    be_stream st);                                  /* decoders/panoptic_deeplab.py:76 */
@@ -76,7 +79,7 @@ int be_median_flush(const float* hist, int n_hist, int ks, int H, int W, int n_s
                     float conf_thr, uint8_t* hard, float* prob_out, be_stream st);
 /* ---- piece (2): find_instance_center (postprocess.py:39-76) */
 int be_centers(const float* ctr, int B, int h4, int w4, float thr, int k, int* centers, int cap,
-               int* counts, be_stream st);
+               int* counts, int* chunk_counts_scratch, be_stream st);
 /* ---- piece (3): group_pixels / get_instance_cells (postprocess.py:79-169, engines.py:258-275) and
  * get_panoptic_seg / merge_semantic_and_instance (engines.py:278-298, postprocess.py:224-296) */
 int be_group_pixels(const float* off, const int* centers, int cap, const int* counts, int B, int h4,
@@ -107,7 +110,7 @@ int be_runs_count(const int* img, long long n, long long seg_len, int* chunk_cou
 int be_scan_i32_to_i64(const int* counts, long long* offsets, long long n, void* temp,
                        size_t temp_bytes, size_t* temp_needed, be_stream st);
 int be_runs_write(const int* img, long long n, long long seg_len, const long long* chunk_offsets,
-                  int* out_label, long long* out_start, int* out_len, long long out_cap,
+                  int* out_label, long long* out_start, long long* out_end, long long out_cap,
                   be_stream st);
 int be_sort_runs(const unsigned long long* keys_in, unsigned long long* keys_out, const int* idx_in,
                  int* idx_out, int n, void* temp, size_t temp_bytes, size_t* temp_needed,
