@@ -13,7 +13,9 @@ using namespace sm100;
 constexpr int MAX_RES_CHUNKS = MAX_N / 32;  // 16-column chunks per epilogue warp (half a tile)
 constexpr int SBIAS_N = 2304;  // >= max Cout (2048) + one tile of zero padding
 // barriers + tmem ptr + s_bias + s_head + s_hpart
-constexpr int TAIL_BYTES = 256 + 32 + (SBIAS_N + 2 * MAX_N + 256) * 4;
+constexpr int EPI_WARPS = (NUM_THREADS / 32) - 2;   // 16
+constexpr int EPI_PARTS = EPI_WARPS / 4;              // column parts per lane quadrant
+constexpr int TAIL_BYTES = 256 + 32 + (SBIAS_N + 2 * MAX_N + 2 * TILE_M * (EPI_PARTS - 1)) * 4 + 2 * TILE_M * 8;
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
@@ -41,7 +43,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint32_t s_bias, 
                                               int lane, int n_iter, int per_nt, bool wstat) {
   const int ew = warp - 2;
   const int q = warp & 3;
-  const int half = ew >> 2;
+  const int part = ew >> 2;            // column part handled by this warp (0 .. EPI_PARTS-1)
   const int m = q * 32 + lane;
   const int TW = p.TW, TH = p.TH, TB = p.TB, Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout;
   const int tiles_x = p.tiles_x, tiles_y = p.tiles_y, tiles_n = p.tiles_n, block_n = p.block_n;
@@ -52,9 +54,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint32_t s_bias, 
   const int tw = m % TW;
   const int th = (m / TW) % TH;
   const int tbi = m / (TW * TH);
-  const int cols_half = (((block_n >> 4) + 1) >> 1) << 4;
-  const int col_begin = half ? cols_half : 0;
-  const int col_end = half ? block_n : cols_half;
+  const int cols_part = (((block_n >> 4) + EPI_PARTS - 1) / EPI_PARTS) << 4;
+  const int col_begin = min(part * cols_part, block_n);
+  const int col_end = min(col_begin + cols_part, block_n);
   const long long hw = static_cast<long long>(Ho) * Wo;
   const bool per_img_bias = (p.bias != nullptr) && (p.bias_img_stride != 0);
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(outp) | (out_ld * 2) | (out_coff * 2)) & 15) == 0;
@@ -172,20 +174,184 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint32_t s_bias, 
       r0 = nr0; r1 = nr1;
     }
     if (HEAD) {
-      // combine the two column halves of each row through shared memory
-      if (half == 1) { s_hpart[2 * m] = hacc0; s_hpart[2 * m + 1] = hacc1; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0 && valid) {
+      // combine the column parts of each row through shared memory
+      if (part > 0) { s_hpart[((part - 1) * TILE_M + m) * 2] = hacc0; s_hpart[((part - 1) * TILE_M + m) * 2 + 1] = hacc1; }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      if (part == 0 && valid) {
+#pragma unroll
+        for (int pp = 0; pp < EPI_PARTS - 1; ++pp) { hacc0 += s_hpart[(pp * TILE_M + m) * 2]; hacc1 += s_hpart[(pp * TILE_M + m) * 2 + 1]; }
         float* hp = p.head_out + static_cast<long long>(b) * p.head_n * hw + (static_cast<long long>(y) * Wo + x);
-        hp[0] = hacc0 + s_hpart[2 * m] + __ldg(p.head_b);
-        if (p.head_n > 1) hp[hw] = hacc1 + s_hpart[2 * m + 1] + __ldg(p.head_b + 1);
+        hp[0] = hacc0 + __ldg(p.head_b);
+        if (p.head_n > 1) hp[hw] = hacc1 + __ldg(p.head_b + 1);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty_bar[buf]);
   }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> the 16 destination bytes are zero filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Staged epilogue: rows live in threads after tcgen05.ld, but HBM wants whole pixel rows per
+// warp. Each 64-channel sub-tile (128 px x 128 B) is therefore transposed through a 16 KiB
+// XOR-swizzled shared buffer and leaves as fully coalesced 16-byte stores; the residual tile
+// arrives the same way (cp.async issued BEFORE the accumulator barrier, so its HBM latency
+// hides under the tile's MMAs). obuf: [2][16 KiB], rbuf: [block_n/64][16 KiB], rowpix: [128] i64.
+template <bool RES>
+__device__ __forceinline__ void epilogue_role_staged(const Params& p, uint32_t s_bias, uint32_t obuf,
+                                                     uint32_t rbuf, long long* rowpix,
+                                                     uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                     uint32_t tmem_base, int warp, int lane,
+                                                     int n_iter, int per_nt, bool wstat) {
+  const int ew = warp - 2;
+  const int q = warp & 3;
+  const int part = ew >> 2;            // 16-column part of the 64-column sub-tile
+  const int m = q * 32 + lane;
+  const int etid = ew * 32 + lane;     // 0 .. EPI_WARPS*32-1
+  const int TW = p.TW, TH = p.TH, TB = p.TB, Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout;
+  const int tiles_x = p.tiles_x, tiles_y = p.tiles_y, tiles_n = p.tiles_n, block_n = p.block_n;
+  const int act = p.act;
+  __nv_bfloat16* const outp = p.out + p.out_coff;
+  const long long out_ld = p.out_ld;
+  const int nsub = (block_n + 63) >> 6;
+  // tile t -> (n0, rowpix table). rowpix is double buffered: the table of tile t+1 is needed
+  // while tile t is processed, to prefetch its residual rows.
+  auto tile_n0 = [&](int t) {
+    int nt;
+    if (wstat) nt = t / per_nt; else nt = (blockIdx.x + t * gridDim.x) % tiles_n;
+    return nt * block_n;
+  };
+  auto fill_rowpix = [&](int t, long long* tab) {
+    if (etid < TILE_M) {
+      int nt, mt;
+      if (wstat) { nt = t / per_nt; mt = blockIdx.x + (t - nt * per_nt) * gridDim.x; }
+      else { const int tile_ = blockIdx.x + t * gridDim.x; nt = tile_ % tiles_n; mt = tile_ / tiles_n; }
+      (void)nt;
+      const int tx = mt % tiles_x; mt /= tiles_x;
+      const int ty = mt % tiles_y;
+      const int tb = mt / tiles_y;
+      const int tw = etid % TW, th = (etid / TW) % TH, tbi = etid / (TW * TH);
+      const int x = tx * TW + tw, y = ty * TH + th, b = tb * TB + tbi;
+      tab[etid] = ((x < Wo) && (y < Ho) && (b < Bn)) ? (static_cast<long long>(b) * Ho + y) * Wo + x : -1;
+    }
+  };
+  auto issue_residual = [&](int j, int n0, const long long* tab) {
+    // sub-tile j of the residual: 128 rows x 8 chunks of 16 B, coalesced along channels
+#pragma unroll
+    for (int u = 0; u < (TILE_M * 8) / (EPI_WARPS * 32); ++u) {
+      const int i = etid + u * (EPI_WARPS * 32);
+      const int chunk = i & 7, row = i >> 3;
+      const long long pix = tab[row];
+      const int n = n0 + 64 * j + 8 * chunk;
+      const bool ok = (pix >= 0) && (n < Cout);
+      const __nv_bfloat16* src = p.residual + (ok ? pix * p.res_ld + n : 0);
+      cp_async16(rbuf + j * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok);
+    }
+  };
+  if (n_iter > 0) {
+    fill_rowpix(0, rowpix);
+    epi_bar();
+    if (RES) for (int j = 0; j < nsub; ++j) issue_residual(j, tile_n0(0), rowpix);
+  }
+  for (int t = 0; t < n_iter; ++t) {
+    const int buf = t & 1;
+    long long* tab = rowpix + (t & 1) * TILE_M;
+    long long* tab_next = rowpix + ((t + 1) & 1) * TILE_M;
+    const int n0 = tile_n0(t);
+    const bool has_next = (t + 1 < n_iter);
+    if (has_next) fill_rowpix(t + 1, tab_next);
+    if (RES) cp_async_wait_all();   // this tile's residual, requested one tile ago
+    mbar_wait(&tfull_bar[buf], (t >> 1) & 1);
+    tc_fence_after();
+    epi_bar();                      // residual chunks + next rowpix table visible to everyone
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * MAX_N;
+    for (int j = 0; j < nsub; ++j) {
+      const int c0 = 64 * j + 16 * part;
+      const uint32_t ob = obuf + (j & 1) * 16384;
+      if (c0 < block_n) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        const int n = n0 + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // s_bias is zero padded past Cout
+          const float4 bb = lds_f32x4(s_bias + (n + 4 * g) * 4);
+          f[4 * g] += bb.x; f[4 * g + 1] += bb.y; f[4 * g + 2] += bb.z; f[4 * g + 3] += bb.w;
+        }
+        if (RES) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int chunk = 2 * part + hh;
+            const uint4 r = lds_u4(rbuf + j * 16384 + m * 128 + ((chunk ^ (m & 7)) << 4));
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+              f[8 * hh + 2 * i] += __bfloat162float(h2.x);
+              f[8 * hh + 2 * i + 1] += __bfloat162float(h2.y);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], act);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * hh + 2 * i], f[8 * hh + 2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int chunk = 2 * part + hh;
+          sts_u4(ob + m * 128 + ((chunk ^ (m & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        }
+      }
+      if (j == nsub - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
+      epi_bar();
+      // rbuf[j] is free again: request the same sub-tile of the NEXT tile's residual now
+      if (RES && has_next) issue_residual(j, tile_n0(t + 1), tab_next);
+      // coalesced stores: 8 lanes cover one pixel row of the sub-tile (128 B)
+#pragma unroll
+      for (int u = 0; u < (TILE_M * 8) / (EPI_WARPS * 32); ++u) {
+        const int i = etid + u * (EPI_WARPS * 32);
+        const int chunk = i & 7, row = i >> 3;
+        const long long pix = tab[row];
+        const int n = n0 + 64 * j + 8 * chunk;
+        if (pix >= 0 && n < Cout) {
+          const uint4 val = lds_u4(ob + row * 128 + ((chunk ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(outp + pix * out_ld + n) = val;
+        }
+      }
+    }
+    epi_bar();  // obuf / rowpix[t&1] are reused
+  }
+  if (RES) cp_async_wait_all();
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -209,7 +375,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* bres = smem;                                                    // [num_kb][b_bytes] (wstat)
   uint8_t* stage_base = smem + (wstat ? static_cast<size_t>(num_kb) * b_bytes : 0);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + static_cast<size_t>(stages) * stage_bytes);
+  const int staging_bytes = p.staged ? (2 + (p.residual != nullptr ? ((p.block_n + 63) >> 6) : 0)) * 16384 : 0;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + static_cast<size_t>(stages) * stage_bytes + staging_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -218,7 +385,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bfree_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);   // [SBIAS_N]   bias, zero padded
   float* s_head = s_bias + SBIAS_N;                         // [2][MAX_N]  fused head weights
-  float* s_hpart = s_head + 2 * MAX_N;                      // [128][2]    head partial sums
+  float* s_hpart = s_head + 2 * MAX_N;                      // [EPI_PARTS-1][128][2] head partial sums
   for (int i = threadIdx.x; i < SBIAS_N; i += blockDim.x)
     s_bias[i] = (p.bias != nullptr && p.bias_img_stride == 0 && i < p.Cout) ? p.bias[i] : 0.0f;
   for (int i = threadIdx.x; i < 2 * MAX_N; i += blockDim.x) {
@@ -235,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     mbar_init(bfull_bar, 1);
     mbar_init(bfree_bar, 1);
@@ -339,6 +506,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (wstat && ((t + 1) % per_nt) == 0) umma_commit(bfree_bar);
       }
     }
+  } else if (p.staged) {
+    const uint32_t obuf = smem_u32(stage_base + static_cast<size_t>(stages) * stage_bytes);
+    const uint32_t rbuf = obuf + 2 * 16384;
+    long long* rowpix = reinterpret_cast<long long*>(s_hpart + 2 * TILE_M * (EPI_PARTS - 1));
+    if (p.residual != nullptr) epilogue_role_staged<true>(p, smem_u32(s_bias), obuf, rbuf, rowpix, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
+    else                       epilogue_role_staged<false>(p, smem_u32(s_bias), obuf, rbuf, rowpix, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
   } else {
     if (p.residual != nullptr) epilogue_role<true, false>(p, smem_u32(s_bias), smem_u32(s_head), s_hpart, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
     else if (p.head_n > 0)     epilogue_role<false, true>(p, smem_u32(s_bias), smem_u32(s_head), s_hpart, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
@@ -442,7 +615,26 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   const int a_bytes_h = TILE_M * KCHUNK * 2, b_bytes_h = bn * KCHUNK * 2;
   const long long num_kb_h = 1LL * R * S * p.kchunks;
   const long long tiles_m_h = 1LL * p.tiles_x * p.tiles_y * p.tiles_b;
-  const long long smem_budget = 227 * 1024 - 1024 - TAIL_BYTES;
+  // staged (smem-transposed, coalesced) epilogue: bf16 NHWC output only, 16-byte aligned rows
+  const bool can_stage = out != nullptr && out_f32 == nullptr && head_n == 0 && bias_img_stride == 0 &&
+                         Cout % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                         (residual == nullptr || (res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
+  const long long staging_h = can_stage ? (2 + (residual != nullptr ? (bn + 63) / 64 : 0)) * 16384LL : 0;
+  long long smem_budget = 227 * 1024 - 1024 - TAIL_BYTES - staging_h;
+  p.staged = can_stage ? 1 : 0;
+  {
+    // deep-K convolutions are MMA bound and want >= 4 operand stages more than a coalesced
+    // epilogue; shallow ones (few K blocks per tile) are epilogue bound
+    const long long kb_total = 1LL * R * S * p.kchunks;
+    const long long stage_full = TILE_M * KCHUNK * 2 + bn * KCHUNK * 2;
+    const bool deep = kb_total > 16;
+    if (can_stage && (smem_budget < 2 * stage_full || (deep && smem_budget < 4 * stage_full))) {
+      p.staged = 0;
+      smem_budget += staging_h;
+    }
+  }
+  const long long staging_used = p.staged ? staging_h : 0;
   // weight-stationary when the whole K extent of one N tile fits beside >= 3 activation stages
   // and every CTA reuses it for at least two M tiles
   p.b_stationary = (num_kb_h * b_bytes_h + 3 * a_bytes_h <= smem_budget && tiles_m_h >= 2LL * num_sms) ? 1 : 0;
@@ -457,7 +649,7 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   p.bias_img_stride = bias_img_stride; p.out_f32_planar = out_f32_planar;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_n = head_n;
   if (head_n > 0 && (p.tiles_n != 1 || head_n > 2 || Cout % 16 != 0)) return -5;
-  L->smem = static_cast<size_t>(stages) * stage_bytes + (p.b_stationary ? num_kb_h * b_bytes_h : 0) + 1024 + TAIL_BYTES;
+  L->smem = static_cast<size_t>(stages) * stage_bytes + (p.b_stationary ? num_kb_h * b_bytes_h : 0) + staging_used + 1024 + TAIL_BYTES;
   const long long total = p.b_stationary ? tiles_m_h : tiles_m_h * p.tiles_n;
   L->grid = static_cast<int>(total < num_sms ? total : num_sms);
 

@@ -22,7 +22,7 @@ namespace convgemm {
 constexpr int TILE_M = 128;   // output pixels per tile (UMMA M)
 constexpr int KCHUNK = 64;    // bf16 channels per pipeline stage (128 B swizzle row)
 constexpr int MAX_N = 256;    // UMMA N limit
-constexpr int NUM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
+constexpr int NUM_THREADS = 576;  // warp0 TMA, warp1 MMA, warps2-17 epilogue
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
 
@@ -39,6 +39,7 @@ struct Params {
   int kchunks;           // ceil(Cin / 64)
   int stages;            // smem pipeline depth
   int b_stationary;      // 1: weights of the current N tile stay resident in smem
+  int staged;            // 1: epilogue transposes through smem for coalesced loads/stores
   // epilogue
   __nv_bfloat16* out;    // NHWC, pixel stride out_ld, written at channel offset out_coff
   long long out_ld;

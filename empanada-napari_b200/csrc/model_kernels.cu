@@ -130,7 +130,7 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int W
 constexpr int DW_TY = 8, DW_TX = 32, DW_PX = 4, DW_CG = 4;  // DW_CG groups of 8 channels
 constexpr int DW_PSTR = DW_CG + 1;                            // padded pixel stride (uint4 units)
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W, int C,
               const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld,
               const bf16* __restrict__ up, int Cup, int Hu, int Wu) {
@@ -152,34 +152,55 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
   const int cup_g = Cup / 8;
   const float sy = (up != nullptr && H > 1) ? static_cast<float>(Hu - 1) / static_cast<float>(H - 1) : 0.0f;
   const float sx = (up != nullptr && W > 1) ? static_cast<float>(Wu - 1) / static_cast<float>(W - 1) : 0.0f;
-  for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
-    const int gl = i % DW_CG;
-    const int pix = i / DW_CG;
-    const int px = pix % PW, py = pix / PW;
-    const int y = y0 - PAD + py, x = x0 - PAD + px;
-    const int g = g0 + gl;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < H && x >= 0 && x < W && g < cgs) {
-      if (g < cup_g) {
-        const float fy = sy * y, fx = sx * x;
-        const int yy0 = static_cast<int>(fy), xx0 = static_cast<int>(fx);
-        const int yy1 = min(yy0 + 1, Hu - 1), xx1 = min(xx0 + 1, Wu - 1);
-        const float ly = fy - yy0, lx = fx - xx0;
-        const bf16* base = up + static_cast<long long>(b) * Hu * Wu * Cup + g * 8;
-        float a[8], c[8], d[8], e[8], o[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx0) * Cup)), a);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx1) * Cup)), c);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx0) * Cup)), d);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx1) * Cup)), e);
+  if (up == nullptr) {
+    // plain path: all global loads of the thread are issued before the first shared store
+    constexpr int NLD = (PH * PW * DW_CG + 255) / 256;
+    uint4 v[NLD];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
-        v = pack8(o);  // same bf16 rounding point as the materialised concat buffer
-      } else {
-        v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g - cup_g) * 8));
-      }
+    for (int u = 0; u < NLD; ++u) {
+      const int i = threadIdx.x + u * 256;
+      const int gl = i % DW_CG, pix = i / DW_CG;
+      const int px = pix % PW, py = pix / PW;
+      const int y = y0 - PAD + py, x = x0 - PAD + px;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < PH * PW * DW_CG && y >= 0 && y < H && x >= 0 && x < W && g0 + gl < cgs)
+        v[u] = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g0 + gl) * 8));
     }
-    patch[pix * DW_PSTR + gl] = v;
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = threadIdx.x + u * 256;
+      if (i < PH * PW * DW_CG) patch[(i / DW_CG) * DW_PSTR + (i % DW_CG)] = v[u];
+    }
+  } else {
+    for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
+      const int gl = i % DW_CG;
+      const int pix = i / DW_CG;
+      const int px = pix % PW, py = pix / PW;
+      const int y = y0 - PAD + py, x = x0 - PAD + px;
+      const int g = g0 + gl;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (y >= 0 && y < H && x >= 0 && x < W && g < cgs) {
+        if (g < cup_g) {
+          const float fy = sy * y, fx = sx * x;
+          const int yy0 = static_cast<int>(fy), xx0 = static_cast<int>(fx);
+          const int yy1 = min(yy0 + 1, Hu - 1), xx1 = min(xx0 + 1, Wu - 1);
+          const float ly = fy - yy0, lx = fx - xx0;
+          const bf16* base = up + static_cast<long long>(b) * Hu * Wu * Cup + g * 8;
+          float a[8], c[8], d[8], e[8], o[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx0) * Cup)), a);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx1) * Cup)), c);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx0) * Cup)), d);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx1) * Cup)), e);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
+          v = pack8(o);  // same bf16 rounding point as the materialised concat buffer
+        } else {
+          v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g - cup_g) * 8));
+        }
+      }
+      patch[pix * DW_PSTR + gl] = v;
+    }
   }
   __syncthreads();
   const int ty = threadIdx.x >> 5;
