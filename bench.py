@@ -191,7 +191,8 @@ def main():
     config = {"workload": workload, "volume": [S, S, S], "median_kernel": 3, "nms_kernel": 3,
               "pixel_vote_thr": 2, "min_size": 500, "min_extent": 5, "slice_batch": args.batch,
               "l2": "inputs larger than L2 (1 GiB volume, >4 GiB of heads per plane)",
-              "parallelism": f"slice-range sharding x{world}" if world > 1 else "single GPU"}
+              "parallelism": (f"forward sharded by slice range x{world}; planes post-processed concurrently on "
+                              f"leader ranks; consensus on rank 0") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -248,6 +249,9 @@ def main():
         n_l = 0
         for name in ("xy", "xz", "yz"):
             _, trackers[name] = eng.infer_on_axis(volume, name)
+            n_l += eng.last_stats.get("kernel_launches", 0)
+        if world > 1:  # deferred post-processing on the plane leaders, results to rank 0
+            trackers = eng.finalize(trackers)
             n_l += eng.last_stats.get("kernel_launches", 0)
         out = None
         if rank == 0:

@@ -183,10 +183,11 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     for tr in trackers:
         labels = [int(l) for l in tr.instances.keys()]
         lut = np.zeros((max(labels) + 1) if labels else 1, dtype=np.int32)
+        known = getattr(tr, "_b200_sizes", None)
         for l in labels:
             nid += 1
             lut[l] = nid
-            node_sizes.append(int(np.sum(tr.instances[l]["runs"])))
+            node_sizes.append(int(known[l]) if known is not None else int(np.sum(tr.instances[l]["runs"])))
             node_boxes.append(tuple(int(v) for v in tr.instances[l]["box"]))
         luts.append(torch.from_numpy(lut).to(dev))
         vols.append(dense_volume(tr, dev))

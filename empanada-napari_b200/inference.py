@@ -173,26 +173,27 @@ class Engine3d:
         if len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
             _unsupported("multi-class / semantic-only models")
 
-    def infer_on_axis(self, volume, axis_name):
-        self._check_supported()
+    def _plane_setup(self, volume, axis_name):
         axis = self.axes[axis_name]
-        dev = self.device
-        vol_d = self._cache.get(volume, dev)
+        vol_d = self._cache.get(volume, self.device)
         shape3d = tuple(int(s) for s in vol_d.shape)
         n = shape3d[axis]
         h, w = [s for i, s in enumerate(shape3d) if i != axis]
         pf = self.padding_factor
         H = h + (pf - h % pf) % pf
         W = w + (pf - w % pf) % pf
-        cls = self.thing_list[0]
-        post = PlanePost(n, h, w, H, W, ks=self.median_kernel_size, thing_class=cls,
+        return axis, vol_d, shape3d, n, h, w, H, W, pf
+
+    def _make_post(self, n, h, w, H, W):
+        return PlanePost(n, h, w, H, W, ks=self.median_kernel_size, thing_class=self.thing_list[0],
                          label_divisor=self.label_divisor, void_label=self.void_label,
                          nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
-                         confidence_thr=self.confidence_thr, device=dev)
-        norms = self.model_config["norms"]
-        launches0 = getattr(self.model, "launches", 0)
-        prof = _Phase(os.environ.get("B200_EMPANADA_PROFILE") == "1")
-        self._forward_all(post, vol_d, axis, n, norms, pf)
+                         confidence_thr=self.confidence_thr, device=self.device)
+
+    def _finish_plane(self, post, axis_name, shape3d, prof=None):
+        """Everything after the head maps are in: median tail, components, tracker replay,
+        filters, relabel, RLE. Returns [InstanceTracker] (with the dense volume attached)."""
+        prof = prof or _Phase(False)
         post.finish_heads()
         prof.mark("forward+median+centres+grouping")
         post.run_cc()
@@ -214,8 +215,20 @@ class Engine3d:
         tr.instances = post.tracker_instances(axis_name, shape3d, lut_f, kept_labels, boxes[keep], dense)
         tr.finish()
         prof.mark("runs + tracker dict")
-        self.last_profile = prof.t
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
+        tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, sizes[keep])}
+        return trackers
+
+    def infer_on_axis(self, volume, axis_name):
+        self._check_supported()
+        axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
+        post = self._make_post(n, h, w, H, W)
+        launches0 = getattr(self.model, "launches", 0)
+        prof = _Phase(os.environ.get("B200_EMPANADA_PROFILE") == "1")
+        self._forward_all(post, vol_d, axis, n, self.model_config["norms"], pf)
+        trackers = self._finish_plane(post, axis_name, shape3d, prof)
+        self.last_profile = prof.t
+        dense = trackers[0]._b200_dense
         stack = dense.cpu().numpy() if self.save_panoptic else None
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
         return stack, trackers

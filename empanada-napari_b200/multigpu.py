@@ -27,74 +27,120 @@ def slice_ranges(n, world):
     return out
 
 
-def gather_slices_to_root(local, ranges, rank, world, group=None):
-    """Gathers per-rank slice blocks (first dim padded to the longest range) to rank 0 and returns
-    the list of per-rank blocks trimmed to their true length (None on other ranks). Works on any
-    backend (NCCL on GPUs, gloo in the CPU tests)."""
-    if rank == 0:
+def gather_slices_to(local, ranges, rank, world, dst=0, group=None):
+    """Gathers per-rank slice blocks (first dim padded to the longest range) to rank `dst` and
+    returns the list of per-rank blocks trimmed to their true length (None on other ranks). Works
+    on any backend (NCCL on GPUs, gloo in the CPU tests)."""
+    if rank == dst:
         bufs = [torch.empty_like(local) for _ in range(world)]
-        dist.gather(local, bufs, dst=0, group=group)
+        dist.gather(local, bufs, dst=dst, group=group)
         return [bufs[r][: ranges[r][1] - ranges[r][0]] for r in range(world)]
-    dist.gather(local, None, dst=0, group=group)
+    dist.gather(local, None, dst=dst, group=group)
     return None
 
 
+def gather_slices_to_root(local, ranges, rank, world, group=None):
+    return gather_slices_to(local, ranges, rank, world, 0, group)
+
+
 class DistributedEngine3d(Engine3d):
-    """Engine3d whose forward pass is sharded by slice range across the ranks of the default
-    process group. `infer_on_axis` must be called by every rank; trackers are complete on rank 0
-    (other ranks return empty trackers)."""
+    """Engine3d for one process per GPU. Every rank must call `infer_on_axis` for the same planes
+    in the same order and then `finalize(trackers)`.
+
+    * the network forward of each plane is sharded by contiguous slice range over ALL ranks;
+    * the head maps of plane p are gathered (NCCL) to that plane's LEADER rank, which owns the
+      sequential part (recursive median, components, tracker replay, RLE) - the three planes'
+      leaders work concurrently, and the post-processing is deferred until `finalize` so that no
+      rank's forward pass waits behind another plane's post-processing;
+    * `finalize` ships each leader's result (dense label volume + instance table) to rank 0, where
+      `tracker_consensus` runs.
+    """
 
     def __init__(self, *args, group=None, **kwargs):
         super().__init__(*args, **kwargs)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self._pending = {}
 
-    def _forward_all(self, post, vol_d, axis, n, norms, pf):
+    def leader_of(self, axis_name):
+        # keep rank 0 (consensus) as free as the world size allows
+        return (self.axes[axis_name] + 1) % self.world
+
+    def infer_on_axis(self, volume, axis_name):
+        self._check_supported()
+        axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
+        leader = self.leader_of(axis_name)
         ranges = slice_ranges(n, self.world)
         lo, hi = ranges[self.rank]
-        H, W = post.H, post.W
         dev = vol_d.device
         nmax = max(b - a for a, b in ranges)
         sem = torch.empty((nmax, H, W), dtype=torch.float32, device=dev)
         ctr = torch.empty((nmax, H // 4, W // 4), dtype=torch.float32, device=dev)
         off = torch.empty((nmax, 2, H // 4, W // 4), dtype=torch.float32, device=dev)
+        launches0 = getattr(self.model, "launches", 0)
         for s0 in range(lo, hi, self.batch_size):
             s1 = min(hi, s0 + self.batch_size)
-            a, b, c = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            a, b, c = self.model.forward_slices(vol_d, axis, s0, s1, self.model_config["norms"], pf)
             sem[s0 - lo:s1 - lo].copy_(a)
             ctr[s0 - lo:s1 - lo].copy_(b)
             off[s0 - lo:s1 - lo].copy_(c)
-        gathered = [gather_slices_to_root(t, ranges, self.rank, self.world, self.group) for t in (sem, ctr, off)]
-        if self.rank == 0:
+        gathered = [gather_slices_to(t, ranges, self.rank, self.world, leader, self.group) for t in (sem, ctr, off)]
+        n_launch = getattr(self.model, "launches", 0) - launches0
+        trackers = self.create_trackers(shape3d, axis_name)
+        if self.rank == leader:
+            post = self._make_post(n, h, w, H, W)
             for r, (a, b) in enumerate(ranges):
                 for s0 in range(a, b, 64):
                     s1 = min(b, s0 + 64)
                     post.push_heads(gathered[0][r][s0 - a:s1 - a], gathered[1][r][s0 - a:s1 - a],
                                     gathered[2][r][s0 - a:s1 - a], is_prob=False)
-        else:
-            # keep the per-rank state machine consistent: nothing to post-process here
-            post.pushed = post.N
-            post.n_hist = min(post.N, post.ks - 1)
+            self._pending[axis_name] = (post, shape3d)
+        self.last_stats = {"kernel_launches": n_launch}
+        return None, trackers
 
-    def infer_on_axis(self, volume, axis_name):
-        if self.rank == 0:
-            return super().infer_on_axis(volume, axis_name)
-        # non-zero ranks: run the sharded forward only
-        self._check_supported()
-        axis = self.axes[axis_name]
-        vol_d = self._cache.get(volume, self.device)
-        shape3d = tuple(int(s) for s in vol_d.shape)
-        n = shape3d[axis]
-        h, w = [s for i, s in enumerate(shape3d) if i != axis]
-        pf = self.padding_factor
-        H, W = h + (pf - h % pf) % pf, w + (pf - w % pf) % pf
-
-        class _Shape:
-            pass
-        post = _Shape()
-        post.H, post.W, post.N, post.ks, post.pushed, post.n_hist = H, W, n, self.median_kernel_size, 0, 0
-        launches0 = getattr(self.model, "launches", 0)
-        self._forward_all(post, vol_d, axis, n, self.model_config["norms"], pf)
-        self.last_stats = {"kernel_launches": getattr(self.model, "launches", 0) - launches0}
-        return None, self.create_trackers(shape3d, axis_name)
+    def finalize(self, trackers):
+        """Collective. Completes the deferred post-processing on the plane leaders and assembles
+        all trackers on rank 0 (dense volume + instance table; the per-instance RLE arrays stay on
+        the leader). Returns the trackers dict (complete on rank 0)."""
+        n_launch = 0
+        for axis_name, (post, shape3d) in list(self._pending.items()):
+            trackers[axis_name] = self._finish_plane(post, axis_name, shape3d)
+            n_launch += post.launches
+        self._pending = {}
+        self.last_stats = {"kernel_launches": n_launch}
+        for axis_name in trackers.keys():
+            leader = self.leader_of(axis_name)
+            if leader == 0:
+                continue
+            tr = trackers[axis_name][0]
+            shape3d = tuple(int(s) for s in tr.shape3d)
+            if self.rank == leader:
+                labels = np.array(list(tr.instances.keys()), dtype=np.int64)
+                meta = np.zeros((len(labels), 8), dtype=np.int64)
+                for i, l in enumerate(labels):
+                    meta[i, 0] = l
+                    meta[i, 1] = tr._b200_sizes[int(l)]
+                    meta[i, 2:8] = tr.instances[int(l)]["box"]
+                cnt = torch.tensor([len(labels)], dtype=torch.int64, device=self.device)
+                dist.send(cnt, dst=0, group=self.group)
+                if len(labels):
+                    dist.send(torch.from_numpy(meta).to(self.device), dst=0, group=self.group)
+                dist.send(tr._b200_dense, dst=0, group=self.group)
+            elif self.rank == 0:
+                cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+                dist.recv(cnt, src=leader, group=self.group)
+                k = int(cnt.item())
+                meta = torch.zeros((k, 8), dtype=torch.int64, device=self.device)
+                if k:
+                    dist.recv(meta, src=leader, group=self.group)
+                dense = torch.empty(shape3d, dtype=torch.int32, device=self.device)
+                dist.recv(dense, src=leader, group=self.group)
+                meta = meta.cpu().numpy()
+                empty = np.zeros(0, dtype=np.int64)
+                tr.instances = {int(m[0]): {"box": tuple(int(v) for v in m[2:8]), "starts": empty, "runs": empty}
+                                for m in meta}
+                tr._b200_sizes = {int(m[0]): int(m[1]) for m in meta}
+                tr._b200_dense = dense
+                tr.finish()
+        return trackers
