@@ -66,12 +66,8 @@ class _VolumeCache:
                 raise Exception("Input image cannot be float type!")
             if volume.dtype != np.uint8:
                 _unsupported(f"{volume.dtype} volumes (uint8 only)")
-            host = torch.from_numpy(np.ascontiguousarray(volume))
-            try:
-                host = host.pin_memory()
-            except Exception:
-                pass
-            self.dev = host.to(device, non_blocking=False)
+            # one pageable -> device copy (the driver stages it); pinning 1 GiB first costs more
+            self.dev = torch.from_numpy(np.ascontiguousarray(volume)).to(device, non_blocking=False)
             self.key = key
         return self.dev
 
@@ -324,6 +320,35 @@ class Engine2d:
         return self.infer_batch(image[None])[0].cpu().numpy().astype(np.int32)
 
 
+class _PinnedPool:
+    """Page-locked host buffers for the label volumes handed back to the caller. A buffer is
+    reused only when the array previously returned from it has been released by the caller."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def to_host(self, vol_d, dtype):
+        import sys
+        dtype = np.dtype(dtype)
+        if dtype.itemsize == 4 and dtype.kind in "iu":
+            src, view_as = vol_d, dtype            # int32 bits reinterpreted (labels are >= 0)
+        else:
+            src, view_as = vol_d.to(getattr(torch, dtype.name)), dtype
+        key = (tuple(src.shape), str(src.dtype))
+        entry = self.bufs.get(key)
+        if entry is not None and sys.getrefcount(entry[1]) > 2:
+            entry = None                            # the caller still holds the previous result
+        if entry is None:
+            host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            entry = (host, host.numpy())
+            self.bufs[key] = entry
+        entry[0].copy_(src, non_blocking=False)
+        return entry[1].view(view_as)
+
+
+_PINNED = _PinnedPool()
+
+
 def get_axis_trackers_by_class(trackers, class_id):
     """patterns.py:154-166."""
     return [t for axis_trackers in trackers.values() for t in axis_trackers if t.class_id == class_id]
@@ -347,7 +372,7 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
         out.instances = instances
         tracker_consensus.last_launches = consensus.LAST_LAUNCHES
         # `to_host=False` (not in the reference signature) leaves the painted volume on the GPU
-        vol = vol_d.cpu().numpy().astype(dtype, copy=False) if to_host else vol_d
+        vol = _PINNED.to_host(vol_d, dtype) if to_host else vol_d
         yield vol, class_name, out.instances
 
 
