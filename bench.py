@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=96)
     ap.add_argument("--no-cpu", action="store_true")

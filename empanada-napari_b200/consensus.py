@@ -53,9 +53,21 @@ def create_graph_of_clusters(G, cluster_iou_thr):
         if d["iou"] <= cluster_iou_thr:
             H.remove_edge(u, v)
     CG = nx.Graph()
+    owner = {}
     for i, cluster in enumerate(nx.connected_components(H)):
         CG.add_node(i, cluster=cluster)
-    for n1, n2 in combinations(CG.nodes, 2):
+        for n in cluster:
+            owner[n] = i
+    # The reference tests every pair of clusters (combinations(CG.nodes, 2)); pairs without a
+    # single edge between them average to exactly 0 and never pass the thresholds, so only pairs
+    # joined by at least one edge are evaluated - in the same lexicographic order, with the same
+    # per-pair arithmetic.
+    linked = set()
+    for u, v in G.edges():
+        a, b = owner[u], owner[v]
+        if a != b:
+            linked.add((a, b) if a < b else (b, a))
+    for n1, n2 in sorted(linked):
         c1, c2 = CG.nodes[n1]["cluster"], CG.nodes[n2]["cluster"]
         iw = _avg_edge(G, c1, c2, "iou")
         ow = _avg_edge(G, c1, c2, "overlap")
@@ -67,7 +79,7 @@ def create_graph_of_clusters(G, cluster_iou_thr):
 def merge_clusters(G):
     H = G.copy()
     while len(H.edges()) > 0:
-        mc = sorted(H.nodes, key=lambda x: len(list(H.neighbors(x))), reverse=True)[0]
+        mc = max(H.nodes, key=H.degree)  # first node of maximal degree == sorted(..., reverse=True)[0]
         nbrs = sorted(H.neighbors(mc), key=lambda x: len(H.nodes[x]["cluster"]), reverse=True)
         if len(H.nodes[nbrs[0]]["cluster"]) > len(H.nodes[mc]["cluster"]):
             for nb in nbrs:
@@ -222,14 +234,20 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
         if iou > 0:
             graph.add_edge(int(a - 1), int(b - 1), iou=iou, overlap=int(it))
 
+    _mark('host build nx graph')
     # clusters per connected component
     cands = []  # (component index, member node list, merged box)
     for ci, comp in enumerate(nx.connected_components(graph)):
         if len(comp) < min_cluster:
             continue
-        cg = merge_clusters(create_graph_of_clusters(graph.subgraph(comp), cluster_iou_thr))
-        for node in cg.nodes:
-            cluster = list(cg.nodes[node]["cluster"])
+        if all(d > cluster_iou_thr for _, _, d in graph.edges(comp, data="iou")):
+            # every edge survives the IoU cut: the component is one cluster and the cluster graph
+            # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
+            clusters = [list(comp)]
+        else:
+            cg = merge_clusters(create_graph_of_clusters(graph.subgraph(comp), cluster_iou_thr))
+            clusters = [list(cg.nodes[node]["cluster"]) for node in cg.nodes]
+        for cluster in clusters:
             if len(cluster) < min_cluster:
                 continue
             box = node_boxes[cluster[0]]

@@ -171,6 +171,42 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
       const int i = threadIdx.x + u * 256;
       if (i < PH * PW * DW_CG) patch[(i / DW_CG) * DW_PSTR + (i % DW_CG)] = v[u];
     }
+  } else if (g0 < cup_g) {
+    // upsampled channel block: stage the (few) low-resolution source pixels this patch needs,
+    // then interpolate out of shared memory
+    constexpr int SH = 8, SW = 14;
+    __shared__ uint4 srcp[SH * SW * DW_CG];
+    const int ya = max(y0 - PAD, 0), xa = max(x0 - PAD, 0);
+    const int ys0 = static_cast<int>(sy * ya), xs0 = static_cast<int>(sx * xa);
+    for (int i = threadIdx.x; i < SH * SW * DW_CG; i += blockDim.x) {
+      const int gl = i % DW_CG, pix = i / DW_CG;
+      const int yy = min(ys0 + pix / SW, Hu - 1), xx = min(xs0 + pix % SW, Wu - 1);
+      srcp[i] = __ldg(reinterpret_cast<const uint4*>(up + ((static_cast<long long>(b) * Hu + yy) * Wu + xx) * Cup + (g0 + gl) * 8));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
+      const int gl = i % DW_CG;
+      const int pix = i / DW_CG;
+      const int px = pix % PW, py = pix / PW;
+      const int y = y0 - PAD + py, x = x0 - PAD + px;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const float fy = sy * y, fx = sx * x;
+        const int yy0 = static_cast<int>(fy), xx0 = static_cast<int>(fx);
+        const int yy1 = min(yy0 + 1, Hu - 1), xx1 = min(xx0 + 1, Wu - 1);
+        const float ly = fy - yy0, lx = fx - xx0;
+        float a[8], c[8], d[8], e[8], o[8];
+        unpack8(srcp[((yy0 - ys0) * SW + (xx0 - xs0)) * DW_CG + gl], a);
+        unpack8(srcp[((yy0 - ys0) * SW + (xx1 - xs0)) * DW_CG + gl], c);
+        unpack8(srcp[((yy1 - ys0) * SW + (xx0 - xs0)) * DW_CG + gl], d);
+        unpack8(srcp[((yy1 - ys0) * SW + (xx1 - xs0)) * DW_CG + gl], e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
+        v = pack8(o);  // same bf16 rounding point as the materialised concat buffer
+      }
+      patch[pix * DW_PSTR + gl] = v;
+    }
   } else {
     for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
       const int gl = i % DW_CG;
@@ -179,26 +215,8 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
       const int y = y0 - PAD + py, x = x0 - PAD + px;
       const int g = g0 + gl;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (y >= 0 && y < H && x >= 0 && x < W && g < cgs) {
-        if (g < cup_g) {
-          const float fy = sy * y, fx = sx * x;
-          const int yy0 = static_cast<int>(fy), xx0 = static_cast<int>(fx);
-          const int yy1 = min(yy0 + 1, Hu - 1), xx1 = min(xx0 + 1, Wu - 1);
-          const float ly = fy - yy0, lx = fx - xx0;
-          const bf16* base = up + static_cast<long long>(b) * Hu * Wu * Cup + g * 8;
-          float a[8], c[8], d[8], e[8], o[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx0) * Cup)), a);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy0) * Wu + xx1) * Cup)), c);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx0) * Cup)), d);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy1) * Wu + xx1) * Cup)), e);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
-          v = pack8(o);  // same bf16 rounding point as the materialised concat buffer
-        } else {
-          v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g - cup_g) * 8));
-        }
-      }
+      if (y >= 0 && y < H && x >= 0 && x < W && g < cgs)
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g - cup_g) * 8));
       patch[pix * DW_PSTR + gl] = v;
     }
   }
@@ -533,6 +551,10 @@ int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int
               const float* wt, __nv_bfloat16* out, long long out_ld, const __nv_bfloat16* up, int Cup,
               int Hu, int Wu, cudaStream_t st) {
   if (C % 8 || Cup % 8) return be_set_error("dwconv: C must be a multiple of 8");
+  // the staged low-resolution source patch is 8 x 14 pixels: needs an upsampling factor >= ~3.3
+  if (up != nullptr && (Cup % (8 * mk::DW_CG) != 0 || 100LL * (Wu - 1) > 31LL * (W - 1) ||
+                        100LL * (Hu - 1) > 45LL * (H - 1)))
+    return be_set_error("dwconv: fused upsampling needs a scale factor >= 3.3 and Cup % 32 == 0");
   const int cblocks = (C / 8 + mk::DW_CG - 1) / mk::DW_CG;
   dim3 grid((W + mk::DW_TX - 1) / mk::DW_TX, (H + mk::DW_TY - 1) / mk::DW_TY, B * cblocks);
   if (k == 5) mk::dwconv_kernel<5><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);

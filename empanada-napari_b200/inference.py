@@ -12,7 +12,7 @@ import torch
 
 from . import _lib, consensus, tracking
 from .model import load_model
-from .postproc import PlanePost
+from .postproc import LazyPlane, PlanePost
 from .tracking import InstanceTracker
 
 __all__ = ["Engine2d", "Engine3d", "tracker_consensus", "stack_postprocessing"]
@@ -83,7 +83,7 @@ class Engine3d:
                  force_connected=True, min_size=500, min_extent=4, fine_boundaries=False,
                  semantic_only=False, use_gpu=True, use_quantized=False, store_url=None,
                  chunk_size=(256, 256, 256), save_panoptic=False, label_erosion=0,
-                 label_dilation=0, fill_holes_in_segmentation=False, batch_size=8):
+                 label_dilation=0, fill_holes_in_segmentation=False, batch_size=16, lazy_rle=True):
         self.device = _require_cuda()
         if not use_gpu:
             raise _lib.B200EmpanadaError("use_gpu=False requested: this engine has no CPU path")
@@ -117,6 +117,7 @@ class Engine3d:
             _unsupported("zarr output stores")
         self.dtype = np.int32
         self.batch_size = batch_size
+        self.lazy_rle = lazy_rle
         self.model = load_model(model_config["model"], self.device, model_config)
         self.engine = self  # widgets call engine.engine.reset(); kept for attribute parity
         self._cache = _VolumeCache()
@@ -208,7 +209,12 @@ class Engine3d:
         prof.mark("relabel")
         trackers = self.create_trackers(shape3d, axis_name)
         tr = trackers[0]
-        tr.instances = post.tracker_instances(axis_name, shape3d, lut_f, kept_labels, boxes[keep], dense)
+        # per-instance RLE arrays are extracted from the dense volume on first access
+        # (tracker_consensus below never needs them); set lazy_rle=False for eager dictionaries
+        plane = LazyPlane(dense, axis_name, kept_labels, boxes[keep])
+        tr.instances = plane.attrs
+        if not self.lazy_rle:
+            plane.materialize()
         tr.finish()
         prof.mark("runs + tracker dict")
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus

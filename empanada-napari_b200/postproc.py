@@ -165,88 +165,124 @@ class PlanePost:
         self._lut_d = lut_d
         return vol
 
-    def extract_runs(self, img, seg_len):
-        """Maximal runs of equal non-zero label over flat indices, split at multiples of
-        seg_len. Returns device tensors (labels int32, starts int64, lens int32), raster order."""
-        n = img.numel()
-        chunks = (n + 1023) // 1024
-        counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=self.dev)
-        st = stream_ptr()
-        call("be_runs_count", ptr(img), n, seg_len, ptr(counts), st)
-        c2 = counts.view(2, chunks + 1)
-        offsets = torch.zeros((2, chunks + 1), dtype=torch.int64, device=self.dev)
-        torch.cumsum(c2[:, :-1], 1, out=offsets[:, 1:])
-        total = int(offsets[0, -1].item())
-        labels = torch.empty(total, dtype=torch.int32, device=self.dev)
-        starts = torch.empty(total, dtype=torch.int64, device=self.dev)
-        ends = torch.empty(total, dtype=torch.int64, device=self.dev)
-        if total:
-            call("be_runs_write", ptr(img), n, seg_len, ptr(offsets), ptr(labels), ptr(starts),
-                 ptr(ends), total, st)
-        lens = (ends - starts).to(torch.int32)
-        self.launches += 2
-        return labels, starts, lens
-
     def tracker_instances(self, axis_name, shape3d, lut, labels, boxes, vol, batch=64):
-        """Builds the reference's `InstanceTracker.instances` dictionary (tracker.py:61-123):
-        per label, runs in arrival order (reverse slice order for xy/xz; sorted for yz)."""
-        D, Hv, Wv = shape3d
-        dev = self.dev
-        if len(labels) == 0:
-            return {}
-        if axis_name == "yz":
-            lab, st3, ln = self.extract_runs(vol, vol.numel())
-            seq = st3
-        else:
-            labs, sts, lns = [], [], []
-            tmp = torch.empty((batch, self.h, self.w), dtype=torch.int32, device=dev)
-            hw = self.h * self.w
-            for s0 in range(0, self.N, batch):
-                s1 = min(self.N, s0 + batch)
-                if axis_name == "xy":
-                    img = vol[s0:s1]
-                else:
-                    img = tmp[: s1 - s0]
-                    call("be_relabel", ptr(self.cc[s0]), s1 - s0, self.h, self.w, s0,
-                         ptr(self._lut_d), self._lut_d.shape[1], ptr(img[0]) - s0 * hw * 4,
-                         hw, self.w, 1, stream_ptr())
-                    self.launches += 1
-                l_, s_, n_ = self.extract_runs(img, hw)
-                labs.append(l_); sts.append(s_ + s0 * hw); lns.append(n_)
-            lab, stg, ln = torch.cat(labs), torch.cat(sts), torch.cat(lns)
-            sl = torch.div(stg, hw, rounding_mode="floor")
-            s2d = stg - sl * hw
-            seq = (self.N - 1 - sl) * hw + s2d
-            if axis_name == "xy":
-                st3 = stg
-            else:  # xz: (z, x) of slice `sl` -> (z, sl, x); run lengths kept (tracker.py:80-84)
-                z = torch.div(s2d, self.w, rounding_mode="floor")
-                st3 = (z * Hv + sl) * Wv + (s2d - z * self.w)
-        # rank of each label in tracker insertion order
-        max_label = int(max(int(labels.max()), int(lab.max().item()) if lab.numel() else 0))
-        rank_lut = torch.full((max_label + 1,), -1, dtype=torch.int64, device=dev)
-        rank_lut[torch.from_numpy(labels.astype(np.int64)).to(dev)] = torch.arange(len(labels), device=dev)
-        rank = rank_lut[lab.long()]
-        keys = (rank << 40) | seq
-        n = keys.numel()
-        idx = torch.arange(n, dtype=torch.int32, device=dev)
-        keys_out = torch.empty_like(keys)
-        idx_out = torch.empty_like(idx)
-        need = _lib.SZ(0)
-        _lib.lib().be_sort_runs(None, None, None, None, n, None, 0, need, None)
-        temp = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
-        call("be_sort_runs", ptr(keys), ptr(keys_out), ptr(idx), ptr(idx_out), n, ptr(temp),
-             temp.numel(), None, stream_ptr())
-        self.launches += 1
-        order = idx_out.long()
-        st_sorted = st3[order].cpu().numpy()
-        ln_sorted = ln[order].long().cpu().numpy()
-        rank_sorted = (keys_out >> 40)
-        counts = torch.bincount(rank_sorted, minlength=len(labels)).cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(counts)])
-        instances = {}
-        for i, lab_i in enumerate(labels):
-            a, b = offs[i], offs[i + 1]
-            instances[int(lab_i)] = {"box": tuple(int(v) for v in boxes[i]),
-                                     "starts": st_sorted[a:b], "runs": ln_sorted[a:b]}
-        return instances
+        """Eager form of `instances_from_dense` (kept for tests)."""
+        return instances_from_dense(vol, axis_name, labels, boxes, batch)
+
+
+def _extract_runs(img, seg_len):
+    """Maximal runs of equal non-zero label over flat indices, split at multiples of seg_len.
+    Returns device tensors (labels int32, starts int64, lens int32) in raster order."""
+    dev = img.device
+    n = img.numel()
+    chunks = (n + 1023) // 1024
+    counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=dev)
+    st = stream_ptr()
+    call("be_runs_count", ptr(img), n, seg_len, ptr(counts), st)
+    c2 = counts.view(2, chunks + 1)
+    offsets = torch.zeros((2, chunks + 1), dtype=torch.int64, device=dev)
+    torch.cumsum(c2[:, :-1], 1, out=offsets[:, 1:])
+    total = int(offsets[0, -1].item())
+    labels = torch.empty(total, dtype=torch.int32, device=dev)
+    starts = torch.empty(total, dtype=torch.int64, device=dev)
+    ends = torch.empty(total, dtype=torch.int64, device=dev)
+    if total:
+        call("be_runs_write", ptr(img), n, seg_len, ptr(offsets), ptr(labels), ptr(starts), ptr(ends),
+             total, st)
+    return labels, starts, (ends - starts).to(torch.int32)
+
+
+def instances_from_dense(vol, axis_name, labels, boxes, batch=64):
+    """The reference's `InstanceTracker.instances` dictionary (tracker.py:61-123) rebuilt from
+    the plane's dense (D,H,W) label volume: per label, runs in arrival order (reverse slice order
+    for xy/xz, where runs are per-slice flat-index runs; sorted 3-D runs for yz)."""
+    D, Hv, Wv = vol.shape
+    dev = vol.device
+    if len(labels) == 0:
+        return {}
+    if axis_name == "yz":
+        lab, st3, ln = _extract_runs(vol, vol.numel())
+        seq = st3
+    else:
+        N = D if axis_name == "xy" else Hv
+        h, w = (Hv, Wv) if axis_name == "xy" else (D, Wv)
+        hw = h * w
+        labs, sts, lns = [], [], []
+        for s0 in range(0, N, batch):
+            s1 = min(N, s0 + batch)
+            img = vol[s0:s1] if axis_name == "xy" else vol[:, s0:s1, :].permute(1, 0, 2).contiguous()
+            l_, s_, n_ = _extract_runs(img, hw)
+            labs.append(l_); sts.append(s_ + s0 * hw); lns.append(n_)
+        lab, stg, ln = torch.cat(labs), torch.cat(sts), torch.cat(lns)
+        sl = torch.div(stg, hw, rounding_mode="floor")
+        s2d = stg - sl * hw
+        seq = (N - 1 - sl) * hw + s2d
+        if axis_name == "xy":
+            st3 = stg
+        else:  # xz: (z, x) of slice `sl` -> (z, sl, x); run lengths kept (tracker.py:80-84)
+            z = torch.div(s2d, w, rounding_mode="floor")
+            st3 = (z * Hv + sl) * Wv + (s2d - z * w)
+    labels = np.asarray(labels)
+    max_label = int(max(int(labels.max()), int(lab.max().item()) if lab.numel() else 0))
+    rank_lut = torch.full((max_label + 1,), -1, dtype=torch.int64, device=dev)
+    rank_lut[torch.from_numpy(labels.astype(np.int64)).to(dev)] = torch.arange(len(labels), device=dev)
+    rank = rank_lut[lab.long()]
+    keys = (rank << 40) | seq
+    n = keys.numel()
+    idx = torch.arange(n, dtype=torch.int32, device=dev)
+    keys_out = torch.empty_like(keys)
+    idx_out = torch.empty_like(idx)
+    need = _lib.SZ(0)
+    _lib.lib().be_sort_runs(None, None, None, None, n, None, 0, need, None)
+    temp = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
+    call("be_sort_runs", ptr(keys), ptr(keys_out), ptr(idx), ptr(idx_out), n, ptr(temp), temp.numel(),
+         None, stream_ptr())
+    order = idx_out.long()
+    st_sorted = st3[order].cpu().numpy()
+    ln_sorted = ln[order].long().cpu().numpy()
+    counts = torch.bincount(keys_out >> 40, minlength=len(labels)).cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    instances = {}
+    for i, lab_i in enumerate(labels):
+        a, b = offs[i], offs[i + 1]
+        instances[int(lab_i)] = {"box": tuple(int(v) for v in boxes[i]),
+                                 "starts": st_sorted[a:b], "runs": ln_sorted[a:b]}
+    return instances
+
+
+class LazyAttrs(dict):
+    """Instance attributes whose RLE ('starts', 'runs') is materialised from the device-resident
+    label volume on first access; 'box' is always present."""
+
+    def __init__(self, box, owner):
+        super().__init__(box=box)
+        self._owner = owner
+
+    def __missing__(self, key):
+        if key in ("starts", "runs"):
+            self._owner.materialize()
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __reduce__(self):
+        self._owner.materialize()
+        return (dict, (dict(self),))
+
+
+class LazyPlane:
+    """Owner of the deferred RLE extraction of one plane's tracker."""
+
+    def __init__(self, dense, axis_name, labels, boxes):
+        self.dense, self.axis_name, self.labels, self.boxes = dense, axis_name, labels, boxes
+        self.attrs = {int(l): LazyAttrs(tuple(int(v) for v in b), self) for l, b in zip(labels, boxes)}
+        self.done = False
+
+    def materialize(self):
+        if self.done:
+            return
+        self.done = True
+        full = instances_from_dense(self.dense, self.axis_name, self.labels, self.boxes)
+        for l, a in full.items():
+            if l in self.attrs:
+                dict.__setitem__(self.attrs[l], "starts", a["starts"])
+                dict.__setitem__(self.attrs[l], "runs", a["runs"])

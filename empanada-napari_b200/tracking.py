@@ -48,7 +48,9 @@ class InstanceTracker:
     def write_to_json(self, savepath):
         if not self.finished:
             self.finish()
-        save = deepcopy({k: v for k, v in self.__dict__.items() if not k.startswith("_")})
+        save = {k: v for k, v in self.__dict__.items() if not k.startswith("_") and k != "instances"}
+        save = deepcopy(save)
+        save["instances"] = self.instances
         inst = {}
         for k, v in save["instances"].items():
             inst[str(k)] = {"box": [int(b) for b in v["box"]],
