@@ -245,13 +245,15 @@ __device__ __forceinline__ void epilogue_role_staged(const Params& p, uint32_t s
       int nt, mt;
       if (wstat) { nt = t / per_nt; mt = blockIdx.x + (t - nt * per_nt) * gridDim.x; }
       else { const int tile_ = blockIdx.x + t * gridDim.x; nt = tile_ % tiles_n; mt = tile_ / tiles_n; }
-      (void)nt;
       const int tx = mt % tiles_x; mt /= tiles_x;
       const int ty = mt % tiles_y;
       const int tb = mt / tiles_y;
       const int tw = etid % TW, th = (etid / TW) % TH, tbi = etid / (TW * TH);
       const int x = tx * TW + tw, y = ty * TH + th, b = tb * TB + tbi;
-      tab[etid] = ((x < Wo) && (y < Ho) && (b < Bn)) ? (static_cast<long long>(b) * Ho + y) * Wo + x : -1;
+      long long pix = (static_cast<long long>(b) * Ho + y) * Wo + x;
+      if (p.shuffle2x2)  // output pixel (2y + dy, 2x + dx) of the 2Ho x 2Wo map, (dy, dx) = N tile
+        pix = ((static_cast<long long>(b) * Ho + y) * 2 + (nt >> 1)) * (2LL * Wo) + 2 * x + (nt & 1);
+      tab[etid] = ((x < Wo) && (y < Ho) && (b < Bn)) ? pix : -1;
     }
   };
   auto issue_residual = [&](int j, int n0, const long long* tab) {
@@ -345,7 +347,7 @@ __device__ __forceinline__ void epilogue_role_staged(const Params& p, uint32_t s
         const int n = n0 + 64 * j + 8 * chunk;
         if (pix >= 0 && n < Cout) {
           const uint4 val = lds_u4(ob + row * 128 + ((chunk ^ (row & 7)) << 4));
-          *reinterpret_cast<uint4*>(outp + pix * out_ld + n) = val;
+          *reinterpret_cast<uint4*>(outp + pix * out_ld + (p.shuffle2x2 ? n - n0 : n)) = val;
         }
       }
     }
@@ -569,7 +571,7 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
                       float* out_f32, long long out_f32_ld, int out_f32_planar, const float* bias,
                       long long bias_img_stride, const __nv_bfloat16* residual, long long res_ld,
                       int act, const float* head_w, const float* head_b, float* head_out,
-                      int head_n, int num_sms);
+                      int head_n, int num_sms, int shuffle2x2);
 
 // Describes one convolution call. Input: NHWC bf16 [B, Hi, Wi, >=Cin] with pixel stride in_ld.
 // Weights: [Cout][R*S*Cin] bf16. Output map: Ho x Wo.
@@ -580,7 +582,7 @@ int conv_gemm_plan(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, i
                    const __nv_bfloat16* residual, long long res_ld, int act, int num_sms) {
   return conv_gemm_plan_ex(L, in, in_ld, B, Hi, Wi, Cin, w, Cout, R, S, stride, dil, pad, Ho, Wo, out,
                            out_ld, out_coff, out_f32, out_f32_ld, 0, bias, 0, residual, res_ld, act,
-                           nullptr, nullptr, nullptr, 0, num_sms);
+                           nullptr, nullptr, nullptr, 0, num_sms, 0);
 }
 
 int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi,
@@ -589,7 +591,7 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
                       float* out_f32, long long out_f32_ld, int out_f32_planar, const float* bias,
                       long long bias_img_stride, const __nv_bfloat16* residual, long long res_ld,
                       int act, const float* head_w, const float* head_b, float* head_out,
-                      int head_n, int num_sms) {
+                      int head_n, int num_sms, int shuffle2x2) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return -1;
   if (Cin % 8 != 0 || in_ld % 8 != 0) return -2;
@@ -608,6 +610,13 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   p.tiles_b = (B + p.TB - 1) / p.TB;
   int bn = ((Cout + 15) / 16) * 16;
   if (bn > MAX_N) bn = (Cout % 256 == 0) ? 256 : ((Cout % 192 == 0) ? 192 : ((Cout % 128 == 0) ? 128 : 256));
+  if (shuffle2x2) {
+    if (Cout % 4 != 0 || (Cout / 4) % 16 != 0 || Cout / 4 > MAX_N || R * S != 1 || stride != 1 ||
+        residual != nullptr || head_n != 0 || out_f32 != nullptr)
+      return -7;
+    bn = Cout / 4;
+  }
+  p.shuffle2x2 = shuffle2x2 ? 1 : 0;
   p.block_n = bn;
   p.tiles_n = (Cout + bn - 1) / bn;
   p.kchunks = (Cin + KCHUNK - 1) / KCHUNK;
@@ -634,6 +643,7 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
       smem_budget += staging_h;
     }
   }
+  if (shuffle2x2 && !p.staged) return -8;
   const long long staging_used = p.staged ? staging_h : 0;
   // weight-stationary when the whole K extent of one N tile fits beside >= 3 activation stages
   // and every CTA reuses it for at least two M tiles

@@ -58,6 +58,9 @@ struct Params {
   const __nv_bfloat16* residual;  // optional NHWC addend (pixel stride res_ld)
   long long res_ld;
   int act;
+  // ConvTranspose2d(k=2, s=2) as a 1x1 GEMM with N = 4 * Cout_real: N tile nt = 2*dy + dx holds
+  // the Cout_real channels of output pixel (2y + dy, 2x + dx) (staged epilogue only)
+  int shuffle2x2;
 };
 
 // Host side: builds the two tensor maps and launches. Returns cudaError_t as int.

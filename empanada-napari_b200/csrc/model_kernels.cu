@@ -89,6 +89,101 @@ stem_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long strid
   }
 }
 
+// ------------------------------------------------------------------ stem + maxpool fused
+// conv1 7x7/2 + BN + ReLU followed by MaxPool2d(3, 2, 1) (encoders/resnet.py:217-221) in one
+// kernel: the 64-channel half-resolution map (the largest activation of the network) never
+// reaches HBM. CTA = 8 x 16 pooled pixels: it needs a 17 x 33 tile of conv1 outputs, which needs
+// a 39 x 71 patch of the (gathered, normalised, zero padded) input slice.
+// Lane l owns channels (2l, 2l+1). A warp computes strips of 11 conv1 pixels of one tile row:
+// per filter row it loads 7 tap pairs (conflict-free 8-byte words) and 27 patch values (broadcast
+// 8-byte words) for 11*7*2 FMAs per lane. Same fp32 fmaf chain order as `stem_kernel`
+// (filter-row major, tap ascending, bias added last), so both produce identical bits.
+// Positions of the conv1 tile outside the map hold 0: every pooling window contains at least one
+// real (post-ReLU, >= 0) value, so 0 is equivalent to MaxPool's -inf padding.
+constexpr int SPY = 8, SPX = 16;
+constexpr int STY = 2 * SPY + 1, STX = 2 * SPX + 1;      // 17 x 33 conv1 tile
+constexpr int SIH = 2 * STY + 5, SIW = 2 * STX + 5;      // 39 x 71 input patch
+constexpr int SIWP = 72;
+constexpr int SSTRIP = 11;
+constexpr int stem_pool_smem_bytes() { return STY * STX * 32 * 4 + 49 * 64 * 4 + SIH * SIWP * 4; }
+__global__ void __launch_bounds__(256, 2)
+stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long stride_y,
+                 long long stride_x, int s0, int h, int w, int H, int W, float mean255, float den,
+                 const float* __restrict__ wt /*[49][64]*/, const float* __restrict__ bias,
+                 bf16* __restrict__ out /*[B][H/4][W/4][64]*/) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  uint32_t* tile = reinterpret_cast<uint32_t*>(sp_smem);           // [STY*STX][32] bf16x2
+  float* ws = reinterpret_cast<float*>(tile + STY * STX * 32);     // [49][64]
+  float* patch = ws + 49 * 64;                                     // [SIH][SIWP]
+  const int b = blockIdx.z;
+  const int py0 = blockIdx.y * SPY, px0 = blockIdx.x * SPX;
+  const int Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4;
+  const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;                  // conv1 tile origin
+  const int iy0 = 2 * sy0 - 3, ix0 = 2 * sx0 - 3;                  // input patch origin
+  const uint8_t* src = vol + static_cast<long long>(s0 + b) * stride_s;
+  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) ws[i] = __ldg(wt + i);
+  for (int i = threadIdx.x; i < SIH * SIWP; i += blockDim.x) {
+    const int py = i / SIWP, px = i - py * SIWP;
+    const int y = iy0 + py, x = ix0 + px;
+    float v = 0.0f;
+    if (px < SIW && y >= 0 && y < h && x >= 0 && x < w)
+      v = __fmul_rn(__fsub_rn(static_cast<float>(src[y * stride_y + x * stride_x]), mean255), den);
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float2 bb = __ldg(reinterpret_cast<const float2*>(bias) + lane);
+  constexpr int NSTRIP = STY * (STX / SSTRIP);
+  for (int j = warp; j < NSTRIP; j += 8) {
+    const int ly = j / (STX / SSTRIP), lx0 = (j - ly * (STX / SSTRIP)) * SSTRIP;
+    float acc[SSTRIP][2];
+#pragma unroll
+    for (int i = 0; i < SSTRIP; ++i) { acc[i][0] = 0.0f; acc[i][1] = 0.0f; }
+#pragma unroll 1
+    for (int r = 0; r < 7; ++r) {
+      float2 wr[7];
+#pragma unroll
+      for (int t = 0; t < 7; ++t) wr[t] = *reinterpret_cast<const float2*>(ws + (r * 7 + t) * 64 + 2 * lane);
+      float pv[2 * SSTRIP + 6];
+      const float2* prow = reinterpret_cast<const float2*>(patch + (2 * ly + r) * SIWP + 2 * lx0);
+#pragma unroll
+      for (int i = 0; i < SSTRIP + 3; ++i) { const float2 q = prow[i]; pv[2 * i] = q.x; pv[2 * i + 1] = q.y; }
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+#pragma unroll
+        for (int i = 0; i < SSTRIP; ++i) {
+          acc[i][0] = fmaf(pv[2 * i + t], wr[t].x, acc[i][0]);
+          acc[i][1] = fmaf(pv[2 * i + t], wr[t].y, acc[i][1]);
+        }
+      }
+    }
+    const int sy = sy0 + ly;
+#pragma unroll
+    for (int i = 0; i < SSTRIP; ++i) {
+      const int sx = sx0 + lx0 + i;
+      __nv_bfloat162 o = __floats2bfloat162_rn(0.0f, 0.0f);
+      if (sy >= 0 && sy < Ho && sx >= 0 && sx < Wo)
+        o = __floats2bfloat162_rn(fmaxf(acc[i][0] + bb.x, 0.0f), fmaxf(acc[i][1] + bb.y, 0.0f));
+      tile[(ly * STX + lx0 + i) * 32 + lane] = *reinterpret_cast<uint32_t*>(&o);
+    }
+  }
+  __syncthreads();
+  for (int pp = warp; pp < SPY * SPX; pp += 8) {
+    const int oyl = pp / SPX, oxl = pp - oyl * SPX;
+    const int oy = py0 + oyl, ox = px0 + oxl;
+    if (oy >= Hp || ox >= Wp) continue;
+    __nv_bfloat162 m = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint32_t u = tile[((2 * oyl + dy) * STX + 2 * oxl + dx) * 32 + lane];
+        m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(&u));
+      }
+    *reinterpret_cast<__nv_bfloat162*>(out + ((static_cast<long long>(b) * Hp + oy) * Wp + ox) * 64 + 2 * lane) = m;
+  }
+}
+
 // ------------------------------------------------------------------ maxpool 3x3 / 2, pad 1
 __global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int Wi, int C,
                                bf16* __restrict__ out, int Ho, int Wo) {
@@ -120,149 +215,206 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in, int B, int Hi, int W
 }
 
 // ------------------------------------------------------------------ depthwise k x k, stride 1
-// CTA = 8 rows x 32 pixels x 32 channels. The (8+K-1) x (32+K-1) input patch is staged once in
-// shared memory (halo re-read ~1.5x instead of K*K x from L2); a thread produces 4 consecutive
-// pixels x 8 channels with the current filter row's taps held in registers.
+// CTA = 8 rows x 32 pixels x 64 channels, 8 warps. The (8+K-1) x (32+K-1) x 64-channel input
+// patch is staged once in shared memory (128 B per pixel). Lane l of a warp owns channel pair
+// (2l, 2l+1): its K*K x 2 filter taps live in registers, every shared load is a conflict-free
+// 4-byte word, every global store instruction writes one pixel's 128 contiguous bytes. A warp
+// owns a strip of 4 pixels and walks down the 8 output rows: each patch row it loads
+// (4+K-1 words) feeds the K output rows that overlap it, held in a ring of K row accumulators,
+// so the FMA : load ratio is 2*4*K*K : (4+K-1) per row and the kernel is FMA-pipe bound.
+// Accumulation order per output is filter-row major, tap ascending (one fp32 fmaf chain).
 // Optional fused producer: channels [0, Cup) of the input are the align_corners=True bilinear
 // upsampling of a low-resolution NHWC tensor `up` (the decoder's `F.interpolate` + `torch.cat`,
 // decoders/panoptic_deeplab.py:76-77), channels [Cup, C) come from `in`; the concatenated
-// tensor is never materialised.
-constexpr int DW_TY = 8, DW_TX = 32, DW_PX = 4, DW_CG = 4;  // DW_CG groups of 8 channels
-constexpr int DW_PSTR = DW_CG + 1;                            // padded pixel stride (uint4 units)
+// tensor is never materialised. The low-resolution source pixels a patch needs are staged in
+// shared memory first (DW_SH x DW_SW pixels), then interpolated out of shared memory.
+constexpr int DW_TY = 8, DW_TX = 32, DW_PX = 4, DW_CB = 64;
+constexpr int DW_SH = 8, DW_SW = 14;
 template <int K>
-__global__ void __launch_bounds__(256, 3)
+constexpr int dw_smem_bytes() { return ((DW_TY + K - 1) * (DW_TX + K - 1) + DW_SH * DW_SW) * DW_CB * 2; }
+
+template <int K>
+__global__ void __launch_bounds__(256, 2)
 dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W, int C,
               const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld,
               const bf16* __restrict__ up, int Cup, int Hu, int Wu) {
   constexpr int PAD = (K - 1) / 2;
   constexpr int PH = DW_TY + K - 1, PW = DW_TX + K - 1;
-  __shared__ uint4 patch[PH * PW * DW_PSTR];
-  __shared__ __align__(16) float wsm[K * K * 2 * DW_CG * 4];
-  const int cgs = C / 8;
-  const int cblocks = (cgs + DW_CG - 1) / DW_CG;
+  constexpr int V = DW_CB / 8;                       // 16-byte vectors per pixel
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  uint4* patch = reinterpret_cast<uint4*>(dw_smem);  // [PH*PW][V]
+  uint4* srcp = patch + PH * PW * V;                 // [DW_SH*DW_SW][V]
+  const int cblocks = (C + DW_CB - 1) / DW_CB;
   const int b = blockIdx.z / cblocks;
-  const int g0 = (blockIdx.z - b * cblocks) * DW_CG;
+  const int c0 = (blockIdx.z - b * cblocks) * DW_CB;
   const int y0 = blockIdx.y * DW_TY, x0 = blockIdx.x * DW_TX;
-  for (int i = threadIdx.x; i < K * K * DW_CG * 8; i += blockDim.x) {
-    const int tap = i / (DW_CG * 8), c = i - tap * (DW_CG * 8);
-    const int gl = c >> 3, hf = (c >> 2) & 1, e = c & 3;
-    const int ch = g0 * 8 + c;
-    wsm[((tap * 2 + hf) * DW_CG + gl) * 4 + e] = (ch < C) ? wt[tap * C + ch] : 0.0f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ch = c0 + 2 * lane;
+  // this lane's filter taps (issued first: their latency hides under the patch fill)
+  float w0[K * K], w1[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) {
+    float2 ww = make_float2(0.0f, 0.0f);
+    if (ch < C) ww = __ldg(reinterpret_cast<const float2*>(wt + t * C + ch));
+    w0[t] = ww.x; w1[t] = ww.y;
   }
-  const int cup_g = Cup / 8;
-  const float sy = (up != nullptr && H > 1) ? static_cast<float>(Hu - 1) / static_cast<float>(H - 1) : 0.0f;
-  const float sx = (up != nullptr && W > 1) ? static_cast<float>(Wu - 1) / static_cast<float>(W - 1) : 0.0f;
-  if (up == nullptr) {
-    // plain path: all global loads of the thread are issued before the first shared store
-    constexpr int NLD = (PH * PW * DW_CG + 255) / 256;
-    uint4 v[NLD];
-#pragma unroll
-    for (int u = 0; u < NLD; ++u) {
-      const int i = threadIdx.x + u * 256;
-      const int gl = i % DW_CG, pix = i / DW_CG;
-      const int px = pix % PW, py = pix / PW;
-      const int y = y0 - PAD + py, x = x0 - PAD + px;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (i < PH * PW * DW_CG && y >= 0 && y < H && x >= 0 && x < W && g0 + gl < cgs)
-        v[u] = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g0 + gl) * 8));
-    }
-#pragma unroll
-    for (int u = 0; u < NLD; ++u) {
-      const int i = threadIdx.x + u * 256;
-      if (i < PH * PW * DW_CG) patch[(i / DW_CG) * DW_PSTR + (i % DW_CG)] = v[u];
-    }
-  } else if (g0 < cup_g) {
-    // upsampled channel block: stage the (few) low-resolution source pixels this patch needs,
-    // then interpolate out of shared memory
-    constexpr int SH = 8, SW = 14;
-    __shared__ uint4 srcp[SH * SW * DW_CG];
+  if (up != nullptr && c0 < Cup) {
+    const float sy = (H > 1) ? static_cast<float>(Hu - 1) / static_cast<float>(H - 1) : 0.0f;
+    const float sx = (W > 1) ? static_cast<float>(Wu - 1) / static_cast<float>(W - 1) : 0.0f;
     const int ya = max(y0 - PAD, 0), xa = max(x0 - PAD, 0);
     const int ys0 = static_cast<int>(sy * ya), xs0 = static_cast<int>(sx * xa);
-    for (int i = threadIdx.x; i < SH * SW * DW_CG; i += blockDim.x) {
-      const int gl = i % DW_CG, pix = i / DW_CG;
-      const int yy = min(ys0 + pix / SW, Hu - 1), xx = min(xs0 + pix % SW, Wu - 1);
-      srcp[i] = __ldg(reinterpret_cast<const uint4*>(up + ((static_cast<long long>(b) * Hu + yy) * Wu + xx) * Cup + (g0 + gl) * 8));
+    for (int i = threadIdx.x; i < DW_SH * DW_SW * V; i += blockDim.x) {
+      const int v = i % V, pix = i / V;
+      const int yy = min(ys0 + pix / DW_SW, Hu - 1), xx = min(xs0 + pix % DW_SW, Wu - 1);
+      srcp[i] = __ldg(reinterpret_cast<const uint4*>(up + ((static_cast<long long>(b) * Hu + yy) * Wu + xx) * Cup + c0 + v * 8));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
-      const int gl = i % DW_CG;
-      const int pix = i / DW_CG;
+    for (int i = threadIdx.x; i < PH * PW * V; i += blockDim.x) {
+      const int v = i % V, pix = i / V;
       const int px = pix % PW, py = pix / PW;
       const int y = y0 - PAD + py, x = x0 - PAD + px;
-      uint4 v = make_uint4(0, 0, 0, 0);
+      uint4 val = make_uint4(0, 0, 0, 0);
       if (y >= 0 && y < H && x >= 0 && x < W) {
         const float fy = sy * y, fx = sx * x;
         const int yy0 = static_cast<int>(fy), xx0 = static_cast<int>(fx);
         const int yy1 = min(yy0 + 1, Hu - 1), xx1 = min(xx0 + 1, Wu - 1);
         const float ly = fy - yy0, lx = fx - xx0;
         float a[8], c[8], d[8], e[8], o[8];
-        unpack8(srcp[((yy0 - ys0) * SW + (xx0 - xs0)) * DW_CG + gl], a);
-        unpack8(srcp[((yy0 - ys0) * SW + (xx1 - xs0)) * DW_CG + gl], c);
-        unpack8(srcp[((yy1 - ys0) * SW + (xx0 - xs0)) * DW_CG + gl], d);
-        unpack8(srcp[((yy1 - ys0) * SW + (xx1 - xs0)) * DW_CG + gl], e);
+        unpack8(srcp[((yy0 - ys0) * DW_SW + (xx0 - xs0)) * V + v], a);
+        unpack8(srcp[((yy0 - ys0) * DW_SW + (xx1 - xs0)) * V + v], c);
+        unpack8(srcp[((yy1 - ys0) * DW_SW + (xx0 - xs0)) * V + v], d);
+        unpack8(srcp[((yy1 - ys0) * DW_SW + (xx1 - xs0)) * V + v], e);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
-        v = pack8(o);  // same bf16 rounding point as the materialised concat buffer
+        val = pack8(o);  // same bf16 rounding point as the materialised concat buffer
       }
-      patch[pix * DW_PSTR + gl] = v;
+      patch[i] = val;
     }
   } else {
-    for (int i = threadIdx.x; i < PH * PW * DW_CG; i += blockDim.x) {
-      const int gl = i % DW_CG;
-      const int pix = i / DW_CG;
-      const int px = pix % PW, py = pix / PW;
-      const int y = y0 - PAD + py, x = x0 - PAD + px;
-      const int g = g0 + gl;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (y >= 0 && y < H && x >= 0 && x < W && g < cgs)
-        v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + (g - cup_g) * 8));
-      patch[pix * DW_PSTR + gl] = v;
+    const int coff = c0 - (up != nullptr ? Cup : 0);   // channel offset inside `in`
+    constexpr int NLD = (PH * PW * V + 255) / 256;
+    constexpr int UNR = 7;
+#pragma unroll 1
+    for (int u0 = 0; u0 < NLD; u0 += UNR) {
+      uint4 val[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = threadIdx.x + (u0 + u) * 256;
+        const int v = i % V, pix = i / V;
+        const int px = pix % PW, py = pix / PW;
+        const int y = y0 - PAD + py, x = x0 - PAD + px;
+        val[u] = make_uint4(0, 0, 0, 0);
+        if (i < PH * PW * V && y >= 0 && y < H && x >= 0 && x < W && c0 + v * 8 < C)
+          val[u] = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * in_ld + coff + v * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = threadIdx.x + (u0 + u) * 256;
+        if (i < PH * PW * V) patch[i] = val[u];
+      }
     }
   }
   __syncthreads();
-  const int ty = threadIdx.x >> 5;
-  const int xq = (threadIdx.x & 31) >> 2;
-  const int gl = threadIdx.x & 3;
-  float acc[DW_PX][8];
+  const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(patch) + (warp * DW_PX) * (DW_CB / 2) + lane;
+  float acc[K][DW_PX][2];
 #pragma unroll
-  for (int px = 0; px < DW_PX; ++px)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[px][j] = 0.0f;
-  const float4* w4 = reinterpret_cast<const float4*>(wsm);
-#pragma unroll
-  for (int ry = 0; ry < K; ++ry) {
-    float wr[K][8];
-#pragma unroll
-    for (int sx2 = 0; sx2 < K; ++sx2) {
-      const float4 wa = w4[((ry * K + sx2) * 2 + 0) * DW_CG + gl];
-      const float4 wb = w4[((ry * K + sx2) * 2 + 1) * DW_CG + gl];
-      wr[sx2][0] = wa.x; wr[sx2][1] = wa.y; wr[sx2][2] = wa.z; wr[sx2][3] = wa.w;
-      wr[sx2][4] = wb.x; wr[sx2][5] = wb.y; wr[sx2][6] = wb.z; wr[sx2][7] = wb.w;
-    }
-    const uint4* prow = patch + ((ty + ry) * PW + xq * DW_PX) * DW_PSTR + gl;
+  for (int pr = 0; pr < PH; ++pr) {
+    float v[DW_PX + K - 1][2];
 #pragma unroll
     for (int c = 0; c < DW_PX + K - 1; ++c) {
-      float f[8];
-      unpack8(prow[c * DW_PSTR], f);
+      const uint32_t u = pw32[(pr * PW + c) * (DW_CB / 2)];
+      v[c][0] = __uint_as_float(u << 16);
+      v[c][1] = __uint_as_float(u & 0xffff0000u);
+    }
 #pragma unroll
-      for (int px = 0; px < DW_PX; ++px) {
-        const int sx2 = c - px;
-        if (sx2 < 0 || sx2 >= K) continue;
+    for (int ry = 0; ry < K; ++ry) {
+      const int orow = pr - ry;
+      if (orow < 0 || orow >= DW_TY) continue;
+      const int slot = orow % K;
+      if (ry == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(f[j], wr[sx2][j], acc[px][j]);
+        for (int px = 0; px < DW_PX; ++px) { acc[slot][px][0] = 0.0f; acc[slot][px][1] = 0.0f; }
+      }
+#pragma unroll
+      for (int sx2 = 0; sx2 < K; ++sx2) {
+#pragma unroll
+        for (int px = 0; px < DW_PX; ++px) {
+          acc[slot][px][0] = fmaf(v[px + sx2][0], w0[ry * K + sx2], acc[slot][px][0]);
+          acc[slot][px][1] = fmaf(v[px + sx2][1], w1[ry * K + sx2], acc[slot][px][1]);
+        }
+      }
+    }
+    const int done = pr - (K - 1);
+    if (done >= 0) {
+      const int slot = done % K;
+      const int y = y0 + done;
+      if (y < H && ch < C) {
+#pragma unroll
+        for (int px = 0; px < DW_PX; ++px) {
+          const int x = x0 + warp * DW_PX + px;
+          if (x < W)
+            *reinterpret_cast<__nv_bfloat162*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + ch) =
+                __floats2bfloat162_rn(acc[slot][px][0], acc[slot][px][1]);
+        }
       }
     }
   }
-  const int y = y0 + ty;
-  if (y < H && g0 + gl < cgs) {
+}
+
+// ------------------------------------------------------------------ BiFPN fast-normalised fusion
+// out = (w1 * R(a) + w2 * b [+ w3 * c]) / denom   (decoders/bifpn.py:52-68,106-133), where R is
+// the nearest x2 upsampling (top-down), MaxPool2d(3, 2, 1) (bottom-up) or the identity; fp32
+// math in the reference's operation order, bf16 NHWC in/out with independent pixel strides.
+// mode: 0 identity, 1 nearest-up2 (a is [B][H/2][W/2]), 2 max-pool (a is [B][Ha][Wa]).
+__global__ void bifpn_fuse_kernel(const bf16* __restrict__ a, long long a_ld, int mode, int Ha, int Wa,
+                                  const bf16* __restrict__ bsrc, long long b_ld,
+                                  const bf16* __restrict__ csrc, long long c_ld, float w1, float w2,
+                                  float w3, float denom, int B, int H, int W, int C,
+                                  bf16* __restrict__ out, long long out_ld) {
+  const int cg = C / 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * cg;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  long long pix = i / cg;
+  const int x = static_cast<int>(pix % W); pix /= W;
+  const int y = static_cast<int>(pix % H);
+  const int b = static_cast<int>(pix / H);
+  float ra[8];
+  if (mode == 2) {
 #pragma unroll
-    for (int px = 0; px < DW_PX; ++px) {
-      const int x = x0 + xq * DW_PX + px;
-      if (x < W)
-        *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + (g0 + gl) * 8) = pack8(acc[px]);
+    for (int j = 0; j < 8; ++j) ra[j] = -INFINITY;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = 2 * y - 1 + dy;
+      if (yy < 0 || yy >= Ha) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = 2 * x - 1 + dx;
+        if (xx < 0 || xx >= Wa) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a + ((static_cast<long long>(b) * Ha + yy) * Wa + xx) * a_ld + g * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ra[j] = fmaxf(ra[j], f[j]);
+      }
     }
+  } else {
+    const int yy = mode == 1 ? min(y >> 1, Ha - 1) : y, xx = mode == 1 ? min(x >> 1, Wa - 1) : x;
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a + ((static_cast<long long>(b) * Ha + yy) * Wa + xx) * a_ld + g * 8)), ra);
   }
+  const long long opix = (static_cast<long long>(b) * H + y) * W + x;
+  float fb[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(bsrc + opix * b_ld + g * 8)), fb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = __fadd_rn(__fmul_rn(w1, ra[j]), __fmul_rn(w2, fb[j]));
+  if (csrc != nullptr) {
+    float fc[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(csrc + opix * c_ld + g * 8)), fc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(w3, fc[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = __fdiv_rn(o[j], denom);
+  *reinterpret_cast<uint4*>(out + opix * out_ld + g * 8) = pack8(o);
 }
 
 // ------------------------------------------------------------------ bilinear, align_corners=True
@@ -541,6 +693,20 @@ int be_stem(const uint8_t* vol, long long stride_s, long long stride_y, long lon
                                                    mean255, den, wt, bias, out);
   return be_check_launch("stem_kernel");
 }
+int be_stem_pool(const uint8_t* vol, long long stride_s, long long stride_y, long long stride_x,
+                 int s0, int B, int h, int w, int H, int W, float mean255, float den, const float* wt,
+                 const float* bias, __nv_bfloat16* out, cudaStream_t st) {
+  if (H % 4 || W % 4) return be_set_error("stem_pool: padded slice size must be a multiple of 4");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mk::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::stem_pool_smem_bytes());
+    attr_set = true;
+  }
+  dim3 grid((W / 4 + mk::SPX - 1) / mk::SPX, (H / 4 + mk::SPY - 1) / mk::SPY, B);
+  mk::stem_pool_kernel<<<grid, 256, mk::stem_pool_smem_bytes(), st>>>(vol, stride_s, stride_y, stride_x, s0, h, w,
+                                                                      H, W, mean255, den, wt, bias, out);
+  return be_check_launch("stem_pool_kernel");
+}
 int be_maxpool(const __nv_bfloat16* in, int B, int Hi, int Wi, int C, __nv_bfloat16* out, int Ho,
                int Wo, cudaStream_t st) {
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
@@ -550,17 +716,35 @@ int be_maxpool(const __nv_bfloat16* in, int B, int Hi, int Wi, int C, __nv_bfloa
 int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int C, int k,
               const float* wt, __nv_bfloat16* out, long long out_ld, const __nv_bfloat16* up, int Cup,
               int Hu, int Wu, cudaStream_t st) {
-  if (C % 8 || Cup % 8) return be_set_error("dwconv: C must be a multiple of 8");
+  if (C % 8 || Cup % 8 || in_ld % 8 || out_ld % 2) return be_set_error("dwconv: C must be a multiple of 8");
   // the staged low-resolution source patch is 8 x 14 pixels: needs an upsampling factor >= ~3.3
-  if (up != nullptr && (Cup % (8 * mk::DW_CG) != 0 || 100LL * (Wu - 1) > 31LL * (W - 1) ||
+  if (up != nullptr && (Cup % mk::DW_CB != 0 || 100LL * (Wu - 1) > 31LL * (W - 1) ||
                         100LL * (Hu - 1) > 45LL * (H - 1)))
-    return be_set_error("dwconv: fused upsampling needs a scale factor >= 3.3 and Cup % 32 == 0");
-  const int cblocks = (C / 8 + mk::DW_CG - 1) / mk::DW_CG;
+    return be_set_error("dwconv: fused upsampling needs a scale factor >= 3.3 and Cup % 64 == 0");
+  const int cblocks = (C + mk::DW_CB - 1) / mk::DW_CB;
   dim3 grid((W + mk::DW_TX - 1) / mk::DW_TX, (H + mk::DW_TY - 1) / mk::DW_TY, B * cblocks);
-  if (k == 5) mk::dwconv_kernel<5><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
-  else if (k == 3) mk::dwconv_kernel<3><<<grid, 256, 0, st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mk::dwconv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::dw_smem_bytes<5>());
+    cudaFuncSetAttribute(mk::dwconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::dw_smem_bytes<3>());
+    attr_set = true;
+  }
+  if (k == 5) mk::dwconv_kernel<5><<<grid, 256, mk::dw_smem_bytes<5>(), st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
+  else if (k == 3) mk::dwconv_kernel<3><<<grid, 256, mk::dw_smem_bytes<3>(), st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
   else return be_set_error("dwconv: only 3x3 and 5x5 kernels are built");
   return be_check_launch("dwconv_kernel");
+}
+int be_bifpn_fuse(const __nv_bfloat16* a, long long a_ld, int mode, int Ha, int Wa,
+                  const __nv_bfloat16* b, long long b_ld, const __nv_bfloat16* c, long long c_ld,
+                  float w1, float w2, float w3, float denom, int B, int H, int W, int C,
+                  __nv_bfloat16* out, long long out_ld, cudaStream_t st) {
+  if (C % 8 || a_ld % 8 || b_ld % 8 || c_ld % 8 || out_ld % 8) return be_set_error("bifpn_fuse: channel counts / strides must be multiples of 8");
+  if (mode == 1 && (H != 2 * Ha || W != 2 * Wa)) return be_set_error("bifpn_fuse: nearest x2 needs (H, W) == 2 * (Ha, Wa)");
+  if (mode == 2 && (H != (Ha + 1) / 2 || W != (Wa + 1) / 2)) return be_set_error("bifpn_fuse: max-pool needs (H, W) == ceil((Ha, Wa) / 2)");
+  if (mode == 0 && (H != Ha || W != Wa)) return be_set_error("bifpn_fuse: identity needs equal sizes");
+  const long long total = static_cast<long long>(B) * H * W * (C / 8);
+  mk::bifpn_fuse_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(a, a_ld, mode, Ha, Wa, b, b_ld, c, c_ld, w1, w2, w3, denom, B, H, W, C, out, out_ld);
+  return be_check_launch("bifpn_fuse_kernel");
 }
 int be_bilinear(const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi, int C,
                 __nv_bfloat16* out, long long out_ld, int out_coff, int Ho, int Wo, cudaStream_t st) {

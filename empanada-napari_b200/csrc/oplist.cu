@@ -18,16 +18,21 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
                       float* out_f32, long long out_f32_ld, int out_f32_planar, const float* bias,
                       long long bias_img_stride, const __nv_bfloat16* residual, long long res_ld,
                       int act, const float* head_w, const float* head_b, float* head_out,
-                      int head_n, int num_sms);
+                      int head_n, int num_sms, int shuffle2x2);
 int conv_gemm_launch(const Launch* L, cudaStream_t stream);
 }  // namespace convgemm
 
 extern "C" {
 int be_stem(const uint8_t*, long long, long long, long long, int, int, int, int, int, int, float,
             float, const float*, const float*, __nv_bfloat16*, cudaStream_t);
+int be_stem_pool(const uint8_t*, long long, long long, long long, int, int, int, int, int, int,
+                 float, float, const float*, const float*, __nv_bfloat16*, cudaStream_t);
 int be_maxpool(const __nv_bfloat16*, int, int, int, int, __nv_bfloat16*, int, int, cudaStream_t);
 int be_dwconv(const __nv_bfloat16*, long long, int, int, int, int, int, const float*,
               __nv_bfloat16*, long long, const __nv_bfloat16*, int, int, int, cudaStream_t);
+int be_bifpn_fuse(const __nv_bfloat16*, long long, int, int, int, const __nv_bfloat16*, long long,
+                  const __nv_bfloat16*, long long, float, float, float, float, int, int, int, int,
+                  __nv_bfloat16*, long long, cudaStream_t);
 int be_bilinear(const __nv_bfloat16*, long long, int, int, int, int, __nv_bfloat16*, long long, int,
                 int, int, cudaStream_t);
 int be_aspp_pool_bias(const __nv_bfloat16*, int, int, int, const float*, int, const float*,
@@ -114,10 +119,34 @@ int be_op_conv(void* list, const void* in, long long in_ld, int B, int Hi, int W
       static_cast<const __nv_bfloat16*>(w), Cout, R, S, stride, dil, pad, Ho, Wo,
       static_cast<__nv_bfloat16*>(out), out_ld, out_coff, out_f32, out_f32_ld, out_f32_planar, bias,
       bias_img_stride, static_cast<const __nv_bfloat16*>(residual), res_ld, act, head_w, head_b,
-      head_out, head_n, num_sms());
+      head_out, head_n, num_sms(), 0);
   if (rc != 0) {
     char msg[128];
     snprintf(msg, sizeof(msg), "conv_gemm_plan failed (%d): Cin=%d Cout=%d R=%d stride=%d", rc, Cin, Cout, R, stride);
+    return be_set_error(msg);
+  }
+  return record_or_run(list, 1, st, [L](cudaStream_t s, const RunArgs&) {
+    const int e = convgemm::conv_gemm_launch(&L, s);
+    return e == 0 ? 0 : be_set_error(cudaGetErrorString(static_cast<cudaError_t>(e)));
+  });
+}
+
+// ConvTranspose2d(Cin -> Cout, kernel 2, stride 2) + folded BN + activation (blocks.py
+// conv_transpose_bn_act; decoders/bifpn.py:213-218) as ONE 1x1 implicit GEMM with N = 4 * Cout:
+// weight rows n = (2*dy + dx) * Cout + co, bias [4 * Cout] (the folded BN shift repeated); the
+// epilogue scatters N tile (dy, dx) to output pixel (2y + dy, 2x + dx) of the [B][2H][2W] map.
+int be_op_convt2x2(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int Cin,
+                   const void* w, int Cout, void* out, long long out_ld, int out_coff,
+                   const float* bias, int act, cudaStream_t st) {
+  convgemm::Launch L;
+  const int rc = convgemm::conv_gemm_plan_ex(
+      &L, static_cast<const __nv_bfloat16*>(in), in_ld, B, Hi, Wi, Cin,
+      static_cast<const __nv_bfloat16*>(w), 4 * Cout, 1, 1, 1, 1, 0, Hi, Wi,
+      static_cast<__nv_bfloat16*>(out), out_ld, out_coff, nullptr, 0, 0, bias, 0, nullptr, 0, act,
+      nullptr, nullptr, nullptr, 0, num_sms(), 1);
+  if (rc != 0) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "conv_gemm_plan (transposed 2x2) failed (%d): Cin=%d Cout=%d", rc, Cin, Cout);
     return be_set_error(msg);
   }
   return record_or_run(list, 1, st, [L](cudaStream_t s, const RunArgs&) {
@@ -138,6 +167,20 @@ int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, flo
   });
 }
 
+// conv1 + BN + ReLU + MaxPool2d(3,2,1) in one kernel; `out` is the quarter-resolution map
+int be_op_stem_pool(void* list, int B, int h, int w, int H, int W, float mean255, float den,
+                    const float* wt, const float* bias, void* out, const uint8_t* vol,
+                    long long stride_s, long long stride_y, long long stride_x, int s0,
+                    cudaStream_t st) {
+  if (list == nullptr)
+    return be_stem_pool(vol, stride_s, stride_y, stride_x, s0, B, h, w, H, W, mean255, den, wt, bias,
+                        static_cast<__nv_bfloat16*>(out), st);
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs& ra) {
+    return be_stem_pool(ra.vol, ra.stride_s, ra.stride_y, ra.stride_x, ra.s0, B, h, w, H, W, mean255,
+                        den, wt, bias, static_cast<__nv_bfloat16*>(out), s);
+  });
+}
+
 int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void* out, int Ho, int Wo,
                   cudaStream_t st) {
   return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
@@ -151,6 +194,17 @@ int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int 
   return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
     return be_dwconv(static_cast<const __nv_bfloat16*>(in), in_ld, B, H, W, C, k, wt,
                      static_cast<__nv_bfloat16*>(out), out_ld, static_cast<const __nv_bfloat16*>(up), Cup, Hu, Wu, s);
+  });
+}
+
+int be_op_bifpn_fuse(void* list, const void* a, long long a_ld, int mode, int Ha, int Wa,
+                     const void* b, long long b_ld, const void* c, long long c_ld, float w1,
+                     float w2, float w3, float denom, int B, int H, int W, int C, void* out,
+                     long long out_ld, cudaStream_t st) {
+  return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs&) {
+    return be_bifpn_fuse(static_cast<const __nv_bfloat16*>(a), a_ld, mode, Ha, Wa,
+                         static_cast<const __nv_bfloat16*>(b), b_ld, static_cast<const __nv_bfloat16*>(c),
+                         c_ld, w1, w2, w3, denom, B, H, W, C, static_cast<__nv_bfloat16*>(out), out_ld, s);
   });
 }
 

@@ -64,9 +64,12 @@ def load_model(model, device, model_config=None):
         sd = load_state_dict_any(path)
     else:
         raise _lib.B200EmpanadaError(f"unsupported model specification: {type(model)}")
+    from .bifpn import BiFPNModel, is_bifpn_state_dict
     from .pdl import PDLModel, is_pdl_state_dict
     if is_pdl_state_dict(sd):
-        return PDLModel(sd, device)
+        return PDLModel(sd, device)       # MitoNet_v1, NucleoNet_base_v2, DropNet_base_v1
+    if is_bifpn_state_dict(sd):
+        return BiFPNModel(sd, device)     # MitoNet_v1_mini
     raise _lib.B200EmpanadaError(
-        "unsupported network: only the PanopticDeepLab-PointRend / ResNet-50 export is built so far "
-        "(PanopticBiFPN is the next model family)")
+        "unsupported network: neither a PanopticDeepLab-PointRend nor a PanopticBiFPN-PointRend "
+        "ResNet-50 export")

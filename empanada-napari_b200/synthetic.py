@@ -144,6 +144,95 @@ def _pdl_shapes(num_classes=1, decoder_channels=256, low_proj=32, ins_ratio=0.5,
     return out
 
 
+def _bifpn_shapes(num_classes=1, fpn_dim=128, fpn_layers=3, num_fc=3):
+    """(key, shape, kind) in export order for PanopticBiFPNPR / resnet50 (output stride 32),
+    `ins_decoder=True`, `depthwise=True` (empanada_napari/training/bifpn_model.yaml). The encoder
+    is exported fused (conv+BN folded), everything else keeps live BatchNorm."""
+    out = [t for t in _pdl_shapes() if t[0].startswith("encoder.")]
+    d = fpn_dim
+
+    def bn(name, c):
+        out.append((name + ".weight", (c,), "bn_w"))
+        out.append((name + ".bias", (c,), "bn_b"))
+        out.append((name + ".running_mean", (c,), "bn_m"))
+        out.append((name + ".running_var", (c,), "bn_v"))
+        out.append((name + ".num_batches_tracked", (), "bn_n"))
+
+    def conv_bn(name, co, ci):
+        out.append((name + ".0.weight", (co, ci, 1, 1), "conv_lin"))
+        bn(name + ".1", co)
+
+    def sep(name, ci, co, k):
+        out.append((name + ".0.sepconv.0.weight", (ci, 1, k, k), "dw"))
+        out.append((name + ".0.sepconv.1.weight", (co, ci, 1, 1), "conv"))
+        bn(name + ".1", co)
+
+    conv_bn("p2_resample.conv", d, 256)
+    for branch in ("semantic", "instance"):
+        fpn = branch + "_fpn"
+        conv_bn(fpn + ".p6_resample.conv", d, 2048)
+        for li in range(fpn_layers):
+            for side, nins in (("top_down_fpn", [d, 2048, 1024, 512]), ("bottom_up_fpn", [1024, 2048, d, d])):
+                pre = f"{fpn}.bifpns.{li}.{side}"
+                out.append((pre + ".weights", (5,), "fuse_w"))
+                if li == 0:
+                    for i, nin in enumerate(nins):
+                        if nin != d:
+                            conv_bn(f"{pre}.resamplings.{i}.conv", d, nin)
+                for i in range(4):  # one shared block, exported under four aliases
+                    sep(f"{pre}.after_combines.{i}", d, d, 3)
+        dec = branch + "_decoder"
+        for i in range(5):
+            out.append((f"{dec}.upsamplings.{i}.0.weight", (d if i == 0 else 2 * d, d, 2, 2), "convT"))
+            bn(f"{dec}.upsamplings.{i}.1", d)
+        sep(dec + ".fusion", 2 * d, d, 5)
+    for head, nout in (("semantic_head", num_classes), ("ins_center", 1), ("ins_xy", 2)):
+        sep(head + ".head.0", d, d, 5)
+        out.append((head + ".head.1.weight", (nout, d, 1, 1), "conv_out"))
+        out.append((head + ".head.1.bias", (nout,), "bias"))
+    for l in range(num_fc):
+        out.append((f"semantic_pr.point_head.fc_layers.{l}.0.weight", (d, d + num_classes, 1), "fc"))
+        out.append((f"semantic_pr.point_head.fc_layers.{l}.0.bias", (d,), "bias"))
+    out.append(("semantic_pr.point_head.predictor.weight", (num_classes, d + num_classes, 1), "fc_out"))
+    out.append(("semantic_pr.point_head.predictor.bias", (num_classes,), "bias"))
+    return out
+
+
+def make_bifpn_state_dict(seed=0, num_classes=1):
+    """Random fp32 state_dict of the PanopticBiFPN-PointRend export with O(1) activations. The
+    four `after_combines.{i}` aliases of one shared block hold identical tensors, as in a real
+    export (decoders/bifpn.py:34-42,90-98)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape, kind in _bifpn_shapes(num_classes=num_classes):
+        if ".after_combines." in key and ".after_combines.0." not in key:
+            i = key.index(".after_combines.") + len(".after_combines.")
+            sd[key] = sd[key[:i] + "0" + key[i + 1:]].clone()
+            continue
+        if kind in ("conv", "conv_res", "conv_out", "conv_lin", "dw", "fc", "fc_out", "convT"):
+            fan_in = int(np.prod(shape[1:])) if kind != "convT" else shape[0]
+            gain = {"conv": math.sqrt(2.0), "conv_res": 0.5, "conv_out": 1.0, "conv_lin": 1.0,
+                    "dw": math.sqrt(2.0), "fc": math.sqrt(2.0), "fc_out": 1.0, "convT": math.sqrt(2.0)}[kind]
+            t = torch.randn(shape, generator=g) * (gain / math.sqrt(fan_in))
+        elif kind == "bias":
+            t = torch.randn(shape, generator=g) * 0.05
+        elif kind == "bn_w":
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif kind in ("bn_b", "bn_m"):
+            t = torch.randn(shape, generator=g) * 0.1
+        elif kind == "bn_v":
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif kind == "fuse_w":
+            t = torch.rand(shape, generator=g) + 0.5
+            t[int(torch.randint(0, shape[0], (1,), generator=g))] -= 0.2
+        else:
+            t = torch.tensor(0, dtype=torch.long)
+        sd[key] = t
+    return sd
+
+
 def make_pdl_state_dict(seed=0, num_classes=1):
     """Random fp32 state_dict (torch tensors) with O(1) activations through the whole net."""
     import torch

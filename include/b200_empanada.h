@@ -49,11 +49,29 @@ int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, flo
                be_stream st);
 int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void* out, int Ho, int Wo,
                   be_stream st);                                   /* encoders/resnet.py:221 */
+/* be_op_stem followed by be_op_maxpool in ONE kernel (encoders/resnet.py:217-221): `out` is the
+ * quarter-resolution [B][H/4][W/4][64] map; the half-resolution map never reaches HBM */
+int be_op_stem_pool(void* list, int B, int h, int w, int H, int W, float mean255, float inv_std255,
+                    const float* wt_49x64, const float* bias64, void* out, const uint8_t* vol,
+                    long long stride_slice, long long stride_y, long long stride_x, int first_slice,
+                    be_stream st);
 /* depthwise k x k (blocks.py:15-35); optional fused producer: channels [0,Cup) are the
  * align_corners=True bilinear upsampling of `up` (decoders/panoptic_deeplab.py:76-77) */
 int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int W, int C, int k,
                  const float* wt, void* out, long long out_ld, const void* up, int Cup, int Hu,
                  int Wu, be_stream st);
+/* ConvTranspose2d(k=2, s=2) + folded BN + activation (blocks.py conv_transpose_bn_act,
+ * decoders/bifpn.py:213-218) as one 1x1 implicit GEMM with N = 4*Cout and a pixel-shuffle
+ * epilogue; w rows n = (2*dy+dx)*Cout + co, bias [4*Cout] */
+int be_op_convt2x2(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int Cin,
+                   const void* w, int Cout, void* out, long long out_ld, int out_coff,
+                   const float* bias, int act, be_stream st);
+/* BiFPN fast-normalised fusion (decoders/bifpn.py:52-68,106-133):
+ * out = (w1*R(a) + w2*b [+ w3*c]) / denom, R = identity (mode 0), nearest x2 (1), MaxPool2d(3,2,1) (2) */
+int be_op_bifpn_fuse(void* list, const void* a, long long a_ld, int mode, int Ha, int Wa,
+                     const void* b, long long b_ld, const void* c, long long c_ld, float w1,
+                     float w2, float w3, float denom, int B, int H, int W, int C, void* out,
+                     long long out_ld, be_stream st);
 int be_op_bilinear(void* list, const void* in, long long in_ld, int B, int Hi, int Wi, int C,
                    void* out, long long out_ld, int out_coff, int Ho, int Wo,
                    be_stream st);                                  /* decoders/panoptic_deeplab.py:76 */

@@ -231,15 +231,47 @@ def gen_model_tiny():
     print("model tiny", {k: tuple(v.shape) for k, v in o.items()})
 
 
+def gen_model_bifpn_tiny():
+    """Reference PanopticBiFPN-PR classes with the seeded weights of
+    synthetic.make_bifpn_state_dict(0), exported as `_train.py:59-73` does."""
+    import yaml
+    from empanada.models.quantization.panoptic_bifpn import QuantizablePanopticBiFPNPR
+
+    cfg = yaml.safe_load(open(os.path.join(ref_shim.REF_ROOT, "empanada_napari/training/bifpn_model.yaml")))
+    cfg.pop("arch")
+    cfg["num_classes"] = 1
+    m = QuantizablePanopticBiFPNPR(**cfg, quantize=False).eval()
+    m.fuse_model()
+    sd = syn.make_bifpn_state_dict(0)
+    ref_keys = list(m.state_dict().keys())
+    assert ref_keys == list(sd.keys()), [k for k in ref_keys if k not in sd][:5]
+    m.load_state_dict(sd)
+    m = torch.jit.script(m)  # the deployed form
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (100, 200), dtype=np.uint8)
+    from empanada_napari.utils import Preprocessor
+    x = Preprocessor(**MODEL_CONFIG["norms"])(img)["image"].unsqueeze(0)
+    from empanada.inference.postprocess import factor_pad
+    x = factor_pad(x, 128)
+    with torch.no_grad():
+        o = m(x, 2, False)
+    np.savez_compressed(os.path.join(GOLD, "model_bifpn_tiny.npz"), img=img, x=x.numpy(),
+                        sem_logits=o["sem_logits"].numpy(), ctr_hmp=o["ctr_hmp"].numpy(),
+                        offsets=o["offsets"].numpy())
+    print("bifpn tiny", {k: tuple(v.shape) for k, v in o.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["post", "median", "model", "volumes"]
+    which = sys.argv[1:] or ["post", "median", "model", "bifpn", "volumes"]
     if "post" in which:
         gen_post_cases()
     if "median" in which:
         gen_median()
     if "model" in which:
         gen_model_tiny()
+    if "bifpn" in which:
+        gen_model_bifpn_tiny()
     if "volumes" in which:
         run_reference_volume((24, 40, 48), seed=1, noise=0.0, ks=3, n_objects=10, min_size=50, min_extent=3, tag="clean")
         run_reference_volume((32, 36, 44), seed=2, noise=0.6, ks=3, n_objects=14, min_size=20, min_extent=2, tag="noisy")

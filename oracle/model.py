@@ -79,7 +79,11 @@ def point_rend(sd, coarse, features, render_steps, num_points=8192):
     """models/point_rend.py:241-269 (eval branch)."""
     sem = coarse.clone()
     nfc = 0
-    while f"semantic_pr.point_head.fc_layers.{nfc}.0.0.weight" in sd:
+    # fused exports (PDL) nest conv+relu one level deeper than unfused ones (BiFPN)
+    fc_fmt = "semantic_pr.point_head.fc_layers.{}.0.0"
+    if fc_fmt.format(0) + ".weight" not in sd:
+        fc_fmt = "semantic_pr.point_head.fc_layers.{}.0"
+    while fc_fmt.format(nfc) + ".weight" in sd:
         nfc += 1
     for _ in range(render_steps):
         sem = F.interpolate(sem, scale_factor=2.0, mode="bilinear", align_corners=False)
@@ -99,7 +103,7 @@ def point_rend(sd, coarse, features, render_steps, num_points=8192):
         fpts = F.grid_sample(features, grid, mode="bilinear", align_corners=False).squeeze(3)
         x = torch.cat([fpts, cpts], dim=1)
         for l in range(nfc):
-            pre = f"semantic_pr.point_head.fc_layers.{l}.0.0"
+            pre = fc_fmt.format(l)
             x = F.relu(F.conv1d(x, sd[pre + ".weight"], sd[pre + ".bias"]))
             x = torch.cat([x, cpts], dim=1)
         logits = F.conv1d(x, sd["semantic_pr.point_head.predictor.weight"],
@@ -129,3 +133,111 @@ def pdl_forward(sd, x, render_steps=2, interpolate_ins=False):
         off = F.interpolate(off, scale_factor=4.0, mode="bilinear", align_corners=True)
     return {"sem_logits": sem, "ctr_hmp": ctr, "offsets": off, "coarse_logits": coarse,
             "semantic_x": semantic_x, "instance_x": instance_x, "p5": feats[-1], "p2": feats[1]}
+
+
+# ------------------------------------------------------------------------- PanopticBiFPN-PR
+def _conv_bn(sd, p, x):
+    """blocks.py conv_bn_act(kernel_size=1, activation=None): p.0 conv (no bias), p.1 live BN."""
+    return _bn(sd, p + ".1", F.conv2d(x, sd[p + ".0.weight"], None))
+
+
+def _sepconv_bn_act(sd, p, x, k, act):
+    """blocks.py separable_conv_bn_act: depthwise k x k -> 1x1 (both bias-free) -> BN -> act."""
+    x = F.conv2d(x, sd[p + ".0.sepconv.0.weight"], None, 1, (k - 1) // 2, 1, x.shape[1])
+    x = F.conv2d(x, sd[p + ".0.sepconv.1.weight"], None)
+    return act(_bn(sd, p + ".1", x))
+
+
+def _resample(sd, p, x):
+    """blocks.py Resample2d: identity when no conv was created (nin == nout)."""
+    return _conv_bn(sd, p + ".conv", x) if (p + ".conv.0.weight") in sd else x
+
+
+def _fusion_weights(w, eps=1e-4):
+    w = F.relu(w)
+    return w / (w.sum() + eps)
+
+
+def bifpn_layer(sd, p, pyr, eps=1e-4):
+    """decoders/bifpn.py:14-158 (TopDownFPN, BottomUpFPN, BiFPNLayer). pyr: large -> small."""
+    up = lambda t: F.interpolate(t, scale_factor=2.0, mode="nearest")
+    down = lambda t: F.max_pool2d(t, 3, 2, 1)
+    # top-down over [small ... large]
+    tp = p + ".top_down_fpn"
+    rev = pyr[::-1]
+    w = _fusion_weights(sd[tp + ".weights"], eps)
+    td = [rev[0]]
+    for i in range(len(rev) - 1):
+        high = _resample(sd, f"{tp}.resamplings.{i}", rev[i + 1])
+        w1, w2 = w[i], w[i + 1]
+        fused = (w1 * up(td[-1]) + w2 * high) / (w1 + w2 + eps)
+        td.append(_sepconv_bn_act(sd, f"{tp}.after_combines.{i}", fused, 3, F.silu))
+    # bottom-up over pyr[1:] with the top-down features large -> small
+    bp = p + ".bottom_up_fpn"
+    tdr = td[::-1]
+    w = _fusion_weights(sd[bp + ".weights"], eps)
+    bu = [tdr[0]]
+    n = len(pyr) - 1
+    for i in range(n):
+        low = _resample(sd, f"{bp}.resamplings.{i}", pyr[1 + i])
+        if i < n - 1:
+            w1, w2, w3 = w[i], w[i + 1], w[i + 2]
+            fused = (w1 * down(bu[-1]) + w2 * low + w3 * tdr[i + 1]) / (w1 + w2 + w3 + eps)
+        else:
+            w1, w2 = w[i], w[i + 1]
+            fused = (w1 * down(bu[-1]) + w2 * low) / (w1 + w2 + eps)
+        bu.append(_sepconv_bn_act(sd, f"{bp}.after_combines.{i}", fused, 3, F.silu))
+    return bu
+
+
+def bifpn(sd, p, feats):
+    """decoders/bifpn.py:160-196. feats: [P3, P4, P5] encoder maps."""
+    p6 = F.max_pool2d(_resample(sd, p + ".p6_resample", feats[-1]), 3, 2, 1)
+    p7 = F.max_pool2d(p6, 3, 2, 1)
+    pyr = list(feats) + [p6, p7]
+    i = 0
+    while f"{p}.bifpns.{i}.top_down_fpn.weights" in sd:
+        pyr = bifpn_layer(sd, f"{p}.bifpns.{i}", pyr)
+        i += 1
+    return pyr
+
+
+def bifpn_decoder(sd, p, fpn_features):
+    """decoders/bifpn.py:198-236. fpn_features: small -> large, last one is the P2 skip."""
+    x = fpn_features[0]
+    for i, skip in enumerate(fpn_features[1:]):
+        x = F.conv_transpose2d(x, sd[f"{p}.upsamplings.{i}.0.weight"], None, stride=2)
+        x = F.relu(_bn(sd, f"{p}.upsamplings.{i}.1", x))
+        x = torch.cat([x, skip], dim=1)
+    return _sepconv_bn_act(sd, p + ".fusion", x, 5, F.relu)
+
+
+@torch.no_grad()
+def bifpn_forward(sd, x, render_steps=2, interpolate_ins=False):
+    """QuantizablePanopticBiFPNPR.forward (models/quantization/panoptic_bifpn.py:147-161), eval
+    mode, float path; encoder = fused ResNet-50 at output stride 32."""
+    feats = resnet50_encoder(sd, x, output_stride=32)
+    p2f = _resample(sd, "p2_resample", feats[1])
+    sem_pyr = [p2f] + bifpn(sd, "semantic_fpn", feats[2:])
+    semantic_x = bifpn_decoder(sd, "semantic_decoder", sem_pyr[::-1])
+    if "instance_fpn.p6_resample.conv.0.weight" in sd:
+        ins_pyr = [p2f] + bifpn(sd, "instance_fpn", feats[2:])
+        instance_x = bifpn_decoder(sd, "instance_decoder", ins_pyr[::-1])
+    else:
+        instance_x = semantic_x
+    coarse = pdl_head(sd, "semantic_head", semantic_x)
+    ctr = pdl_head(sd, "ins_center", instance_x)
+    off = pdl_head(sd, "ins_xy", instance_x)
+    sem = point_rend(sd, coarse, semantic_x, render_steps)
+    if interpolate_ins:
+        ctr = F.interpolate(ctr, scale_factor=4.0, mode="bilinear", align_corners=True)
+        off = F.interpolate(off, scale_factor=4.0, mode="bilinear", align_corners=True)
+    return {"sem_logits": sem, "ctr_hmp": ctr, "offsets": off, "coarse_logits": coarse,
+            "semantic_x": semantic_x, "instance_x": instance_x, "p5": feats[-1], "p2": feats[1],
+            "sem_pyr": sem_pyr, "p2f": p2f}
+
+
+def forward_any(sd, x, render_steps=2, interpolate_ins=False):
+    if "semantic_fpn.p6_resample.conv.0.weight" in sd:
+        return bifpn_forward(sd, x, render_steps, interpolate_ins)
+    return pdl_forward(sd, x, render_steps, interpolate_ins)

@@ -1,0 +1,96 @@
+"""-m gpu: single-layer checks of the non-GEMM forward kernels (csrc/model_kernels.cu) against
+plain PyTorch fp32 references of the same op, and of the fused variants against their unfused
+compositions (bit-exact: the fusions keep the same rounding points)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    import torch
+    from empanada_napari_b200 import pdl  # noqa: F401  (declares the be_op_* signatures)
+    from empanada_napari_b200._lib import call, ptr
+    return torch, call, ptr
+
+
+@pytest.mark.parametrize("B,H,W,C,k", [(2, 64, 64, 256, 5), (1, 37, 51, 72, 5), (3, 16, 24, 128, 3), (1, 9, 70, 8, 3)])
+def test_dwconv_vs_torch(B, H, W, C, k):
+    torch, call, ptr = _setup()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + C + k)
+    x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(dev)
+    w = torch.randn(C, 1, k, k, generator=g) * 0.2
+    wt = w.reshape(C, k * k).t().contiguous().to(dev)          # [k*k][C] fp32
+    out = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=dev)
+    call("be_op_dwconv", None, ptr(x), C, B, H, W, C, k, ptr(wt), ptr(out), C, None, 0, 0, 0, None)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.to(dev), padding=k // 2, groups=C)
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 1e-3      # one bf16 rounding of an fp32-accumulated sum
+    assert bool((err <= tol).all()), float(err.max())
+
+
+@pytest.mark.parametrize("B,Hu,Wu,clow", [(2, 8, 8, 32), (1, 5, 7, 16)])
+def test_dwconv_fused_upsample_equals_unfused(B, Hu, Wu, clow):
+    """bilinear(align_corners=True) + concat + depthwise 5x5 in one kernel == the three steps."""
+    torch, call, ptr = _setup()
+    dev = torch.device("cuda:0")
+    H, W, Cup = 4 * Hu, 4 * Wu, 256
+    C = Cup + clow
+    g = torch.Generator(device="cpu").manual_seed(7)
+    up = torch.randn(B, Hu, Wu, Cup, generator=g).to(torch.bfloat16).to(dev)
+    low = torch.randn(B, H, W, clow, generator=g).to(torch.bfloat16).to(dev)
+    wt = (torch.randn(25, C, generator=g) * 0.2).to(dev)
+    fused = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=dev)
+    call("be_op_dwconv", None, ptr(low), clow, B, H, W, C, 5, ptr(wt), ptr(fused), C, ptr(up), Cup, Hu, Wu, None)
+    cat = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=dev)
+    call("be_op_bilinear", None, ptr(up), Cup, B, Hu, Wu, Cup, ptr(cat), C, 0, H, W, None)
+    cat[..., Cup:] = low
+    plain = torch.zeros_like(fused)
+    call("be_op_dwconv", None, ptr(cat), C, B, H, W, C, 5, ptr(wt), ptr(plain), C, None, 0, 0, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, plain)
+    # and the bilinear producer itself against torch
+    ref = torch.nn.functional.interpolate(up.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)
+    got = cat[..., :Cup].float().permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("B,h,w,axis", [(2, 64, 64, 0), (1, 100, 72, 0), (2, 48, 80, 1), (2, 80, 48, 2)])
+def test_stem_pool_equals_stem_then_maxpool(B, h, w, axis):
+    """Fused conv1+BN+ReLU+MaxPool kernel == stem kernel followed by the max-pool kernel (bits),
+    and both agree with torch conv2d + max_pool2d on the normalised, padded slice."""
+    torch, call, ptr = _setup()
+    dev = torch.device("cuda:0")
+    pf = 16
+    H, W = h + (pf - h % pf) % pf, w + (pf - w % pf) % pf
+    g = torch.Generator(device="cpu").manual_seed(11)
+    shape = [B + 1, h, w]
+    shape3d = {0: (B + 1, h, w), 1: (h, B + 1, w), 2: (h, w, B + 1)}[axis]
+    vol = torch.randint(0, 256, shape3d, generator=g, dtype=torch.uint8).to(dev)
+    D, Hv, Wv = shape3d
+    strides = [(Hv * Wv, Wv, 1), (Wv, Hv * Wv, 1), (1, Hv * Wv, Wv)][axis]
+    wt = (torch.randn(64, 1, 7, 7, generator=g) * 0.1)
+    bias = torch.randn(64, generator=g) * 0.1
+    wt_d = wt.reshape(64, 49).t().contiguous().to(dev)
+    bias_d = bias.to(dev)
+    mean255 = float(np.float32(0.57571) * np.float32(255))
+    den = float(np.reciprocal(np.float32(np.float32(0.12765) * np.float32(255)), dtype=np.float32))
+    s0 = 1
+    stem = torch.zeros(B, H // 2, W // 2, 64, dtype=torch.bfloat16, device=dev)
+    pooled = torch.zeros(B, H // 4, W // 4, 64, dtype=torch.bfloat16, device=dev)
+    fused = torch.zeros_like(pooled)
+    call("be_op_stem", None, B, h, w, H, W, mean255, den, ptr(wt_d), ptr(bias_d), ptr(stem), ptr(vol), *strides, s0, None)
+    call("be_op_maxpool", None, ptr(stem), B, H // 2, W // 2, 64, ptr(pooled), H // 4, W // 4, None)
+    call("be_op_stem_pool", None, B, h, w, H, W, mean255, den, ptr(wt_d), ptr(bias_d), ptr(fused), ptr(vol), *strides, s0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, pooled)
+    sl = vol.movedim(axis, 0)[s0:s0 + B].float()
+    x = torch.zeros(B, 1, H, W, device=dev)
+    x[:, 0, :h, :w] = (sl - mean255) * den
+    ref = torch.nn.functional.conv2d(x, wt.to(dev), bias_d, stride=2, padding=3).relu()
+    ref = torch.nn.functional.max_pool2d(ref, 3, 2, 1).permute(0, 2, 3, 1)
+    err = (fused.float() - ref).abs()
+    assert float(err.max()) <= 2.0 ** -7 * float(ref.abs().max()) + 2e-3, float(err.max())

@@ -78,3 +78,72 @@ def test_engine2d_end_to_end_agreement():
     fg_agree = float(((out > 0) == (want > 0)).mean())
     print("foreground agreement", fg_agree, "objects", len(np.unique(out)) - 1, len(np.unique(want)) - 1)
     assert fg_agree >= 0.99
+
+
+@pytest.mark.parametrize("h,w,B", [(100, 200, 2), (256, 128, 1)])
+def test_bifpn_forward_vs_oracle(h, w, B):
+    """PanopticBiFPN-PointRend (MitoNet_v1_mini architecture, padding factor 128) on the bf16
+    tcgen05 path vs the fp32 oracle restatement (pinned on tests/golden/model_bifpn_tiny.npz).
+    Same tolerances as the PanopticDeepLab test."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.bifpn import BiFPNModel
+    from oracle import model as omodel, post
+    sd = syn.make_bifpn_state_dict(0)
+    dev = torch.device("cuda:0")
+    m = BiFPNModel(sd, dev)
+    rng = np.random.default_rng(6)
+    vol = rng.integers(0, 256, (B, h, w), dtype=np.uint8)
+    sem, ctr, off = m.forward_slices(torch.from_numpy(vol).to(dev), 0, 0, B, NORMS, 128)
+    torch.cuda.synchronize()
+    plan = m.last_plan
+    x = np.stack([post.factor_pad(post.normalize(vol[i], NORMS["mean"], NORMS["std"]), 128) for i in range(B)])[:, None]
+    ref = omodel.bifpn_forward(sd, torch.from_numpy(x), 2, False)
+    nhwc = lambda t: t.float().cpu().numpy().transpose(0, 3, 1, 2)
+    D = plan.W.D
+    errs = {
+        "p2": rel_l2(nhwc(plan.p2), ref["p2"].numpy()),
+        "p5": rel_l2(nhwc(plan.p5), ref["p5"].numpy()),
+        "p2_resampled": rel_l2(nhwc(plan.p2f[..., D:]), ref["p2f"].numpy()),
+        "semantic_x": rel_l2(nhwc(plan.semantic_x), ref["semantic_x"].numpy()),
+        "instance_x": rel_l2(nhwc(plan.instance_x), ref["instance_x"].numpy()),
+        "coarse": rel_l2(plan.coarse.cpu().numpy(), ref["coarse_logits"].numpy()),
+        "ctr": rel_l2(ctr.cpu().numpy(), ref["ctr_hmp"].numpy()[:, 0]),
+        "off": rel_l2(off.cpu().numpy(), ref["offsets"].numpy()),
+    }
+    print(errs)
+    for k, v in errs.items():
+        assert v <= 3e-2, (k, v, errs)
+    got = sem.cpu().numpy()
+    want = ref["sem_logits"].numpy()[:, 0]
+    scale = float(np.abs(want).mean())
+    bad = np.abs(got - want) > 0.1 * scale + 0.05 * np.abs(want)
+    frac = float(bad.mean())
+    print("sem_logits rel_l2", rel_l2(got, want), "mismatch fraction", frac)
+    assert frac <= 0.03, frac
+
+
+def test_engine2d_bifpn_mini_config():
+    """BASELINE config C1: MitoNet_v1_mini-class 2D inference (padding factor 128, nms_kernel 7)
+    through Engine2d vs the oracle pipeline fed by the oracle BiFPN."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import Engine2d
+    from oracle import model as omodel, pipeline
+    sd = syn.make_bifpn_state_dict(0)
+    cfg = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 128,
+           "norms": NORMS, "model": sd}
+    eng = Engine2d(cfg, confidence_thr=0.5, nms_threshold=0.1, nms_kernel=7)
+    img, _, _ = syn.make_volume((1, 200, 184), seed=3, scale=1.0)
+    img = img[0]
+    out = eng.infer(img)
+    assert out.shape == img.shape and out.dtype == np.int32
+
+    def heads_fn(i, x):
+        o = omodel.bifpn_forward(sd, torch.from_numpy(x[None, None]), 2, False)
+        return o["sem_logits"][0].numpy(), o["ctr_hmp"][0, 0].numpy(), o["offsets"][0].numpy()
+
+    want = pipeline.engine2d_infer(img, heads_fn, cfg, confidence_thr=0.5, nms_threshold=0.1, nms_kernel=7)
+    fg_agree = float(((out > 0) == (want > 0)).mean())
+    print("foreground agreement", fg_agree, "objects", len(np.unique(out)) - 1, len(np.unique(want)) - 1)
+    assert fg_agree >= 0.99

@@ -122,3 +122,17 @@ def test_model_restatement_matches_reference_fixture():
     out = model.pdl_forward(syn.make_pdl_state_dict(0), torch.from_numpy(x), 2, False)
     for k in ("sem_logits", "ctr_hmp", "offsets"):
         assert np.allclose(out[k].numpy(), z[k], atol=2e-4, rtol=1e-4), k
+
+
+def test_bifpn_restatement_matches_reference_fixture():
+    """oracle.model.bifpn_forward vs the scripted reference QuantizablePanopticBiFPNPR
+    (MitoNet_v1_mini architecture) on seeded weights; fixture by oracle/make_golden.py."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from oracle import model
+    z = np.load(os.path.join(GOLDEN, "model_bifpn_tiny.npz"))
+    x = post.factor_pad(post.normalize(z["img"], 0.57571, 0.12765), 128)[None, None]
+    assert np.array_equal(x, z["x"])
+    out = model.bifpn_forward(syn.make_bifpn_state_dict(0), torch.from_numpy(x), 2, False)
+    for k in ("sem_logits", "ctr_hmp", "offsets"):
+        assert np.allclose(out[k].numpy(), z[k], atol=2e-4, rtol=1e-4), k
