@@ -14,6 +14,8 @@ from itertools import combinations
 import networkx as nx
 import numpy as np
 import torch
+from scipy.sparse import coo_matrix
+from scipy.sparse.csgraph import connected_components
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
@@ -224,28 +226,45 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     pa, pb, inter = _hash_items(keys, vals, cap, dev)
     _mark('plane pairs kernel')
     order = np.lexsort((pb, pa))
-    graph = nx.Graph()
-    for n in range(n_nodes):
-        graph.add_node(n)
     sizes = np.array(node_sizes, dtype=np.int64)
-    for a, b, it in zip(pa[order], pb[order], inter[order]):
-        union = sizes[a - 1] + sizes[b - 1] - it
-        iou = it / union
-        if iou > 0:
-            graph.add_edge(int(a - 1), int(b - 1), iou=iou, overlap=int(it))
-
+    ea, eb, eit = pa[order] - 1, pb[order] - 1, inter[order]
+    eiou = eit / (sizes[ea] + sizes[eb] - eit)          # float64, as `intersection / union`
+    pos = eiou > 0
+    ea, eb, eit, eiou = ea[pos], eb[pos], eit[pos], eiou[pos]
     _mark('host build nx graph')
-    # clusters per connected component
+    # Connected components of the instance graph. networkx yields them in order of their first
+    # node in insertion order (0..n-1), i.e. by smallest node id; scipy's labelling is renumbered
+    # to that order. Member order inside a component never reaches the output (boxes are
+    # min/max merges, memberships are sets).
+    adj = coo_matrix((np.ones(len(ea), dtype=np.int8), (ea, eb)), shape=(n_nodes, n_nodes))
+    _, lab = connected_components(adj, directed=False)
+    first = np.full(int(lab.max()) + 1, n_nodes, dtype=np.int64)
+    np.minimum.at(first, lab, np.arange(n_nodes))
+    rank = np.empty_like(first)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(first))
+    comp_of = rank[lab]                                   # node -> component index (nx order)
+    n_comp = len(first)
+    comp_size = np.bincount(comp_of, minlength=n_comp)
+    comp_min_iou = np.full(n_comp, np.inf)
+    np.minimum.at(comp_min_iou, comp_of[ea], eiou)
+    node_order = np.argsort(comp_of, kind="stable")       # nodes grouped by component, ascending ids
+    node_start = np.concatenate([[0], np.cumsum(comp_size)])
+    edge_order = np.argsort(comp_of[ea], kind="stable")   # edges grouped by component, lexsorted inside
+    edge_start = np.concatenate([[0], np.cumsum(np.bincount(comp_of[ea], minlength=n_comp))])
     cands = []  # (component index, member node list, merged box)
-    for ci, comp in enumerate(nx.connected_components(graph)):
-        if len(comp) < min_cluster:
-            continue
-        if all(d > cluster_iou_thr for _, _, d in graph.edges(comp, data="iou")):
+    for ci in np.flatnonzero(comp_size >= min_cluster):
+        members = node_order[node_start[ci]:node_start[ci + 1]]
+        if comp_min_iou[ci] > cluster_iou_thr:
             # every edge survives the IoU cut: the component is one cluster and the cluster graph
             # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
-            clusters = [list(comp)]
+            clusters = [members.tolist()]
         else:
-            cg = merge_clusters(create_graph_of_clusters(graph.subgraph(comp), cluster_iou_thr))
+            # same node / adjacency insertion orders as `graph.subgraph(comp)` of the full graph
+            sub = nx.Graph()
+            sub.add_nodes_from(members.tolist())
+            for k in edge_order[edge_start[ci]:edge_start[ci + 1]]:
+                sub.add_edge(int(ea[k]), int(eb[k]), iou=float(eiou[k]), overlap=int(eit[k]))
+            cg = merge_clusters(create_graph_of_clusters(sub, cluster_iou_thr))
             clusters = [list(cg.nodes[node]["cluster"]) for node in cg.nodes]
         for cluster in clusters:
             if len(cluster) < min_cluster:
@@ -253,7 +272,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             box = node_boxes[cluster[0]]
             for m in cluster[1:]:
                 box = merge_boxes(box, node_boxes[m])
-            cands.append((ci, cluster, box))
+            cands.append((int(ci), cluster, box))
     _mark('host graph clustering')
     if not cands:
         return empty_vol, {}
@@ -374,17 +393,21 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     st_s = starts[order].cpu().numpy()
     ln_s = lens[order].long().cpu().numpy()
     bounds = np.searchsorted(lab_s, np.arange(1, n_final + 2))
+    if len(hv):
+        # voxels claimed by an instance but painted with another id (after the fix-up above):
+        # one gather for all of them, then grouped by instance
+        still = out.view(-1)[torch.from_numpy(hv).to(dev)].cpu().numpy() != hi
+        hv, hi = hv[still], hi[still]
+        o = np.argsort(hi, kind="stable")
+        hv, hi = hv[o], hi[o]
+    hb = np.searchsorted(hi, np.arange(1, n_final + 2))
     instances = {}
     for fid in range(1, n_final + 1):
         if not keep[fid]:
             continue
         a, b = bounds[fid - 1], bounds[fid]
         s, r = st_s[a:b], ln_s[a:b]
-        extra = hv[hi == fid] if len(hv) else hv
-        if len(extra):
-            # re-check against the volume after the fix-up: still hidden?
-            still = out.view(-1)[torch.from_numpy(extra).to(dev)].cpu().numpy() != fid
-            extra = extra[still]
+        extra = hv[hb[fid - 1]:hb[fid]]
         if len(extra):
             rng = np.concatenate([np.stack([s, s + r], 1), np.stack([extra, extra + 1], 1)])
             rng = rng[np.argsort(rng[:, 0], kind="stable")]

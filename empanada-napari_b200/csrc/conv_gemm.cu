@@ -549,6 +549,22 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box,
+                     const unsigned* elem_strides, int swizzle_128b) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -1;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                         const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzle_128b ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -100 - static_cast<int>(r);
+}
+
 static void pick_tile_geometry(int B, int Ho, int Wo, int* TW, int* TH, int* TB) {
   // minimise padded pixels; prefer wide rows on ties (longer contiguous TMA segments)
   long long best = -1;

@@ -72,4 +72,11 @@ struct Launch {
   size_t smem;
 };
 
+// cuTensorMapEncodeTiled for a bf16 tensor (dims / box innermost first, strides in bytes for
+// dims 1..rank-1); zero fill out of bounds. Returns 0 or a negative error. Shared with the
+// TMA-fed CUDA-core kernels (depthwise convolution).
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box,
+                     const unsigned* elem_strides, int swizzle_128b);
+
 }  // namespace convgemm

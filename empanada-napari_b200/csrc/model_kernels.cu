@@ -15,6 +15,8 @@
 #include <cstdint>
 
 #include "common.cuh"
+#include "conv_gemm.cuh"
+#include "sm100_ptx.cuh"
 
 namespace mk {
 
@@ -359,6 +361,112 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
         }
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------ depthwise, TMA-fed persistent
+// Same arithmetic and thread mapping as `dwconv_kernel`, but the input patch of a tile is ONE 4-D
+// TMA box {64 channels, PW, PH, 1 image} of the NHWC tensor (out-of-bounds zero fill = the conv
+// padding and the channel tail), double buffered: a persistent CTA prefetches the patch of its
+// next tile while the FMA pipe works on the current one, and no thread spends issue slots on
+// address arithmetic or shared-memory stores for the fill.
+template <int K>
+constexpr int dw_tma_smem_bytes() { return 2 * (DW_TY + K - 1) * (DW_TX + K - 1) * DW_CB * 2 + 128 + 64; }
+
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, int H, int W, int C,
+                  const float* __restrict__ wt /*[K*K][C]*/, bf16* __restrict__ out, long long out_ld,
+                  int tiles_x, int tiles_y, int cblocks, int total_tiles) {
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int PH = DW_TY + K - 1, PW = DW_TX + K - 1;
+  constexpr int PATCH_BYTES = PH * PW * DW_CB * 2;
+  extern __shared__ uint8_t dwt_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dwt_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * PATCH_BYTES);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    sm100::tma_prefetch_desc(&tmap);
+    sm100::mbar_init(&bars[0], 1);
+    sm100::mbar_init(&bars[1], 1);
+    sm100::fence_mbar_init();
+  }
+  __syncthreads();
+  const int spatial = tiles_x * tiles_y;
+  int t = blockIdx.x;
+  auto issue = [&](int tile, int buf) {
+    const int bc = tile / spatial, sp = tile - bc * spatial;
+    const int b = bc / cblocks, c0 = (bc - b * cblocks) * DW_CB;
+    const int ty = sp / tiles_x, tx = sp - ty * tiles_x;
+    sm100::mbar_expect_tx(&bars[buf], PATCH_BYTES);
+    sm100::tma_load_4d(base + buf * PATCH_BYTES, &tmap, &bars[buf], c0, tx * DW_TX - PAD, ty * DW_TY - PAD, b);
+  };
+  if (t < total_tiles && threadIdx.x == 0) issue(t, 0);
+  float w0[K * K], w1[K * K];
+  int prev_c0 = -1;
+  for (int it = 0; t < total_tiles; ++it, t += gridDim.x) {
+    const int buf = it & 1;
+    if (t + static_cast<int>(gridDim.x) < total_tiles && threadIdx.x == 0) issue(t + gridDim.x, buf ^ 1);
+    const int bc = t / spatial, sp = t - bc * spatial;
+    const int b = bc / cblocks, c0 = (bc - b * cblocks) * DW_CB;
+    const int ty = sp / tiles_x, tx = sp - ty * tiles_x;
+    const int y0 = ty * DW_TY, x0 = tx * DW_TX;
+    const int ch = c0 + 2 * lane;
+    if (c0 != prev_c0) {
+      prev_c0 = c0;
+#pragma unroll
+      for (int k = 0; k < K * K; ++k) {
+        float2 ww = make_float2(0.0f, 0.0f);
+        if (ch < C) ww = __ldg(reinterpret_cast<const float2*>(wt + k * C + ch));
+        w0[k] = ww.x; w1[k] = ww.y;
+      }
+    }
+    sm100::mbar_wait(&bars[buf], (it >> 1) & 1);
+    const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(base + buf * PATCH_BYTES) + (warp * DW_PX) * (DW_CB / 2) + lane;
+    float acc[K][DW_PX][2];
+#pragma unroll
+    for (int pr = 0; pr < PH; ++pr) {
+      float v[DW_PX + K - 1][2];
+#pragma unroll
+      for (int c = 0; c < DW_PX + K - 1; ++c) {
+        const uint32_t u = pw32[(pr * PW + c) * (DW_CB / 2)];
+        v[c][0] = __uint_as_float(u << 16);
+        v[c][1] = __uint_as_float(u & 0xffff0000u);
+      }
+#pragma unroll
+      for (int ry = 0; ry < K; ++ry) {
+        const int orow = pr - ry;
+        if (orow < 0 || orow >= DW_TY) continue;
+        const int slot = orow % K;
+        if (ry == 0) {
+#pragma unroll
+          for (int px = 0; px < DW_PX; ++px) { acc[slot][px][0] = 0.0f; acc[slot][px][1] = 0.0f; }
+        }
+#pragma unroll
+        for (int sx2 = 0; sx2 < K; ++sx2) {
+#pragma unroll
+          for (int px = 0; px < DW_PX; ++px) {
+            acc[slot][px][0] = fmaf(v[px + sx2][0], w0[ry * K + sx2], acc[slot][px][0]);
+            acc[slot][px][1] = fmaf(v[px + sx2][1], w1[ry * K + sx2], acc[slot][px][1]);
+          }
+        }
+      }
+      const int done = pr - (K - 1);
+      if (done >= 0) {
+        const int slot = done % K;
+        const int y = y0 + done;
+        if (y < H && ch < C) {
+#pragma unroll
+          for (int px = 0; px < DW_PX; ++px) {
+            const int x = x0 + warp * DW_PX + px;
+            if (x < W)
+              *reinterpret_cast<__nv_bfloat162*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + ch) =
+                  __floats2bfloat162_rn(acc[slot][px][0], acc[slot][px][1]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with this buffer before it is refilled
   }
 }
 
@@ -722,16 +830,42 @@ int be_dwconv(const __nv_bfloat16* in, long long in_ld, int B, int H, int W, int
                         100LL * (Hu - 1) > 45LL * (H - 1)))
     return be_set_error("dwconv: fused upsampling needs a scale factor >= 3.3 and Cup % 64 == 0");
   const int cblocks = (C + mk::DW_CB - 1) / mk::DW_CB;
-  dim3 grid((W + mk::DW_TX - 1) / mk::DW_TX, (H + mk::DW_TY - 1) / mk::DW_TY, B * cblocks);
+  const int tiles_x = (W + mk::DW_TX - 1) / mk::DW_TX, tiles_y = (H + mk::DW_TY - 1) / mk::DW_TY;
   static bool attr_set = false;
+  static int num_sms = 148;
   if (!attr_set) {
     cudaFuncSetAttribute(mk::dwconv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::dw_smem_bytes<5>());
     cudaFuncSetAttribute(mk::dwconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::dw_smem_bytes<3>());
+    cudaFuncSetAttribute(mk::dwconv_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::dw_tma_smem_bytes<5>());
+    cudaFuncSetAttribute(mk::dwconv_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mk::dw_tma_smem_bytes<3>());
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_set = true;
   }
+  if (k != 5 && k != 3) return be_set_error("dwconv: only 3x3 and 5x5 kernels are built");
+  if (up == nullptr && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    // TMA-fed persistent kernel: patch = one 4-D box of the NHWC input
+    CUtensorMap tmap;
+    const unsigned long long dims[4] = {static_cast<unsigned long long>(C), static_cast<unsigned long long>(W),
+                                        static_cast<unsigned long long>(H), static_cast<unsigned long long>(B)};
+    const unsigned long long strides[3] = {static_cast<unsigned long long>(in_ld) * 2,
+                                           static_cast<unsigned long long>(in_ld) * 2 * W,
+                                           static_cast<unsigned long long>(in_ld) * 2 * W * H};
+    const unsigned box[4] = {static_cast<unsigned>(mk::DW_CB), static_cast<unsigned>(mk::DW_TX + k - 1),
+                             static_cast<unsigned>(mk::DW_TY + k - 1), 1u};
+    const unsigned estr[4] = {1, 1, 1, 1};
+    const int rc = convgemm::encode_tmap_bf16(&tmap, in, 4, dims, strides, box, estr, 0);
+    if (rc != 0) return be_set_error("dwconv: cuTensorMapEncodeTiled failed");
+    const long long total = 1LL * B * cblocks * tiles_x * tiles_y;
+    const int grid = static_cast<int>(total < 2LL * num_sms ? total : 2LL * num_sms);
+    if (k == 5) mk::dwconv_tma_kernel<5><<<grid, 256, mk::dw_tma_smem_bytes<5>(), st>>>(tmap, H, W, C, wt, out, out_ld, tiles_x, tiles_y, cblocks, static_cast<int>(total));
+    else mk::dwconv_tma_kernel<3><<<grid, 256, mk::dw_tma_smem_bytes<3>(), st>>>(tmap, H, W, C, wt, out, out_ld, tiles_x, tiles_y, cblocks, static_cast<int>(total));
+    return be_check_launch("dwconv_tma_kernel");
+  }
+  dim3 grid(tiles_x, tiles_y, B * cblocks);
   if (k == 5) mk::dwconv_kernel<5><<<grid, 256, mk::dw_smem_bytes<5>(), st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
-  else if (k == 3) mk::dwconv_kernel<3><<<grid, 256, mk::dw_smem_bytes<3>(), st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
-  else return be_set_error("dwconv: only 3x3 and 5x5 kernels are built");
+  else mk::dwconv_kernel<3><<<grid, 256, mk::dw_smem_bytes<3>(), st>>>(in, in_ld, B, H, W, C, wt, out, out_ld, up, Cup, Hu, Wu);
   return be_check_launch("dwconv_kernel");
 }
 int be_bifpn_fuse(const __nv_bfloat16* a, long long a_ld, int mode, int Ha, int Wa,

@@ -5,6 +5,7 @@ sm_100a kernels of this package. There is no CPU path: a CUDA device is required
 """
 import math
 import os
+import threading
 import time
 
 import numpy as np
@@ -39,6 +40,27 @@ class _Phase:
             t1 = time.perf_counter()
             self.t[name] = self.t.get(name, 0.0) + (t1 - self.t0)
             self.t0 = t1
+
+
+class _Async:
+    """One function call on a worker thread; `result()` joins and re-raises."""
+
+    def __init__(self, fn, *args):
+        self._out, self._err = None, None
+
+        def run():
+            try:
+                self._out = fn(*args)
+            except BaseException as e:  # re-raised on the caller's thread
+                self._err = e
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def result(self):
+        self._t.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
 
 
 def _unsupported(name):
@@ -83,7 +105,8 @@ class Engine3d:
                  force_connected=True, min_size=500, min_extent=4, fine_boundaries=False,
                  semantic_only=False, use_gpu=True, use_quantized=False, store_url=None,
                  chunk_size=(256, 256, 256), save_panoptic=False, label_erosion=0,
-                 label_dilation=0, fill_holes_in_segmentation=False, batch_size=16, lazy_rle=True):
+                 label_dilation=0, fill_holes_in_segmentation=False, batch_size=16, lazy_rle=True,
+                 overlap_replay=True):
         self.device = _require_cuda()
         if not use_gpu:
             raise _lib.B200EmpanadaError("use_gpu=False requested: this engine has no CPU path")
@@ -118,6 +141,8 @@ class Engine3d:
         self.dtype = np.int32
         self.batch_size = batch_size
         self.lazy_rle = lazy_rle
+        self.overlap_replay = overlap_replay
+        self.deferred_launches = 0
         self.model = load_model(model_config["model"], self.device, model_config)
         self.engine = self  # widgets call engine.engine.reset(); kept for attribute parity
         self._cache = _VolumeCache()
@@ -187,16 +212,35 @@ class Engine3d:
                          nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
                          confidence_thr=self.confidence_thr, device=self.device)
 
-    def _finish_plane(self, post, axis_name, shape3d, prof=None):
+    def _finish_plane(self, post, axis_name, shape3d, prof=None, defer=False):
         """Everything after the head maps are in: median tail, components, tracker replay,
-        filters, relabel, RLE. Returns [InstanceTracker] (with the dense volume attached)."""
+        filters, relabel, RLE. Returns [InstanceTracker] (with the dense volume attached).
+        defer=True: the host matcher replay runs on a worker thread and the tracker completes
+        itself on first access (overlaps with the next plane's forward pass)."""
         prof = prof or _Phase(False)
         post.finish_heads()
         prof.mark("forward+median+centres+grouping")
         post.run_cc()
         prof.mark("merge+cc+tables+overlaps")
-        lut, labels, sizes, boxes = post.replay(axis_name, self.merge_iou_thr, self.merge_ioa_thr)
+        if defer:
+            tr = tracking.PendingTracker(self.labels[0], self.label_divisor, shape3d, axis_name)
+            inputs = post.replay_inputs()
+            job = _Async(post.replay_host, inputs, axis_name, self.merge_iou_thr, self.merge_ioa_thr)
+
+            def resolve():
+                n0 = post.launches
+                self._fill_tracker(tr, post, job.result(), axis_name, shape3d, _Phase(False))
+                self.deferred_launches += post.launches - n0
+            tr._resolver = resolve
+            return [tr]
+        trackers = self.create_trackers(shape3d, axis_name)
+        replayed = post.replay(axis_name, self.merge_iou_thr, self.merge_ioa_thr)
         prof.mark("host matcher replay")
+        self._fill_tracker(trackers[0], post, replayed, axis_name, shape3d, prof)
+        return trackers
+
+    def _fill_tracker(self, tr, post, replayed, axis_name, shape3d, prof):
+        lut, labels, sizes, boxes = replayed
         # filters.remove_small_objects / remove_pancakes (inference.py:556-558), applied on tables
         spans = boxes[:, 3:] - boxes[:, :3] if len(boxes) else np.zeros((0, 3), np.int32)
         keep = (sizes >= self.min_size) & (spans >= self.min_extent).all(axis=1) if len(labels) else np.zeros(0, bool)
@@ -207,8 +251,6 @@ class Engine3d:
         lut_f = keep_lut[lut]
         dense = post.relabel(lut_f, axis_name, shape3d)
         prof.mark("relabel")
-        trackers = self.create_trackers(shape3d, axis_name)
-        tr = trackers[0]
         # per-instance RLE arrays are extracted from the dense volume on first access
         # (tracker_consensus below never needs them); set lazy_rle=False for eager dictionaries
         plane = LazyPlane(dense, axis_name, kept_labels, boxes[keep])
@@ -219,7 +261,6 @@ class Engine3d:
         prof.mark("runs + tracker dict")
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
         tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, sizes[keep])}
-        return trackers
 
     def infer_on_axis(self, volume, axis_name):
         self._check_supported()
@@ -228,10 +269,10 @@ class Engine3d:
         launches0 = getattr(self.model, "launches", 0)
         prof = _Phase(os.environ.get("B200_EMPANADA_PROFILE") == "1")
         self._forward_all(post, vol_d, axis, n, self.model_config["norms"], pf)
-        trackers = self._finish_plane(post, axis_name, shape3d, prof)
+        defer = self.overlap_replay and not self.save_panoptic and not prof.on
+        trackers = self._finish_plane(post, axis_name, shape3d, prof, defer=defer)
         self.last_profile = prof.t
-        dense = trackers[0]._b200_dense
-        stack = dense.cpu().numpy() if self.save_panoptic else None
+        stack = trackers[0]._b200_dense.cpu().numpy() if self.save_panoptic else None
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
         return stack, trackers
 
@@ -297,22 +338,31 @@ class Engine2d:
             _unsupported("multi-class / semantic-only models")
         if self.tile_size > 0 and any(s > self.tile_size for s in images.shape[1:]):
             _unsupported("tiled 2-D inference")
-        if np.issubdtype(images.dtype, np.floating):
-            raise Exception("Input image cannot be float type!")
-        if images.dtype != np.uint8:
-            _unsupported(f"{images.dtype} images (uint8 only)")
         dev = self.device
-        n, h, w = images.shape
+        if isinstance(images, torch.Tensor):   # already resident (benchmarks / pipelines)
+            if images.dtype != torch.uint8 or not images.is_cuda:
+                _unsupported("device images other than cuda uint8")
+            vol_d = images.contiguous()
+        else:
+            if np.issubdtype(images.dtype, np.floating):
+                raise Exception("Input image cannot be float type!")
+            if images.dtype != np.uint8:
+                _unsupported(f"{images.dtype} images (uint8 only)")
+            vol_d = torch.from_numpy(np.ascontiguousarray(images)).to(dev)
+        n, h, w = vol_d.shape
         pf = self.padding_factor
         H = h + (pf - h % pf) % pf
         W = w + (pf - w % pf) % pf
-        vol_d = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images)).to(dev)
         cls = self.thing_list[0]
         post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=self.label_divisor,
                          void_label=0, nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
                          confidence_thr=self.confidence_thr, device=dev)
-        sem, ctr, off = self.model.forward_slices(vol_d, 0, 0, n, self.model_config["norms"], pf)
-        post.push_heads(sem, ctr, off, is_prob=False)
+        # chunks of ~16 MPixel keep the activation buffers of one launch list near 10 GB
+        chunk = max(1, min(n, (16 << 20) // (H * W)))
+        for s0 in range(0, n, chunk):
+            s1 = min(n, s0 + chunk)
+            sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)
+            post.push_heads(sem, ctr, off, is_prob=False)
         post.finish_heads()
         # force_connected (inference.py:263-279): pan <- class*div + component id
         post.run_cc(batch=min(n, 16))

@@ -15,6 +15,7 @@ place by their producers; the ASPP image-pool branch is a per-image bias of the 
 the 256->1/2 head convolutions are fused into the epilogue of the preceding pointwise conv.
 """
 import ctypes
+import os
 from ctypes import c_float, c_int, c_longlong, c_void_p
 
 import numpy as np
@@ -46,6 +47,8 @@ _lib.declare("be_op_pr_sample", [P, P, I, I, I, I, P, P, I, I, I, P, P, I, P, P]
 _lib.declare("be_op_pr_predict", [P, P, I, I, P, P, F, P, I, I, I, P, P])
 
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+# decoder `F.interpolate` + `torch.cat` fused into the depthwise kernel (1) or materialised (0)
+FUSED_UPSAMPLE = os.environ.get("B200_EMPANADA_FUSED_UPSAMPLE", "1") == "1"
 BN_EPS = 1e-5
 
 
@@ -341,11 +344,20 @@ class _Plan(_PlanBase):
             aspp, _, _ = conv(cat, H16, W16, 1024, dec + ".proj", 256, bias=pbias, bias_img_stride=256)
             clow = W[dec + ".low.w"].shape[0]
             cf = 256 + clow
-            low, _, _ = conv(p2, H4, W4, 256, dec + ".low", clow)
             dw = buf(B, H4, W4, cf)
-            # bilinear upsampling + concat fused into the depthwise producer
-            self._rec("be_op_dwconv", L, ptr(low), clow, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf,
-                      ptr(aspp), 256, H16, W16, None)
+            if FUSED_UPSAMPLE:
+                # bilinear upsampling + concat fused into the depthwise producer
+                low, _, _ = conv(p2, H4, W4, 256, dec + ".low", clow)
+                self._rec("be_op_dwconv", L, ptr(low), clow, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf,
+                          ptr(aspp), 256, H16, W16, None)
+            else:
+                # concat buffer materialised once (bilinear producer + low-level projection write
+                # their channel slots), then the TMA-fed depthwise kernel
+                cat4 = buf(B, H4, W4, cf)
+                self._rec("be_op_bilinear", L, ptr(aspp), 256, B, H16, W16, 256, ptr(cat4), cf, 0, H4, W4, None)
+                conv(p2, H4, W4, 256, dec + ".low", clow, out=cat4, out_ld=cf, coff=256)
+                self._rec("be_op_dwconv", L, ptr(cat4), cf, B, H4, W4, cf, 5, ptr(W[dec + ".fuse.dw"]), ptr(dw), cf,
+                          None, 0, 0, 0, None)
             feats[dec], _, _ = conv(dw, H4, W4, cf, dec + ".fuse.pw", 256)
         semantic_x = feats["semantic_decoder"]
         instance_x = feats.get("instance_decoder", semantic_x)

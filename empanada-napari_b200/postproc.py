@@ -143,12 +143,21 @@ class PlanePost:
         self.pair_vals = out_vals[:n_pairs].cpu().numpy()
 
     # ------------------------------------------------------------------ stage 3: host replay
-    def replay(self, axis_name, iou_thr=0.25, ioa_thr=0.25):
+    def replay_inputs(self):
+        """Host copies of the component tables (synchronises the stream)."""
         n_cc = self.n_cc.cpu().numpy()
         cap = max(1, int(n_cc.max()))
         table = self.cc_table[:, :cap].contiguous().cpu().numpy()
+        return n_cc, table
+
+    def replay_host(self, inputs, axis_name, iou_thr=0.25, ioa_thr=0.25):
+        """Pure host part (native code, releases the GIL): safe to run on a worker thread."""
+        n_cc, table = inputs
         return tracking.match_replay(n_cc, table, self.pair_keys, self.pair_vals, self.cls,
                                      self.div, axis_name, iou_thr, ioa_thr)
+
+    def replay(self, axis_name, iou_thr=0.25, ioa_thr=0.25):
+        return self.replay_host(self.replay_inputs(), axis_name, iou_thr, ioa_thr)
 
     # ------------------------------------------------------------------ stage 4: relabel + runs
     def relabel(self, lut, axis_name, shape3d, batch=64):

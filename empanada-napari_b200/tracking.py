@@ -70,6 +70,31 @@ class InstanceTracker:
         self.__dict__.update(d)
 
 
+class PendingTracker(InstanceTracker):
+    """Tracker whose tables are completed on first access of `instances` (or of the attached
+    device volume): `Engine3d` overlaps the host matcher replay of one plane with the next plane's
+    forward pass and resolves the tracker when somebody looks at it."""
+
+    _LAZY = ("instances", "_b200_dense", "_b200_sizes")
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__.pop("instances", None)
+        self._resolver = None
+
+    def __getattr__(self, name):  # only called when normal lookup fails
+        if name in PendingTracker._LAZY:
+            resolver = self.__dict__.get("_resolver")
+            if resolver is not None:
+                self.__dict__["_resolver"] = None
+                resolver()
+                return self.__dict__[name]
+            if name == "instances":
+                self.__dict__["instances"] = {}
+                return self.__dict__["instances"]
+        raise AttributeError(name)
+
+
 def remove_small_objects(tracker, min_size=64):
     """filters.py:22-36."""
     for iid in list(tracker.instances.keys()):

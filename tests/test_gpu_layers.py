@@ -94,3 +94,51 @@ def test_stem_pool_equals_stem_then_maxpool(B, h, w, axis):
     ref = torch.nn.functional.max_pool2d(ref, 3, 2, 1).permute(0, 2, 3, 1)
     err = (fused.float() - ref).abs()
     assert float(err.max()) <= 2.0 ** -7 * float(ref.abs().max()) + 2e-3, float(err.max())
+
+
+@pytest.mark.parametrize("B,Hi,Wi,Cin", [(2, 1, 2, 128), (1, 8, 16, 256), (3, 5, 3, 256)])
+def test_convt2x2_vs_torch(B, Hi, Wi, Cin):
+    """ConvTranspose2d(k=2, s=2) + bias + ReLU as one GEMM with a pixel-shuffle epilogue, written
+    into the first half of a 2*Cout-channel concat buffer (decoders/bifpn.py:226-234)."""
+    torch, call, ptr = _setup()
+    dev = torch.device("cuda:0")
+    Cout = 128
+    g = torch.Generator(device="cpu").manual_seed(Cin + Hi)
+    x = torch.randn(B, Hi, Wi, Cin, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    wg = w.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous().to(dev)
+    bias4 = bias.repeat(4).to(dev)
+    out = torch.full((B, 2 * Hi, 2 * Wi, 2 * Cout), 7.0, dtype=torch.bfloat16, device=dev)
+    call("be_op_convt2x2", None, ptr(x), Cin, B, Hi, Wi, Cin, ptr(wg), Cout, ptr(out), 2 * Cout, 0, ptr(bias4), 1, None)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.float().to(dev), bias.to(dev), stride=2).relu()
+    ref = ref.permute(0, 2, 3, 1)
+    got = out[..., :Cout].float()
+    assert float((got - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 2e-3
+    assert bool((out[..., Cout:] == 7.0).all())      # the skip half of the concat buffer is untouched
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_bifpn_fuse_vs_torch(mode):
+    torch, call, ptr = _setup()
+    dev = torch.device("cuda:0")
+    B, H, W, C = 2, 6, 10, 128
+    Ha, Wa = {0: (H, W), 1: (H // 2, W // 2), 2: (2 * H, 2 * W - 1)}[mode]
+    g = torch.Generator(device="cpu").manual_seed(mode)
+    a = torch.randn(B, Ha, Wa, C, generator=g).to(torch.bfloat16).to(dev)
+    bcat = torch.randn(B, H, W, 2 * C, generator=g).to(torch.bfloat16).to(dev)   # b lives in a concat slot
+    c = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(dev)
+    w1, w2, w3 = 0.31, 0.42, 0.27
+    denom = w1 + w2 + w3 + 1e-4
+    out = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=dev)
+    call("be_op_bifpn_fuse", None, ptr(a), C, mode, Ha, Wa, ptr(bcat[..., C:]), 2 * C, ptr(c), C,
+         w1, w2, w3, denom, B, H, W, C, ptr(out), C, None)
+    torch.cuda.synchronize()
+    an = a.float().permute(0, 3, 1, 2)
+    if mode == 1:
+        an = torch.nn.functional.interpolate(an, scale_factor=2.0, mode="nearest")
+    elif mode == 2:
+        an = torch.nn.functional.max_pool2d(an, 3, 2, 1)
+    ref = (w1 * an.permute(0, 2, 3, 1) + w2 * bcat[..., C:].float() + w3 * c.float()) / denom
+    assert float((out.float() - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 1e-3
