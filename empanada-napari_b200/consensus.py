@@ -99,6 +99,25 @@ def merge_clusters(G):
     return H
 
 
+def component_subgraph(members, edges, n_nodes):
+    """The graph `G.subgraph(comp)` of the reference's full instance graph G (consensus.py:427-431)
+    for one connected component, rebuilt from tables with IDENTICAL container orders - cluster ids
+    depend on them. members: ascending node ids; edges: (a, b, iou, overlap) in G's edge-insertion
+    order; n_nodes: len(G). Adjacency lists keep edge-insertion order; nodes come in the iteration
+    order of the set networkx builds for the view (the BFS set of `connected_components`,
+    re-inserted by `show_nodes`) when that set is less than half of G (FilterAtlas), else ascending."""
+    g0 = nx.Graph()
+    g0.add_nodes_from(members)
+    g0.add_edges_from((a, b) for a, b, _, _ in edges)
+    comp_set = next(nx.connected_components(g0))
+    node_seq = list(set(v for v in comp_set)) if 2 * len(comp_set) < n_nodes else list(members)
+    sub = nx.Graph()
+    sub.add_nodes_from(node_seq)
+    for a, b, iou, overlap in edges:
+        sub.add_edge(a, b, iou=iou, overlap=overlap)
+    return sub
+
+
 # ------------------------------------------------------------------------- device helpers
 def _hash_table(cap, dev):
     keys = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -259,11 +278,8 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
             clusters = [members.tolist()]
         else:
-            # same node / adjacency insertion orders as `graph.subgraph(comp)` of the full graph
-            sub = nx.Graph()
-            sub.add_nodes_from(members.tolist())
-            for k in edge_order[edge_start[ci]:edge_start[ci + 1]]:
-                sub.add_edge(int(ea[k]), int(eb[k]), iou=float(eiou[k]), overlap=int(eit[k]))
+            eidx = edge_order[edge_start[ci]:edge_start[ci + 1]]
+            sub = component_subgraph(members.tolist(), [(int(ea[k]), int(eb[k]), float(eiou[k]), int(eit[k])) for k in eidx], n_nodes)
             cg = merge_clusters(create_graph_of_clusters(sub, cluster_iou_thr))
             clusters = [list(cg.nodes[node]["cluster"]) for node in cg.nodes]
         for cluster in clusters:
@@ -409,16 +425,16 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
         s, r = st_s[a:b], ln_s[a:b]
         extra = hv[hb[fid - 1]:hb[fid]]
         if len(extra):
+            # join touching / overlapping ranges (array_utils.py:659-752 `_join_ranges`)
             rng = np.concatenate([np.stack([s, s + r], 1), np.stack([extra, extra + 1], 1)])
             rng = rng[np.argsort(rng[:, 0], kind="stable")]
-            joined = [list(rng[0])]
-            for s0, e0 in rng[1:]:
-                if s0 <= joined[-1][1]:
-                    joined[-1][1] = max(joined[-1][1], e0)
-                else:
-                    joined.append([s0, e0])
-            joined = np.array(joined, dtype=np.int64)
-            s, r = joined[:, 0], joined[:, 1] - joined[:, 0]
+            st_, en_ = rng[:, 0], rng[:, 1]
+            reach = np.maximum.accumulate(en_)
+            head = np.ones(len(st_), dtype=bool)
+            head[1:] = st_[1:] > reach[:-1]
+            hidx = np.flatnonzero(head)
+            s = st_[hidx]
+            r = np.maximum.reduceat(en_, hidx) - s
         instances[fid] = {"box": final_boxes[fid], "starts": s, "runs": r}
     _mark('runs + instances dict')
     return out, instances

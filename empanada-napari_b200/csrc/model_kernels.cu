@@ -27,6 +27,11 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { f[2 * i] = __bfloat162float(h[i].x); f[2 * i + 1] = __bfloat162float(h[i].y); }
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 v;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -107,7 +112,7 @@ constexpr int STY = 2 * SPY + 1, STX = 2 * SPX + 1;      // 17 x 33 conv1 tile
 constexpr int SIH = 2 * STY + 5, SIW = 2 * STX + 5;      // 39 x 71 input patch
 constexpr int SIWP = 72;
 constexpr int SSTRIP = 11;
-constexpr int stem_pool_smem_bytes() { return STY * STX * 32 * 4 + 49 * 64 * 4 + SIH * SIWP * 4; }
+constexpr int stem_pool_smem_bytes() { return STY * STX * 32 * 4 + 49 * 64 * 4 + SIH * SIWP * 8; }
 __global__ void __launch_bounds__(256, 2)
 stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long stride_y,
                  long long stride_x, int s0, int h, int w, int H, int W, float mean255, float den,
@@ -116,7 +121,9 @@ stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long 
   extern __shared__ __align__(16) uint8_t sp_smem[];
   uint32_t* tile = reinterpret_cast<uint32_t*>(sp_smem);           // [STY*STX][32] bf16x2
   float* ws = reinterpret_cast<float*>(tile + STY * STX * 32);     // [49][64]
-  float* patch = ws + 49 * 64;                                     // [SIH][SIWP]
+  // every input value is stored twice, (v, v): one broadcast 8-byte load yields the packed
+  // multiplicand of an FFMA2 (two channels per lane) without a register move
+  float2* patch = reinterpret_cast<float2*>(ws + 49 * 64);         // [SIH][SIWP]
   const int b = blockIdx.z;
   const int py0 = blockIdx.y * SPY, px0 = blockIdx.x * SPX;
   const int Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4;
@@ -130,7 +137,7 @@ stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long 
     float v = 0.0f;
     if (px < SIW && y >= 0 && y < h && x >= 0 && x < w)
       v = __fmul_rn(__fsub_rn(static_cast<float>(src[y * stride_y + x * stride_x]), mean255), den);
-    patch[i] = v;
+    patch[i] = make_float2(v, v);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -138,25 +145,22 @@ stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long 
   constexpr int NSTRIP = STY * (STX / SSTRIP);
   for (int j = warp; j < NSTRIP; j += 8) {
     const int ly = j / (STX / SSTRIP), lx0 = (j - ly * (STX / SSTRIP)) * SSTRIP;
-    float acc[SSTRIP][2];
+    float2 acc[SSTRIP];   // packed fp32 FMAs (FFMA2): both channels of the lane per instruction
 #pragma unroll
-    for (int i = 0; i < SSTRIP; ++i) { acc[i][0] = 0.0f; acc[i][1] = 0.0f; }
+    for (int i = 0; i < SSTRIP; ++i) acc[i] = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int r = 0; r < 7; ++r) {
       float2 wr[7];
 #pragma unroll
       for (int t = 0; t < 7; ++t) wr[t] = *reinterpret_cast<const float2*>(ws + (r * 7 + t) * 64 + 2 * lane);
-      float pv[2 * SSTRIP + 6];
-      const float2* prow = reinterpret_cast<const float2*>(patch + (2 * ly + r) * SIWP + 2 * lx0);
+      float2 pv[2 * SSTRIP + 5];
+      const float2* prow = patch + (2 * ly + r) * SIWP + 2 * lx0;
 #pragma unroll
-      for (int i = 0; i < SSTRIP + 3; ++i) { const float2 q = prow[i]; pv[2 * i] = q.x; pv[2 * i + 1] = q.y; }
+      for (int i = 0; i < 2 * SSTRIP + 5; ++i) pv[i] = prow[i];
 #pragma unroll
       for (int t = 0; t < 7; ++t) {
 #pragma unroll
-        for (int i = 0; i < SSTRIP; ++i) {
-          acc[i][0] = fmaf(pv[2 * i + t], wr[t].x, acc[i][0]);
-          acc[i][1] = fmaf(pv[2 * i + t], wr[t].y, acc[i][1]);
-        }
+        for (int i = 0; i < SSTRIP; ++i) acc[i] = __ffma2_rn(pv[2 * i + t], wr[t], acc[i]);
       }
     }
     const int sy = sy0 + ly;
@@ -165,7 +169,7 @@ stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long 
       const int sx = sx0 + lx0 + i;
       __nv_bfloat162 o = __floats2bfloat162_rn(0.0f, 0.0f);
       if (sy >= 0 && sy < Ho && sx >= 0 && sx < Wo)
-        o = __floats2bfloat162_rn(fmaxf(acc[i][0] + bb.x, 0.0f), fmaxf(acc[i][1] + bb.y, 0.0f));
+        o = __floats2bfloat162_rn(fmaxf(acc[i].x + bb.x, 0.0f), fmaxf(acc[i].y + bb.y, 0.0f));
       tile[(ly * STX + lx0 + i) * 32 + lane] = *reinterpret_cast<uint32_t*>(&o);
     }
   }
@@ -253,12 +257,11 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch = c0 + 2 * lane;
   // this lane's filter taps (issued first: their latency hides under the patch fill)
-  float w0[K * K], w1[K * K];
+  float2 wk[K * K];
 #pragma unroll
   for (int t = 0; t < K * K; ++t) {
-    float2 ww = make_float2(0.0f, 0.0f);
-    if (ch < C) ww = __ldg(reinterpret_cast<const float2*>(wt + t * C + ch));
-    w0[t] = ww.x; w1[t] = ww.y;
+    wk[t] = make_float2(0.0f, 0.0f);
+    if (ch < C) wk[t] = __ldg(reinterpret_cast<const float2*>(wt + t * C + ch));
   }
   if (up != nullptr && c0 < Cup) {
     const float sy = (H > 1) ? static_cast<float>(Hu - 1) / static_cast<float>(H - 1) : 0.0f;
@@ -319,15 +322,15 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
   }
   __syncthreads();
   const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(patch) + (warp * DW_PX) * (DW_CB / 2) + lane;
-  float acc[K][DW_PX][2];
+  // packed fp32 FMAs (FFMA2: two channels per instruction, same rounding as two fmaf)
+  float2 acc[K][DW_PX];
 #pragma unroll
   for (int pr = 0; pr < PH; ++pr) {
-    float v[DW_PX + K - 1][2];
+    float2 v[DW_PX + K - 1];
 #pragma unroll
     for (int c = 0; c < DW_PX + K - 1; ++c) {
       const uint32_t u = pw32[(pr * PW + c) * (DW_CB / 2)];
-      v[c][0] = __uint_as_float(u << 16);
-      v[c][1] = __uint_as_float(u & 0xffff0000u);
+      v[c] = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
     }
 #pragma unroll
     for (int ry = 0; ry < K; ++ry) {
@@ -336,15 +339,13 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
       const int slot = orow % K;
       if (ry == 0) {
 #pragma unroll
-        for (int px = 0; px < DW_PX; ++px) { acc[slot][px][0] = 0.0f; acc[slot][px][1] = 0.0f; }
+        for (int px = 0; px < DW_PX; ++px) acc[slot][px] = make_float2(0.0f, 0.0f);
       }
 #pragma unroll
       for (int sx2 = 0; sx2 < K; ++sx2) {
 #pragma unroll
-        for (int px = 0; px < DW_PX; ++px) {
-          acc[slot][px][0] = fmaf(v[px + sx2][0], w0[ry * K + sx2], acc[slot][px][0]);
-          acc[slot][px][1] = fmaf(v[px + sx2][1], w1[ry * K + sx2], acc[slot][px][1]);
-        }
+        for (int px = 0; px < DW_PX; ++px)
+          acc[slot][px] = __ffma2_rn(v[px + sx2], wk[ry * K + sx2], acc[slot][px]);
       }
     }
     const int done = pr - (K - 1);
@@ -357,7 +358,7 @@ dwconv_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
           const int x = x0 + warp * DW_PX + px;
           if (x < W)
             *reinterpret_cast<__nv_bfloat162*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + ch) =
-                __floats2bfloat162_rn(acc[slot][px][0], acc[slot][px][1]);
+                __floats2bfloat162_rn(acc[slot][px].x, acc[slot][px].y);
         }
       }
     }
@@ -402,7 +403,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, int H, int W, int C,
     sm100::tma_load_4d(base + buf * PATCH_BYTES, &tmap, &bars[buf], c0, tx * DW_TX - PAD, ty * DW_TY - PAD, b);
   };
   if (t < total_tiles && threadIdx.x == 0) issue(t, 0);
-  float w0[K * K], w1[K * K];
+  float2 wk[K * K];
   int prev_c0 = -1;
   for (int it = 0; t < total_tiles; ++it, t += gridDim.x) {
     const int buf = it & 1;
@@ -416,54 +417,54 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, int H, int W, int C,
       prev_c0 = c0;
 #pragma unroll
       for (int k = 0; k < K * K; ++k) {
-        float2 ww = make_float2(0.0f, 0.0f);
-        if (ch < C) ww = __ldg(reinterpret_cast<const float2*>(wt + k * C + ch));
-        w0[k] = ww.x; w1[k] = ww.y;
+        wk[k] = make_float2(0.0f, 0.0f);
+        if (ch < C) wk[k] = __ldg(reinterpret_cast<const float2*>(wt + k * C + ch));
       }
     }
     sm100::mbar_wait(&bars[buf], (it >> 1) & 1);
-    const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(base + buf * PATCH_BYTES) + (warp * DW_PX) * (DW_CB / 2) + lane;
-    float acc[K][DW_PX][2];
+    const uint32_t pw32 = sm100::smem_u32(base + buf * PATCH_BYTES) + ((warp * DW_PX) * (DW_CB / 2) + lane) * 4;
+    // output addressing hoisted out of the row loop: one row pointer, four column predicates
+    bf16* orow = out + ((static_cast<long long>(b) * H + y0) * W + x0 + warp * DW_PX) * out_ld + ch;
+    const long long row_step = static_cast<long long>(W) * out_ld;
+    bool xok[DW_PX];
+#pragma unroll
+    for (int px = 0; px < DW_PX; ++px) xok[px] = (x0 + warp * DW_PX + px < W) && (ch < C);
+    // packed fp32 FMAs (FFMA2: two channels per instruction, same rounding as two fmaf)
+    float2 acc[K][DW_PX];
 #pragma unroll
     for (int pr = 0; pr < PH; ++pr) {
-      float v[DW_PX + K - 1][2];
+      float2 v[DW_PX + K - 1];
 #pragma unroll
       for (int c = 0; c < DW_PX + K - 1; ++c) {
-        const uint32_t u = pw32[(pr * PW + c) * (DW_CB / 2)];
-        v[c][0] = __uint_as_float(u << 16);
-        v[c][1] = __uint_as_float(u & 0xffff0000u);
+        const uint32_t u = lds_u32(pw32 + (pr * PW + c) * (DW_CB * 2));
+        v[c] = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
       }
 #pragma unroll
       for (int ry = 0; ry < K; ++ry) {
-        const int orow = pr - ry;
-        if (orow < 0 || orow >= DW_TY) continue;
-        const int slot = orow % K;
+        const int orw = pr - ry;
+        if (orw < 0 || orw >= DW_TY) continue;
+        const int slot = orw % K;
         if (ry == 0) {
 #pragma unroll
-          for (int px = 0; px < DW_PX; ++px) { acc[slot][px][0] = 0.0f; acc[slot][px][1] = 0.0f; }
+          for (int px = 0; px < DW_PX; ++px) acc[slot][px] = make_float2(0.0f, 0.0f);
         }
 #pragma unroll
         for (int sx2 = 0; sx2 < K; ++sx2) {
 #pragma unroll
-          for (int px = 0; px < DW_PX; ++px) {
-            acc[slot][px][0] = fmaf(v[px + sx2][0], w0[ry * K + sx2], acc[slot][px][0]);
-            acc[slot][px][1] = fmaf(v[px + sx2][1], w1[ry * K + sx2], acc[slot][px][1]);
-          }
+          for (int px = 0; px < DW_PX; ++px)
+            acc[slot][px] = __ffma2_rn(v[px + sx2], wk[ry * K + sx2], acc[slot][px]);
         }
       }
       const int done = pr - (K - 1);
       if (done >= 0) {
         const int slot = done % K;
-        const int y = y0 + done;
-        if (y < H && ch < C) {
+        if (y0 + done < H) {
 #pragma unroll
-          for (int px = 0; px < DW_PX; ++px) {
-            const int x = x0 + warp * DW_PX + px;
-            if (x < W)
-              *reinterpret_cast<__nv_bfloat162*>(out + ((static_cast<long long>(b) * H + y) * W + x) * out_ld + ch) =
-                  __floats2bfloat162_rn(acc[slot][px][0], acc[slot][px][1]);
-          }
+          for (int px = 0; px < DW_PX; ++px)
+            if (xok[px])
+              *reinterpret_cast<__nv_bfloat162*>(orow + px * out_ld) = __floats2bfloat162_rn(acc[slot][px].x, acc[slot][px].y);
         }
+        orow += row_step;
       }
     }
     __syncthreads();  // every warp is done with this buffer before it is refilled

@@ -1,0 +1,37 @@
+"""Host-side consensus graph logic (no GPU): the table-driven component graph must have exactly
+the container orders of the reference's `graph.subgraph(comp)` (networkx view), because cluster
+ids and merge decisions depend on them (empanada/consensus.py:35-142,427-431)."""
+import networkx as nx
+import numpy as np
+
+
+def test_component_subgraph_matches_networkx_view():
+    from empanada_napari_b200.consensus import component_subgraph, create_graph_of_clusters, merge_clusters
+    rng = np.random.default_rng(1)
+    checked = 0
+    for trial in range(150):
+        n = int(rng.integers(5, 400))
+        m = int(rng.integers(3, 300))
+        ea, eb = rng.integers(0, n, m), rng.integers(0, n, m)
+        keep = ea < eb
+        key = np.unique(ea[keep] * 100000 + eb[keep])
+        ea, eb = key // 100000, key % 100000
+        iou, ov = rng.random(len(ea)), rng.integers(1, 300, len(ea))
+        G = nx.Graph()
+        for i in range(n):
+            G.add_node(i)
+        for a, b, i, o in zip(ea, eb, iou, ov):
+            G.add_edge(int(a), int(b), iou=float(i), overlap=int(o))
+        for comp in nx.connected_components(G):
+            if len(comp) < 3:
+                continue
+            view = G.subgraph(comp)
+            edges = [(int(ea[k]), int(eb[k]), float(iou[k]), int(ov[k])) for k in range(len(ea)) if int(ea[k]) in comp]
+            sub = component_subgraph(sorted(comp), edges, n)
+            assert list(sub.nodes) == list(view.nodes)
+            assert [list(sub.adj[v]) for v in sub.nodes] == [list(view.adj[v]) for v in view.nodes]
+            ref = merge_clusters(create_graph_of_clusters(view, 0.75))
+            got = merge_clusters(create_graph_of_clusters(sub, 0.75))
+            assert [sorted(ref.nodes[x]["cluster"]) for x in ref.nodes] == [sorted(got.nodes[x]["cluster"]) for x in got.nodes]
+            checked += 1
+    assert checked > 500

@@ -150,3 +150,36 @@ def test_volume_vs_oracle(seed, shape, noise, ks):
         assert_instances_equal(inst, oinst)
         assert np.array_equal(v, ov)
         assert len(inst) > 0
+
+
+def test_deferred_replay_and_lazy_rle_equal_eager():
+    """The overlapped (worker-thread) matcher replay + lazily extracted per-plane RLE give the
+    same trackers and the same consensus as the eager path and the oracle."""
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import tracker_consensus
+    from empanada_napari_b200.tracking import PendingTracker
+    from oracle import consensus as ocons, pipeline
+    shape, seed, ks = (44, 60, 52), 21, 3
+    vol, lab, _ = syn.make_volume(shape, seed=seed, scale=1.0)
+    heads = {}
+    for axis in range(3):
+        hs = [syn.analytic_heads(np.take(lab, i, axis=axis), pad_to=16) for i in range(shape[axis])]
+        heads[axis] = tuple(np.stack([h[k] for h in hs]).astype(np.float32) for k in range(3))
+    kw = dict(median_kernel_size=ks, nms_kernel=3, confidence_thr=0.5, min_size=30, min_extent=3, batch_size=6)
+    eng, cfg = _engine(heads, save_panoptic=False, **kw)
+    got, want = {}, {}
+    for axis_name in ("xy", "xz", "yz"):      # all three planes first: replays overlap the next plane
+        stack, got[axis_name] = eng.infer_on_axis(vol, axis_name)
+        assert stack is None and isinstance(got[axis_name][0], PendingTracker)
+    for a, axis_name in enumerate(("xy", "xz", "yz")):
+        sem, ctr, off = heads[a]
+        _, want[axis_name] = pipeline.infer_on_axis(vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), cfg,
+                                                    median_kernel_size=ks, nms_kernel=3, confidence_thr=0.5,
+                                                    min_size=30, min_extent=3)
+    for (v, _, inst), (ov, _, oinst) in zip(
+            tracker_consensus(got, None, cfg, pixel_vote_thr=2, min_size=30, min_extent=3, dtype=np.int32),
+            ocons.tracker_consensus(want, cfg, pixel_vote_thr=2, min_size=30, min_extent=3, dtype=np.int32)):
+        assert_instances_equal(inst, oinst)
+        assert np.array_equal(v, ov)
+    for axis_name in ("xy", "xz", "yz"):      # RLE materialised on first access, after consensus
+        assert_instances_equal(got[axis_name][0].instances, want[axis_name][0].instances)

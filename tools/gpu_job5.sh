@@ -1,0 +1,11 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+R=${ROUND_TAG:-r01}
+python -m pytest tests -m gpu -q 2>&1 | tail -8
+python tools/profile_forward.py 16 1024 > gpurun_out/prof_fwd_${R}.txt 2>&1
+head -12 gpurun_out/prof_fwd_${R}.txt; grep -n "dwconv\|bilinear" gpurun_out/prof_fwd_${R}.txt
+B200_EMPANADA_PROFILE=1 python tools/profile_pipeline.py 1024 16 > gpurun_out/phases_${R}.txt 2>&1
+tail -3 gpurun_out/phases_${R}.txt
+python bench.py --steps 2 --warmup 3 > gpurun_out/bench_${R}.json 2> gpurun_out/bench_${R}.err
+tail -c 1500 gpurun_out/bench_${R}.json; tail -5 gpurun_out/bench_${R}.err
