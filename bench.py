@@ -213,12 +213,16 @@ def bench_2d_tiles(pdl, lab_d, n_obj, dev, tiles=64, size=2048, steps=2):
 
     eng.infer_batch(img_d)
     ms_dev = timed(lambda: eng.infer_batch(img_d))
-    eng.infer_batch(img_h).cpu()
-    ms_e2e = timed(lambda: eng.infer_batch(img_h).cpu().numpy())
+    eng.infer_batch_host(img_h)
+    ms_e2e = timed(lambda: eng.infer_batch_host(img_h))
     return {"metric": "2D tiles/sec", "workload": f"MitoNet_v1-class PDL 2D batch inference, {tiles} tiles of {size}x{size}",
             "value": tiles / (ms_dev * 1e-3), "e2e": tiles / (ms_e2e * 1e-3), "unit": "tiles/s",
             "ms_per_batch": ms_dev, "e2e_ms_per_batch": ms_e2e,
             "h2d_bytes_per_step": int(tiles * size * size), "d2h_bytes_per_step": int(tiles * size * size * 4)}
+
+
+def vox_f(S):
+    return float(S) ** 3
 
 
 # ------------------------------------------------------------------------------ main
@@ -367,13 +371,41 @@ def main():
         conv_fl = float(sum(f for (k, f) in plan.op_info if k == "conv"))
         n_conv = sum(1 for (k, _) in plan.op_info if k == "conv")
         achieved = conv_fl / (conv_ms * 1e-3) * 1e-12
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu capture of the same launch list
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))
+            if int(tr.get("batch_slices", 0)) == B and S == 1024:
+                traffic = float(tr["traffic_bytes_per_launch"])
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                 "per_launch": {"launches_per_batch": n_conv, "avg_ms": conv_ms / n_conv,
                                "flops_per_batch": conv_fl, "batch_slices": B},
                 "forward_ms_per_slice": float(ms.sum()) / B,
                 "share_of_forward": conv_ms / float(ms.sum())}
+
+    # live HBM roofline of the post-processing / consensus kernels (24.75 B per pixel
+    # per plane + 16 B per voxel of algorithmic traffic) from CUDA events around every C-ABI call
+    # of one extra, untimed job
+    post_roof = None
+    if rank == 0 and world == 1:
+        from empanada_napari_b200 import _lib as be
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        be.timing_start()
+        job(vol_d, to_host=False)
+        times = be.timing_summary()
+        fwd_names = ("be_oplist_run",)
+        post_ms = sum(ms for k, (n, ms) in times.items() if k not in fwd_names)
+        alg_bytes = 3 * vox_f(S) * 24.75 + vox_f(S) * 16.0
+        post_roof = {"bound": "hbm", "kernels": "all post-processing + consensus entry points (median, centres, grouping, merge, CC, overlap, relabel, vote, RLE)",
+                     "achieved": alg_bytes / (post_ms * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
+                     "frac": alg_bytes / (post_ms * 1e-3) * 1e-9 / hbm, "device_ms_per_step": post_ms,
+                     "algorithmic_bytes_per_step": alg_bytes,
+                     "per_entry_point_ms": {k: round(ms, 3) for k, (n, ms) in sorted(times.items(), key=lambda kv: -kv[1][1]) if k not in fwd_names},
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
 
     tiles2d = None
     if rank == 0 and world == 1 and not args.no_2d:
@@ -400,7 +432,7 @@ def main():
             "e2e": {"value": vox / (ms_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(S ** 3), "d2h_bytes_per_step": d2h},
             "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu,
-            "consensus_instances": n_instances, "tiles_2d": tiles2d,
+            "post_roofline": post_roof, "consensus_instances": n_instances, "tiles_2d": tiles2d,
         }
         print(json.dumps(line))
     if world > 1:

@@ -74,10 +74,38 @@ def declare(name, argtypes, restype=c_int):
         fn.restype = restype
 
 
+# Optional per-entry-point device timing (bench.py's live roofline figures): when TIMING is a
+# dict, every call is bracketed by CUDA events on the current stream; `timing_summary()`
+# synchronises and returns {entry point: (calls, total ms)}. Never enabled inside a timed region.
+TIMING = None
+
+
+def timing_start():
+    global TIMING
+    TIMING = {}
+
+
+def timing_summary():
+    global TIMING
+    import torch
+    torch.cuda.synchronize()
+    out = {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in (TIMING or {}).items()}
+    TIMING = None
+    return out
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise with be_last_error() on failure."""
     L = lib()
-    rc = getattr(L, name)(*args)
+    if TIMING is not None and name != "be_match_replay":
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L, name)(*args)
+        e1.record()
+        TIMING.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(L, name)(*args)
     if rc != 0:
         raise B200EmpanadaError(f"{name} failed ({rc}): {L.be_last_error().decode(errors='replace')}")
     return rc

@@ -370,6 +370,10 @@ class Engine2d:
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0)}
         return out
 
+    def infer_batch_host(self, images):
+        """Host uint8 (n, h, w) in, host int32 (n, h, w) out (page-locked staging buffer)."""
+        return _PINNED.to_host(self.infer_batch(images), np.int32)
+
     def infer(self, image):
         if image.ndim != 2:
             raise ValueError("Engine2d.infer expects a 2-D image")

@@ -183,3 +183,97 @@ def test_deferred_replay_and_lazy_rle_equal_eager():
         assert np.array_equal(v, ov)
     for axis_name in ("xy", "xz", "yz"):      # RLE materialised on first access, after consensus
         assert_instances_equal(got[axis_name][0].instances, want[axis_name][0].instances)
+
+
+def _heads_from_labels(lab, shape):
+    import empanada_napari_b200.synthetic as syn
+    heads = {}
+    for axis in range(3):
+        hs = [syn.analytic_heads(np.take(lab, i, axis=axis), pad_to=16) for i in range(shape[axis])]
+        heads[axis] = tuple(np.stack([h[k] for h in hs]).astype(np.float32) for k in range(3))
+    return heads
+
+
+def test_empty_volume_all_background():
+    """Edge case: no foreground anywhere -> empty trackers, zero volumes, empty consensus."""
+    from empanada_napari_b200.inference import stack_postprocessing, tracker_consensus
+    shape = (12, 40, 33)
+    lab = np.zeros(shape, dtype=np.int32)
+    vol = np.full(shape, 170, dtype=np.uint8)
+    eng, cfg = _engine(_heads_from_labels(lab, shape), median_kernel_size=3, nms_kernel=3, confidence_thr=0.5,
+                       min_size=10, min_extent=2, save_panoptic=True, batch_size=5)
+    trackers = {}
+    for axis_name in ("xy", "xz", "yz"):
+        stack, trs = eng.infer_on_axis(vol, axis_name)
+        assert stack.shape == shape and stack.dtype == np.int32 and not stack.any()
+        assert trs[0].instances == {}
+        trackers[axis_name] = trs
+    for v, name, inst in tracker_consensus(trackers, None, cfg, pixel_vote_thr=2, min_size=10, min_extent=2, dtype=np.uint32):
+        assert inst == {} and v.shape == shape and v.dtype == np.uint32 and not v.any()
+    for v, name, inst in stack_postprocessing({"xy": trackers["xy"]}, None, cfg, min_size=10, min_extent=2, dtype=np.uint32):
+        assert inst == {} and not v.any()
+
+
+def test_stack_shorter_than_median_kernel_raises():
+    """The reference's median queue never emits for stacks shorter than the kernel; here the
+    engine refuses loudly instead of returning an empty stack."""
+    lab = np.zeros((2, 32, 32), dtype=np.int32)
+    eng, cfg = _engine(_heads_from_labels(lab, lab.shape), median_kernel_size=3, confidence_thr=0.5, batch_size=2)
+    with pytest.raises(ValueError):
+        eng.infer_on_axis(np.zeros(lab.shape, dtype=np.uint8), "xy")
+
+
+def test_float_and_non_uint8_inputs_rejected():
+    lab = np.zeros((4, 32, 32), dtype=np.int32)
+    eng, cfg = _engine(_heads_from_labels(lab, lab.shape), median_kernel_size=1, confidence_thr=0.5)
+    with pytest.raises(Exception, match="float"):
+        eng.infer_on_axis(np.zeros(lab.shape, dtype=np.float32), "xy")
+    with pytest.raises(NotImplementedError):
+        eng.infer_on_axis(np.zeros(lab.shape, dtype=np.uint16), "xy")
+
+
+def test_rle_volume_round_trip_properties_256():
+    """Size-independent properties on a 256^3 job (the benchmark's synthetic generator): every
+    tracker's RLE decodes to exactly its dense label volume; consensus ids are 1..n; run lengths
+    sum to the label histogram; the painted consensus volume re-encodes to the same runs."""
+    import torch
+    import bench
+    from empanada_napari_b200 import consensus
+    from empanada_napari_b200.inference import Engine3d, tracker_consensus
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    S = 256
+    dev = torch.device("cuda:0")
+    vol_d, lab_d, n_obj = bench.synth_on_device(S, dev)
+    heads = {a: bench.analytic_heads_on_device(lab_d, a, n_obj) for a in range(3)}
+    cfg = dict(bench.MODEL_CONFIG)
+    cfg["model"] = SyntheticHeadsModel(lambda a, s0, s1: tuple(t[s0:s1] for t in heads[a]))
+    eng = Engine3d(cfg, median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5, batch_size=16)
+    trackers = {name: eng.infer_on_axis(vol_d, name)[1] for name in ("xy", "xz", "yz")}
+
+    def decode(instances, n):
+        out = np.zeros(n, dtype=np.int32)
+        for label, a in instances.items():
+            for s, r in zip(a["starts"], a["runs"]):
+                out[s:s + r] = label
+        return out
+
+    for name, trs in trackers.items():
+        tr = trs[0]
+        dense = tr._b200_dense.cpu().numpy()
+        assert len(tr.instances) > 5
+        if name != "xz":   # xz runs may wrap a 2-D row (tracker.py:80-84; DESIGN.md section 5)
+            assert np.array_equal(decode(tr.instances, S ** 3).reshape(dense.shape), dense), name
+        hist = np.bincount(dense.ravel())
+        for label, a in tr.instances.items():
+            assert int(a["runs"].sum()) == int(hist[label]) == tr._b200_sizes[label], (name, label)
+    for v, _, inst in tracker_consensus(trackers, None, cfg, pixel_vote_thr=2, min_size=500, min_extent=5, dtype=np.int32):
+        assert list(inst.keys()) == sorted(inst.keys()) and len(inst) > 5
+        painted = decode(inst, S ** 3)          # later ids overwrite earlier ones, as fill_volume does
+        assert np.array_equal(painted.reshape(v.shape), v)
+        lab2, st2, ln2 = consensus.extract_runs(torch.from_numpy(v.copy()).to(dev))
+        assert int(ln2.sum().item()) == int((v > 0).sum())
+        for label, a in inst.items():
+            z0, y0, x0, z1, y1, x1 = a["box"]
+            zz, yy, xx = np.nonzero(v == label)
+            if len(zz):
+                assert z0 <= zz.min() and zz.max() < z1 and y0 <= yy.min() and yy.max() < y1 and x0 <= xx.min() and xx.max() < x1
