@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200_empanada.so")
 
 _lib = None
+RUN_CHUNK = 4096  # elements per CTA of be_runs_count / be_runs_write (csrc/cc_kernels.cu)
 
 P = c_void_p  # device or host pointer passed as an integer address
 I, F, D, LL, ULL, SZ = c_int, c_float, c_double, c_longlong, c_ulonglong, c_size_t

@@ -163,7 +163,7 @@ def extract_runs(vol):
     """(labels, starts, lens) of maximal flat-index runs of a (D,H,W) int32 device volume."""
     dev = vol.device
     n = vol.numel()
-    chunks = (n + 1023) // 1024
+    chunks = (n + _lib.RUN_CHUNK - 1) // _lib.RUN_CHUNK
     counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=dev)
     st = stream_ptr()
     call("be_runs_count", ptr(vol), n, n, ptr(counts), st)
@@ -183,7 +183,7 @@ def extract_runs(vol):
 
 # ------------------------------------------------------------------------- consensus
 def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75, bypass=False,
-                                min_size=None, min_extent=None):
+                                min_size=None, min_extent=None, on_volume_ready=None):
     """consensus.py:348-469 followed by the two tracker filters (inference.py:149-150).
     Returns (device int32 volume with the final ids painted, instances dict)."""
     global LAST_LAUNCHES, LAST_PROFILE
@@ -401,6 +401,10 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             sid = torch.from_numpy(keep_lut).to(dev)[side_id.long()]
             flat.scatter_reduce_(0, side_vox, sid, reduce="amax", include_self=True)
 
+    # the painted volume is final from here on: let the caller start its device->host copy while
+    # the run-length tables are extracted
+    if on_volume_ready is not None:
+        on_volume_ready(out)
     # instances: runs of the painted volume (+ hidden voxels of overlapped instances)
     _mark('hist + filters')
     labels, starts, lens = extract_runs(out)

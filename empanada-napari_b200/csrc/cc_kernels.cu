@@ -53,6 +53,10 @@ cc_init_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w, i
   const int p = y * w + x;
   const int v = (x < w) ? cls_val(pan, base + p, lo, hi) : 0;
   const int vl = (x < w && threadIdx.x > 0) ? cls_val(pan, base + p - 1, lo, hi) : 0;
+  if (!__syncthreads_or(v != 0)) {  // nothing of this class in the row chunk
+    if (x < w) L[base + p] = -1;
+    return;
+  }
   const bool head = v != 0 && (threadIdx.x == 0 || vl != v);
   // start index of the run containing this pixel = max head position <= x
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,6 +206,161 @@ __global__ void cc_stats_kernel(const int* __restrict__ ccimg, int h, int w, int
   atomicMax(&t[4], e);
 }
 
+// ------------------------------------------------------------------ quad variants (w % 4 == 0)
+// One thread = four consecutive pixels (16-byte vectors). Component images are mostly background,
+// so every kernel leaves a background quad after its first vector load; passes are fused where
+// the second pass only needs what the first one has in registers.
+__device__ __forceinline__ int4 ldq(const int* p) { return *reinterpret_cast<const int4*>(p); }
+
+// cc_merge over quads: a quad without any pixel of the class has nothing to union
+__global__ void cc_merge_v4_kernel(const int* __restrict__ pan, int* __restrict__ L, int h, int w,
+                                   int lo, int hi) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x0 >= w) return;
+  const long long base = static_cast<long long>(b) * h * w;
+  const int4 q = ldq(pan + base + static_cast<long long>(y) * w + x0);
+  const int vq[4] = {q.x, q.y, q.z, q.w};
+  int* Lb = L + base;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = (vq[j] >= lo && vq[j] < hi && vq[j] != 0) ? vq[j] : 0;
+    if (!v) continue;
+    const int x = x0 + j, p = y * w + x;
+    const bool left_same = (x > 0) && (cls_val(pan, base + p - 1, lo, hi) == v);
+    const bool right_same = (x + 1 < w) && (cls_val(pan, base + p + 1, lo, hi) == v);
+    if (left_same && (x % ROWCHUNK) == 0) unite(Lb, p, p - 1);
+    if (y > 0) {
+      const bool n_same = cls_val(pan, base + p - w, lo, hi) == v;
+      const bool nw_same = (x > 0) && (cls_val(pan, base + p - w - 1, lo, hi) == v);
+      const bool ne_same = (x + 1 < w) && (cls_val(pan, base + p - w + 1, lo, hi) == v);
+      if (n_same) {
+        if (!(left_same && nw_same)) unite(Lb, p, p - w);
+      } else {
+        if (nw_same && !left_same) unite(Lb, p, p - w - 1);
+        if (ne_same && !right_same) unite(Lb, p, p - w + 1);
+      }
+    }
+  }
+}
+
+// path compression fused with the per-chunk root count (CHUNK = 1024 pixels = 256 threads x 4)
+__global__ void __launch_bounds__(CHUNK / 4)
+cc_compress_count_v4_kernel(int* __restrict__ L, int hw, int chunks, int* __restrict__ chunk_counts) {
+  __shared__ int total;
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int p0 = ch * CHUNK + 4 * threadIdx.x;
+  int* Lb = L + static_cast<long long>(b) * hw;
+  if (threadIdx.x == 0) total = 0;
+  int roots = 0;
+  if (p0 < hw) {
+    const int4 q = ldq(Lb + p0);
+    if ((q.x & q.y & q.z & q.w) >= 0) {   // some lane is not -1
+      const int vq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (vq[j] < 0) continue;
+        const int r = find_root(Lb, vq[j]);
+        if (r != vq[j]) Lb[p0 + j] = r;
+        roots += (r == p0 + j);
+      }
+    }
+  }
+  __syncthreads();
+  if (__syncthreads_or(roots != 0)) {
+    if (roots) atomicAdd(&total, roots);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) chunk_counts[b * chunks + ch] = total;
+}
+
+// raster-order ids of the roots; chunks without a root (almost all) return before reading L
+__global__ void __launch_bounds__(CHUNK / 4)
+cc_number_roots_v4_kernel(const int* __restrict__ L, int hw, int chunks,
+                          const int* __restrict__ chunk_offsets, const int* __restrict__ n_cc,
+                          int* __restrict__ out) {
+  typedef cub::BlockScan<int, CHUNK / 4> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int off = chunk_offsets[b * chunks + ch];
+  const int next = (ch + 1 < chunks) ? chunk_offsets[b * chunks + ch + 1] : n_cc[b];
+  if (next == off) return;
+  const int p0 = ch * CHUNK + 4 * threadIdx.x;
+  const long long base = static_cast<long long>(b) * hw;
+  int root[4] = {0, 0, 0, 0};
+  if (p0 < hw) {
+    const int4 q = ldq(L + base + p0);
+    root[0] = q.x == p0; root[1] = q.y == p0 + 1; root[2] = q.z == p0 + 2; root[3] = q.w == p0 + 3;
+  }
+  const int nr = root[0] + root[1] + root[2] + root[3];
+  int ex;
+  Scan(tmp).ExclusiveSum(nr, ex);
+  if (nr) {
+    int id = off + ex + 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (root[j]) out[base + p0 + j] = id++;
+  }
+}
+
+// final ids for every pixel fused with the per-component area / bbox statistics
+__global__ void cc_apply_stats_v4_kernel(const int* __restrict__ L, int* __restrict__ out, int h, int w,
+                                         int cap, int* __restrict__ table) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x0 >= w) return;
+  const long long base = static_cast<long long>(b) * h * w;
+  const long long i0 = base + static_cast<long long>(y) * w + x0;
+  const int4 q = ldq(L + i0);
+  if (q.x < 0 && q.y < 0 && q.z < 0 && q.w < 0) {
+    *reinterpret_cast<int4*>(out + i0) = make_int4(0, 0, 0, 0);
+    return;
+  }
+  const int rq[4] = {q.x, q.y, q.z, q.w};
+  int id[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) id[j] = (rq[j] < 0) ? 0 : out[base + rq[j]];   // roots were numbered already
+  *reinterpret_cast<int4*>(out + i0) = make_int4(id[0], id[1], id[2], id[3]);
+  if (table == nullptr) return;
+  const int before = (x0 > 0 && rq[0] >= 0) ? L[i0 - 1] : -1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (rq[j] < 0 || id[j] > cap) continue;
+    const int pv = (j == 0) ? before : rq[j - 1];
+    if (pv == rq[j]) continue;                  // not a run head (same root <=> same component)
+    const int x = x0 + j;
+    int e = x + 1;
+    const int* Lrow = L + base + static_cast<long long>(y) * w;
+    while (e < w && Lrow[e] == rq[j]) ++e;
+    int* t = table + (static_cast<long long>(b) * cap + (id[j] - 1)) * 5;
+    atomicAdd(&t[0], e - x);
+    atomicMin(&t[1], y);
+    atomicMin(&t[2], x);
+    atomicMax(&t[3], y + 1);
+    atomicMax(&t[4], e);
+  }
+}
+
+// relabel through the LUT, rows contiguous in the destination (xy / xz planes)
+__global__ void relabel_v4_kernel(const int* __restrict__ src, int h, int w, int s0,
+                                  const int* __restrict__ lut, int lut_stride, int* __restrict__ dst,
+                                  long long stride_s, long long stride_y) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x0 >= w) return;
+  const int4 q = ldq(src + (static_cast<long long>(b) * h + y) * w + x0);
+  const int s = s0 + b;
+  int4 o = make_int4(0, 0, 0, 0);
+  if ((q.x | q.y | q.z | q.w) != 0) {
+    const int* l = lut + static_cast<long long>(s) * lut_stride;
+    if (q.x > 0 && q.x < lut_stride) o.x = l[q.x];
+    if (q.y > 0 && q.y < lut_stride) o.y = l[q.y];
+    if (q.z > 0 && q.z < lut_stride) o.z = l[q.z];
+    if (q.w > 0 && q.w < lut_stride) o.w = l[q.w];
+  }
+  *reinterpret_cast<int4*>(dst + s * stride_s + y * stride_y + x0) = o;
+}
+
 // ------------------------------------------------------------------ adjacent-slice overlaps
 // open-addressing table: key = slice(24) | prev_cc(20) | cur_cc(20); val = pixel count
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
@@ -242,6 +401,37 @@ __global__ void pair_overlap_kernel(const int* __restrict__ ccimg, int h, int w,
                                  (static_cast<unsigned long long>(q) << 20) |
                                  static_cast<unsigned long long>(c);
   if (!hash_add(keys, vals, cap_mask, key, e - x)) atomicExch(overflow, 1);
+}
+
+// quad variant: a quad with no labelled pixel in either slice ends after two vector loads
+__global__ void pair_overlap_v4_kernel(const int* __restrict__ ccimg, int h, int w, int s0,
+                                       unsigned long long* __restrict__ keys, int* __restrict__ vals,
+                                       unsigned long long cap_mask, int* __restrict__ overflow) {
+  const int s = s0 + blockIdx.z, y = blockIdx.y;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x0 >= w || s < 1) return;
+  const int* cur = ccimg + (static_cast<long long>(s) * h + y) * w;
+  const int* prv = cur - static_cast<long long>(h) * w;
+  const int4 cq = *reinterpret_cast<const int4*>(cur + x0);
+  if ((cq.x | cq.y | cq.z | cq.w) == 0) return;
+  const int4 pq = *reinterpret_cast<const int4*>(prv + x0);
+  if ((pq.x | pq.y | pq.z | pq.w) == 0) return;
+  const int cv[4] = {cq.x, cq.y, cq.z, cq.w}, pv[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cv[j], q = pv[j];
+    if (c == 0 || q == 0) continue;
+    const int x = x0 + j;
+    const int cl = (j == 0) ? (x > 0 ? cur[x - 1] : 0) : cv[j - 1];
+    const int ql = (j == 0) ? (x > 0 ? prv[x - 1] : 0) : pv[j - 1];
+    if (x > 0 && cl == c && ql == q) continue;  // not the head of this pair run
+    int e = x + 1;
+    while (e < w && cur[e] == c && prv[e] == q) ++e;
+    const unsigned long long key = (static_cast<unsigned long long>(s) << 40) |
+                                   (static_cast<unsigned long long>(q) << 20) |
+                                   static_cast<unsigned long long>(c);
+    if (!hash_add(keys, vals, cap_mask, key, e - x)) atomicExch(overflow, 1);
+  }
 }
 
 // generic compaction of a (key, count) table into dense arrays (order unspecified)
@@ -316,37 +506,84 @@ __device__ __forceinline__ bool is_run_tail(const int* img, long long i, long lo
 }
 // chunk_counts[c] = heads in chunk c, chunk_counts[chunks + 1 + c] = tails in chunk c. The k-th
 // head and the k-th tail (global raster rank) delimit the same run, so no thread walks a run.
-__global__ void __launch_bounds__(CHUNK)
+// One CTA = one chunk of RUN_CHUNK = 4096 elements, one thread = four consecutive elements read
+// as one 16-byte vector; chunks without any label (most of a volume) leave after one vote.
+constexpr int RUN_CHUNK = 4096;
+constexpr int RUN_THREADS = RUN_CHUNK / 4;
+struct Quad { int v[4]; int head[4]; int tail[4]; };
+__device__ __forceinline__ bool load_quad(const int* __restrict__ img, long long i0, long long n,
+                                          long long seg_len, Quad& q) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { q.v[j] = 0; q.head[j] = 0; q.tail[j] = 0; }
+  if (i0 >= n) return false;
+  if (i0 + 4 <= n && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+    const int4 t = __ldg(reinterpret_cast<const int4*>(img + i0));
+    q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+  } else {  // tail of the image, or a view that does not start on a 16-byte boundary
+    for (int j = 0; j < 4 && i0 + j < n; ++j) q.v[j] = img[i0 + j];
+  }
+  if ((q.v[0] | q.v[1] | q.v[2] | q.v[3]) == 0) return false;
+  const int before = (q.v[0] != 0 && i0 > 0) ? img[i0 - 1] : 0;
+  const int after = (q.v[3] != 0 && i0 + 4 < n) ? img[i0 + 4] : 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = i0 + j;
+    if (q.v[j] == 0 || i >= n) continue;
+    const int pv = (j == 0) ? before : q.v[j - 1];
+    const int nv = (j == 3) ? after : q.v[j + 1];
+    q.head[j] = (i % seg_len == 0) || (pv != q.v[j]);
+    q.tail[j] = ((i + 1) % seg_len == 0) || (i + 1 >= n) || (nv != q.v[j]);
+  }
+  return true;
+}
+__global__ void __launch_bounds__(RUN_THREADS)
 runs_count_kernel(const int* __restrict__ img, long long n, long long seg_len, int chunks,
                   int* __restrict__ chunk_counts) {
-  const long long i = blockIdx.x * static_cast<long long>(CHUNK) + threadIdx.x;
-  const bool head = (i < n) && is_run_head(img, i, seg_len);
-  const bool tail = (i < n) && is_run_tail(img, i, n, seg_len);
-  const int ch = __syncthreads_count(head);
-  const int ct = __syncthreads_count(tail);
-  if (threadIdx.x == 0) { chunk_counts[blockIdx.x] = ch; chunk_counts[chunks + 1 + blockIdx.x] = ct; }
+  __shared__ int sh[2];
+  const long long i0 = blockIdx.x * static_cast<long long>(RUN_CHUNK) + 4LL * threadIdx.x;
+  Quad q;
+  const bool any = load_quad(img, i0, n, seg_len, q);
+  if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+  if (!__syncthreads_or(any)) {
+    if (threadIdx.x == 0) { chunk_counts[blockIdx.x] = 0; chunk_counts[chunks + 1 + blockIdx.x] = 0; }
+    return;
+  }
+  int nh = q.head[0] + q.head[1] + q.head[2] + q.head[3];
+  int nt = q.tail[0] + q.tail[1] + q.tail[2] + q.tail[3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { nh += __shfl_xor_sync(0xffffffffu, nh, o); nt += __shfl_xor_sync(0xffffffffu, nt, o); }
+  if ((threadIdx.x & 31) == 0 && (nh | nt)) { atomicAdd(&sh[0], nh); atomicAdd(&sh[1], nt); }
+  __syncthreads();
+  if (threadIdx.x == 0) { chunk_counts[blockIdx.x] = sh[0]; chunk_counts[chunks + 1 + blockIdx.x] = sh[1]; }
 }
 // out_label / out_start by head rank, out_len (= tail - start + 1) by tail rank
-__global__ void __launch_bounds__(CHUNK)
+__global__ void __launch_bounds__(RUN_THREADS)
 runs_write_kernel(const int* __restrict__ img, long long n, long long seg_len, int chunks,
                   const long long* __restrict__ chunk_offsets, int* __restrict__ out_label,
                   long long* __restrict__ out_start, long long* __restrict__ out_end, long long out_cap) {
-  typedef cub::BlockScan<int, CHUNK> Scan;
+  typedef cub::BlockScan<int, RUN_THREADS> Scan;
   __shared__ typename Scan::TempStorage tmp;
-  const long long i = blockIdx.x * static_cast<long long>(CHUNK) + threadIdx.x;
-  const int head = (i < n) && is_run_head(img, i, seg_len);
-  const int tail = (i < n) && is_run_tail(img, i, n, seg_len);
+  const long long i0 = blockIdx.x * static_cast<long long>(RUN_CHUNK) + 4LL * threadIdx.x;
+  Quad q;
+  const bool any = load_quad(img, i0, n, seg_len, q);
+  if (!__syncthreads_or(any)) return;
+  const int nh = q.head[0] + q.head[1] + q.head[2] + q.head[3];
+  const int nt = q.tail[0] + q.tail[1] + q.tail[2] + q.tail[3];
   int exh, ext;
-  Scan(tmp).ExclusiveSum(head, exh);
+  Scan(tmp).ExclusiveSum(nh, exh);
   __syncthreads();
-  Scan(tmp).ExclusiveSum(tail, ext);
-  if (head) {
-    const long long pos = chunk_offsets[blockIdx.x] + exh;
-    if (pos < out_cap) { out_label[pos] = img[i]; out_start[pos] = i; }
+  Scan(tmp).ExclusiveSum(nt, ext);
+  if (nh) {
+    long long pos = chunk_offsets[blockIdx.x] + exh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q.head[j]) { if (pos < out_cap) { out_label[pos] = q.v[j]; out_start[pos] = i0 + j; } ++pos; }
   }
-  if (tail) {
-    const long long pos = chunk_offsets[chunks + 1 + blockIdx.x] + ext;
-    if (pos < out_cap) out_end[pos] = i + 1;
+  if (nt) {
+    long long pos = chunk_offsets[chunks + 1 + blockIdx.x] + ext;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q.tail[j]) { if (pos < out_cap) out_end[pos] = i0 + j + 1; ++pos; }
   }
 }
 
@@ -368,10 +605,25 @@ int be_cc_label(const int* pan, int B, int h, int w, int lo, int hi, int* L, int
   dim3 grid((w + 255) / 256, h, B);
   dim3 grid_rows((w + cc::ROWCHUNK - 1) / cc::ROWCHUNK, h, B);
   cc::cc_init_kernel<<<grid_rows, cc::ROWCHUNK, 0, stream>>>(pan, L, h, w, lo, hi);
+  const int chunks = (hw + cc::CHUNK - 1) / cc::CHUNK;
+  const bool quads = (w % 4 == 0) && (((reinterpret_cast<uintptr_t>(pan) | reinterpret_cast<uintptr_t>(L) |
+                                        reinterpret_cast<uintptr_t>(cc_out)) & 15) == 0);
+  if (quads) {
+    dim3 gridq((w / 4 + 127) / 128, h, B);
+    cc::cc_merge_v4_kernel<<<gridq, 128, 0, stream>>>(pan, L, h, w, lo, hi);
+    cc::cc_compress_count_v4_kernel<<<dim3(chunks, B), cc::CHUNK / 4, 0, stream>>>(L, hw, chunks, chunk_counts);
+    cc::cc_scan_chunks_kernel<<<B, 1024, 0, stream>>>(chunk_counts, chunks, n_cc);
+    cc::cc_number_roots_v4_kernel<<<dim3(chunks, B), cc::CHUNK / 4, 0, stream>>>(L, hw, chunks, chunk_counts, n_cc, cc_out);
+    if (table != nullptr) {
+      const long long tn = static_cast<long long>(B) * cap * 5;
+      cc::cc_table_init_kernel<<<static_cast<unsigned>((tn + 255) / 256), 256, 0, stream>>>(table, tn);
+    }
+    cc::cc_apply_stats_v4_kernel<<<gridq, 128, 0, stream>>>(L, cc_out, h, w, cap, table);
+    return be_check_launch("cc_label kernels (quad)");
+  }
   cc::cc_merge_kernel<<<grid, 256, 0, stream>>>(pan, L, h, w, lo, hi);
   const unsigned nb = static_cast<unsigned>((total + 255) / 256);
   cc::cc_compress_kernel<<<nb, 256, 0, stream>>>(L, total, hw);
-  const int chunks = (hw + cc::CHUNK - 1) / cc::CHUNK;
   cc::cc_count_roots_kernel<<<dim3(chunks, B), cc::CHUNK, 0, stream>>>(L, hw, chunks, chunk_counts);
   cc::cc_scan_chunks_kernel<<<B, 1024, 0, stream>>>(chunk_counts, chunks, n_cc);
   cc::cc_number_roots_kernel<<<dim3(chunks, B), cc::CHUNK, 0, stream>>>(L, hw, chunks, chunk_counts, cc_out);
@@ -395,6 +647,11 @@ int be_pair_overlap(const int* cc_plane, int h, int w, int s0, int s1, unsigned 
                     int* vals, unsigned long long cap, int* overflow, cudaStream_t stream) {
   if (cap & (cap - 1)) return be_set_error("hash capacity must be a power of two");
   if (s1 <= s0) return 0;
+  if (w % 4 == 0 && (reinterpret_cast<uintptr_t>(cc_plane) & 15) == 0) {
+    dim3 gridq((w / 4 + 127) / 128, h, s1 - s0);
+    cc::pair_overlap_v4_kernel<<<gridq, 128, 0, stream>>>(cc_plane, h, w, s0, keys, vals, cap - 1, overflow);
+    return be_check_launch("pair_overlap_v4_kernel");
+  }
   dim3 grid((w + 255) / 256, h, s1 - s0);
   cc::pair_overlap_kernel<<<grid, 256, 0, stream>>>(cc_plane, h, w, s0, keys, vals, cap - 1, overflow);
   return be_check_launch("pair_overlap_kernel");
@@ -418,6 +675,10 @@ int be_relabel(const int* cc_batch, int B, int h, int w, int s0, const int* lut,
     dim3 grid((w + 31) / 32, h, (B + 31) / 32);
     cc::relabel_yz_kernel<<<grid, dim3(32, 8), 0, stream>>>(cc_batch, h, w, s0, B, lut, lut_stride,
                                                             dst, stride_y, static_cast<int>(stride_x));
+  } else if (stride_x == 1 && w % 4 == 0 && stride_s % 4 == 0 && stride_y % 4 == 0 &&
+             ((reinterpret_cast<uintptr_t>(cc_batch) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    dim3 gridq((w / 4 + 127) / 128, h, B);
+    cc::relabel_v4_kernel<<<gridq, 128, 0, stream>>>(cc_batch, h, w, s0, lut, lut_stride, dst, stride_s, stride_y);
   } else {
     dim3 grid((w + 255) / 256, h, B);
     cc::relabel_kernel<<<grid, 256, 0, stream>>>(cc_batch, h, w, s0, lut, lut_stride, dst, stride_s,
@@ -431,8 +692,8 @@ int be_relabel(const int* cc_batch, int B, int h, int w, int s0, const int* lut,
 // chunk_counts: [2 * (chunks + 1)] int32 (heads then tails; entry `chunks` of each half unused)
 int be_runs_count(const int* img, long long n, long long seg_len, int* chunk_counts,
                   cudaStream_t stream) {
-  const unsigned chunks = static_cast<unsigned>((n + cc::CHUNK - 1) / cc::CHUNK);
-  cc::runs_count_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, static_cast<int>(chunks), chunk_counts);
+  const unsigned chunks = static_cast<unsigned>((n + cc::RUN_CHUNK - 1) / cc::RUN_CHUNK);
+  cc::runs_count_kernel<<<chunks, cc::RUN_THREADS, 0, stream>>>(img, n, seg_len, static_cast<int>(chunks), chunk_counts);
   return be_check_launch("runs_count_kernel");
 }
 
@@ -453,8 +714,8 @@ int be_scan_i32_to_i64(const int* counts, long long* offsets, long long n, void*
 int be_runs_write(const int* img, long long n, long long seg_len, const long long* chunk_offsets,
                   int* out_label, long long* out_start, long long* out_end, long long out_cap,
                   cudaStream_t stream) {
-  const unsigned chunks = static_cast<unsigned>((n + cc::CHUNK - 1) / cc::CHUNK);
-  cc::runs_write_kernel<<<chunks, cc::CHUNK, 0, stream>>>(img, n, seg_len, static_cast<int>(chunks),
+  const unsigned chunks = static_cast<unsigned>((n + cc::RUN_CHUNK - 1) / cc::RUN_CHUNK);
+  cc::runs_write_kernel<<<chunks, cc::RUN_THREADS, 0, stream>>>(img, n, seg_len, static_cast<int>(chunks),
                                                           chunk_offsets, out_label, out_start, out_end, out_cap);
   return be_check_launch("runs_write_kernel");
 }

@@ -299,6 +299,48 @@ __global__ void write_pan_kernel(const uint8_t* __restrict__ hard, const int* __
   pan[(static_cast<long long>(b) * h + y) * w + x] = v;
 }
 
+// Quad variants (W % 4 == 0, w % 4 == 0): one thread = four pixels of a row, `hard` read as one
+// 32-bit word. Slices are mostly background, so most quads end after that single load (flags) or
+// after one 16-byte store of void labels (pan).
+__global__ void merge_flags_v4_kernel(const uint8_t* __restrict__ hard, const int* __restrict__ cells4,
+                                      int H, int W, int scale, int cap, int* __restrict__ present) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x0 >= W) return;
+  const long long hw = static_cast<long long>(H) * W;
+  const uint32_t hq = __ldg(reinterpret_cast<const uint32_t*>(hard + b * hw + static_cast<long long>(y) * W + x0));
+  if (hq == 0) return;
+  const int w4 = W / scale;
+  const int* crow = cells4 + (static_cast<long long>(b) * (H / scale) + y / scale) * w4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (((hq >> (8 * j)) & 0xff) == 0) continue;
+    const int id = crow[(x0 + j) / scale];
+    if (id > 0) present[static_cast<long long>(b) * (cap + 1) + id] = 1;
+  }
+}
+__global__ void write_pan_v4_kernel(const uint8_t* __restrict__ hard, const int* __restrict__ cells4,
+                                    const int* __restrict__ newid, int H, int W, int h, int w,
+                                    int scale, int cap, int void_label, int* __restrict__ pan) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x0 >= w) return;
+  const long long hw = static_cast<long long>(H) * W;
+  const uint32_t hq = __ldg(reinterpret_cast<const uint32_t*>(hard + b * hw + static_cast<long long>(y) * W + x0));
+  int v[4] = {void_label, void_label, void_label, void_label};
+  if (hq != 0) {
+    const int w4 = W / scale;
+    const int* crow = cells4 + (static_cast<long long>(b) * (H / scale) + y / scale) * w4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (((hq >> (8 * j)) & 0xff) == 0) continue;
+      const int id = crow[(x0 + j) / scale];
+      if (id > 0) v[j] = newid[static_cast<long long>(b) * (cap + 1) + id];
+    }
+  }
+  *reinterpret_cast<int4*>(pan + (static_cast<long long>(b) * h + y) * w + x0) = make_int4(v[0], v[1], v[2], v[3]);
+}
+
 }  // namespace post
 
 // ------------------------------------------------------------------------------ launchers
@@ -361,12 +403,24 @@ int be_merge_pan(const uint8_t* hard, const int* cells4, int B, int H, int W, in
   cudaError_t e = cudaMemsetAsync(present, 0, sizeof(int) * static_cast<size_t>(B) * (cap + 1), stream);
   if (e != cudaSuccess) return be_set_error(cudaGetErrorString(e));
   // flags over the PADDED extent (H x W), pan over the cropped extent (h x w)
-  dim3 gridp((W + 255) / 256, H, B);
-  post::merge_flags_kernel<<<gridp, 256, 0, stream>>>(hard, cells4, B, H, W, H, W, scale, cap, present);
+  const bool quads = (W % 4 == 0) && (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(hard) & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(pan) & 15) == 0);
+  if (quads) {
+    dim3 gridp((W / 4 + 127) / 128, H, B);
+    post::merge_flags_v4_kernel<<<gridp, 128, 0, stream>>>(hard, cells4, H, W, scale, cap, present);
+  } else {
+    dim3 gridp((W + 255) / 256, H, B);
+    post::merge_flags_kernel<<<gridp, 256, 0, stream>>>(hard, cells4, B, H, W, H, W, scale, cap, present);
+  }
   post::rank_ids_kernel<<<B, 1024, 0, stream>>>(present, cap, label_divisor, class_id);
-  dim3 grid((w + 255) / 256, h, B);
-  post::write_pan_kernel<<<grid, 256, 0, stream>>>(hard, cells4, present, H, W, h, w, scale, cap,
-                                                   void_label, pan);
+  if (quads) {
+    dim3 grid((w / 4 + 127) / 128, h, B);
+    post::write_pan_v4_kernel<<<grid, 128, 0, stream>>>(hard, cells4, present, H, W, h, w, scale, cap, void_label, pan);
+  } else {
+    dim3 grid((w + 255) / 256, h, B);
+    post::write_pan_kernel<<<grid, 256, 0, stream>>>(hard, cells4, present, H, W, h, w, scale, cap,
+                                                     void_label, pan);
+  }
   return be_check_launch("merge_pan kernels");
 }
 

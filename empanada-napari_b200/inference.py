@@ -386,6 +386,7 @@ class _PinnedPool:
 
     def __init__(self):
         self.bufs = {}
+        self.stream = None
 
     def to_host(self, vol_d, dtype):
         import sys
@@ -404,6 +405,33 @@ class _PinnedPool:
             self.bufs[key] = entry
         entry[0].copy_(src, non_blocking=False)
         return entry[1].view(view_as)
+
+    def start(self, vol_d, dtype):
+        """Asynchronous form: enqueues the copy on a side stream (ordered after the work already
+        queued on the current stream) and returns a handle for `finish`."""
+        import sys
+        dtype = np.dtype(dtype)
+        if not (dtype.itemsize == 4 and dtype.kind in "iu"):
+            return None
+        key = (tuple(vol_d.shape), str(vol_d.dtype))
+        entry = self.bufs.get(key)
+        if entry is not None and sys.getrefcount(entry[1]) > 2:
+            entry = None
+        if entry is None:
+            host = torch.empty(vol_d.shape, dtype=vol_d.dtype, pin_memory=True)
+            entry = (host, host.numpy())
+            self.bufs[key] = entry
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            entry[0].copy_(vol_d, non_blocking=True)
+        return (entry, dtype, vol_d)
+
+    def finish(self, handle):
+        entry, dtype, _keepalive = handle
+        self.stream.synchronize()
+        return entry[1].view(dtype)
 
 
 _PINNED = _PinnedPool()
@@ -427,12 +455,21 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
         if class_id not in thing_list:
             _unsupported("semantic (stuff) class consensus")
         out = InstanceTracker(class_id, class_trackers[0].label_divisor, shape3d, "xy")
+        pending = []
+        # the device->host copy of the painted volume overlaps the extraction of the RLE tables
+        hook = (lambda v: pending.append(_PINNED.start(v, dtype))) if to_host else None
         vol_d, instances = consensus.merge_objects_from_trackers(
-            class_trackers, pixel_vote_thr, cluster_iou_thr, allow_one_view, min_size, min_extent)
+            class_trackers, pixel_vote_thr, cluster_iou_thr, allow_one_view, min_size, min_extent,
+            on_volume_ready=hook)
         out.instances = instances
         tracker_consensus.last_launches = consensus.LAST_LAUNCHES
         # `to_host=False` (not in the reference signature) leaves the painted volume on the GPU
-        vol = _PINNED.to_host(vol_d, dtype) if to_host else vol_d
+        if not to_host:
+            vol = vol_d
+        elif pending and pending[0] is not None:
+            vol = _PINNED.finish(pending[0])
+        else:
+            vol = _PINNED.to_host(vol_d, dtype)
         yield vol, class_name, out.instances
 
 

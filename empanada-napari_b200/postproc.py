@@ -184,7 +184,7 @@ def _extract_runs(img, seg_len):
     Returns device tensors (labels int32, starts int64, lens int32) in raster order."""
     dev = img.device
     n = img.numel()
-    chunks = (n + 1023) // 1024
+    chunks = (n + _lib.RUN_CHUNK - 1) // _lib.RUN_CHUNK
     counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=dev)
     st = stream_ptr()
     call("be_runs_count", ptr(img), n, seg_len, ptr(counts), st)
