@@ -35,6 +35,7 @@ _SIGNATURES = {
     "be_scan_i32_to_i64": ([P, P, LL, P, SZ, POINTER(SZ), P], I),
     "be_runs_write": ([P, LL, LL, P, P, P, P, LL, P], I),
     "be_sort_runs": ([P, P, P, P, I, P, SZ, POINTER(SZ), P], I),
+    "be_up4": ([P, I, I, I, P, P], I),
     # consensus_kernels.cu
     "be_plane_pairs": ([P, P, P, P, P, P, I, I, I, LL, I, P, P, ULL, P, P], I),
     "be_vote_stats": ([P, P, P, P, P, P, I, I, I, LL, I, P, P, I, P, P, P, ULL, P, P], I),

@@ -527,34 +527,41 @@ __global__ void bifpn_fuse_kernel(const bf16* __restrict__ a, long long a_ld, in
 }
 
 // ------------------------------------------------------------------ bilinear, align_corners=True
-__global__ void bilinear_kernel(const bf16* __restrict__ in, long long in_ld, int B, int Hi, int Wi,
-                                int C, bf16* __restrict__ out, long long out_ld, int out_coff,
-                                int Ho, int Wo) {
-  const int cg = C / 8;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
-  if (i >= total) return;
-  const int g = static_cast<int>(i % cg);
-  long long pix = i / cg;
-  const int ox = static_cast<int>(pix % Wo); pix /= Wo;
-  const int oy = static_cast<int>(pix % Ho);
-  const int b = static_cast<int>(pix / Ho);
+// CTA = 32 output pixels of one row; 8 lanes cover 64 channels of a pixel with 16-byte vectors
+// (128 contiguous bytes per pixel per step) and walk over the channel groups, so the
+// interpolation weights and source offsets are computed once per pixel, not once per vector.
+__global__ void __launch_bounds__(256)
+bilinear_kernel(const bf16* __restrict__ in, long long in_ld, int B, int Hi, int Wi,
+                int C, bf16* __restrict__ out, long long out_ld, int out_coff,
+                int Ho, int Wo) {
+  const int b = blockIdx.z, oy = blockIdx.y;
+  const int ox = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int lane8 = threadIdx.x & 7;
+  if (ox >= Wo) return;
+  (void)B;
   const float sy = (Ho > 1) ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.0f;
   const float sx = (Wo > 1) ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.0f;
   const float fy = sy * oy, fx = sx * ox;
   const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
   const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
   const float ly = fy - y0, lx = fx - x0;
-  const bf16* base = in + static_cast<long long>(b) * Hi * Wi * in_ld + g * 8;
-  float a[8], c[8], d[8], e[8], o[8];
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x0) * in_ld), a);
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * Wi + x1) * in_ld), c);
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x0) * in_ld), d);
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * Wi + x1) * in_ld), e);
+  const bf16* base = in + static_cast<long long>(b) * Hi * Wi * in_ld;
+  const bf16* p00 = base + (static_cast<long long>(y0) * Wi + x0) * in_ld;
+  const bf16* p01 = base + (static_cast<long long>(y0) * Wi + x1) * in_ld;
+  const bf16* p10 = base + (static_cast<long long>(y1) * Wi + x0) * in_ld;
+  const bf16* p11 = base + (static_cast<long long>(y1) * Wi + x1) * in_ld;
+  bf16* op = out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * out_ld + out_coff;
+  for (int g = lane8; g < C / 8; g += 8) {
+    float a[8], c[8], d[8], e[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p00 + g * 8)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p01 + g * 8)), c);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p10 + g * 8)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p11 + g * 8)), e);
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
-  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * out_ld + out_coff + g * 8) = pack8(o);
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.0f - ly) * ((1.0f - lx) * a[j] + lx * c[j]) + ly * ((1.0f - lx) * d[j] + lx * e[j]);
+    *reinterpret_cast<uint4*>(op + g * 8) = pack8(o);
+  }
 }
 
 // ------------------------------------------------------------------ ASPP image-pool branch
@@ -616,6 +623,34 @@ __global__ void up2_kernel(const float* __restrict__ in, int B, int h, int w, fl
   const float* p = in + static_cast<long long>(b) * h * w;
   out[i] = (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) +
            ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+}
+
+// bilinear x4, align_corners=True on planar fp32 maps: `Interpolate2d(4, 'bilinear',
+// align_corners=True)` applied to ctr_hmp / offsets when `interpolate_ins` is set
+// (quantization/panoptic_deeplab.py:233-234, blocks.py:74-92). One thread = 4 output pixels of a row.
+__global__ void up4_kernel(const float* __restrict__ in, int planes, int h, int w, float* __restrict__ out) {
+  const int Ho = 4 * h, Wo = 4 * w;
+  const int pl = blockIdx.z, oy = blockIdx.y;
+  const int ox0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (ox0 >= Wo) return;
+  (void)planes;
+  const float sy = (Ho > 1) ? static_cast<float>(h - 1) / static_cast<float>(Ho - 1) : 0.0f;
+  const float sx = (Wo > 1) ? static_cast<float>(w - 1) / static_cast<float>(Wo - 1) : 0.0f;
+  const float fy = sy * oy;
+  const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, h - 1);
+  const float ly = fy - y0;
+  const float* p0 = in + (static_cast<long long>(pl) * h + y0) * w;
+  const float* p1 = in + (static_cast<long long>(pl) * h + y1) * w;
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float fx = sx * (ox0 + j);
+    const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, w - 1);
+    const float lx = fx - x0;
+    o[j] = (1.f - ly) * ((1.f - lx) * __ldg(p0 + x0) + lx * __ldg(p0 + x1)) +
+           ly * ((1.f - lx) * __ldg(p1 + x0) + lx * __ldg(p1 + x1));
+  }
+  *reinterpret_cast<float4*>(out + (static_cast<long long>(pl) * Ho + oy) * Wo + ox0) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // top-k of uncertainty = -|x|  <=>  k smallest |x|. 3-pass radix select (11/11/10 bits) on the
@@ -883,8 +918,9 @@ int be_bifpn_fuse(const __nv_bfloat16* a, long long a_ld, int mode, int Ha, int 
 }
 int be_bilinear(const __nv_bfloat16* in, long long in_ld, int B, int Hi, int Wi, int C,
                 __nv_bfloat16* out, long long out_ld, int out_coff, int Ho, int Wo, cudaStream_t st) {
-  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
-  mk::bilinear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, in_ld, B, Hi, Wi, C, out, out_ld, out_coff, Ho, Wo);
+  if (C % 8 || in_ld % 8 || out_ld % 8 || out_coff % 8) return be_set_error("bilinear: channel counts / strides must be multiples of 8");
+  dim3 grid((Wo + 31) / 32, Ho, B);
+  mk::bilinear_kernel<<<grid, 256, 0, st>>>(in, in_ld, B, Hi, Wi, C, out, out_ld, out_coff, Ho, Wo);
   return be_check_launch("bilinear_kernel");
 }
 // bias_out[b][n] = bias_proj[n] + sum_j Wproj_pool[n][j] * relu(sum_c Wpool[j][c] * mean_pix(in[b,:,c]))
@@ -897,6 +933,12 @@ int be_aspp_pool_bias(const __nv_bfloat16* in, int B, int HW, int C, const float
   mk::gemv_relu_kernel<<<dim3((Cmid + 7) / 8, B), 256, 0, st>>>(w_pool, pooled, C, Cmid, 1, nullptr, mid);
   mk::gemv_relu_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(w_proj_pool, mid, Cmid, N, 0, bias_proj, bias_out);
   return be_check_launch("aspp_pool_bias kernels");
+}
+int be_up4(const float* in, int planes, int h, int w, float* out, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(out) & 15) return be_set_error("up4: output must be 16-byte aligned");
+  dim3 grid((w + 127) / 128, 4 * h, planes);
+  mk::up4_kernel<<<grid, 128, 0, st>>>(in, planes, h, w, out);
+  return be_check_launch("up4_kernel");
 }
 int be_up2(const float* in, int B, int h, int w, float* out, cudaStream_t st) {
   const long long total = static_cast<long long>(B) * 4 * h * w;

@@ -68,6 +68,18 @@ def _unsupported(name):
         f"{name} is outside the hot path built so far (SURVEY.md section 8f 'next' rows)")
 
 
+def upsample_instance_heads(ctr, off):
+    """`interpolate_ins=True` of the deployed models (fine boundaries): centre heat map and offsets
+    bilinearly upsampled x4 with align_corners=True (quantization/panoptic_deeplab.py:233-234), so
+    that centres are found and pixels grouped at full resolution (engines.py:263-275, step = 1)."""
+    B, h4, w4 = ctr.shape
+    ctr_f = torch.empty((B, 4 * h4, 4 * w4), dtype=torch.float32, device=ctr.device)
+    off_f = torch.empty((B, 2, 4 * h4, 4 * w4), dtype=torch.float32, device=ctr.device)
+    _lib.call("be_up4", _lib.ptr(ctr), B, h4, w4, _lib.ptr(ctr_f), _lib.stream_ptr())
+    _lib.call("be_up4", _lib.ptr(off), 2 * B, h4, w4, _lib.ptr(off_f), _lib.stream_ptr())
+    return ctr_f, off_f
+
+
 class _VolumeCache:
     """Keeps the uint8 volume resident in HBM across the xy/xz/yz passes."""
 
@@ -188,8 +200,6 @@ class Engine3d:
     def _check_supported(self):
         if self.inference_scale != 1:
             _unsupported("inference_scale > 1")
-        if self.fine_boundaries:
-            _unsupported("fine_boundaries")
         if self.label_erosion or self.label_dilation or self.fill_holes_in_segmentation:
             _unsupported("tracker morphology (erode / dilate / fill holes)")
         if len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
@@ -210,7 +220,8 @@ class Engine3d:
         return PlanePost(n, h, w, H, W, ks=self.median_kernel_size, thing_class=self.thing_list[0],
                          label_divisor=self.label_divisor, void_label=self.void_label,
                          nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
-                         confidence_thr=self.confidence_thr, device=self.device)
+                         confidence_thr=self.confidence_thr, device=self.device,
+                         scale=1 if self.fine_boundaries else 4)
 
     def _finish_plane(self, post, axis_name, shape3d, prof=None, defer=False):
         """Everything after the head maps are in: median tail, components, tracker replay,
@@ -278,10 +289,18 @@ class Engine3d:
 
     def _forward_all(self, post, vol_d, axis, n, norms, pf):
         """Model forward over every slice of the plane, heads pushed into the post-processor."""
-        for s0 in range(0, n, self.batch_size):
-            s1 = min(n, s0 + self.batch_size)
+        bs = self.slice_batch(post.H, post.W)
+        for s0 in range(0, n, bs):
+            s1 = min(n, s0 + bs)
             sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            if self.fine_boundaries:
+                ctr, off = upsample_instance_heads(ctr, off)
             post.push_heads(sem, ctr, off, is_prob=False)
+
+    def slice_batch(self, H, W):
+        """Slices per launch list: `batch_size`, capped so that one batch stays near 16 MPixel
+        (activation buffers of one launch list near 10 GB) for large slices."""
+        return max(1, min(self.batch_size, (16 << 20) // max(1, H * W)))
 
     def release(self):
         """Drop the cached device copy of the input volume."""
@@ -332,8 +351,6 @@ class Engine2d:
         """images: uint8 array (n, h, w) -> int32 (n, h, w). One launch sequence for the batch."""
         if self.inference_scale != 1:
             _unsupported("inference_scale > 1")
-        if self.fine_boundaries:
-            _unsupported("fine_boundaries")
         if self.semantic_only or len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
             _unsupported("multi-class / semantic-only models")
         if self.tile_size > 0 and any(s > self.tile_size for s in images.shape[1:]):
@@ -356,12 +373,15 @@ class Engine2d:
         cls = self.thing_list[0]
         post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=self.label_divisor,
                          void_label=0, nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
-                         confidence_thr=self.confidence_thr, device=dev)
+                         confidence_thr=self.confidence_thr, device=dev,
+                         scale=1 if self.fine_boundaries else 4)
         # chunks of ~16 MPixel keep the activation buffers of one launch list near 10 GB
         chunk = max(1, min(n, (16 << 20) // (H * W)))
         for s0 in range(0, n, chunk):
             s1 = min(n, s0 + chunk)
             sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)
+            if self.fine_boundaries:
+                ctr, off = upsample_instance_heads(ctr, off)
             post.push_heads(sem, ctr, off, is_prob=False)
         post.finish_heads()
         # force_connected (inference.py:263-279): pan <- class*div + component id

@@ -3,17 +3,41 @@ NVLink). Replaces the reference's `MultiGPUEngine3d` (empanada_napari/multigpu.p
 round-robins slices over ranks and all_gathers full-resolution `sem` and `instance_cells` on
 every step (patterns.py:226-240, multigpu.py:90-91).
 
-Here each rank runs the network on a CONTIGUOUS slice range of the plane and the head maps are
-gathered once per plane to rank 0 (`dist.gather` into the plane buffers), which runs the
-sequential part (recursive median, tracker replay) and the remaining post-processing.
-Round-1 scope: the conv stack (>90 % of the single-GPU time) is what is sharded; sharding the
-post-processing by slice range with halo exchange is the next step (multi-GPU).
+Here each rank runs the network on a CONTIGUOUS slice range of every plane and the head maps are
+gathered once per plane to that plane's leader rank (`dist.gather`), which runs the sequential
+part (recursive median, tracker replay) and the remaining post-processing; the three planes have
+different leaders, so their post-processing runs concurrently, and rank 0 receives the finished
+label volumes for the consensus. Round-1 scope: the conv stack (90 % of the single-GPU time) is
+what is sharded by slice; sharding the post-processing by slice range with halo exchange is the
+next step.
 """
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from .inference import Engine3d
+from .inference import Engine3d, upsample_instance_heads
+
+_PROFILE = os.environ.get("B200_EMPANADA_PROFILE") == "1"
+
+
+class _Timer:
+    """Per-rank phase times (B200_EMPANADA_PROFILE=1): device-synchronised wall clock."""
+
+    def __init__(self):
+        self.t = {}
+        if _PROFILE:
+            torch.cuda.synchronize()
+        self.t0 = time.perf_counter()
+
+    def mark(self, name):
+        if _PROFILE:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            self.t[name] = self.t.get(name, 0.0) + t1 - self.t0
+            self.t0 = t1
 
 
 def slice_ranges(n, world):
@@ -79,13 +103,17 @@ class DistributedEngine3d(Engine3d):
         ctr = torch.empty((nmax, H // 4, W // 4), dtype=torch.float32, device=dev)
         off = torch.empty((nmax, 2, H // 4, W // 4), dtype=torch.float32, device=dev)
         launches0 = getattr(self.model, "launches", 0)
-        for s0 in range(lo, hi, self.batch_size):
-            s1 = min(hi, s0 + self.batch_size)
+        tm = _Timer()
+        bs = self.slice_batch(H, W)
+        for s0 in range(lo, hi, bs):
+            s1 = min(hi, s0 + bs)
             a, b, c = self.model.forward_slices(vol_d, axis, s0, s1, self.model_config["norms"], pf)
             sem[s0 - lo:s1 - lo].copy_(a)
             ctr[s0 - lo:s1 - lo].copy_(b)
             off[s0 - lo:s1 - lo].copy_(c)
+        tm.mark("forward")
         gathered = [gather_slices_to(t, ranges, self.rank, self.world, leader, self.group) for t in (sem, ctr, off)]
+        tm.mark("gather heads")
         n_launch = getattr(self.model, "launches", 0) - launches0
         trackers = self.create_trackers(shape3d, axis_name)
         if self.rank == leader:
@@ -93,9 +121,14 @@ class DistributedEngine3d(Engine3d):
             for r, (a, b) in enumerate(ranges):
                 for s0 in range(a, b, 64):
                     s1 = min(b, s0 + 64)
-                    post.push_heads(gathered[0][r][s0 - a:s1 - a], gathered[1][r][s0 - a:s1 - a],
-                                    gathered[2][r][s0 - a:s1 - a], is_prob=False)
+                    c_, o_ = gathered[1][r][s0 - a:s1 - a], gathered[2][r][s0 - a:s1 - a]
+                    if self.fine_boundaries:
+                        c_, o_ = upsample_instance_heads(c_.contiguous(), o_.contiguous())
+                    post.push_heads(gathered[0][r][s0 - a:s1 - a], c_, o_, is_prob=False)
             self._pending[axis_name] = (post, shape3d)
+        tm.mark("leader push_heads")
+        if _PROFILE:
+            print(f"[rank {self.rank}] {axis_name} " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
         self.last_stats = {"kernel_launches": n_launch}
         return None, trackers
 
@@ -104,10 +137,16 @@ class DistributedEngine3d(Engine3d):
         all trackers on rank 0 (dense volume + instance table; the per-instance RLE arrays stay on
         the leader). Returns the trackers dict (complete on rank 0)."""
         n_launch = 0
+        tm = _Timer()
+        # a leader that owns several planes (world < 4) runs their matcher replays concurrently on
+        # worker threads while the next plane's component kernels are queued
         for axis_name, (post, shape3d) in list(self._pending.items()):
-            trackers[axis_name] = self._finish_plane(post, axis_name, shape3d)
+            trackers[axis_name] = self._finish_plane(post, axis_name, shape3d, defer=len(self._pending) > 1)
+        for axis_name, (post, shape3d) in list(self._pending.items()):
+            _ = trackers[axis_name][0].instances      # completes a deferred tracker
             n_launch += post.launches
         self._pending = {}
+        tm.mark("leader post-processing")
         self.last_stats = {"kernel_launches": n_launch}
         for axis_name in trackers.keys():
             leader = self.leader_of(axis_name)
@@ -143,4 +182,7 @@ class DistributedEngine3d(Engine3d):
                 tr._b200_sizes = {int(m[0]): int(m[1]) for m in meta}
                 tr._b200_dense = dense
                 tr.finish()
+        tm.mark("ship volumes to rank 0")
+        if _PROFILE:
+            print(f"[rank {self.rank}] finalize " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
         return trackers

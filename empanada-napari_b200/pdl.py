@@ -48,7 +48,7 @@ _lib.declare("be_op_pr_predict", [P, P, I, I, P, P, F, P, I, I, I, P, P])
 
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 # decoder `F.interpolate` + `torch.cat` fused into the depthwise kernel (1) or materialised (0)
-FUSED_UPSAMPLE = os.environ.get("B200_EMPANADA_FUSED_UPSAMPLE", "1") == "1"
+FUSED_UPSAMPLE = os.environ.get("B200_EMPANADA_FUSED_UPSAMPLE", "0") == "1"
 BN_EPS = 1e-5
 
 

@@ -94,9 +94,11 @@ class PlanePost:
         self.launches += 4
         return pan
 
-    def run_cc(self, batch=16):
+    def run_cc(self, batch=None):
         """Connected components + tables for all slices; overlap table between neighbours."""
         N, h, w, d = self.N, self.h, self.w, self.dev
+        if batch is None:   # ~64 MPixel per launch: few, large launches (the kernels are HBM bound)
+            batch = max(1, min(N, (64 << 20) // max(1, h * w)))
         while True:
             self.cc = torch.empty((N, h, w), dtype=torch.int32, device=d)
             self.n_cc = torch.zeros(N, dtype=torch.int32, device=d)

@@ -35,6 +35,19 @@ def smoke():
         if not err < 3e-2:
             raise AssertionError(f"forward mismatch on {name}: rel L2 {err}")
 
+    # (1b) PanopticBiFPN-PointRend (MitoNet_v1_mini architecture, padding factor 128)
+    from .bifpn import BiFPNModel
+    sdb = syn.make_bifpn_state_dict(0)
+    bif = BiFPNModel(sdb, dev)
+    _, ctr_b, off_b = bif.forward_slices(vol_d, 0, 0, 1, norms, 128)
+    xb = post.factor_pad(post.normalize(vol[0], norms["mean"], norms["std"]), 128)[None, None]
+    refb = omodel.bifpn_forward(sdb, torch.from_numpy(xb), 2, False)
+    for got, want, name in ((ctr_b.cpu().numpy(), refb["ctr_hmp"].numpy()[:, 0], "bifpn ctr_hmp"),
+                            (off_b.cpu().numpy(), refb["offsets"].numpy(), "bifpn offsets")):
+        err = np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-12)
+        if not err < 3e-2:
+            raise AssertionError(f"forward mismatch on {name}: rel L2 {err}")
+
     # (2) post-processing + tracking + consensus vs the oracle, bit exact
     heads = {}
     for a in range(3):

@@ -79,6 +79,9 @@ int be_op_aspp_pool_bias(void* list, const void* in, int B, int HW, int C, const
                          int Cmid, const float* w_proj_pool, const float* bias_proj, int N,
                          float* pooled, float* mid, float* bias_out,
                          be_stream st);                            /* decoders/aspp.py:30-48,97-102 */
+/* Interpolate2d(4, bilinear, align_corners=True) of ctr_hmp / offsets for `interpolate_ins`
+ * (fine boundaries; quantization/panoptic_deeplab.py:233-234): planar fp32 [planes][h][w] -> [planes][4h][4w] */
+int be_up4(const float* in, int planes, int h, int w, float* out, be_stream st);
 int be_op_up2(void* list, const float* in, int B, int h, int w, float* out, be_stream st);
 int be_op_topk(void* list, const float* x, int B, int n, int k, unsigned* state, unsigned* hist,
                int* idx_out, be_stream st);                        /* point_rend.py:110-137 */

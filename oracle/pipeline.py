@@ -26,14 +26,16 @@ def take_slice(volume, idx, axis):
 def infer_on_axis(volume, axis_name, heads_fn, model_config, label_divisor=1000,
                   median_kernel_size=3, stuff_area=64, void_label=0, nms_threshold=0.1,
                   nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=4,
-                  save_panoptic=True, dtype=np.int32):
+                  save_panoptic=True, dtype=np.int32, fine_boundaries=False):
+    """`fine_boundaries=True`: `heads_fn` returns FULL-resolution ctr_hmp / offsets (the model's
+    `interpolate_ins=True` output) and pixels are grouped with step 1 (engines.py:263-275)."""
     axis = AXES[axis_name]
     labels = model_config["labels"]
     thing_list = model_config["thing_list"]
     pf = model_config["padding_factor"]
     norms = model_config["norms"]
     eng = post.RenderEnginePost(thing_list, label_divisor, stuff_area, void_label, nms_threshold,
-                                nms_kernel, confidence_thr, median_kernel_size, True)
+                                nms_kernel, confidence_thr, median_kernel_size, not fine_boundaries)
     trackers = [InstanceTracker(l, label_divisor, volume.shape, axis_name) for l in labels]
     matchers = [RLEMatcher(c, label_divisor, 0.25, 0.25) for c in thing_list]
     pan_segs = []
@@ -68,7 +70,7 @@ def _softmax(x):
 
 
 def engine2d_infer(image, heads_fn, model_config, label_divisor=1000, nms_threshold=0.1,
-                   nms_kernel=3, confidence_thr=0.3, stuff_area=64, void_label=0):
+                   nms_kernel=3, confidence_thr=0.3, stuff_area=64, void_label=0, fine_boundaries=False):
     """Engine2d.infer, no tiling, inference_scale 1 (empanada_napari/inference.py:319-325,263-279)."""
     thing_list = model_config["thing_list"]
     norms = model_config["norms"]
@@ -77,7 +79,7 @@ def engine2d_infer(image, heads_fn, model_config, label_divisor=1000, nms_thresh
     sem_logits, ctr, off = heads_fn(0, x)
     sem = post.sigmoid(sem_logits) if sem_logits.shape[0] == 1 else _softmax(sem_logits)
     eng = post.RenderEnginePost(thing_list, label_divisor, stuff_area, void_label, nms_threshold,
-                                nms_kernel, confidence_thr, None, True)
+                                nms_kernel, confidence_thr, None, not fine_boundaries)
     pan = eng(sem, ctr, off, (h, w)).astype(np.int32)
     for label in thing_list:
         lo = label * label_divisor

@@ -277,3 +277,52 @@ def test_rle_volume_round_trip_properties_256():
             zz, yy, xx = np.nonzero(v == label)
             if len(zz):
                 assert z0 <= zz.min() and zz.max() < z1 and y0 <= yy.min() and yy.max() < y1 and x0 <= xx.min() and xx.max() < x1
+
+
+def test_up4_align_corners_vs_torch():
+    """be_up4 == F.interpolate(scale_factor=4, mode='bilinear', align_corners=True) (fp32; the
+    reference applies it inside the model when interpolate_ins=True)."""
+    import torch
+    from empanada_napari_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    for planes, h, w in ((3, 13, 17), (2, 32, 64), (1, 1, 5)):
+        x = torch.randn(planes, h, w, generator=g)
+        out = torch.empty(planes, 4 * h, 4 * w, device=dev)
+        _lib.call("be_up4", _lib.ptr(x.to(dev)), planes, h, w, _lib.ptr(out), _lib.stream_ptr())
+        ref = torch.nn.functional.interpolate(x[None], scale_factor=4.0, mode="bilinear", align_corners=True)[0]
+        assert float((out.cpu() - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
+
+
+def test_fine_boundaries_vs_oracle():
+    """`fine_boundaries=True` (interpolate_ins, grouping step 1): bit-exact against the oracle fed
+    with the same full-resolution centre / offset maps."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import tracker_consensus, upsample_instance_heads
+    from oracle import consensus as ocons, pipeline
+    shape, seed, ks = (28, 48, 40), 41, 3
+    vol, lab, _ = syn.make_volume(shape, seed=seed, scale=1.0)
+    heads = _heads_from_labels(lab, shape)
+    dev = torch.device("cuda:0")
+    full = {}
+    for a in range(3):
+        c, o = upsample_instance_heads(torch.from_numpy(heads[a][1]).to(dev), torch.from_numpy(heads[a][2]).to(dev))
+        full[a] = (heads[a][0], c.cpu().numpy(), o.cpu().numpy())
+    kw = dict(median_kernel_size=ks, nms_kernel=3, confidence_thr=0.5, min_size=30, min_extent=3, batch_size=5)
+    eng, cfg = _engine(heads, save_panoptic=True, fine_boundaries=True, **kw)
+    got, want = {}, {}
+    for a, axis_name in enumerate(("xy", "xz", "yz")):
+        stack, got[axis_name] = eng.infer_on_axis(vol, axis_name)
+        sem, ctr, off = full[a]
+        ostack, want[axis_name] = pipeline.infer_on_axis(
+            vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), cfg, median_kernel_size=ks, nms_kernel=3,
+            confidence_thr=0.5, min_size=30, min_extent=3, fine_boundaries=True)
+        assert_instances_equal(got[axis_name][0].instances, want[axis_name][0].instances)
+        assert np.array_equal(stack, ostack)
+    for (v, _, inst), (ov, _, oinst) in zip(
+            tracker_consensus(got, None, cfg, pixel_vote_thr=2, min_size=30, min_extent=3, dtype=np.int32),
+            ocons.tracker_consensus(want, cfg, pixel_vote_thr=2, min_size=30, min_extent=3, dtype=np.int32)):
+        assert_instances_equal(inst, oinst)
+        assert np.array_equal(v, ov)
+        assert len(inst) > 0
