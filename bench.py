@@ -221,6 +221,47 @@ def bench_2d_tiles(pdl, lab_d, n_obj, dev, tiles=64, size=2048, steps=2):
             "h2d_bytes_per_step": int(tiles * size * size), "d2h_bytes_per_step": int(tiles * size * size * 4)}
 
 
+def bench_mini_tile(lab_d, n_obj, dev, size=1024, steps=10):
+    """BASELINE config C1: MitoNet_v1_mini-class (PanopticBiFPN-PointRend, padding factor 128,
+    nms_kernel 7) 2-D inference on one size x size uint8 tile through Engine2d.infer (host in,
+    host out). Analytic head maps replace the network's heads after the forward pass."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.bifpn import BiFPNModel
+    from empanada_napari_b200.inference import Engine2d
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    if lab_d.shape[1] != size:
+        return None
+    lab2 = lab_d[lab_d.shape[0] // 2][None].contiguous()
+    img_d = (torch.where(lab2 > 0, 70.0, 170.0) + torch.randn(lab2.shape, device=dev) * 8.0).clamp_(0, 255).to(torch.uint8)
+    sem, ctr, off = analytic_heads_on_device(lab2, 0, n_obj, pf=128)
+    net = BiFPNModel(syn.make_bifpn_state_dict(0), dev)
+    cfg = dict(MODEL_CONFIG)
+    cfg["padding_factor"] = 128
+    cfg["model"] = SyntheticHeadsModel(lambda a, s0, s1: (sem[s0:s1], ctr[s0:s1], off[s0:s1]), inner=net)
+    eng = Engine2d(cfg, confidence_thr=0.5, nms_threshold=0.1, nms_kernel=7)
+    img_h = img_d[0].cpu().numpy()
+    for _ in range(3):
+        eng.infer(img_h)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = eng.infer(img_h)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # forward pass alone (device resident)
+    e0.record()
+    for _ in range(steps):
+        net.forward_slices(img_d, 0, 0, 1, NORMS, 128)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"workload": f"MitoNet_v1_mini-class PanopticBiFPN 2D inference, one {size}x{size} tile (Engine2d.infer, host in / host out)",
+            "e2e_ms_per_tile": ms, "tiles_per_s": 1e3 / ms, "forward_ms_per_tile": e0.elapsed_time(e1) / steps,
+            "objects": int(len(np.unique(out)) - 1)}
+
+
 def vox_f(S):
     return float(S) ** 3
 
@@ -247,8 +288,9 @@ def main():
     config = {"workload": workload, "volume": [S, S, S], "median_kernel": 3, "nms_kernel": 3,
               "pixel_vote_thr": 2, "min_size": 500, "min_extent": 5, "slice_batch": args.batch,
               "l2": "inputs larger than L2 (1 GiB volume, >4 GiB of heads per plane)",
-              "parallelism": (f"forward sharded by slice range x{world}; planes post-processed concurrently on "
-                              f"leader ranks; consensus on rank 0") if world > 1 else "single GPU"}
+              "parallelism": (f"every plane sharded by slice range x{world} (network + post-processing; median "
+                              f"wavefront, boundary-overlap and table exchange over NCCL); tracker replay on one "
+                              f"leader rank per plane; consensus on rank 0") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -294,7 +336,8 @@ def main():
     cfg["model"] = SyntheticHeadsModel(heads_fn, inner=pdl)
     kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5,
               batch_size=args.batch)
-    eng = Engine3d(cfg, **kw) if world == 1 else multigpu.DistributedEngine3d(cfg, **kw)
+    multi_cls = multigpu.DistributedEngine3d if os.environ.get("B200_EMPANADA_MULTIGPU") == "gather" else multigpu.ShardedEngine3d
+    eng = Engine3d(cfg, **kw) if world == 1 else multi_cls(cfg, **kw)
     vol_h = vol_d.cpu().numpy()
     launches = {"n": 0}
 
@@ -413,6 +456,8 @@ def main():
         eng.release()
         torch.cuda.empty_cache()
         tiles2d = bench_2d_tiles(pdl, lab_d, n_obj, dev)
+        if tiles2d is not None:
+            tiles2d["mini_tile"] = bench_mini_tile(lab_d, n_obj, dev)
     del lab_d
 
     cpu = None

@@ -186,3 +186,217 @@ class DistributedEngine3d(Engine3d):
         if _PROFILE:
             print(f"[rank {self.rank}] finalize " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
         return trackers
+
+
+def owned_ranges(n, world, mid):
+    """Slice-sharded planes: rank r runs the network on F_r = slice_ranges(n, world)[r] and OWNS
+    (emits, labels, paints) E_r = F_r shifted down by the median latency `mid` - pushing slice t
+    into the recursive median queue emits slice t - mid (engines.py:68-82). Rank 0 starts at 0 and
+    the last rank also owns the unfiltered tail (engines.py:351-361). Returns (F, E) lists."""
+    F = slice_ranges(n, world)
+    E = []
+    for r, (lo, hi) in enumerate(F):
+        e_lo = lo - mid if r > 0 else 0
+        e_hi = hi - mid if r < world - 1 else n
+        E.append((e_lo, e_hi))
+    return F, E
+
+
+def merge_shard_tables(parts, owned):
+    """Leader side: per-rank (n_cc [n_r], table [n_r, cap_r, 5], pair_keys u64, pair_vals) with
+    LOCAL slice indices -> plane-wide tables with absolute slice indices (keys carry the slice in
+    bits 40+)."""
+    cap = max(1, max(int(p[1].shape[1]) for p in parts))
+    n_cc = np.concatenate([p[0] for p in parts]).astype(np.int32)
+    tables = []
+    for p in parts:
+        t = p[1]
+        if t.shape[1] < cap:
+            t = np.concatenate([t, np.zeros((t.shape[0], cap - t.shape[1], 5), dtype=t.dtype)], axis=1)
+        tables.append(t)
+    table = np.concatenate(tables, axis=0).astype(np.int32)
+    keys = np.concatenate([p[2].astype(np.uint64) + (np.uint64(e_lo) << np.uint64(40)) for p, (e_lo, _) in zip(parts, owned)])
+    vals = np.concatenate([p[3] for p in parts]).astype(np.int32)
+    return n_cc, table, keys, vals
+
+
+class ShardedEngine3d(Engine3d):
+    """Engine3d for one process per GPU with the WHOLE per-plane path sharded by slice range
+    (SURVEY.md section 8e): every rank runs the network, centres, grouping, merge, connected
+    components and overlap tables for its own slices; what crosses NVLink is
+
+    * the median queue state ((ks-1) filtered/raw fp32 slices) handed from rank r to r+1 - the
+      recursion makes this a wavefront, but only the cheap median kernel is serialised;
+    * one component-label slice per shard boundary for the cross-boundary overlap table;
+    * the sparse per-slice tables (component areas / boxes, overlap pairs) gathered to the plane's
+      leader, which replays the sequential tracker and broadcasts the (slice, component) -> label
+      table; each rank paints its own slab;
+    * the painted slabs, gathered to rank 0 for the consensus.
+
+    Rank r also runs the network on the `mid` slices before its range so that it holds the
+    instance heads of every slice it owns (no halo exchange for them). Every rank must call
+    `infer_on_axis` for the same planes in the same order and then `finalize(trackers)`.
+    Falls back to `DistributedEngine3d`'s gather scheme when a shard would be shorter than the
+    median kernel."""
+
+    def __init__(self, *args, group=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._pending = {}
+
+    def leader_of(self, axis_name):
+        return (self.axes[axis_name] + 1) % self.world
+
+    def infer_on_axis(self, volume, axis_name):
+        self._check_supported()
+        axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
+        ks = self.median_kernel_size
+        mid = (ks - 1) // 2
+        G, r = self.world, self.rank
+        F, E = owned_ranges(n, G, mid)
+        if min(b - a for a, b in F) < ks + mid or min(b - a for a, b in E) < ks:
+            raise _lib_error(f"plane of {n} slices is too short to shard over {G} ranks with a median kernel of {ks}")
+        (lo, hi), (e_lo, e_hi) = F[r], E[r]
+        c_lo = lo - mid if r > 0 else 0
+        dev = vol_d.device
+        tm = _Timer()
+        launches0 = getattr(self.model, "launches", 0)
+        post = self._make_post(e_hi - e_lo, h, w, H, W)
+        raw = torch.empty((hi - lo, H, W), dtype=torch.float32, device=dev)
+        bs = self.slice_batch(H, W)
+        norms = self.model_config["norms"]
+        for s0 in range(c_lo, hi, bs):
+            s1 = min(hi, s0 + bs)
+            sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            a = max(s0, lo)
+            if a < s1:
+                raw[a - lo:s1 - lo].copy_(sem[a - s0:])
+            a, b = max(s0, e_lo), min(s1, e_hi)
+            if a < b:
+                c_, o_ = ctr[a - s0:b - s0], off[a - s0:b - s0]
+                if self.fine_boundaries:
+                    c_, o_ = upsample_instance_heads(c_.contiguous(), o_.contiguous())
+                post.push_instance(c_, o_, a - e_lo)
+        tm.mark("forward + centres + grouping")
+        # recursive median: wavefront over the ranks (state = the queue after the previous shard)
+        if ks > 1 and r > 0:
+            dist.recv(post.hist, src=r - 1, group=self.group)
+            post.n_hist = ks - 1
+        for i in range(0, hi - lo, 64):
+            j = min(hi - lo, i + 64)
+            post.push_semantic(raw[i:j], (lo + i) - e_lo)
+        if ks > 1 and r < G - 1:
+            dist.send(post.hist, dst=r + 1, group=self.group)
+        if r == G - 1:
+            post.flush_semantic()
+        del raw
+        post.pushed = post.N
+        post.check_centers()
+        tm.mark("median wavefront")
+        post.run_cc()
+        # cross-boundary overlaps: previous shard's last component slice vs this shard's first
+        ops, prev = [], None
+        if r < G - 1:
+            last = post.cc[post.N - 1].contiguous()
+            ops.append(dist.P2POp(dist.isend, last, r + 1, group=self.group))
+        if r > 0:
+            prev = torch.empty((h, w), dtype=torch.int32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, prev, r - 1, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if prev is not None:
+            bk, bv = post.boundary_pairs(prev)
+            post.pair_keys = np.concatenate([post.pair_keys, bk])
+            post.pair_vals = np.concatenate([post.pair_vals, bv])
+        tm.mark("components + tables + boundary overlap")
+        if _PROFILE:
+            print(f"[rank {self.rank}] {axis_name} " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
+        self._pending[axis_name] = (post, shape3d, (F, E))
+        self.last_stats = {"kernel_launches": getattr(self.model, "launches", 0) - launches0 + post.launches}
+        return None, self.create_trackers(shape3d, axis_name)
+
+    def finalize(self, trackers):
+        """Collective: gathers the sparse tables of every plane to its leader, replays the tracker
+        there (the leaders of different planes work concurrently), broadcasts the label tables,
+        paints the local slabs and assembles the dense label volumes on rank 0. Returns the
+        trackers dict (complete on rank 0)."""
+        from .postproc import LazyPlane
+        from .inference import _Async
+        tm = _Timer()
+        G, r = self.world, self.rank
+        names = list(self._pending.keys())
+        jobs = {}
+        for name in names:                      # (1) sparse tables -> leader
+            post, shape3d, (F, E) = self._pending[name]
+            leader = self.leader_of(name)
+            n_cc, table = post.replay_inputs()
+            obj = (n_cc, table, post.pair_keys, post.pair_vals)
+            parts = [None] * G if r == leader else None
+            dist.gather_object(obj, parts, dst=leader, group=self.group)
+            if r == leader:                     # (2) tracker replay on a worker thread
+                merged = merge_shard_tables(parts, E)
+                jobs[name] = _Async(tracking_replay, merged, post.cls, post.div, name, self.merge_iou_thr,
+                                    self.merge_ioa_thr, self.min_size, self.min_extent)
+        tm.mark("gather tables")
+        n_launch = 0
+        for name in names:                      # (3) label tables back, paint the local slab
+            post, shape3d, (F, E) = self._pending[name]
+            leader = self.leader_of(name)
+            payload = [jobs[name].result() if r == leader else None]
+            dist.broadcast_object_list(payload, src=leader, group=self.group)
+            lut_f, kept_labels, kept_boxes, kept_sizes = payload[0]
+            e_lo, e_hi = E[r]
+            D, Hv, Wv = shape3d
+            local_shape = {"xy": (e_hi - e_lo, Hv, Wv), "xz": (D, e_hi - e_lo, Wv), "yz": (D, Hv, e_hi - e_lo)}[name]
+            n0 = post.launches
+            slab = post.relabel(np.ascontiguousarray(lut_f[e_lo:e_hi]), name, local_shape)
+            n_launch += post.launches - n0
+            ax = self.axes[name]
+            if r == 0:                          # (4) slabs -> rank 0
+                dense = torch.empty(shape3d, dtype=torch.int32, device=self.device)
+                dense.narrow(ax, e_lo, e_hi - e_lo).copy_(slab)
+                for src in range(1, G):
+                    a, b = E[src]
+                    shp = list(shape3d)
+                    shp[ax] = b - a
+                    tmp = torch.empty(shp, dtype=torch.int32, device=self.device)
+                    dist.recv(tmp, src=src, group=self.group)
+                    dense.narrow(ax, a, b - a).copy_(tmp)
+                tr = trackers[name][0]
+                plane = LazyPlane(dense, name, kept_labels, kept_boxes)
+                tr.instances = plane.attrs
+                tr._b200_dense = dense
+                tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, kept_sizes)}
+                tr.finish()
+            else:
+                dist.send(slab.contiguous(), dst=0, group=self.group)
+        self._pending = {}
+        tm.mark("replay + broadcast + paint + slabs to rank 0")
+        if _PROFILE:
+            print(f"[rank {self.rank}] finalize " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
+        self.last_stats = {"kernel_launches": n_launch}
+        return trackers
+
+
+def tracking_replay(merged, cls, div, axis_name, iou_thr, ioa_thr, min_size, min_extent):
+    """Leader side (worker thread): tracker replay on the merged tables + the two tracker filters
+    (inference.py:556-558). Returns (lut [N, stride] with dropped instances zeroed, kept labels,
+    kept boxes, kept sizes)."""
+    from . import tracking
+    n_cc, table, keys, vals = merged
+    lut, labels, sizes, boxes = tracking.match_replay(n_cc, table, keys, vals, cls, div, axis_name, iou_thr, ioa_thr)
+    spans = boxes[:, 3:] - boxes[:, :3] if len(boxes) else np.zeros((0, 3), np.int32)
+    keep = (sizes >= min_size) & (spans >= min_extent).all(axis=1) if len(labels) else np.zeros(0, bool)
+    kept_labels = labels[keep]
+    max_label = int(lut.max()) if lut.size else 0
+    keep_lut = np.zeros(max_label + 1, dtype=np.int32)
+    keep_lut[kept_labels] = kept_labels
+    return keep_lut[lut], kept_labels, boxes[keep], sizes[keep]
+
+
+def _lib_error(msg):
+    from ._lib import B200EmpanadaError
+    return B200EmpanadaError(msg)

@@ -71,6 +71,42 @@ class PlanePost:
         self.pushed += B
         self.n_hist = min(self.n_hist + B, self.ks - 1)
 
+    # split form of push_heads for slice-sharded planes (multigpu.ShardedEngine3d): the instance
+    # heads of a slice and its (recursively median-filtered) semantic slice arrive separately
+    def push_instance(self, ctr, off, i0):
+        """Centres + grouping of B slices into local slots [i0, i0 + B)."""
+        B = ctr.shape[0]
+        assert i0 >= 0 and i0 + B <= self.N
+        st = stream_ptr()
+        scratch = torch.empty(B * ((self.h4 * self.w4 + 1023) // 1024), dtype=torch.int32, device=self.dev)
+        call("be_centers", ptr(ctr), B, self.h4, self.w4, float(self.thr), int(self.k),
+             ptr(self.centers[i0]), self.center_cap, ptr(self.center_counts[i0:]), ptr(scratch), st)
+        call("be_group_pixels", ptr(off), ptr(self.centers[i0]), self.center_cap,
+             ptr(self.center_counts[i0:]), B, self.h4, self.w4, float(self.scale),
+             ptr(self.cells4[i0]), st)
+        self.launches += 3
+
+    def push_semantic(self, sem, slot0, is_prob=False):
+        """Median queue push of B slices; the slice pushed at slot t emits slot t - mid."""
+        B = sem.shape[0]
+        call("be_median_push", ptr(sem), B, self.H, self.W, self.ks, ptr(self.hist), self.n_hist,
+             slot0, float(self.conf), int(is_prob), ptr(self.hard), ptr(self.prob), stream_ptr())
+        self.launches += 1
+        self.n_hist = min(self.n_hist + B, self.ks - 1)
+
+    def flush_semantic(self):
+        """End of the stack: the queue tail is emitted unfiltered into the last slots."""
+        if self.ks > 1:
+            call("be_median_flush", ptr(self.hist), self.n_hist, self.ks, self.H, self.W, self.N,
+                 float(self.conf), ptr(self.hard), ptr(self.prob), stream_ptr())
+            self.launches += 1
+
+    def check_centers(self):
+        cmax = int(self.center_counts.max().item())
+        if cmax > self.center_cap:
+            raise _lib.B200EmpanadaError(
+                f"{cmax} centres in one slice exceed center_cap={self.center_cap}")
+
     def finish_heads(self):
         assert self.pushed == self.N
         if self.ks > 1:
@@ -143,6 +179,31 @@ class PlanePost:
         n_pairs = int(cursor.item())
         self.pair_keys = out_keys[:n_pairs].cpu().numpy().view(np.uint64)
         self.pair_vals = out_vals[:n_pairs].cpu().numpy()
+
+    def boundary_pairs(self, prev_cc):
+        """Overlap pairs between `prev_cc` (the last component slice of the previous shard, (h, w)
+        int32 device tensor) and this shard's first slice, keyed as local slice 0."""
+        d, h, w = self.dev, self.h, self.w
+        two = torch.stack([prev_cc, self.cc[0]]).contiguous()
+        cap = 1 << 16
+        while True:
+            keys = torch.empty(cap, dtype=torch.int64, device=d)
+            vals = torch.empty(cap, dtype=torch.int32, device=d)
+            overflow = torch.zeros(1, dtype=torch.int32, device=d)
+            call("be_hash_clear", ptr(keys), ptr(vals), cap, stream_ptr())
+            call("be_pair_overlap", ptr(two), h, w, 1, 2, ptr(keys), ptr(vals), cap, ptr(overflow), stream_ptr())
+            self.launches += 3
+            if int(overflow.item()) == 0:
+                break
+            cap *= 4
+        out_keys = torch.empty(cap, dtype=torch.int64, device=d)
+        out_vals = torch.empty(cap, dtype=torch.int32, device=d)
+        cursor = torch.zeros(1, dtype=torch.int32, device=d)
+        call("be_hash_compact", ptr(keys), ptr(vals), cap, ptr(out_keys), ptr(out_vals), cap, ptr(cursor), stream_ptr())
+        n_pairs = int(cursor.item())
+        k = out_keys[:n_pairs].cpu().numpy().view(np.uint64)
+        k = k - (np.uint64(1) << np.uint64(40))      # slice index 1 of the pair buffer -> local slice 0
+        return k, out_vals[:n_pairs].cpu().numpy()
 
     # ------------------------------------------------------------------ stage 3: host replay
     def replay_inputs(self):

@@ -47,3 +47,26 @@ def test_async_reraises_on_caller_thread():
         raise ValueError("x")
     with pytest.raises(ValueError):
         _Async(boom).result()
+
+
+def test_owned_ranges_cover_plane_and_shift_by_median_latency():
+    from empanada_napari_b200.multigpu import owned_ranges
+    for n, world, mid in ((20, 3, 1), (1024, 8, 2), (61, 4, 0), (50, 2, 2)):
+        F, E = owned_ranges(n, world, mid)
+        assert F[0][0] == 0 and F[-1][1] == n and E[0][0] == 0 and E[-1][1] == n
+        for r in range(world - 1):
+            assert F[r][1] == F[r + 1][0] and E[r][1] == E[r + 1][0]      # contiguous, disjoint
+            assert E[r][1] == F[r][1] - mid                               # pushing slice t emits t - mid
+        for r in range(1, world):
+            assert E[r][0] == F[r][0] - mid
+
+
+def test_merge_shard_tables_absolute_slice_keys():
+    from empanada_napari_b200.multigpu import merge_shard_tables
+    k = lambda s, q, c: np.uint64((s << 40) | (q << 20) | c)
+    p0 = (np.array([2, 1], np.int32), np.zeros((2, 2, 5), np.int32), np.array([k(1, 1, 1)], np.uint64), np.array([7], np.int32))
+    p1 = (np.array([3], np.int32), np.ones((1, 3, 5), np.int32), np.array([k(0, 1, 2)], np.uint64), np.array([9], np.int32))
+    n_cc, table, keys, vals = merge_shard_tables([p0, p1], [(0, 2), (2, 3)])
+    assert n_cc.tolist() == [2, 1, 3] and table.shape == (3, 3, 5) and table[2].min() == 1 and table[:2].max() == 0
+    assert [int(x) >> 40 for x in keys] == [1, 2] and vals.tolist() == [7, 9]
+    assert int(keys[1]) & ((1 << 40) - 1) == (1 << 20) | 2

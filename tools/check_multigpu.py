@@ -33,7 +33,12 @@ cfg = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_fa
        "norms": {"mean": 0.57571, "std": 0.12765}}
 cfg["model"] = SyntheticHeadsModel(lambda a, s0, s1: (heads[a][0][s0:s1, 0], heads[a][1][s0:s1], heads[a][2][s0:s1]), inner=pdl)
 kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=30, min_extent=3, batch_size=4)
-deng = multigpu.DistributedEngine3d(cfg, **kw)
+engine_cls = {"sharded": multigpu.ShardedEngine3d, "gather": multigpu.DistributedEngine3d}[os.environ.get("CHECK_ENGINE", "sharded")]
+if os.environ.get("CHECK_FINE") == "1":
+    kw["fine_boundaries"] = True
+if os.environ.get("CHECK_KS"):
+    kw["median_kernel_size"] = int(os.environ["CHECK_KS"])
+deng = engine_cls(cfg, **kw)
 trackers = {}
 for name in ("xy", "xz", "yz"):
     _, trackers[name] = deng.infer_on_axis(vol, name)
@@ -62,5 +67,5 @@ flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
 if rank == 0:
-    print("MULTIGPU_CHECK", "PASS" if ok else "FAIL")
+    print("MULTIGPU_CHECK", engine_cls.__name__, "PASS" if ok else "FAIL")
 sys.exit(0 if int(flag.item()) == 1 else 1)
