@@ -32,9 +32,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// Epilogue role (8 warps): TMEM -> registers -> bias / residual / activation -> bf16 NHWC stores
-// (or the fused 1x1 head). Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps
-// of a lane quadrant split the tile's columns in halves. The chunk loop stays rolled so that the
+// Epilogue role (EPI_WARPS = 16 warps): TMEM -> registers -> bias / residual / activation -> bf16
+// NHWC stores (or the fused 1x1 head). Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the
+// EPI_PARTS warps of a lane quadrant split the tile's columns. The chunk loop stays rolled so that the
 // whole role fits the instruction cache; RES / HEAD are compile-time so unused paths vanish.
 template <bool RES, bool HEAD>
 __device__ __forceinline__ void epilogue_role(const Params& p, uint32_t s_bias, uint32_t s_head,

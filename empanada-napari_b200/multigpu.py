@@ -236,8 +236,8 @@ class ShardedEngine3d(Engine3d):
     Rank r also runs the network on the `mid` slices before its range so that it holds the
     instance heads of every slice it owns (no halo exchange for them). Every rank must call
     `infer_on_axis` for the same planes in the same order and then `finalize(trackers)`.
-    Falls back to `DistributedEngine3d`'s gather scheme when a shard would be shorter than the
-    median kernel."""
+    Raises when a shard would be shorter than the median kernel (use fewer ranks, or
+    `DistributedEngine3d`, for very short stacks)."""
 
     def __init__(self, *args, group=None, **kwargs):
         super().__init__(*args, **kwargs)

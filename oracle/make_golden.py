@@ -204,6 +204,54 @@ def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent
           "consensus", len(out["consensus_labels"]))
 
 
+def gen_post_cases_fine():
+    """Per-slice vectors with `coarse_boundaries=False` (fine boundaries: full-resolution centre /
+    offset maps, grouping step 1; engines.py:258-275) from the reference engine."""
+    from empanada.inference.engines import PanopticDeepLabRenderEngine
+    from empanada.inference.postprocess import find_instance_center
+
+    rng = np.random.default_rng(17)
+    cases = []
+    for ci, (H, W) in enumerate([(64, 64), (48, 80), (32, 96), (16, 16), (80, 48), (64, 32)]):
+        kind = ci % 3
+        nms_kernel = [3, 7, 5][kind]
+        thr, conf = 0.1, 0.5
+        sem = rng.normal(0.5, 3, (1, H, W)).astype(np.float32)
+        if kind == 0:      # smooth heat map with a handful of peaks, offsets towards them
+            yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+            ctr = np.zeros((H, W), np.float32)
+            off = np.zeros((2, H, W), np.float32)
+            pts = [(rng.integers(4, H - 4), rng.integers(4, W - 4)) for _ in range(5)]
+            d2 = np.stack([(yy - py) ** 2 + (xx - px) ** 2 for py, px in pts])
+            near = d2.argmin(0)
+            ctr = np.exp(-d2.min(0) / 50.0).astype(np.float32)
+            off[0] = np.array([p[0] for p in pts], np.float32)[near] - yy
+            off[1] = np.array([p[1] for p in pts], np.float32)[near] - xx
+            off += rng.normal(0, 0.7, off.shape).astype(np.float32)
+        elif kind == 1:    # random, many centres (> 20 -> chunked path)
+            ctr = rng.uniform(0, 1, (H, W)).astype(np.float32) ** 6
+            off = rng.normal(0, 5, (2, H, W)).astype(np.float32)
+        else:              # plateaus and integer offsets: exact ties
+            ctr = (rng.integers(0, 4, (H, W)) / 4.0).astype(np.float32) * (rng.uniform(0, 1, (H, W)) > 0.9)
+            off = rng.integers(-6, 7, (2, H, W)).astype(np.float32)
+        eng = PanopticDeepLabRenderEngine(
+            torch.nn.Conv2d(1, 1, 1), thing_list=[1], label_divisor=1000, stuff_area=64, void_label=0,
+            nms_threshold=thr, nms_kernel=nms_kernel, confidence_thr=conf, padding_factor=16,
+            coarse_boundaries=False)
+        prob = torch.sigmoid(torch.from_numpy(sem)[None])
+        centers = find_instance_center(torch.from_numpy(ctr.copy())[None, None], thr, nms_kernel).numpy()
+        cells = eng.get_instance_cells(torch.from_numpy(ctr.copy())[None, None], torch.from_numpy(off)[None], 1)
+        pan = eng.postprocess(prob, cells)
+        cases.append(dict(prob=prob[0].numpy(), ctr=ctr.astype(np.float32), off=off, nms_kernel=nms_kernel, thr=thr,
+                          conf=conf, centers=centers, cells=cells[0, 0].numpy(), pan=pan[0].numpy()))
+    out = {"n": len(cases)}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            out[f"c{i}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(GOLD, "post_cases_fine.npz"), **out)
+    print("post_cases_fine", len(cases), [len(c["centers"]) for c in cases])
+
+
 def gen_model_tiny():
     """Reference PDL classes with the seeded weights of synthetic.make_pdl_state_dict(0)."""
     import yaml
@@ -263,9 +311,11 @@ def gen_model_bifpn_tiny():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["post", "median", "model", "bifpn", "volumes"]
+    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes"]
     if "post" in which:
         gen_post_cases()
+    if "post_fine" in which:
+        gen_post_cases_fine()
     if "median" in which:
         gen_median()
     if "model" in which:

@@ -67,6 +67,19 @@ def test_post_cases_match_reference():
         assert np.array_equal(pan, z[f"c{i}_pan"]), i
 
 
+def test_post_cases_fine_boundaries_match_reference():
+    """coarse_boundaries=False (fine boundaries): full-resolution centre / offset maps, step 1."""
+    z = np.load(os.path.join(GOLDEN, "post_cases_fine.npz"))
+    for i in range(int(z["n"])):
+        ctr, off, prob = z[f"c{i}_ctr"], z[f"c{i}_off"], z[f"c{i}_prob"]
+        k, thr, conf = int(z[f"c{i}_nms_kernel"]), float(z[f"c{i}_thr"]), float(z[f"c{i}_conf"])
+        assert np.array_equal(post.find_instance_center(ctr, thr, k), z[f"c{i}_centers"].reshape(-1, 2)), i
+        cells = post.get_instance_cells(ctr, off, thr, k, False, 1)
+        assert np.array_equal(cells, z[f"c{i}_cells"]), i
+        pan = post.get_panoptic_seg(post.harden_seg(prob, conf), cells, 1000, [1], 64, 0)
+        assert np.array_equal(pan, z[f"c{i}_pan"]), i
+
+
 def test_median_queue_matches_reference():
     z = np.load(os.path.join(GOLDEN, "median_cases.npz"))
     for i in range(int(z["n"])):
