@@ -5,6 +5,7 @@
 #include "sm100_ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace convgemm {
@@ -372,12 +373,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // weight-stationary mode: all K blocks of the current N tile stay resident in shared memory
   // and only the activation tiles stream through the pipeline stages
   const bool wstat = p.b_stationary != 0;
-  const int stage_bytes = wstat ? a_bytes : a_bytes + b_bytes;
+  const int halo = p.halo;
+  const int halo_bytes = (p.TH + 2) * HALO_PW * KCHUNK * 2;   // one (TH+2) x 16 px x 64 ch patch
+  const int stage_bytes = halo ? halo_bytes : (wstat ? a_bytes : a_bytes + b_bytes);
   const int stages = p.stages;
   uint8_t* bres = smem;                                                    // [num_kb][b_bytes] (wstat)
   uint8_t* stage_base = smem + (wstat ? static_cast<size_t>(num_kb) * b_bytes : 0);
 
-  const int staging_bytes = p.staged ? (2 + (p.residual != nullptr ? ((p.block_n + 63) >> 6) : 0)) * 16384 : 0;
+  const int nsub_k = (p.block_n + 63) >> 6;   // one output staging buffer is enough for a single sub-tile
+  const int staging_bytes = p.staged ? ((nsub_k > 1 ? 2 : 1) + (p.residual != nullptr ? nsub_k : 0)) * 16384 : 0;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + static_cast<size_t>(stages) * stage_bytes + staging_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;   // [2]
@@ -458,6 +462,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         tap * p.Cin + kc * KCHUNK, n0);
           }
         }
+        if (halo) {  // one patch per tile: rows y_in .. y_in+TH+1, pixels x_in .. x_in+15
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = stage_base + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_4d(a_dst, &tmap_a, &full_bar[stage], 0, x_in, y_in, b0);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / p.S, s = tap - r * p.S;
           for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -489,6 +501,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&tempty_bar[buf], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * MAX_N;
+        if (halo) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t patch = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, sx = tap - 3 * r;
+            // rows of tile row th are pixels sx .. sx+7 of patch row th + r: 8 consecutive 128 B rows;
+            // consecutive tile rows are one patch row (16 px = 2 KiB) apart
+            const uint64_t a_desc = make_sw128_kmajor_desc_ex(patch + (r * HALO_PW + sx) * 128, HALO_PW * 128,
+                                                              halo == 2 ? sx : 0);
+            const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(bres + static_cast<size_t>(tap) * b_bytes));
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 16; ++k)
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          umma_commit(&tfull_bar[buf]);
+          if (wstat && ((t + 1) % per_nt) == 0) umma_commit(bfree_bar);
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -510,7 +544,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (p.staged) {
     const uint32_t obuf = smem_u32(stage_base + static_cast<size_t>(stages) * stage_bytes);
-    const uint32_t rbuf = obuf + 2 * 16384;
+    const uint32_t rbuf = obuf + (nsub_k > 1 ? 2 : 1) * 16384;
     long long* rowpix = reinterpret_cast<long long*>(s_hpart + 2 * TILE_M * (EPI_PARTS - 1));
     if (p.residual != nullptr) epilogue_role_staged<true>(p, smem_u32(s_bias), obuf, rbuf, rowpix, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
     else                       epilogue_role_staged<false>(p, smem_u32(s_bias), obuf, rbuf, rowpix, tfull_bar, tempty_bar, tmem_base, warp, lane, n_iter, per_nt, wstat);
@@ -621,6 +655,18 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
     // TMA box limit: fall back to narrower rows
     while (p.TW * stride > 256) { p.TW >>= 1; p.TH <<= 1; }
   }
+  // halo schedule for the L2-bound 3x3 / Cin = 64 convolutions (ResNet layer1)
+  int halo_mode = 0;
+  {
+    const char* e = getenv("B200_CONV_HALO");
+    const int want = e ? atoi(e) : 1;   // on by default; B200_CONV_HALO=0 selects the nine-box schedule
+    // (nine resident weight blocks + two patches + the output staging must fit: Cout <= 80)
+    if (want > 0 && R == 3 && S == 3 && stride == 1 && dil == 1 && pad == 1 && Cin == KCHUNK && Cout <= 80 &&
+        Cout % 16 == 0 && Wo >= HALO_TW && Ho >= HALO_TH && residual == nullptr && head_n == 0 && !shuffle2x2)
+      halo_mode = want;
+  }
+  if (halo_mode) { p.TW = HALO_TW; p.TH = HALO_TH; p.TB = 1; }
+  p.halo = halo_mode;
   p.tiles_x = (Wo + p.TW - 1) / p.TW;
   p.tiles_y = (Ho + p.TH - 1) / p.TH;
   p.tiles_b = (B + p.TB - 1) / p.TB;
@@ -645,7 +691,7 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
                          Cout % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0 &&
                          (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                          (residual == nullptr || (res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
-  const long long staging_h = can_stage ? (2 + (residual != nullptr ? (bn + 63) / 64 : 0)) * 16384LL : 0;
+  const long long staging_h = can_stage ? (((bn + 63) / 64 > 1 ? 2 : 1) + (residual != nullptr ? (bn + 63) / 64 : 0)) * 16384LL : 0;
   long long smem_budget = 227 * 1024 - 1024 - TAIL_BYTES - staging_h;
   p.staged = can_stage ? 1 : 0;
   {
@@ -664,7 +710,12 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
   // weight-stationary when the whole K extent of one N tile fits beside >= 3 activation stages
   // and every CTA reuses it for at least two M tiles
   p.b_stationary = (num_kb_h * b_bytes_h + 3 * a_bytes_h <= smem_budget && tiles_m_h >= 2LL * num_sms) ? 1 : 0;
-  const int stage_bytes = p.b_stationary ? a_bytes_h : a_bytes_h + b_bytes_h;
+  const int halo_bytes_h = (p.TH + 2) * HALO_PW * KCHUNK * 2;
+  if (halo_mode) {
+    if (num_kb_h * b_bytes_h + 2LL * halo_bytes_h > smem_budget) return -9;
+    p.b_stationary = 1;
+  }
+  const int stage_bytes = halo_mode ? halo_bytes_h : (p.b_stationary ? a_bytes_h : a_bytes_h + b_bytes_h);
   int stages = static_cast<int>((smem_budget - (p.b_stationary ? num_kb_h * b_bytes_h : 0)) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return -4;
@@ -687,6 +738,7 @@ int conv_gemm_plan_ex(Launch* L, const __nv_bfloat16* in, long long in_ld, int B
                           static_cast<cuuint64_t>(in_ld) * 2 * Wi * Hi};
     cuuint32_t box[4] = {KCHUNK, static_cast<cuuint32_t>(p.TW * stride),
                          static_cast<cuuint32_t>(p.TH * stride), static_cast<cuuint32_t>(p.TB)};
+    if (halo_mode) { box[1] = HALO_PW; box[2] = static_cast<cuuint32_t>(p.TH + 2); box[3] = 1; }
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
     CUresult r = enc(&L->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                      const_cast<__nv_bfloat16*>(in), gdim, gstr, box, estr,

@@ -61,7 +61,14 @@ struct Params {
   // ConvTranspose2d(k=2, s=2) as a 1x1 GEMM with N = 4 * Cout_real: N tile nt = 2*dy + dx holds
   // the Cout_real channels of output pixel (2y + dy, 2x + dx) (staged epilogue only)
   int shuffle2x2;
+  // 3x3 / stride 1 / Cin = 64 "halo" schedule: ONE TMA box per tile holds the (TH+2) x 16-pixel
+  // input patch (row pitch 16 pixels = 2 KiB, so every 8-row group of every tap starts at the
+  // same swizzle phase); the nine taps are nine UMMA descriptors into that patch instead of nine
+  // boxes from L2. 0 = off, 1 / 2 = on (descriptor base_offset 0 / = tap column)
+  int halo;
 };
+constexpr int HALO_PW = 16;                    // patch row pitch in pixels
+constexpr int HALO_TW = 8, HALO_TH = 16;       // output tile of the halo schedule
 
 // Host side: builds the two tensor maps and launches. Returns cudaError_t as int.
 struct Launch {

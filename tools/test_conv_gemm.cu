@@ -50,7 +50,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
                           Ho, Wo, d_out, c.Cout, 0, c.f32 ? d_f32 : nullptr, c.Cout, c.bias ? d_bias : nullptr,
                           c.res ? d_res : nullptr, c.Cout, c.act, num_sms);
   if (rc != 0) { printf("[%s] plan failed rc=%d\n", c.name, rc); return 1; }
-  printf("[%s] Ho=%d Wo=%d tile TW=%d TH=%d TB=%d bn=%d stages=%d wstat=%d grid=%d smem=%zu\n", c.name, Ho, Wo, L.p.TW, L.p.TH, L.p.TB, L.p.block_n, L.p.stages, L.p.b_stationary, L.grid, L.smem);
+  printf("[%s] Ho=%d Wo=%d tile TW=%d TH=%d TB=%d bn=%d stages=%d wstat=%d halo=%d grid=%d smem=%zu\n", c.name, Ho, Wo, L.p.TW, L.p.TH, L.p.TB, L.p.block_n, L.p.stages, L.p.b_stationary, L.p.halo, L.grid, L.smem);
   rc = conv_gemm_launch(&L, 0);
   if (rc != 0) { printf("[%s] launch failed rc=%d\n", c.name, rc); return 1; }
   CK(cudaDeviceSynchronize());
@@ -115,11 +115,12 @@ int main(int argc, char** argv) {
     {"wstat 1x1 res 64->256", 3, 128, 128, 64, 256, 1, 1, 1, 0, true, true, ACT_RELU, false, 1},
     {"wstat 1x1 128->512 (2 n-tiles)", 3, 128, 128, 128, 512, 1, 1, 1, 0, true, true, ACT_RELU, false, 1},
     {"wstat 3x3 64->64", 3, 128, 128, 64, 64, 3, 1, 1, 1, true, false, ACT_RELU, false, 1},
+    {"3x3 64->64 odd 50x37", 2, 50, 37, 64, 64, 3, 1, 1, 1, true, false, ACT_RELU, false, 1},
     {"wstat 1x1 k288 odd 250x130", 3, 250, 130, 288, 256, 1, 1, 1, 0, true, false, ACT_RELU, false, 1},
   };
   int fails = 0;
   const int only = (argc > 2) ? atoi(argv[2]) : -1;
-  if (only < 0) for (const Case& c : cases) fails += run_case(c, sms, false);
+  if (only < 0 || argc > 3) for (const Case& c : cases) fails += run_case(c, sms, false);
   if (argc > 1) {
     Case perf[] = {
       {"ASPP 3x3 d6 2048->512 B8", 8, 64, 64, 2048, 512, 3, 1, 6, 6, true, false, ACT_RELU, false, 0},
@@ -128,6 +129,7 @@ int main(int argc, char** argv) {
       {"l3 1x1 1024->256 B8", 8, 64, 64, 1024, 256, 1, 1, 1, 0, true, false, ACT_RELU, false, 0},
       {"l1 1x1 64->256 B8 256^2", 8, 256, 256, 64, 256, 1, 1, 1, 0, true, true, ACT_RELU, false, 0},
       {"head 1x1 256->256 B8 256^2", 8, 256, 256, 256, 256, 1, 1, 1, 0, true, false, ACT_RELU, false, 0},
+      {"l1 3x3 64->64 B16 256^2", 16, 256, 256, 64, 64, 3, 1, 1, 1, true, false, ACT_RELU, false, 0},
     };
     int idx = 0;
     for (const Case& c : perf) { if (only < 0 || only == idx) fails += run_case(c, sms, true); ++idx; }
