@@ -29,6 +29,7 @@ _lib.declare("be_oplist_create", [ctypes.POINTER(c_void_p)])
 _lib.declare("be_oplist_destroy", [P])
 _lib.declare("be_oplist_launches", [P])
 _lib.declare("be_oplist_run", [P, P, LL, LL, LL, I, P])
+_lib.declare("be_oplist_set_graph", [P, I])
 _lib.declare("be_oplist_run_timed", [P, P, LL, LL, LL, I, P, I, P])
 _lib.declare("be_oplist_size", [P])
 _lib.declare("be_op_conv", [P, P, LL, I, I, I, I, P, I, I, I, I, I, I, I, I, P, LL, I, P, LL, I, P, LL,
@@ -49,6 +50,8 @@ _lib.declare("be_op_pr_predict", [P, P, I, I, P, P, F, P, I, I, I, P, P])
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 # decoder `F.interpolate` + `torch.cat` fused into the depthwise kernel (1) or materialised (0)
 FUSED_UPSAMPLE = os.environ.get("B200_EMPANADA_FUSED_UPSAMPLE", "0") == "1"
+USE_GRAPHS = os.environ.get("B200_EMPANADA_GRAPHS", "1") == "1"
+GRAPH_MAX_PIXELS = 4 << 20
 BN_EPS = 1e-5
 
 
@@ -397,6 +400,10 @@ class _NetModel:
         if plan is None:
             with torch.cuda.device(self.dev):
                 plan = self.plan_cls(self.W, B, h, w, H, Wd, float(mean255), float(den), self.render_steps)
+            # small batches are launch bound (hundreds of kernels of a few microseconds): replay
+            # them as one CUDA graph; large batches keep plain launches (kernels >> launch cost)
+            if USE_GRAPHS and B * H * Wd <= GRAPH_MAX_PIXELS:
+                call("be_oplist_set_graph", plan.handle, 1)
             self.plans[key] = plan
         plan.run(vol_d, strides, s0)
         self.launches += plan.launches

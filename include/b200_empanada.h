@@ -26,6 +26,9 @@ int be_oplist_create(void** list);
 int be_oplist_destroy(void* list);
 int be_oplist_launches(void* list);
 int be_oplist_size(void* list);
+/* replay everything after the slice-gather prefix of the list as one CUDA graph (launch-bound
+ * lists: single small tiles); the first replay after enabling runs plainly, the second captures */
+int be_oplist_set_graph(void* list, int enable);
 int be_oplist_run(void* list, const uint8_t* volume_u8, long long stride_slice, long long stride_y,
                   long long stride_x, int first_slice, be_stream st);
 int be_oplist_run_timed(void* list, const uint8_t* volume_u8, long long stride_slice,

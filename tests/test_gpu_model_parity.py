@@ -147,3 +147,35 @@ def test_engine2d_bifpn_mini_config():
     fg_agree = float(((out > 0) == (want > 0)).mean())
     print("foreground agreement", fg_agree, "objects", len(np.unique(out)) - 1, len(np.unique(want)) - 1)
     assert fg_agree >= 0.99
+
+
+@pytest.mark.parametrize("net", ["pdl", "bifpn"])
+def test_graph_replay_equals_plain_replay(net):
+    """Small launch lists are replayed as one CUDA graph after the first call; every replay must
+    give exactly the bits of the plain launch sequence (different slices of the volume per call)."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200 import pdl as pdl_mod
+    from empanada_napari_b200.bifpn import BiFPNModel
+    from empanada_napari_b200.pdl import PDLModel
+    dev = torch.device("cuda:0")
+    sd = syn.make_pdl_state_dict(0) if net == "pdl" else syn.make_bifpn_state_dict(0)
+    cls, pf = (PDLModel, 16) if net == "pdl" else (BiFPNModel, 128)
+    vol = torch.randint(0, 256, (6, 128, 128), dtype=torch.uint8, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    outs = {}
+    for use in (True, False):
+        pdl_mod.USE_GRAPHS = use
+        m = cls(sd, dev)
+        res = []
+        for s0 in (0, 2, 4, 2):
+            sem, ctr, off = m.forward_slices(vol, 0, s0, s0 + 2, NORMS, pf)
+            res.append((sem.clone(), ctr.clone(), off.clone()))
+        torch.cuda.synchronize()
+        outs[use] = res
+    pdl_mod.USE_GRAPHS = True
+    for a, b in zip(outs[True], outs[False]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # and replays of the same slices agree with each other
+    for x, y in zip(outs[True][1], outs[True][3]):
+        assert torch.equal(x, y)
