@@ -262,6 +262,40 @@ def bench_mini_tile(lab_d, n_obj, dev, size=1024, steps=10):
             "objects": int(len(np.unique(out)) - 1)}
 
 
+def bench_stack_512(pdl, dev, S=512, steps=2):
+    """BASELINE config C3: MitoNet_v1-class 3-D xy-only stack inference with median smoothing
+    (ks 3) + tracker + stack_postprocessing on a S^3 volume (device-resident volume, host label
+    volume out). Returns voxels/s."""
+    import torch
+    from empanada_napari_b200.inference import Engine3d, stack_postprocessing
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    vol_d, lab_d, n_obj = synth_on_device(S, dev, seed=2)
+    sem, ctr, off = analytic_heads_on_device(lab_d, 0, n_obj)
+    del lab_d
+    cfg = dict(MODEL_CONFIG)
+    cfg["model"] = SyntheticHeadsModel(lambda a, s0, s1: (sem[s0:s1], ctr[s0:s1], off[s0:s1]), inner=pdl)
+    eng = Engine3d(cfg, median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5, batch_size=16)
+
+    def job():
+        _, trackers = eng.infer_on_axis(vol_d, "xy")
+        out = None
+        for vol, _, inst in stack_postprocessing({"xy": trackers}, None, cfg, min_size=500, min_extent=5, dtype=np.int32):
+            out = (vol, inst)
+        return out
+
+    out = job()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = job()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": f"MitoNet_v1-class PDL 3D xy-only stack inference, median ks 3 + tracker + stack_postprocessing, {S}^3 volume",
+            "ms_per_step": ms, "voxels_per_s": float(S) ** 3 / (ms * 1e-3), "instances": len(out[1])}
+
+
 def vox_f(S):
     return float(S) ** 3
 
@@ -459,6 +493,10 @@ def main():
         if tiles2d is not None:
             tiles2d["mini_tile"] = bench_mini_tile(lab_d, n_obj, dev)
     del lab_d
+    stack512 = None
+    if rank == 0 and world == 1 and not args.no_2d and S >= 512:
+        torch.cuda.empty_cache()
+        stack512 = bench_stack_512(pdl, dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -478,6 +516,7 @@ def main():
                     "h2d_bytes_per_step": int(S ** 3), "d2h_bytes_per_step": d2h},
             "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu,
             "post_roofline": post_roof, "consensus_instances": n_instances, "tiles_2d": tiles2d,
+            "stack_xy_512": stack512,
         }
         print(json.dumps(line))
     if world > 1:

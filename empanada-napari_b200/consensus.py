@@ -456,9 +456,10 @@ def instance_relabel(tracker):
     return out
 
 
-def fill_volume_device(src_tracker, new_instances, dtype):
+def fill_volume_device(src_tracker, new_instances, dtype, to_host=None):
     """`fill_volume` (patterns.py:204-213) for the relabelled stack: tracker label -> 1..n on the
-    device-resident volume; instances filtered out become 0."""
+    device-resident volume; instances filtered out become 0. `to_host(vol_d, dtype)`: optional
+    device->host copier (page-locked staging pool of the caller)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     vol = dense_volume(src_tracker, dev).clone()
     labels = [int(l) for l in src_tracker.instances.keys()]
@@ -467,4 +468,6 @@ def fill_volume_device(src_tracker, new_instances, dtype):
         if new_id in new_instances:
             lut[l] = new_id
     call("be_lut_inplace", ptr(vol), vol.numel(), ptr(torch.from_numpy(lut).to(dev)), int(lut.shape[0]), stream_ptr())
+    if to_host is not None:
+        return to_host(vol, dtype)
     return vol.cpu().numpy().astype(dtype, copy=False)

@@ -506,5 +506,5 @@ def stack_postprocessing(trackers, store_url, model_config, label_divisor=1000, 
         if class_id in thing_list:
             tracking.remove_small_objects(st, min_size=min_size)
             tracking.remove_pancakes(st, min_span=min_extent)
-        vol = consensus.fill_volume_device(ct, st.instances, dtype)
+        vol = consensus.fill_volume_device(ct, st.instances, dtype, to_host=_PINNED.to_host)
         yield vol, class_name, st.instances
