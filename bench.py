@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=0, help="slices per launch list (0 = engine default: whole SM waves)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=96)
     ap.add_argument("--no-cpu", action="store_true")
@@ -320,7 +320,8 @@ def main():
     S = args.size
     workload = f"MitoNet_v1-class PDL 3D orthoplane (xy/xz/yz) consensus on {S}^3 uint8 volume"
     config = {"workload": workload, "volume": [S, S, S], "median_kernel": 3, "nms_kernel": 3,
-              "pixel_vote_thr": 2, "min_size": 500, "min_extent": 5, "slice_batch": args.batch,
+              "pixel_vote_thr": 2, "min_size": 500, "min_extent": 5,
+              "slice_batch": args.batch if args.batch > 0 else "auto (37 at 1024^2 on 148 SMs)",
               "l2": "inputs larger than L2 (1 GiB volume, >4 GiB of heads per plane)",
               "parallelism": (f"every plane sharded by slice range x{world} (network + post-processing; median "
                               f"wavefront, boundary-overlap and table exchange over NCCL); tracker replay on one "
@@ -369,7 +370,7 @@ def main():
     cfg = dict(MODEL_CONFIG)
     cfg["model"] = SyntheticHeadsModel(heads_fn, inner=pdl)
     kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5,
-              batch_size=args.batch)
+              batch_size=args.batch if args.batch > 0 else None)
     multi_cls = multigpu.DistributedEngine3d if os.environ.get("B200_EMPANADA_MULTIGPU") == "gather" else multigpu.ShardedEngine3d
     eng = Engine3d(cfg, **kw) if world == 1 else multi_cls(cfg, **kw)
     vol_h = vol_d.cpu().numpy()
@@ -440,8 +441,8 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        plan = pdl.last_plan
-        B = args.batch
+        plan = max(pdl.plans.values(), key=lambda pl: pl.B)   # the full-batch launch list
+        B = plan.B
         ms = plan.run_timed(vol_d, (S * S, S, 1), 0)
         ms = plan.run_timed(vol_d, (S * S, S, 1), 0)
         conv_ms = float(sum(t for (k, _), t in zip(plan.op_info, ms) if k == "conv"))
@@ -451,7 +452,7 @@ def main():
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture of the same launch list
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))
-            if int(tr.get("batch_slices", 0)) == B and S == 1024:
+            if S == 1024 and int(tr.get("batch_slices", 0)) == B:
                 traffic = float(tr["traffic_bytes_per_launch"])
         except Exception:
             pass
