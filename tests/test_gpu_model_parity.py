@@ -179,3 +179,46 @@ def test_graph_replay_equals_plain_replay(net):
     # and replays of the same slices agree with each other
     for x, y in zip(outs[True][1], outs[True][3]):
         assert torch.equal(x, y)
+
+
+def test_engine3d_end_to_end_agreement():
+    """Whole 3-D path with the network's OWN heads (no substitution): bf16 tcgen05 forward +
+    CUDA post-processing + consensus vs the fp32 oracle model + oracle pipeline on the same
+    volume. Voxel agreement of the consensus foreground >= 0.99 and instance F1 (IoU >= 0.5
+    matching) >= 0.9 when there are instances to match."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import Engine3d, tracker_consensus
+    from oracle import consensus as ocons, model as omodel, pipeline
+    sd = syn.make_pdl_state_dict(0)
+    cfg = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 16,
+           "norms": NORMS, "model": sd}
+    shape = (20, 48, 40)
+    vol, _, _ = syn.make_volume(shape, seed=9, scale=1.0)
+    kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=8, min_extent=1)
+    eng = Engine3d(cfg, batch_size=4, **kw)
+    got = {ax: eng.infer_on_axis(vol, ax)[1] for ax in ("xy", "xz", "yz")}
+
+    def heads_fn(i, x):
+        o = omodel.pdl_forward(sd, torch.from_numpy(x[None, None]), 2, False)
+        return o["sem_logits"][0].numpy(), o["ctr_hmp"][0, 0].numpy(), o["offsets"][0].numpy()
+
+    want = {ax: pipeline.infer_on_axis(vol, ax, heads_fn, cfg, save_panoptic=False, **kw)[1] for ax in ("xy", "xz", "yz")}
+    (v, _, inst), = list(tracker_consensus(got, None, cfg, pixel_vote_thr=2, min_size=8, min_extent=1, dtype=np.int32))
+    (ov, _, oinst), = list(ocons.tracker_consensus(want, cfg, pixel_vote_thr=2, min_size=8, min_extent=1, dtype=np.int32))
+    fg = float(((v > 0) == (ov > 0)).mean())
+    # instance matching at IoU >= 0.5
+    tp = 0
+    for l in np.unique(ov)[1:]:
+        m = ov == l
+        cand, cnt = np.unique(v[m], return_counts=True)
+        for c, n in zip(cand, cnt):
+            if c > 0 and n / float((m | (v == c)).sum()) >= 0.5:
+                tp += 1
+                break
+    n_got, n_want = len(np.unique(v)) - 1, len(np.unique(ov)) - 1
+    f1 = 2 * tp / max(1, n_got + n_want)
+    print("foreground agreement", fg, "instances", n_got, n_want, "matched", tp, "F1", f1)
+    assert fg >= 0.99
+    if min(n_got, n_want) >= 3:
+        assert f1 >= 0.9
