@@ -80,6 +80,22 @@ def upsample_instance_heads(ctr, off):
     return ctr_f, off_f
 
 
+def auto_slice_batch(H, W, sms=148, requested=None, max_pixels=40 << 20):
+    """Slices per launch list for padded H x W slices. The deep, compute-heavy layers run on the
+    1/16-resolution map, whose 128-pixel tiles should fill the SMs in whole waves (at 1024^2: 32
+    tiles per slice, 148 SMs -> 37 slices = 8 full waves; +6 % conv throughput over 16), within
+    `max_pixels` per batch (activation buffers near 25 GB at 40 MPixel). An explicit request is only
+    capped by `max_pixels`."""
+    cap = max(1, max_pixels // max(1, H * W))
+    if requested is not None:
+        return max(1, min(int(requested), cap))
+    tiles = max(1, -(-((H // 16) * (W // 16)) // 128))
+    for b in range(min(cap, 48), 7, -1):
+        if (b * tiles) % sms == 0:
+            return b
+    return max(1, min(cap, 32))
+
+
 class _VolumeCache:
     """Keeps the uint8 volume resident in HBM across the xy/xz/yz passes."""
 
@@ -298,22 +314,9 @@ class Engine3d:
             post.push_heads(sem, ctr, off, is_prob=False)
 
     def slice_batch(self, H, W):
-        """Slices per launch list. `batch_size=None` (default) picks it: the deep, compute-heavy
-        layers run on the 1/16-resolution map, whose 128-pixel tiles should fill the SMs in whole
-        waves (at 1024^2: 32 tiles per slice, 148 SMs -> 37 slices = 8 full waves; +6 % conv
-        throughput over 16), within ~40 MPixel per batch (activation buffers near 25 GB). An
-        explicit `batch_size` is capped at 16 MPixel per batch for large slices."""
-        if self.batch_size is not None:
-            return max(1, min(self.batch_size, max(1, (16 << 20) // max(1, H * W))))
-        cap = max(1, (40 << 20) // max(1, H * W))
+        """Slices per launch list (see `auto_slice_batch`)."""
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        tiles = max(1, -(-(H // 16) * (W // 16) // 128))
-        best = None
-        for b in range(min(cap, 48), 7, -1):
-            if (b * tiles) % sms == 0:
-                best = b
-                break
-        return best if best is not None else max(1, min(cap, 32))
+        return auto_slice_batch(H, W, sms, self.batch_size)
 
     def release(self):
         """Drop the cached device copy of the input volume."""
@@ -388,8 +391,9 @@ class Engine2d:
                          void_label=0, nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
                          confidence_thr=self.confidence_thr, device=dev,
                          scale=1 if self.fine_boundaries else 4)
-        # chunks of ~16 MPixel keep the activation buffers of one launch list near 10 GB
-        chunk = max(1, min(n, (16 << 20) // (H * W)))
+        # tiles per launch list: whole SM waves on the 1/16 map, activation buffers within ~25 GB
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        chunk = max(1, min(n, auto_slice_batch(H, W, sms)))
         for s0 in range(0, n, chunk):
             s1 = min(n, s0 + chunk)
             sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)

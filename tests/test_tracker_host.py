@@ -70,3 +70,14 @@ def test_merge_shard_tables_absolute_slice_keys():
     assert n_cc.tolist() == [2, 1, 3] and table.shape == (3, 3, 5) and table[2].min() == 1 and table[:2].max() == 0
     assert [int(x) >> 40 for x in keys] == [1, 2] and vals.tolist() == [7, 9]
     assert int(keys[1]) & ((1 << 40) - 1) == (1 << 20) | 2
+
+
+def test_auto_slice_batch():
+    from empanada_napari_b200.inference import auto_slice_batch
+    assert auto_slice_batch(1024, 1024, 148) == 37          # 37 * 32 tiles = 8 waves of 148
+    assert (auto_slice_batch(1024, 1024, 148) * 32) % 148 == 0
+    assert auto_slice_batch(2048, 2048, 148) == 10          # capped by the 40 MPixel budget
+    assert auto_slice_batch(64, 64, 148) == 32              # tiny slices: plain default
+    assert auto_slice_batch(1024, 1024, 148, requested=16) == 16
+    assert auto_slice_batch(2048, 2048, 148, requested=64) == 10
+    assert auto_slice_batch(8192, 8192, 148) == 1
