@@ -340,7 +340,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "3D orthoplane voxels/sec", "value": v, "unit": "voxels/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * args.cpu_sample ** 3 / v, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * args.cpu_sample ** 3 / v, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
