@@ -86,10 +86,10 @@ class _BiFPNWeights(_WeightsBase):
 
 
 class _BiFPNPlan(_PlanBase):
-    def __init__(self, W, B, h, w, H, Wd, mean255, den, render_steps=2, num_points=8192, fused_stem=True):
+    def __init__(self, W, B, h, w, H, Wd, mean255, den, render_steps=2, num_points=8192, fused_stem=True, elem=0):
         super().__init__(W, B)
         D = W.D
-        levels = self.record_encoder(h, w, H, Wd, mean255, den, 32, fused_stem)
+        levels = self.record_encoder(h, w, H, Wd, mean255, den, 32, fused_stem, elem)
         p2, H4, W4, _ = levels[2]
         self.p2, self.p5 = p2, levels[5][0]
         # P2 skip goes straight into the second half of both decoders' last concat buffers

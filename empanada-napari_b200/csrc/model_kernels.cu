@@ -40,12 +40,29 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return v;
 }
 
+
+// Input volume element types (numpy integer dtypes accepted by Preprocessor, empanada_napari/
+// utils.py:189-201: `image.astype(np.float32)` then (x - mean*max) * 1/(std*max), max = iinfo.max)
+__device__ __forceinline__ float load_elem(const void* __restrict__ base, long long i, int elem) {
+  switch (elem) {
+    case 0: return static_cast<float>(static_cast<const uint8_t*>(base)[i]);
+    case 1: return static_cast<float>(static_cast<const int8_t*>(base)[i]);
+    case 2: return static_cast<float>(static_cast<const uint16_t*>(base)[i]);
+    case 3: return static_cast<float>(static_cast<const int16_t*>(base)[i]);
+    case 4: return static_cast<float>(static_cast<const uint32_t*>(base)[i]);
+    case 5: return static_cast<float>(static_cast<const int32_t*>(base)[i]);
+    case 6: return static_cast<float>(static_cast<const unsigned long long*>(base)[i]);
+    case 7: return static_cast<float>(static_cast<const long long*>(base)[i]);
+    default: return static_cast<const float*>(base)[i];   // 8: already normalised fp32 (engine API)
+  }
+}
+
 // ------------------------------------------------------------------ stem
 // One thread = one output pixel x 64 channels. 16x16 output tile per CTA, 37x37 input patch.
 constexpr int ST = 16;
 constexpr int SP = 2 * ST + 5;
 __global__ void __launch_bounds__(ST * ST)
-stem_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long stride_y,
+stem_kernel(const void* __restrict__ vol, int elem, long long stride_s, long long stride_y,
             long long stride_x, int s0, int h, int w, int H, int W, float mean255, float den,
             const float* __restrict__ wt /*[49][64]*/, const float* __restrict__ bias,
             bf16* __restrict__ out) {
@@ -54,14 +71,14 @@ stem_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long strid
   const int b = blockIdx.z;
   const int oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
   const int Ho = H / 2, Wo = W / 2;
-  const uint8_t* src = vol + static_cast<long long>(s0 + b) * stride_s;
+  const long long src0 = static_cast<long long>(s0 + b) * stride_s;
   for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) ws[i] = wt[i];
   for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) {
     const int py = i / SP, px = i - py * SP;
     const int y = 2 * oy0 - 3 + py, x = 2 * ox0 - 3 + px;
     float v = 0.0f;
     if (y >= 0 && y < h && x >= 0 && x < w)
-      v = __fmul_rn(__fsub_rn(static_cast<float>(src[y * stride_y + x * stride_x]), mean255), den);
+      v = __fmul_rn(__fsub_rn(load_elem(vol, src0 + y * stride_y + x * stride_x, elem), mean255), den);
     patch[py][px] = v;
   }
   __syncthreads();
@@ -114,7 +131,7 @@ constexpr int SIWP = 72;
 constexpr int SSTRIP = 11;
 constexpr int stem_pool_smem_bytes() { return STY * STX * 32 * 4 + 49 * 64 * 4 + SIH * SIWP * 8; }
 __global__ void __launch_bounds__(256, 2)
-stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long stride_y,
+stem_pool_kernel(const void* __restrict__ vol, int elem, long long stride_s, long long stride_y,
                  long long stride_x, int s0, int h, int w, int H, int W, float mean255, float den,
                  const float* __restrict__ wt /*[49][64]*/, const float* __restrict__ bias,
                  bf16* __restrict__ out /*[B][H/4][W/4][64]*/) {
@@ -129,14 +146,14 @@ stem_pool_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long 
   const int Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4;
   const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;                  // conv1 tile origin
   const int iy0 = 2 * sy0 - 3, ix0 = 2 * sx0 - 3;                  // input patch origin
-  const uint8_t* src = vol + static_cast<long long>(s0 + b) * stride_s;
+  const long long src0 = static_cast<long long>(s0 + b) * stride_s;
   for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) ws[i] = __ldg(wt + i);
   for (int i = threadIdx.x; i < SIH * SIWP; i += blockDim.x) {
     const int py = i / SIWP, px = i - py * SIWP;
     const int y = iy0 + py, x = ix0 + px;
     float v = 0.0f;
     if (px < SIW && y >= 0 && y < h && x >= 0 && x < w)
-      v = __fmul_rn(__fsub_rn(static_cast<float>(src[y * stride_y + x * stride_x]), mean255), den);
+      v = __fmul_rn(__fsub_rn(load_elem(vol, src0 + y * stride_y + x * stride_x, elem), mean255), den);
     patch[i] = make_float2(v, v);
   }
   __syncthreads();
@@ -829,15 +846,15 @@ __global__ void pr_predict_kernel(const bf16* __restrict__ X, int ldp, int C,
 
 extern "C" {
 
-int be_stem(const uint8_t* vol, long long stride_s, long long stride_y, long long stride_x, int s0,
+int be_stem(const void* vol, int elem, long long stride_s, long long stride_y, long long stride_x, int s0,
             int B, int h, int w, int H, int W, float mean255, float den, const float* wt,
             const float* bias, __nv_bfloat16* out, cudaStream_t st) {
   dim3 grid((W / 2 + mk::ST - 1) / mk::ST, (H / 2 + mk::ST - 1) / mk::ST, B);
-  mk::stem_kernel<<<grid, mk::ST * mk::ST, 0, st>>>(vol, stride_s, stride_y, stride_x, s0, h, w, H, W,
+  mk::stem_kernel<<<grid, mk::ST * mk::ST, 0, st>>>(vol, elem, stride_s, stride_y, stride_x, s0, h, w, H, W,
                                                    mean255, den, wt, bias, out);
   return be_check_launch("stem_kernel");
 }
-int be_stem_pool(const uint8_t* vol, long long stride_s, long long stride_y, long long stride_x,
+int be_stem_pool(const void* vol, int elem, long long stride_s, long long stride_y, long long stride_x,
                  int s0, int B, int h, int w, int H, int W, float mean255, float den, const float* wt,
                  const float* bias, __nv_bfloat16* out, cudaStream_t st) {
   if (H % 4 || W % 4) return be_set_error("stem_pool: padded slice size must be a multiple of 4");
@@ -847,7 +864,7 @@ int be_stem_pool(const uint8_t* vol, long long stride_s, long long stride_y, lon
     attr_set = true;
   }
   dim3 grid((W / 4 + mk::SPX - 1) / mk::SPX, (H / 4 + mk::SPY - 1) / mk::SPY, B);
-  mk::stem_pool_kernel<<<grid, 256, mk::stem_pool_smem_bytes(), st>>>(vol, stride_s, stride_y, stride_x, s0, h, w,
+  mk::stem_pool_kernel<<<grid, 256, mk::stem_pool_smem_bytes(), st>>>(vol, elem, stride_s, stride_y, stride_x, s0, h, w,
                                                                       H, W, mean255, den, wt, bias, out);
   return be_check_launch("stem_pool_kernel");
 }

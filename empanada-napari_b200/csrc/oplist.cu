@@ -23,9 +23,9 @@ int conv_gemm_launch(const Launch* L, cudaStream_t stream);
 }  // namespace convgemm
 
 extern "C" {
-int be_stem(const uint8_t*, long long, long long, long long, int, int, int, int, int, int, float,
+int be_stem(const void*, int, long long, long long, long long, int, int, int, int, int, int, float,
             float, const float*, const float*, __nv_bfloat16*, cudaStream_t);
-int be_stem_pool(const uint8_t*, long long, long long, long long, int, int, int, int, int, int,
+int be_stem_pool(const void*, int, long long, long long, long long, int, int, int, int, int, int,
                  float, float, const float*, const float*, __nv_bfloat16*, cudaStream_t);
 int be_maxpool(const __nv_bfloat16*, int, int, int, int, __nv_bfloat16*, int, int, cudaStream_t);
 int be_dwconv(const __nv_bfloat16*, long long, int, int, int, int, int, const float*,
@@ -48,7 +48,7 @@ int be_pr_predict(const __nv_bfloat16*, int, int, const float*, const float*, fl
 namespace {
 
 struct RunArgs {  // per-replay parameters (the only things that change between batches)
-  const uint8_t* vol;
+  const void* vol;
   long long stride_s, stride_y, stride_x;
   int s0;
 };
@@ -144,7 +144,7 @@ static int oplist_capture(OpList* l, const RunArgs& ra) {
   return 0;
 }
 
-int be_oplist_run(void* list, const uint8_t* vol, long long stride_s, long long stride_y,
+int be_oplist_run(void* list, const void* vol, long long stride_s, long long stride_y,
                   long long stride_x, int s0, cudaStream_t st) {
   OpList* l = static_cast<OpList*>(list);
   RunArgs ra{vol, stride_s, stride_y, stride_x, s0};
@@ -220,27 +220,29 @@ int be_op_convt2x2(void* list, const void* in, long long in_ld, int B, int Hi, i
 }
 
 int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, float den,
-               const float* wt, const float* bias, void* out, const uint8_t* vol, long long stride_s,
-               long long stride_y, long long stride_x, int s0, cudaStream_t st) {
+               const float* wt, const float* bias, void* out, const void* vol, long long stride_s,
+               long long stride_y, long long stride_x, int s0, int elem, cudaStream_t st) {
+  if (elem < 0 || elem > 8) return be_set_error("stem: unknown element type code");
   if (list == nullptr)
-    return be_stem(vol, stride_s, stride_y, stride_x, s0, B, h, w, H, W, mean255, den, wt, bias,
+    return be_stem(vol, elem, stride_s, stride_y, stride_x, s0, B, h, w, H, W, mean255, den, wt, bias,
                    static_cast<__nv_bfloat16*>(out), st);
   return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs& ra) {
-    return be_stem(ra.vol, ra.stride_s, ra.stride_y, ra.stride_x, ra.s0, B, h, w, H, W, mean255, den,
+    return be_stem(ra.vol, elem, ra.stride_s, ra.stride_y, ra.stride_x, ra.s0, B, h, w, H, W, mean255, den,
                    wt, bias, static_cast<__nv_bfloat16*>(out), s);
   }, true);
 }
 
 // conv1 + BN + ReLU + MaxPool2d(3,2,1) in one kernel; `out` is the quarter-resolution map
 int be_op_stem_pool(void* list, int B, int h, int w, int H, int W, float mean255, float den,
-                    const float* wt, const float* bias, void* out, const uint8_t* vol,
-                    long long stride_s, long long stride_y, long long stride_x, int s0,
+                    const float* wt, const float* bias, void* out, const void* vol,
+                    long long stride_s, long long stride_y, long long stride_x, int s0, int elem,
                     cudaStream_t st) {
+  if (elem < 0 || elem > 8) return be_set_error("stem_pool: unknown element type code");
   if (list == nullptr)
-    return be_stem_pool(vol, stride_s, stride_y, stride_x, s0, B, h, w, H, W, mean255, den, wt, bias,
+    return be_stem_pool(vol, elem, stride_s, stride_y, stride_x, s0, B, h, w, H, W, mean255, den, wt, bias,
                         static_cast<__nv_bfloat16*>(out), st);
   return record_or_run(list, 1, st, [=](cudaStream_t s, const RunArgs& ra) {
-    return be_stem_pool(ra.vol, ra.stride_s, ra.stride_y, ra.stride_x, ra.s0, B, h, w, H, W, mean255,
+    return be_stem_pool(ra.vol, elem, ra.stride_s, ra.stride_y, ra.stride_x, ra.s0, B, h, w, H, W, mean255,
                         den, wt, bias, static_cast<__nv_bfloat16*>(out), s);
   }, true);
 }
@@ -321,7 +323,7 @@ int be_op_pr_predict(void* list, const void* X, int ldp, int C, const float* coa
 
 // Replays the list with a CUDA event between consecutive ops; ms_out[i] = device time of op i.
 // Used by bench.py for the live per-kernel roofline figures (never inside the timed region).
-extern "C" int be_oplist_run_timed(void* list, const uint8_t* vol, long long stride_s,
+extern "C" int be_oplist_run_timed(void* list, const void* vol, long long stride_s,
                                    long long stride_y, long long stride_x, int s0, float* ms_out,
                                    int max_ops, cudaStream_t st) {
   OpList* l = static_cast<OpList*>(list);

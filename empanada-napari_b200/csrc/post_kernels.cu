@@ -207,7 +207,7 @@ group_pixels_kernel(const float* __restrict__ off, const int* __restrict__ cente
     __syncthreads();
     for (int i = threadIdx.x; i < kn; i += blockDim.x) {
       const int packed = cb[k0 + i];
-      cy[i] = __fmul_rn(step, static_cast<float>(packed >> 16));
+      cy[i] = __fmul_rn(step, static_cast<float>(static_cast<unsigned>(packed) >> 16));
       cx[i] = __fmul_rn(step, static_cast<float>(packed & 0xFFFF));
     }
     __syncthreads();

@@ -12,8 +12,9 @@ import numpy as np
 import torch
 
 from . import _lib, consensus, tracking
+from .engines import PanopticDeepLabRenderEngine, PanopticDeepLabRenderEngine3d
 from .model import load_model
-from .postproc import LazyPlane, PlanePost
+from .postproc import CenterOverflow, LazyPlane, PlanePost, _next_pow2
 from .tracking import InstanceTracker
 
 __all__ = ["Engine2d", "Engine3d", "tracker_consensus", "stack_postprocessing"]
@@ -96,33 +97,56 @@ def auto_slice_batch(H, W, sms=148, requested=None, max_pixels=40 << 20):
     return max(1, min(cap, 32))
 
 
+def _as_device_volume(array, device):
+    """Host integer array -> contiguous device tensor of the same dtype (any integer dtype the
+    reference's Preprocessor accepts, empanada_napari/utils.py:189-201)."""
+    if np.issubdtype(array.dtype, np.floating):
+        raise Exception("Input image cannot be float type!")
+    if not np.issubdtype(array.dtype, np.integer):
+        raise Exception(f"Input image must have an integer dtype, got {array.dtype}")
+    # one pageable -> device copy (the driver stages it); pinning 1 GiB first costs more
+    return torch.from_numpy(np.ascontiguousarray(array)).to(device, non_blocking=False)
+
+
 class _VolumeCache:
-    """Keeps the uint8 volume resident in HBM across the xy/xz/yz passes."""
+    """Keeps the input volume resident in HBM across the xy/xz/yz passes of ONE host array.
+
+    A cached copy is reused only for the very same array object (held through a weak reference,
+    so a recycled `id()` of a freed array can never match) whose sampled content fingerprint is
+    unchanged; anything else is uploaded again. `Engine3d.release()` drops the copy explicitly
+    (call it after in-place edits that the sparse fingerprint might miss)."""
 
     def __init__(self):
-        self.key = None
+        self.ref = None
+        self.sig = None
         self.dev = None
+
+    @staticmethod
+    def _signature(volume):
+        import zlib
+        step = tuple(max(1, s // n) for s, n in zip(volume.shape, (16, 64, 64)))
+        sample = np.ascontiguousarray(volume[::step[0], ::step[1], ::step[2]])
+        return (volume.shape, str(volume.dtype), volume.strides, volume.__array_interface__["data"][0],
+                zlib.crc32(sample.tobytes()))
 
     def get(self, volume, device):
         if isinstance(volume, torch.Tensor):  # already resident (benchmarks / pipelines)
-            if volume.dtype != torch.uint8 or not volume.is_cuda:
-                _unsupported("device volumes other than cuda uint8")
+            if not volume.is_cuda or volume.dtype.is_floating_point or volume.dtype == torch.bool:
+                raise _lib.B200EmpanadaError("device volumes must be CUDA tensors of an integer dtype")
             return volume.contiguous()
-        key = (id(volume), volume.shape, str(volume.dtype))
-        if self.key != key:
-            if not isinstance(volume, np.ndarray):
-                _unsupported("zarr / dask input volumes")
-            if np.issubdtype(volume.dtype, np.floating):
-                raise Exception("Input image cannot be float type!")
-            if volume.dtype != np.uint8:
-                _unsupported(f"{volume.dtype} volumes (uint8 only)")
-            # one pageable -> device copy (the driver stages it); pinning 1 GiB first costs more
-            self.dev = torch.from_numpy(np.ascontiguousarray(volume)).to(device, non_blocking=False)
-            self.key = key
+        if not isinstance(volume, np.ndarray):
+            raise _lib.B200EmpanadaError("internal: lazily loaded volumes are streamed, not cached")
+        sig = self._signature(volume)
+        host = self.ref() if self.ref is not None else None
+        if host is not volume or sig != self.sig or self.dev is None:
+            self.dev = None
+            self.dev = _as_device_volume(volume, device)
+            import weakref
+            self.ref, self.sig = weakref.ref(volume), sig
         return self.dev
 
     def clear(self):
-        self.key, self.dev = None, None
+        self.ref, self.sig, self.dev = None, None, None
 
 
 class Engine3d:
@@ -148,15 +172,11 @@ class Engine3d:
         self.label_dilation = label_dilation
         self.fill_holes_in_segmentation = fill_holes_in_segmentation
         self.thing_list = [] if semantic_only else model_config["thing_list"]
-        self.median_kernel_size = median_kernel_size
-        self.stuff_area = stuff_area
-        self.void_label = void_label
-        self.nms_threshold = nms_threshold
-        self.nms_kernel = nms_kernel
-        self.confidence_thr = confidence_thr
         self.axes = {"xy": 0, "xz": 1, "yz": 2}
         self.merge_iou_thr = 0.25
         self.merge_ioa_thr = 0.25
+        # stored and never read, exactly as in the reference: forward_matching always encodes
+        # thing classes as connected components (empanada/inference/patterns.py:94)
         self.force_connected = force_connected
         self.min_size = min_size
         self.min_extent = min_extent
@@ -172,21 +192,24 @@ class Engine3d:
         self.overlap_replay = overlap_replay
         self.deferred_launches = 0
         self.model = load_model(model_config["model"], self.device, model_config)
-        self.engine = self  # widgets call engine.engine.reset(); kept for attribute parity
+        # per-slice engine object of the reference API; it owns the post-processing parameters
+        # (the widgets mutate them through `engine.engine`, inference.py:439-455) and the batched
+        # plane driver below reads them from it
+        self.engine = PanopticDeepLabRenderEngine3d(
+            self.model, thing_list=self.thing_list, median_kernel_size=median_kernel_size,
+            label_divisor=label_divisor, stuff_area=stuff_area, void_label=void_label,
+            nms_threshold=nms_threshold, nms_kernel=nms_kernel, confidence_thr=confidence_thr,
+            padding_factor=self.padding_factor, coarse_boundaries=not fine_boundaries)
         self._cache = _VolumeCache()
         self.last_stats = {}
 
-    # attribute parity with PanopticDeepLabRenderEngine3d (mutated by the widgets)
-    @property
-    def ks(self):
-        return self.median_kernel_size
-
-    @ks.setter
-    def ks(self, v):
-        self.median_kernel_size = v
-
-    def reset(self):
-        pass
+    # post-processing parameters live on the engine object (attribute parity with the reference)
+    median_kernel_size = property(lambda self: self.engine.ks)
+    stuff_area = property(lambda self: self.engine.stuff_area)
+    void_label = property(lambda self: self.engine.void_label)
+    nms_threshold = property(lambda self: self.engine.nms_threshold)
+    nms_kernel = property(lambda self: self.engine.nms_kernel)
+    confidence_thr = property(lambda self: self.engine.confidence_thr)
 
     def update_params(self, inference_scale, label_divisor, median_kernel_size, nms_threshold,
                       nms_kernel, confidence_thr, min_size, min_extent, fine_boundaries,
@@ -197,14 +220,19 @@ class Engine3d:
         self.min_size = min_size
         self.min_extent = min_extent
         self.fine_boundaries = fine_boundaries
-        self.median_kernel_size = median_kernel_size
-        self.nms_threshold = nms_threshold
-        self.nms_kernel = nms_kernel
-        self.confidence_thr = confidence_thr
+        self.engine.label_divisor = label_divisor
+        self.engine.ks = median_kernel_size
+        self.engine.mid_idx = (median_kernel_size - 1) // 2
+        self.engine.nms_threshold = nms_threshold
+        self.engine.nms_kernel = nms_kernel
+        self.engine.confidence_thr = confidence_thr
+        self.engine.coarse_boundaries = not fine_boundaries
         self.label_erosion = label_erosion
         self.label_dilation = label_dilation
         self.fill_holes_in_segmentation = fill_holes_in_segmentation
         self.thing_list = [] if semantic_only else self.model_config["thing_list"]
+        self.engine.thing_list = self.thing_list
+        self.engine.reset()
         self.save_panoptic = save_panoptic
         self.chunk_size = chunk_size
         if store_url is not None:
@@ -218,7 +246,7 @@ class Engine3d:
             _unsupported("inference_scale > 1")
         if self.label_erosion or self.label_dilation or self.fill_holes_in_segmentation:
             _unsupported("tracker morphology (erode / dilate / fill holes)")
-        if len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
+        if len(self.labels) != 1 or list(self.engine.thing_list) != list(self.labels):
             _unsupported("multi-class / semantic-only models")
 
     def _plane_setup(self, volume, axis_name):
@@ -233,11 +261,12 @@ class Engine3d:
         return axis, vol_d, shape3d, n, h, w, H, W, pf
 
     def _make_post(self, n, h, w, H, W):
-        return PlanePost(n, h, w, H, W, ks=self.median_kernel_size, thing_class=self.thing_list[0],
-                         label_divisor=self.label_divisor, void_label=self.void_label,
-                         nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
-                         confidence_thr=self.confidence_thr, device=self.device,
-                         scale=1 if self.fine_boundaries else 4)
+        e = self.engine
+        return PlanePost(n, h, w, H, W, ks=e.ks, thing_class=e.thing_list[0],
+                         label_divisor=e.label_divisor, void_label=e.void_label,
+                         nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
+                         confidence_thr=e.confidence_thr, device=self.device,
+                         scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap)
 
     def _finish_plane(self, post, axis_name, shape3d, prof=None, defer=False):
         """Everything after the head maps are in: median tail, components, tracker replay,
@@ -292,12 +321,19 @@ class Engine3d:
     def infer_on_axis(self, volume, axis_name):
         self._check_supported()
         axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
-        post = self._make_post(n, h, w, H, W)
         launches0 = getattr(self.model, "launches", 0)
         prof = _Phase(os.environ.get("B200_EMPANADA_PROFILE") == "1")
-        self._forward_all(post, vol_d, axis, n, self.model_config["norms"], pf)
         defer = self.overlap_replay and not self.save_panoptic and not prof.on
-        trackers = self._finish_plane(post, axis_name, shape3d, prof, defer=defer)
+        while True:
+            post = self._make_post(n, h, w, H, W)
+            self._forward_all(post, vol_d, axis, n, self.model_config["norms"], pf)
+            try:
+                trackers = self._finish_plane(post, axis_name, shape3d, prof, defer=defer)
+                break
+            except CenterOverflow as e:
+                # the reference has no limit on centres per slice: run the plane again with room
+                # for the densest slice (rare: > 4096 centres in one slice)
+                self.engine.center_cap = _next_pow2(e.needed)
         self.last_profile = prof.t
         stack = trackers[0]._b200_dense.cpu().numpy() if self.save_panoptic else None
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
@@ -309,7 +345,7 @@ class Engine3d:
         for s0 in range(0, n, bs):
             s1 = min(n, s0 + bs)
             sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
-            if self.fine_boundaries:
+            if not self.engine.coarse_boundaries:
                 ctr, off = upsample_instance_heads(ctr, off)
             post.push_heads(sem, ctr, off, is_prob=False)
 
@@ -344,60 +380,64 @@ class Engine2d:
         self.padding_factor = model_config["padding_factor"]
         self.inference_scale = inference_scale
         self.fine_boundaries = fine_boundaries
-        self.semantic_only = semantic_only
         self.tile_size = tile_size
-        self.nms_threshold = nms_threshold
-        self.nms_kernel = nms_kernel
-        self.confidence_thr = confidence_thr
         self.model = load_model(model_config["model"], self.device, model_config)
-        self.engine = self
+        self.engine = PanopticDeepLabRenderEngine(
+            self.model, thing_list=[] if semantic_only else self.thing_list, label_divisor=label_divisor,
+            nms_threshold=nms_threshold, nms_kernel=nms_kernel, confidence_thr=confidence_thr,
+            padding_factor=self.padding_factor, coarse_boundaries=not fine_boundaries)
+
+    nms_threshold = property(lambda self: self.engine.nms_threshold)
+    nms_kernel = property(lambda self: self.engine.nms_kernel)
+    confidence_thr = property(lambda self: self.engine.confidence_thr)
+    semantic_only = property(lambda self: list(self.engine.thing_list) == [])
 
     def update_params(self, inference_scale, label_divisor, nms_threshold, nms_kernel,
                       confidence_thr, fine_boundaries, semantic_only=False, tile_size=0):
         self.inference_scale = inference_scale
+        self.engine.input_scale = inference_scale
         self.label_divisor = label_divisor
-        self.nms_threshold = nms_threshold
-        self.nms_kernel = nms_kernel
-        self.confidence_thr = confidence_thr
+        self.engine.label_divisor = label_divisor
+        self.engine.nms_threshold = nms_threshold
+        self.engine.nms_kernel = nms_kernel
+        self.engine.confidence_thr = confidence_thr
         self.fine_boundaries = fine_boundaries
-        self.semantic_only = semantic_only
+        self.engine.coarse_boundaries = not fine_boundaries
+        self.engine.thing_list = [] if semantic_only else self.thing_list
         self.tile_size = tile_size
 
     def infer_batch(self, images):
         """images: uint8 array (n, h, w) -> int32 (n, h, w). One launch sequence for the batch."""
         if self.inference_scale != 1:
             _unsupported("inference_scale > 1")
-        if self.semantic_only or len(self.labels) != 1 or list(self.thing_list) != list(self.labels):
+        if len(self.labels) != 1 or list(self.engine.thing_list) != list(self.labels):
             _unsupported("multi-class / semantic-only models")
         if self.tile_size > 0 and any(s > self.tile_size for s in images.shape[1:]):
             _unsupported("tiled 2-D inference")
         dev = self.device
         if isinstance(images, torch.Tensor):   # already resident (benchmarks / pipelines)
-            if images.dtype != torch.uint8 or not images.is_cuda:
-                _unsupported("device images other than cuda uint8")
+            if not images.is_cuda or images.dtype.is_floating_point or images.dtype == torch.bool:
+                raise _lib.B200EmpanadaError("device images must be CUDA tensors of an integer dtype")
             vol_d = images.contiguous()
         else:
-            if np.issubdtype(images.dtype, np.floating):
-                raise Exception("Input image cannot be float type!")
-            if images.dtype != np.uint8:
-                _unsupported(f"{images.dtype} images (uint8 only)")
-            vol_d = torch.from_numpy(np.ascontiguousarray(images)).to(dev)
+            vol_d = _as_device_volume(images, dev)
         n, h, w = vol_d.shape
         pf = self.padding_factor
         H = h + (pf - h % pf) % pf
         W = w + (pf - w % pf) % pf
-        cls = self.thing_list[0]
-        post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=self.label_divisor,
-                         void_label=0, nms_threshold=self.nms_threshold, nms_kernel=self.nms_kernel,
-                         confidence_thr=self.confidence_thr, device=dev,
-                         scale=1 if self.fine_boundaries else 4)
+        e = self.engine
+        cls = e.thing_list[0]
+        post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=e.label_divisor,
+                         void_label=e.void_label, nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
+                         confidence_thr=e.confidence_thr, device=dev,
+                         scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap)
         # tiles per launch list: whole SM waves on the 1/16 map, activation buffers within ~25 GB
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         chunk = max(1, min(n, auto_slice_batch(H, W, sms)))
         for s0 in range(0, n, chunk):
             s1 = min(n, s0 + chunk)
             sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)
-            if self.fine_boundaries:
+            if not e.coarse_boundaries:
                 ctr, off = upsample_instance_heads(ctr, off)
             post.push_heads(sem, ctr, off, is_prob=False)
         post.finish_heads()

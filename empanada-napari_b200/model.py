@@ -47,6 +47,31 @@ def load_state_dict_any(path):
         return sd
 
 
+def resolve_model_file(fpath_or_url, download=True):
+    """Local file for a model URL: the reference's cache location `torch.hub.get_dir()/<basename
+    of the URL path>` (empanada_napari/utils.py:84-104), downloaded there when absent exactly as
+    the reference does; `~/.empanada/<basename>` is accepted as a second cache location."""
+    from urllib.parse import urlparse
+    filename = os.path.basename(urlparse(fpath_or_url).path)
+    hub_dir = torch.hub.get_dir()
+    cached = os.path.join(hub_dir, filename)
+    if os.path.exists(cached):
+        return cached
+    alt = os.path.join(os.path.expanduser("~"), ".empanada", filename)
+    if os.path.isfile(alt):
+        return alt
+    if not download or not (fpath_or_url.startswith("http://") or fpath_or_url.startswith("https://")):
+        raise _lib.B200EmpanadaError(f"model file {fpath_or_url} not found (looked in {cached} and {alt})")
+    os.makedirs(hub_dir, exist_ok=True)
+    try:
+        import sys
+        sys.stderr.write(f'Downloading: "{fpath_or_url}" to {cached}\n')
+        torch.hub.download_url_to_file(fpath_or_url, cached, None, progress=True)
+    except Exception as e:
+        raise _lib.B200EmpanadaError(f"model URL {fpath_or_url} is not cached at {cached} and the download failed: {e}")
+    return cached
+
+
 def load_model(model, device, model_config=None):
     if hasattr(model, "forward_slices"):
         return model
@@ -54,13 +79,8 @@ def load_model(model, device, model_config=None):
         sd = model
     elif isinstance(model, str):
         path = model
-        if path.startswith("http://") or path.startswith("https://"):
-            # same cache location as the reference (utils.py:86-104); no download here
-            cached = os.path.join(os.path.expanduser("~"), ".empanada", os.path.basename(path).split("?")[0])
-            if not os.path.isfile(cached):
-                raise _lib.B200EmpanadaError(
-                    f"model URL {path} is not cached at {cached} and this build does not download")
-            path = cached
+        if not os.path.isfile(path):
+            path = resolve_model_file(path)
         sd = load_state_dict_any(path)
     else:
         raise _lib.B200EmpanadaError(f"unsupported model specification: {type(model)}")

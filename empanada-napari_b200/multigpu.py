@@ -122,7 +122,7 @@ class DistributedEngine3d(Engine3d):
                 for s0 in range(a, b, 64):
                     s1 = min(b, s0 + 64)
                     c_, o_ = gathered[1][r][s0 - a:s1 - a], gathered[2][r][s0 - a:s1 - a]
-                    if self.fine_boundaries:
+                    if not self.engine.coarse_boundaries:
                         c_, o_ = upsample_instance_heads(c_.contiguous(), o_.contiguous())
                     post.push_heads(gathered[0][r][s0 - a:s1 - a], c_, o_, is_prob=False)
             self._pending[axis_name] = (post, shape3d)
@@ -276,7 +276,7 @@ class ShardedEngine3d(Engine3d):
             a, b = max(s0, e_lo), min(s1, e_hi)
             if a < b:
                 c_, o_ = ctr[a - s0:b - s0], off[a - s0:b - s0]
-                if self.fine_boundaries:
+                if not self.engine.coarse_boundaries:
                     c_, o_ = upsample_instance_heads(c_.contiguous(), o_.contiguous())
                 post.push_instance(c_, o_, a - e_lo)
         tm.mark("forward + centres + grouping")

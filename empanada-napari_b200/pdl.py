@@ -34,9 +34,9 @@ _lib.declare("be_oplist_run_timed", [P, P, LL, LL, LL, I, P, I, P])
 _lib.declare("be_oplist_size", [P])
 _lib.declare("be_op_conv", [P, P, LL, I, I, I, I, P, I, I, I, I, I, I, I, I, P, LL, I, P, LL, I, P, LL,
                             P, LL, I, P, P, P, I, P])
-_lib.declare("be_op_stem", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, P])
+_lib.declare("be_op_stem", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, I, P])
 _lib.declare("be_op_maxpool", [P, P, I, I, I, I, P, I, I, P])
-_lib.declare("be_op_stem_pool", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, P])
+_lib.declare("be_op_stem_pool", [P, I, I, I, I, I, F, F, P, P, P, P, LL, LL, LL, I, I, P])
 _lib.declare("be_op_dwconv", [P, P, LL, I, I, I, I, I, P, P, LL, P, I, I, I, P])
 _lib.declare("be_op_bilinear", [P, P, LL, I, I, I, I, P, LL, I, I, I, P])
 _lib.declare("be_op_convt2x2", [P, P, LL, I, I, I, I, P, I, P, LL, I, P, I, P])
@@ -225,7 +225,7 @@ class _PlanBase:
         self.op_desc.append(f"{wname} {Cin}->{Cout} k{k} s{stride} d{dil} {Hi}x{Wi} bytes={nbytes/1e6:.0f}MB")
         return out, Ho, Wo
 
-    def record_encoder(self, h, w, H, Wd, mean255, den, output_stride=16, fused_stem=True):
+    def record_encoder(self, h, w, H, Wd, mean255, den, output_stride=16, fused_stem=True, elem=0):
         """Stem + max-pool + the 16 bottlenecks. Returns {level: (tensor, H, W, C)} for the
         outputs of layer1..layer4 (levels 2..5)."""
         W, L, B = self.W, self.handle, self.B
@@ -233,11 +233,11 @@ class _PlanBase:
         x = self.buf(B, H4, W4, 64)
         if fused_stem:
             self._rec("be_op_stem_pool", L, B, h, w, H, Wd, mean255, den, ptr(W["stem.w"]), ptr(W["stem.b"]),
-                      ptr(x), None, 0, 0, 0, 0, None)
+                      ptr(x), None, 0, 0, 0, 0, elem, None)
         else:
             stem = self.buf(B, H2, W2, 64)
             self._rec("be_op_stem", L, B, h, w, H, Wd, mean255, den, ptr(W["stem.w"]), ptr(W["stem.b"]),
-                      ptr(stem), None, 0, 0, 0, 0, None)
+                      ptr(stem), None, 0, 0, 0, 0, elem, None)
             self._rec("be_op_maxpool", L, ptr(stem), B, H2, W2, 64, ptr(x), H4, W4, None)
         Hc, Wc, Cin = H4, W4, 64
         levels = {}
@@ -327,11 +327,11 @@ class _PlanBase:
 class _Plan(_PlanBase):
     """PanopticDeepLab-PointRend launch list."""
 
-    def __init__(self, W, B, h, w, H, Wd, mean255, den, render_steps=2, num_points=8192, fused_stem=True):
+    def __init__(self, W, B, h, w, H, Wd, mean255, den, render_steps=2, num_points=8192, fused_stem=True, elem=0):
         super().__init__(W, B)
         L, buf, conv = self.handle, self.buf, self.conv
         H4, W4 = H // 4, Wd // 4
-        levels = self.record_encoder(h, w, H, Wd, mean255, den, 16, fused_stem)
+        levels = self.record_encoder(h, w, H, Wd, mean255, den, 16, fused_stem, elem)
         p2 = levels[2][0]
         p5, H16, W16, _ = levels[5]
         feats = {}
@@ -368,22 +368,66 @@ class _Plan(_PlanBase):
         self.record_heads_pointrend(semantic_x, instance_x, H4, W4, 256, render_steps, num_points)
 
 
+# element type codes of the C-ABI (include/b200_empanada.h be_op_stem): any integer dtype the
+# reference's Preprocessor accepts (empanada_napari/utils.py:189-201)
+ELEM_CODES = {"uint8": 0, "int8": 1, "uint16": 2, "int16": 3, "uint32": 4, "int32": 5, "uint64": 6, "int64": 7,
+              "float32": 8}   # 8: image already normalised (engine-level API, norms=None)
+
+
+def elem_code(dtype):
+    name = str(dtype).replace("torch.", "")
+    if name not in ELEM_CODES:
+        raise _lib.B200EmpanadaError(f"unsupported volume dtype {dtype} (integer dtypes only)")
+    return ELEM_CODES[name]
+
+
+def norm_constants(norms, dtype):
+    """fp32 (mean * max, 1 / (std * max)) exactly as `normalize` computes them
+    (empanada_napari/utils.py:170-185) with max = np.iinfo(dtype).max."""
+    name = str(dtype).replace("torch.", "")
+    if name == "float32" or norms is None:
+        if name != "float32" or norms is not None:
+            raise _lib.B200EmpanadaError("float volumes are only accepted already normalised (norms=None)")
+        return np.float32(0.0), np.float32(1.0)
+    maxv = np.float32(np.iinfo(np.dtype(name)).max)
+    mean = np.float32(np.float32(norms["mean"]) * maxv)
+    den = np.reciprocal(np.float32(np.float32(norms["std"]) * maxv), dtype=np.float32)
+    return mean, den
+
+
 class _NetModel:
-    """A network = kernel-layout weights + one recorded launch list per (batch, slice shape)."""
+    """A network = kernel-layout weights + one recorded launch list per (batch, slice shape).
+    Launch lists own their activation buffers, so the cache is bounded: least-recently-used lists
+    are dropped beyond `max_plans` entries or `max_plan_bytes` of activations, and a shorter tail
+    batch re-uses the full-batch list of the same slice shape (shifted back over slices that were
+    already computed) instead of recording a second one."""
     weights_cls = None
     plan_cls = None
     min_factor = 16      # the padded slice size must be a multiple of this
+    max_plans = 4
 
     def __init__(self, sd, device):
         self.dev = device
         with torch.cuda.device(device):
             self.W = self.weights_cls(sd, device)
-        self.plans = {}
+        self.plans = {}          # insertion order = recency (re-inserted on use)
         self.launches = 0
         self.render_steps = 2
+        total = torch.cuda.get_device_properties(device).total_memory
+        self.max_plan_bytes = int(0.45 * total)
+
+    @staticmethod
+    def _plan_bytes(plan):
+        return sum(t.numel() * t.element_size() for t in plan.bufs)
+
+    def _evict(self, need_bytes):
+        while self.plans and (len(self.plans) >= self.max_plans or
+                              sum(self._plan_bytes(p) for p in self.plans.values()) + need_bytes > self.max_plan_bytes):
+            oldest = next(iter(self.plans))
+            del self.plans[oldest]
 
     def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
-        """Slices [s0, s1) of the (D,H,W) uint8 device volume along `axis` -> (sem_logits (B,H,W),
+        """Slices [s0, s1) of the (D,H,W) integer device volume along `axis` -> (sem_logits (B,H,W),
         ctr_hmp (B,H/4,W/4), offsets (B,2,H/4,W/4)) fp32 device tensors owned by the plan."""
         D, Hv, Wv = vol_d.shape
         h, w = [(Hv, Wv), (D, Wv), (D, Hv)][axis]
@@ -393,22 +437,36 @@ class _NetModel:
         if H % self.min_factor or Wd % self.min_factor:
             raise _lib.B200EmpanadaError(f"padded slice size must be a multiple of {self.min_factor}")
         B = s1 - s0
-        mean255 = np.float32(np.float32(norms["mean"]) * np.float32(255))
-        den = np.reciprocal(np.float32(np.float32(norms["std"]) * np.float32(255)), dtype=np.float32)
-        key = (B, h, w, H, Wd, float(mean255), float(den))
-        plan = self.plans.get(key)
+        elem = elem_code(vol_d.dtype)
+        mean255, den = norm_constants(norms, vol_d.dtype)
+        shape_key = (h, w, H, Wd, float(mean255), float(den), elem)
+        key = (B,) + shape_key
+        plan = self.plans.pop(key, None)
+        skip = 0
         if plan is None:
+            # tail batch: replay a longer list of the same slice shape over [s1 - Bp, s1)
+            for k2 in list(self.plans.keys()):
+                if k2[1:] == shape_key and k2[0] > B and s1 - k2[0] >= 0:
+                    key, plan = k2, self.plans.pop(k2)
+                    skip = k2[0] - B
+                    break
+        if plan is None:
+            self._evict(0)
             with torch.cuda.device(self.dev):
-                plan = self.plan_cls(self.W, B, h, w, H, Wd, float(mean255), float(den), self.render_steps)
+                plan = self.plan_cls(self.W, B, h, w, H, Wd, float(mean255), float(den), self.render_steps, elem=elem)
             # small batches are launch bound (hundreds of kernels of a few microseconds): replay
             # them as one CUDA graph; large batches keep plain launches (kernels >> launch cost)
             if USE_GRAPHS and B * H * Wd <= GRAPH_MAX_PIXELS:
                 call("be_oplist_set_graph", plan.handle, 1)
-            self.plans[key] = plan
-        plan.run(vol_d, strides, s0)
+        self.plans[key] = plan
+        plan.run(vol_d, strides, s0 - skip)
         self.launches += plan.launches
         self.last_plan = plan
-        return plan.sem, plan.ctr, plan.off
+        return plan.sem[skip:], plan.ctr[skip:], plan.off[skip:]
+
+    def release_plans(self):
+        """Drop every recorded launch list and its activation buffers."""
+        self.plans.clear()
 
 
 class PDLModel(_NetModel):

@@ -16,6 +16,14 @@ from . import tracking
 AXES = {"xy": 0, "xz": 1, "yz": 2}
 
 
+class CenterOverflow(_lib.B200EmpanadaError):
+    """More centres in one slice than `center_cap` slots: the plane is re-run with `needed`."""
+
+    def __init__(self, needed, cap):
+        super().__init__(f"{needed} centres in one slice exceed center_cap={cap}")
+        self.needed = needed
+
+
 def _next_pow2(n):
     p = 1
     while p < n:
@@ -104,8 +112,7 @@ class PlanePost:
     def check_centers(self):
         cmax = int(self.center_counts.max().item())
         if cmax > self.center_cap:
-            raise _lib.B200EmpanadaError(
-                f"{cmax} centres in one slice exceed center_cap={self.center_cap}")
+            raise CenterOverflow(cmax, self.center_cap)
 
     def finish_heads(self):
         assert self.pushed == self.N
@@ -113,10 +120,7 @@ class PlanePost:
             call("be_median_flush", ptr(self.hist), self.n_hist, self.ks, self.H, self.W, self.N,
                  float(self.conf), ptr(self.hard), ptr(self.prob), stream_ptr())
             self.launches += 1
-        cmax = int(self.center_counts.max().item())
-        if cmax > self.center_cap:
-            raise _lib.B200EmpanadaError(
-                f"{cmax} centres in one slice exceed center_cap={self.center_cap}")
+        self.check_centers()
 
     # ------------------------------------------------------------------ stage 2: pan -> cc
     def pan_batch(self, s0, s1):
@@ -324,20 +328,69 @@ def instances_from_dense(vol, axis_name, labels, boxes, batch=64):
 
 class LazyAttrs(dict):
     """Instance attributes whose RLE ('starts', 'runs') is materialised from the device-resident
-    label volume on first access; 'box' is always present."""
+    label volume on first use. Only `attrs['box']` is answered without materialising; every other
+    way of looking at the dictionary (membership tests, get, iteration, keys / items / values,
+    len, copy, equality, pickling, json) sees the complete {'box', 'starts', 'runs'} mapping."""
 
     def __init__(self, box, owner):
         super().__init__(box=box)
         self._owner = owner
 
+    def _fill(self):
+        if self._owner is not None:
+            owner, self._owner = self._owner, None
+            owner.materialize()
+
     def __missing__(self, key):
-        if key in ("starts", "runs"):
-            self._owner.materialize()
+        if key in ("starts", "runs") and self._owner is not None:
+            self._fill()
             return dict.__getitem__(self, key)
         raise KeyError(key)
 
+    def __contains__(self, key):
+        self._fill()
+        return dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        self._fill()
+        return dict.get(self, key, default)
+
+    def keys(self):
+        self._fill()
+        return dict.keys(self)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+    def __iter__(self):
+        self._fill()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._fill()
+        return dict.__len__(self)
+
+    def __eq__(self, other):
+        self._fill()
+        return dict.__eq__(self, other)
+
+    __hash__ = None
+
+    def copy(self):
+        self._fill()
+        return dict(self)
+
+    def __repr__(self):
+        self._fill()
+        return dict.__repr__(self)
+
     def __reduce__(self):
-        self._owner.materialize()
+        self._fill()
         return (dict, (dict(self),))
 
 
@@ -355,6 +408,8 @@ class LazyPlane:
         self.done = True
         full = instances_from_dense(self.dense, self.axis_name, self.labels, self.boxes)
         for l, a in full.items():
-            if l in self.attrs:
-                dict.__setitem__(self.attrs[l], "starts", a["starts"])
-                dict.__setitem__(self.attrs[l], "runs", a["runs"])
+            attrs = self.attrs.get(l)
+            if attrs is not None:
+                attrs._owner = None
+                dict.__setitem__(attrs, "starts", a["starts"])
+                dict.__setitem__(attrs, "runs", a["runs"])

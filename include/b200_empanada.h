@@ -29,9 +29,9 @@ int be_oplist_size(void* list);
 /* replay everything after the slice-gather prefix of the list as one CUDA graph (launch-bound
  * lists: single small tiles); the first replay after enabling runs plainly, the second captures */
 int be_oplist_set_graph(void* list, int enable);
-int be_oplist_run(void* list, const uint8_t* volume_u8, long long stride_slice, long long stride_y,
+int be_oplist_run(void* list, const void* volume, long long stride_slice, long long stride_y,
                   long long stride_x, int first_slice, be_stream st);
-int be_oplist_run_timed(void* list, const uint8_t* volume_u8, long long stride_slice,
+int be_oplist_run_timed(void* list, const void* volume, long long stride_slice,
                         long long stride_y, long long stride_x, int first_slice, float* ms_per_op,
                         int max_ops, be_stream st);
 /* implicit-GEMM convolution on tcgen05/TMEM fed by TMA (every nn.Conv2d / Conv1d with groups == 1:
@@ -45,19 +45,23 @@ int be_op_conv(void* list, const void* in, long long in_ld, int B, int Hi, int W
                const float* head_b, float* head_out, int head_n, be_stream st);
 /* slice gather + Preprocessor.normalize + factor_pad + conv1 7x7/2 + BN + ReLU
  * (data/volume_dataset.py:37-53, empanada_napari/utils.py:170-201, inference/postprocess.py:26-36,
- * encoders/resnet.py:217-220) */
+ * encoders/resnet.py:217-220). `elem` = element type of the volume: 0 u8, 1 i8, 2 u16, 3 i16,
+ * 4 u32, 5 i32, 6 u64, 7 i64 (any integer dtype, utils.py:189-201), 8 = fp32 that is already
+ * normalised (the engine-level API, engines.py:300-325; pass mean255 0 and inv_std255 1);
+ * mean255 / inv_std255 are mean*iinfo.max and 1/(std*iinfo.max) of that dtype; strides are in
+ * elements */
 int be_op_stem(void* list, int B, int h, int w, int H, int W, float mean255, float inv_std255,
-               const float* wt_49x64, const float* bias64, void* out, const uint8_t* vol,
+               const float* wt_49x64, const float* bias64, void* out, const void* vol,
                long long stride_slice, long long stride_y, long long stride_x, int first_slice,
-               be_stream st);
+               int elem, be_stream st);
 int be_op_maxpool(void* list, const void* in, int B, int Hi, int Wi, int C, void* out, int Ho, int Wo,
                   be_stream st);                                   /* encoders/resnet.py:221 */
 /* be_op_stem followed by be_op_maxpool in ONE kernel (encoders/resnet.py:217-221): `out` is the
  * quarter-resolution [B][H/4][W/4][64] map; the half-resolution map never reaches HBM */
 int be_op_stem_pool(void* list, int B, int h, int w, int H, int W, float mean255, float inv_std255,
-                    const float* wt_49x64, const float* bias64, void* out, const uint8_t* vol,
+                    const float* wt_49x64, const float* bias64, void* out, const void* vol,
                     long long stride_slice, long long stride_y, long long stride_x, int first_slice,
-                    be_stream st);
+                    int elem, be_stream st);
 /* depthwise k x k (blocks.py:15-35); optional fused producer: channels [0,Cup) are the
  * align_corners=True bilinear upsampling of `up` (decoders/panoptic_deeplab.py:76-77) */
 int be_op_dwconv(void* list, const void* in, long long in_ld, int B, int H, int W, int C, int k,

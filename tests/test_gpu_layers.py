@@ -58,8 +58,10 @@ def test_dwconv_fused_upsample_equals_unfused(B, Hu, Wu, clow):
     assert float((got - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 1e-3
 
 
-@pytest.mark.parametrize("B,h,w,axis", [(2, 64, 64, 0), (1, 100, 72, 0), (2, 48, 80, 1), (2, 80, 48, 2)])
-def test_stem_pool_equals_stem_then_maxpool(B, h, w, axis):
+@pytest.mark.parametrize("B,h,w,axis,dtype", [(2, 64, 64, 0, "uint8"), (1, 100, 72, 0, "uint8"), (2, 48, 80, 1, "uint8"),
+                                              (2, 80, 48, 2, "uint8"), (2, 48, 80, 1, "uint16"), (1, 64, 48, 2, "int16"),
+                                              (1, 48, 64, 0, "int32"), (1, 48, 64, 0, "int8")])
+def test_stem_pool_equals_stem_then_maxpool(B, h, w, axis, dtype):
     """Fused conv1+BN+ReLU+MaxPool kernel == stem kernel followed by the max-pool kernel (bits),
     and both agree with torch conv2d + max_pool2d on the normalised, padded slice."""
     torch, call, ptr = _setup()
@@ -69,25 +71,29 @@ def test_stem_pool_equals_stem_then_maxpool(B, h, w, axis):
     g = torch.Generator(device="cpu").manual_seed(11)
     shape = [B + 1, h, w]
     shape3d = {0: (B + 1, h, w), 1: (h, B + 1, w), 2: (h, w, B + 1)}[axis]
-    vol = torch.randint(0, 256, shape3d, generator=g, dtype=torch.uint8).to(dev)
+    from empanada_napari_b200.pdl import elem_code, norm_constants
+    info = np.iinfo(np.dtype(dtype))
+    # values spread over the dtype's whole range (the reference normalises by iinfo.max, utils.py:189-201)
+    vol_np = (torch.rand(shape3d, generator=g, dtype=torch.float64).numpy() * (float(info.max) - float(info.min)) + float(info.min)).astype(dtype)
+    vol = torch.from_numpy(vol_np).to(dev)
+    elem = elem_code(vol.dtype)
     D, Hv, Wv = shape3d
     strides = [(Hv * Wv, Wv, 1), (Wv, Hv * Wv, 1), (1, Hv * Wv, Wv)][axis]
     wt = (torch.randn(64, 1, 7, 7, generator=g) * 0.1)
     bias = torch.randn(64, generator=g) * 0.1
     wt_d = wt.reshape(64, 49).t().contiguous().to(dev)
     bias_d = bias.to(dev)
-    mean255 = float(np.float32(0.57571) * np.float32(255))
-    den = float(np.reciprocal(np.float32(np.float32(0.12765) * np.float32(255)), dtype=np.float32))
+    mean255, den = (float(v) for v in norm_constants({"mean": 0.57571, "std": 0.12765}, vol.dtype))
     s0 = 1
     stem = torch.zeros(B, H // 2, W // 2, 64, dtype=torch.bfloat16, device=dev)
     pooled = torch.zeros(B, H // 4, W // 4, 64, dtype=torch.bfloat16, device=dev)
     fused = torch.zeros_like(pooled)
-    call("be_op_stem", None, B, h, w, H, W, mean255, den, ptr(wt_d), ptr(bias_d), ptr(stem), ptr(vol), *strides, s0, None)
+    call("be_op_stem", None, B, h, w, H, W, mean255, den, ptr(wt_d), ptr(bias_d), ptr(stem), ptr(vol), *strides, s0, elem, None)
     call("be_op_maxpool", None, ptr(stem), B, H // 2, W // 2, 64, ptr(pooled), H // 4, W // 4, None)
-    call("be_op_stem_pool", None, B, h, w, H, W, mean255, den, ptr(wt_d), ptr(bias_d), ptr(fused), ptr(vol), *strides, s0, None)
+    call("be_op_stem_pool", None, B, h, w, H, W, mean255, den, ptr(wt_d), ptr(bias_d), ptr(fused), ptr(vol), *strides, s0, elem, None)
     torch.cuda.synchronize()
     assert torch.equal(fused, pooled)
-    sl = vol.movedim(axis, 0)[s0:s0 + B].float()
+    sl = torch.from_numpy(np.moveaxis(vol_np, axis, 0)[s0:s0 + B].astype(np.float32)).to(dev)
     x = torch.zeros(B, 1, H, W, device=dev)
     x[:, 0, :h, :w] = (sl - mean255) * den
     ref = torch.nn.functional.conv2d(x, wt.to(dev), bias_d, stride=2, padding=3).relu()
