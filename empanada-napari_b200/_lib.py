@@ -25,6 +25,15 @@ _SIGNATURES = {
     "be_centers": ([P, I, I, I, F, I, P, I, P, P, P], I),
     "be_group_pixels": ([P, P, I, P, I, I, I, F, P, P], I),
     "be_merge_pan": ([P, P, I, I, I, I, I, I, I, I, I, I, P, P, P], I),
+    "be_rank_ids": ([P, I, I, I, I, P], I),
+    # run_kernels.cu
+    "be_group_flags": ([P, P, P, I, P, I, I, I, I, P, P, P], I),
+    "be_rowruns_count": ([P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P], I),
+    "be_rowruns_write": ([P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P], I),
+    "be_runs_cc": ([P, P, P, P, P, I, I, I, P, P, P, P], I),
+    "be_runs_stats": ([P, P, P, P, I, I, I, P, P], I),
+    "be_runs_overlap": ([P, P, P, P, P, I, I, I, I, P, P, ULL, P, P], I),
+    "be_runs_paint": ([P, P, P, P, P, P, I, I, I, I, I, I, P, LL, LL, LL, P], I),
     # cc_kernels.cu
     "be_cc_label": ([P, I, I, I, I, I, P, P, P, P, I, P, P], I),
     "be_hash_clear": ([P, P, ULL, P], I),

@@ -78,6 +78,94 @@ __global__ void median_harden_kernel(const float* __restrict__ logits, int B, lo
     if (i < nq) hist[i * HW + p] = q[i];
 }
 
+
+// Vectorised form: one thread owns FOUR consecutive pixels (16-byte loads of the logits and of
+// the queue, one 4-byte store of the hardened mask) and the slice loop is unrolled so that several
+// independent 16-byte loads are in flight per thread. Same arithmetic per pixel as above.
+template <int KS>
+__global__ void __launch_bounds__(256)
+median_harden_v4_kernel(const float4* __restrict__ logits, int B, long long HW4,
+                        float4* __restrict__ hist, int n_hist, int slice0, float conf_thr,
+                        int is_prob, uchar4* __restrict__ hard, float4* __restrict__ prob_out) {
+  constexpr int MID = (KS - 1) / 2;
+  const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (p >= HW4) return;
+  float q[KS][4];
+  int nq = n_hist;
+#pragma unroll
+  for (int i = 0; i < KS - 1; ++i) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_hist) t = hist[i * HW4 + p];
+    q[i][0] = t.x; q[i][1] = t.y; q[i][2] = t.z; q[i][3] = t.w;
+  }
+  constexpr int UNROLL = 4;
+  for (int b0 = 0; b0 < B; b0 += UNROLL) {
+    float4 in[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (b0 + u < B) in[u] = __ldcs(&logits[(b0 + u) * HW4 + p]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int b = b0 + u;
+      if (b >= B) break;
+      float v[4] = {in[u].x, in[u].y, in[u].z, in[u].w};
+      if (!is_prob) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+      }
+      if (nq == KS) {
+#pragma unroll
+        for (int i = 0; i < KS - 1; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[i][j] = q[i + 1][j];
+        nq = KS - 1;
+      }
+#pragma unroll
+      for (int i = 0; i < KS; ++i)
+        if (i == nq) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[i][j] = v[j];
+        }
+      ++nq;
+      const int t = slice0 + b;
+      if (nq <= MID) {
+        hard[t * HW4 + p] = make_uchar4(v[0] >= conf_thr, v[1] >= conf_thr, v[2] >= conf_thr, v[3] >= conf_thr);
+        if (prob_out) prob_out[t * HW4 + p] = make_float4(v[0], v[1], v[2], v[3]);
+      } else if (nq == KS) {
+        float med[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float s[KS];
+#pragma unroll
+          for (int i = 0; i < KS; ++i) s[i] = q[i][j];
+#pragma unroll
+          for (int i = 0; i <= MID; ++i) {
+#pragma unroll
+            for (int k = i + 1; k < KS; ++k) {
+              const float lo = fminf(s[i], s[k]), hi = fmaxf(s[i], s[k]);
+              s[i] = lo; s[k] = hi;
+            }
+          }
+          med[j] = s[MID];
+          q[MID][j] = med[j];
+        }
+        hard[(t - MID) * HW4 + p] = make_uchar4(med[0] >= conf_thr, med[1] >= conf_thr, med[2] >= conf_thr, med[3] >= conf_thr);
+        if (prob_out) prob_out[(t - MID) * HW4 + p] = make_float4(med[0], med[1], med[2], med[3]);
+      }
+    }
+  }
+  if (nq == KS) {
+#pragma unroll
+    for (int i = 0; i < KS - 1; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[i][j] = q[i + 1][j];
+    nq = KS - 1;
+  }
+#pragma unroll
+  for (int i = 0; i < KS - 1; ++i)
+    if (i < nq) hist[i * HW4 + p] = make_float4(q[i][0], q[i][1], q[i][2], q[i][3]);
+}
+
 // end(): queue[mid+1:] are emitted unfiltered (engines.py:351-361)
 __global__ void median_flush_kernel(const float* __restrict__ hist, int n_hist, int ks,
                                     long long HW, int n_slices_total, float conf_thr,
@@ -351,6 +439,27 @@ int be_median_push(const float* logits, int B, int H, int W, int ks, float* hist
                    cudaStream_t stream) {
   const long long HW = static_cast<long long>(H) * W;
   const int threads = 256;
+  const bool vec = (HW % 4 == 0) && ks <= 7 &&
+                   (((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(hist) |
+                      reinterpret_cast<uintptr_t>(prob_out)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(hard) & 3) == 0);
+  if (vec) {
+    const long long HW4 = HW / 4;
+    const unsigned blocks4 = static_cast<unsigned>((HW4 + threads - 1) / threads);
+#define LAUNCH_MED4(KS)                                                                          \
+  post::median_harden_v4_kernel<KS><<<blocks4, threads, 0, stream>>>(                            \
+      reinterpret_cast<const float4*>(logits), B, HW4, reinterpret_cast<float4*>(hist), n_hist,  \
+      slice0, conf_thr, is_prob, reinterpret_cast<uchar4*>(hard), reinterpret_cast<float4*>(prob_out))
+    switch (ks) {
+      case 1: LAUNCH_MED4(1); break;
+      case 3: LAUNCH_MED4(3); break;
+      case 5: LAUNCH_MED4(5); break;
+      case 7: LAUNCH_MED4(7); break;
+      default: return be_set_error("median kernel size must be odd and <= 11");
+    }
+#undef LAUNCH_MED4
+    return be_check_launch("median_harden_v4_kernel");
+  }
   const unsigned blocks = static_cast<unsigned>((HW + threads - 1) / threads);
 #define LAUNCH_MED(KS)                                                                         \
   post::median_harden_kernel<KS><<<blocks, threads, 0, stream>>>(logits, B, HW, hist, n_hist,  \
@@ -395,6 +504,12 @@ int be_group_pixels(const float* off, const int* centers, int cap, const int* co
   post::group_pixels_kernel<<<grid, 256, 0, stream>>>(off, centers, cap, counts, h4, w4, step,
                                                       cells4);
   return be_check_launch("group_pixels_kernel");
+}
+
+// in-place: presence flags [B][cap+1] -> dense per-class ids class*div + rank (0 where absent)
+int be_rank_ids(int* present, int B, int cap, int label_divisor, int class_id, cudaStream_t stream) {
+  post::rank_ids_kernel<<<B, 1024, 0, stream>>>(present, cap, label_divisor, class_id);
+  return be_check_launch("rank_ids_kernel");
 }
 
 int be_merge_pan(const uint8_t* hard, const int* cells4, int B, int H, int W, int h, int w,

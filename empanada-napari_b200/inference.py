@@ -427,24 +427,30 @@ class Engine2d:
         W = w + (pf - w % pf) % pf
         e = self.engine
         cls = e.thing_list[0]
-        post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=e.label_divisor,
-                         void_label=e.void_label, nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
-                         confidence_thr=e.confidence_thr, device=dev,
-                         scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap)
         # tiles per launch list: whole SM waves on the 1/16 map, activation buffers within ~25 GB
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         chunk = max(1, min(n, auto_slice_batch(H, W, sms)))
-        for s0 in range(0, n, chunk):
-            s1 = min(n, s0 + chunk)
-            sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)
-            if not e.coarse_boundaries:
-                ctr, off = upsample_instance_heads(ctr, off)
-            post.push_heads(sem, ctr, off, is_prob=False)
-        post.finish_heads()
+        launches0 = getattr(self.model, "launches", 0)
+        while True:
+            post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=e.label_divisor,
+                             void_label=e.void_label, nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
+                             confidence_thr=e.confidence_thr, device=dev,
+                             scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap)
+            for s0 in range(0, n, chunk):
+                s1 = min(n, s0 + chunk)
+                sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)
+                if not e.coarse_boundaries:
+                    ctr, off = upsample_instance_heads(ctr, off)
+                post.push_heads(sem, ctr, off, is_prob=False)
+            try:
+                post.finish_heads()
+                break
+            except CenterOverflow as err:
+                e.center_cap = _next_pow2(err.needed)
         # force_connected (inference.py:263-279): pan <- class*div + component id
-        post.run_cc(batch=min(n, 16))
-        out = torch.where(post.cc > 0, post.cc + cls * self.label_divisor, torch.zeros_like(post.cc))
-        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0)}
+        post.run_cc()
+        out = post.cc_images(0, n, add=cls * self.label_divisor)
+        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
         return out
 
     def infer_batch_host(self, images):

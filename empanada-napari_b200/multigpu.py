@@ -299,7 +299,7 @@ class ShardedEngine3d(Engine3d):
         # cross-boundary overlaps: previous shard's last component slice vs this shard's first
         ops, prev = [], None
         if r < G - 1:
-            last = post.cc[post.N - 1].contiguous()
+            last = post.cc_images(post.N - 1, post.N)[0].contiguous()
             ops.append(dist.P2POp(dist.isend, last, r + 1, group=self.group))
         if r > 0:
             prev = torch.empty((h, w), dtype=torch.int32, device=dev)

@@ -32,11 +32,19 @@ def _next_pow2(n):
 
 
 class PlanePost:
-    """State for one `infer_on_axis` pass over `n_slices` slices of size (h, w), padded (H, W)."""
+    """State for one `infer_on_axis` pass over `n_slices` slices of size (h, w), padded (H, W).
+
+    Stage 1 (per batch of slices, while the network runs): recursive median + harden -> `hard`,
+    centre NMS -> `centers`; the offsets are kept (`off_all`) because grouping is deferred until the
+    filtered mask is known and then evaluated only where it matters (csrc/run_kernels.cu).
+    Stage 2 (`run_cc`, whole plane): grouping + presence flags, renumbering, row-run extraction,
+    union-find over runs, component tables, adjacent-slice overlap table.
+    Stage 3: host matcher replay on the tables (tracking.match_replay).
+    Stage 4 (`relabel`): the (D,H,W) label volume painted once from the runs."""
 
     def __init__(self, n_slices, h, w, H, W, *, ks, thing_class, label_divisor, void_label=0,
                  nms_threshold=0.1, nms_kernel=3, confidence_thr=0.5, scale=4, device="cuda:0",
-                 center_cap=4096, cc_cap=4096, keep_prob=False):
+                 center_cap=4096, cc_cap=None, keep_prob=False, hash_cap=None):
         if ks % 2 != 1:
             raise AssertionError("Kernel size must be odd integer!")
         if n_slices < ks:
@@ -47,52 +55,47 @@ class PlanePost:
         self.thr, self.k, self.conf, self.scale = nms_threshold, nms_kernel, confidence_thr, scale
         self.dev = torch.device(device)
         self.h4, self.w4 = H // scale, W // scale
-        self.center_cap, self.cc_cap = center_cap, cc_cap
+        self.center_cap = center_cap
+        self.hash_cap = hash_cap            # initial overlap-table capacity (tests force regrowth)
         d = self.dev
         self.hard = torch.zeros((n_slices, H, W), dtype=torch.uint8, device=d)
         self.prob = torch.zeros((n_slices, H, W), dtype=torch.float32, device=d) if keep_prob else None
-        self.cells4 = torch.zeros((n_slices, self.h4, self.w4), dtype=torch.int32, device=d)
+        self.off_all = torch.empty((n_slices, 2, self.h4, self.w4), dtype=torch.float32, device=d)
         self.hist = torch.zeros((max(ks - 1, 1), H, W), dtype=torch.float32, device=d)
         self.n_hist = 0
         self.pushed = 0
         self.centers = torch.zeros((n_slices, center_cap), dtype=torch.int32, device=d)
         self.center_counts = torch.zeros(n_slices, dtype=torch.int32, device=d)
-        self.cc = None
+        self.cells4 = None
+        self.newid = None
+        self.runs = None
         self.launches = 0
 
     # ------------------------------------------------------------------ stage 1: heads in
+    def _centers(self, ctr, off, i0):
+        B = ctr.shape[0]
+        st = stream_ptr()
+        scratch = torch.empty(B * ((self.h4 * self.w4 + 1023) // 1024), dtype=torch.int32, device=self.dev)
+        call("be_centers", ptr(ctr), B, self.h4, self.w4, float(self.thr), int(self.k),
+             ptr(self.centers[i0]), self.center_cap, ptr(self.center_counts[i0:]), ptr(scratch), st)
+        self.off_all[i0:i0 + B].copy_(off)
+        self.launches += 3
+
     def push_heads(self, sem, ctr, off, is_prob=False):
         """sem (B,H,W) fp32 logits (or probabilities), ctr (B,h4,w4), off (B,2,h4,w4)."""
         B = sem.shape[0]
         s0 = self.pushed
         assert s0 + B <= self.N
-        st = stream_ptr()
-        call("be_median_push", ptr(sem), B, self.H, self.W, self.ks, ptr(self.hist), self.n_hist,
-             s0, float(self.conf), int(is_prob), ptr(self.hard), ptr(self.prob), st)
-        scratch = torch.empty(B * ((self.h4 * self.w4 + 1023) // 1024), dtype=torch.int32, device=self.dev)
-        call("be_centers", ptr(ctr), B, self.h4, self.w4, float(self.thr), int(self.k),
-             ptr(self.centers[s0]), self.center_cap, ptr(self.center_counts[s0:]), ptr(scratch), st)
-        call("be_group_pixels", ptr(off), ptr(self.centers[s0]), self.center_cap,
-             ptr(self.center_counts[s0:]), B, self.h4, self.w4, float(self.scale),
-             ptr(self.cells4[s0]), st)
-        self.launches += 4
+        self.push_semantic(sem, s0, is_prob)
+        self._centers(ctr, off, s0)
         self.pushed += B
-        self.n_hist = min(self.n_hist + B, self.ks - 1)
 
     # split form of push_heads for slice-sharded planes (multigpu.ShardedEngine3d): the instance
     # heads of a slice and its (recursively median-filtered) semantic slice arrive separately
     def push_instance(self, ctr, off, i0):
-        """Centres + grouping of B slices into local slots [i0, i0 + B)."""
-        B = ctr.shape[0]
-        assert i0 >= 0 and i0 + B <= self.N
-        st = stream_ptr()
-        scratch = torch.empty(B * ((self.h4 * self.w4 + 1023) // 1024), dtype=torch.int32, device=self.dev)
-        call("be_centers", ptr(ctr), B, self.h4, self.w4, float(self.thr), int(self.k),
-             ptr(self.centers[i0]), self.center_cap, ptr(self.center_counts[i0:]), ptr(scratch), st)
-        call("be_group_pixels", ptr(off), ptr(self.centers[i0]), self.center_cap,
-             ptr(self.center_counts[i0:]), B, self.h4, self.w4, float(self.scale),
-             ptr(self.cells4[i0]), st)
-        self.launches += 3
+        """Centres (and kept offsets) of B slices into local slots [i0, i0 + B)."""
+        assert i0 >= 0 and i0 + ctr.shape[0] <= self.N
+        self._centers(ctr, off, i0)
 
     def push_semantic(self, sem, slot0, is_prob=False):
         """Median queue push of B slices; the slice pushed at slot t emits slot t - mid."""
@@ -116,64 +119,107 @@ class PlanePost:
 
     def finish_heads(self):
         assert self.pushed == self.N
-        if self.ks > 1:
-            call("be_median_flush", ptr(self.hist), self.n_hist, self.ks, self.H, self.W, self.N,
-                 float(self.conf), ptr(self.hard), ptr(self.prob), stream_ptr())
-            self.launches += 1
+        self.flush_semantic()
         self.check_centers()
 
-    # ------------------------------------------------------------------ stage 2: pan -> cc
+    # ------------------------------------------------------------------ stage 2: groups -> runs -> cc
+    def group(self):
+        """Nearest-centre ids for every head-grid cell that holds a thing pixel + dense
+        renumbering table (`newid`, the per-class running counter of postprocess.py:273-288)."""
+        if self.cells4 is not None:
+            return
+        N, d = self.N, self.dev
+        self.cells4 = torch.zeros((N, self.h4, self.w4), dtype=torch.int32, device=d)
+        self.newid = torch.zeros((N, self.center_cap + 1), dtype=torch.int32, device=d)
+        call("be_group_flags", ptr(self.hard), ptr(self.off_all), ptr(self.centers), self.center_cap,
+             ptr(self.center_counts), N, self.H, self.W, self.scale, ptr(self.cells4), ptr(self.newid),
+             stream_ptr())
+        call("be_rank_ids", ptr(self.newid), N, self.center_cap, int(self.div), int(self.cls), stream_ptr())
+        self.launches += 2
+
+    def group_all(self, s0=0, s1=None):
+        """Reference-complete `get_instance_cells` output (every cell, background included) for
+        slices [s0, s1): used by tests and the per-slice engine API, not by the plane path."""
+        s1 = self.N if s1 is None else s1
+        out = torch.empty((s1 - s0, self.h4, self.w4), dtype=torch.int32, device=self.dev)
+        call("be_group_pixels", ptr(self.off_all[s0]), ptr(self.centers[s0]), self.center_cap,
+             ptr(self.center_counts[s0:]), s1 - s0, self.h4, self.w4, float(self.scale), ptr(out), stream_ptr())
+        return out
+
     def pan_batch(self, s0, s1):
-        """pan_seg (B,h,w) int32 for emitted slices [s0, s1) (the per-slice engine output)."""
+        """Dense pan_seg (B,h,w) int32 for emitted slices [s0, s1) (the per-slice engine output);
+        the plane path itself never materialises it."""
         B = s1 - s0
+        cells = self.group_all(s0, s1)
         pan = torch.empty((B, self.h, self.w), dtype=torch.int32, device=self.dev)
         present = torch.empty((B, self.center_cap + 1), dtype=torch.int32, device=self.dev)
-        call("be_merge_pan", ptr(self.hard[s0]), ptr(self.cells4[s0]), B, self.H, self.W, self.h,
+        call("be_merge_pan", ptr(self.hard[s0]), ptr(cells), B, self.H, self.W, self.h,
              self.w, self.scale, self.center_cap, int(self.div), int(self.cls), int(self.void),
              ptr(present), ptr(pan), stream_ptr())
         self.launches += 4
         return pan
 
     def run_cc(self, batch=None):
-        """Connected components + tables for all slices; overlap table between neighbours."""
+        """Row runs, connected components + tables for all slices; overlap table between
+        neighbouring slices. (`batch` is accepted for compatibility; the run pipeline handles the
+        whole plane in one launch sequence.)"""
         N, h, w, d = self.N, self.h, self.w, self.dev
-        if batch is None:   # ~64 MPixel per launch: few, large launches (the kernels are HBM bound)
-            batch = max(1, min(N, (64 << 20) // max(1, h * w)))
-        while True:
-            self.cc = torch.empty((N, h, w), dtype=torch.int32, device=d)
-            self.n_cc = torch.zeros(N, dtype=torch.int32, device=d)
-            self.cc_table = torch.empty((N, self.cc_cap, 5), dtype=torch.int32, device=d)
-            chunks = (h * w + 1023) // 1024
-            L = torch.empty((batch, h, w), dtype=torch.int32, device=d)
-            chunk_counts = torch.empty((batch, chunks), dtype=torch.int32, device=d)
-            lo, hi = self.cls * self.div, (self.cls + 1) * self.div
-            for s0 in range(0, N, batch):
-                s1 = min(N, s0 + batch)
-                pan = self.pan_batch(s0, s1)
-                call("be_cc_label", ptr(pan), s1 - s0, h, w, lo, hi, ptr(L), ptr(chunk_counts),
-                     ptr(self.cc[s0]), ptr(self.n_cc[s0:]), self.cc_cap, ptr(self.cc_table[s0]),
-                     stream_ptr())
-                self.launches += 9
-            n_cc_max = int(self.n_cc.max().item())
-            if n_cc_max <= self.cc_cap and n_cc_max < (1 << 20):
-                break
-            if n_cc_max >= (1 << 20):
-                raise _lib.B200EmpanadaError("more than 2^20 components in one slice")
-            self.cc_cap = _next_pow2(n_cc_max + 1)
+        self.group()
+        st = stream_ptr()
+        qpr = (w + 3) // 4
+        chunks = (h * qpr + 255) // 256
+        counts = torch.empty(2 * N * chunks, dtype=torch.int32, device=d)
+        n_runs = torch.empty(N, dtype=torch.int32, device=d)
+        slice_off = torch.empty(N + 1, dtype=torch.int32, device=d)
+        stats = torch.empty(2, dtype=torch.int32, device=d)
+        row_ptr = torch.empty((N, h + 1), dtype=torch.int32, device=d)
+        lo, hi = self.cls * self.div, (self.cls + 1) * self.div
+        src = (ptr(self.hard), ptr(self.cells4), ptr(self.newid), N, self.H, self.W, h, w, self.scale,
+               self.center_cap, int(self.void), lo, hi)
+        call("be_rowruns_count", *src, ptr(counts), ptr(n_runs), ptr(slice_off), ptr(stats), ptr(row_ptr), st)
+        total, max_runs = (int(v) for v in stats.cpu().numpy())
+        R = max(total, 1)
+        run_yx = torch.empty((R, 2), dtype=torch.int32, device=d)
+        run_x1 = torch.empty(R, dtype=torch.int32, device=d)
+        run_val = torch.empty(R, dtype=torch.int32, device=d)
+        L = torch.empty(R, dtype=torch.int32, device=d)
+        run_cc = torch.zeros(R, dtype=torch.int32, device=d)
+        self.n_cc = torch.empty(N, dtype=torch.int32, device=d)
+        call("be_rowruns_write", *src, ptr(counts), ptr(slice_off), ptr(row_ptr), ptr(run_yx), ptr(run_x1),
+             ptr(run_val), ptr(L), st)
+        call("be_runs_cc", ptr(row_ptr), ptr(run_yx), ptr(run_x1), ptr(run_val), ptr(slice_off), N, h,
+             max_runs, ptr(L), ptr(run_cc), ptr(self.n_cc), st)
+        self.launches += 7
+        self.runs = dict(row_ptr=row_ptr, yx=run_yx, x1=run_x1, cc=run_cc, slice_off=slice_off,
+                         total=total, max_runs=max_runs)
+        n_cc_host = self.n_cc.cpu().numpy()
+        self._n_cc_host = n_cc_host
+        n_cc_max = int(n_cc_host.max()) if N else 0
+        if n_cc_max >= (1 << 20):
+            raise _lib.B200EmpanadaError("more than 2^20 components in one slice")
+        self.cc_cap = max(1, n_cc_max)
+        self.cc_table = torch.empty((N, self.cc_cap, 5), dtype=torch.int32, device=d)
+        call("be_runs_stats", ptr(run_yx), ptr(run_x1), ptr(run_cc), ptr(slice_off), N, max_runs,
+             self.cc_cap, ptr(self.cc_table), st)
+        self.launches += 2
         # overlap table (slice s vs s-1)
-        total_cc = int(self.n_cc.sum().item())
-        cap = _next_pow2(max(1 << 16, 8 * total_cc))
+        total_cc = int(n_cc_host.sum())
+        cap = self.hash_cap or _next_pow2(max(1 << 16, 8 * total_cc))
         while True:
             keys = torch.empty(cap, dtype=torch.int64, device=d)
             vals = torch.empty(cap, dtype=torch.int32, device=d)
             overflow = torch.zeros(1, dtype=torch.int32, device=d)
-            call("be_hash_clear", ptr(keys), ptr(vals), cap, stream_ptr())
-            call("be_pair_overlap", ptr(self.cc), h, w, 0, N, ptr(keys), ptr(vals), cap,
-                 ptr(overflow), stream_ptr())
+            call("be_hash_clear", ptr(keys), ptr(vals), cap, st)
+            call("be_runs_overlap", ptr(row_ptr), ptr(run_yx), ptr(run_x1), ptr(run_cc), ptr(slice_off), N, h,
+                 max_runs, 0, ptr(keys), ptr(vals), cap, ptr(overflow), st)
             self.launches += 3
             if int(overflow.item()) == 0:
                 break
             cap *= 4
+        self.pair_keys, self.pair_vals = self._compact(keys, vals, cap)
+
+    def _compact(self, keys, vals, cap):
+        d = self.dev
         out_keys = torch.empty(cap, dtype=torch.int64, device=d)
         out_vals = torch.empty(cap, dtype=torch.int32, device=d)
         cursor = torch.zeros(1, dtype=torch.int32, device=d)
@@ -181,14 +227,24 @@ class PlanePost:
              ptr(cursor), stream_ptr())
         self.launches += 1
         n_pairs = int(cursor.item())
-        self.pair_keys = out_keys[:n_pairs].cpu().numpy().view(np.uint64)
-        self.pair_vals = out_vals[:n_pairs].cpu().numpy()
+        return out_keys[:n_pairs].cpu().numpy().view(np.uint64), out_vals[:n_pairs].cpu().numpy()
+
+    def cc_images(self, s0, s1, add=0):
+        """Dense (B,h,w) int32 images of the component ids (+ `add` on labelled pixels) of slices
+        [s0, s1): Engine2d output, shard-boundary exchange, tests."""
+        r = self.runs
+        out = torch.empty((s1 - s0, self.h, self.w), dtype=torch.int32, device=self.dev)
+        call("be_runs_paint", ptr(r["row_ptr"]), ptr(r["yx"]), ptr(r["x1"]), ptr(r["cc"]), ptr(r["slice_off"]),
+             None, 0, int(add), s0, s1 - s0, self.h, self.w,
+             ptr(out) - 4 * s0 * self.h * self.w, self.h * self.w, self.w, 1, stream_ptr())
+        self.launches += 1
+        return out
 
     def boundary_pairs(self, prev_cc):
         """Overlap pairs between `prev_cc` (the last component slice of the previous shard, (h, w)
         int32 device tensor) and this shard's first slice, keyed as local slice 0."""
         d, h, w = self.dev, self.h, self.w
-        two = torch.stack([prev_cc, self.cc[0]]).contiguous()
+        two = torch.cat([prev_cc[None], self.cc_images(0, 1)]).contiguous()
         cap = 1 << 16
         while True:
             keys = torch.empty(cap, dtype=torch.int64, device=d)
@@ -200,22 +256,15 @@ class PlanePost:
             if int(overflow.item()) == 0:
                 break
             cap *= 4
-        out_keys = torch.empty(cap, dtype=torch.int64, device=d)
-        out_vals = torch.empty(cap, dtype=torch.int32, device=d)
-        cursor = torch.zeros(1, dtype=torch.int32, device=d)
-        call("be_hash_compact", ptr(keys), ptr(vals), cap, ptr(out_keys), ptr(out_vals), cap, ptr(cursor), stream_ptr())
-        n_pairs = int(cursor.item())
-        k = out_keys[:n_pairs].cpu().numpy().view(np.uint64)
+        k, v = self._compact(keys, vals, cap)
         k = k - (np.uint64(1) << np.uint64(40))      # slice index 1 of the pair buffer -> local slice 0
-        return k, out_vals[:n_pairs].cpu().numpy()
+        return k, v
 
     # ------------------------------------------------------------------ stage 3: host replay
     def replay_inputs(self):
         """Host copies of the component tables (synchronises the stream)."""
-        n_cc = self.n_cc.cpu().numpy()
-        cap = max(1, int(n_cc.max()))
-        table = self.cc_table[:, :cap].contiguous().cpu().numpy()
-        return n_cc, table
+        n_cc = self._n_cc_host
+        return n_cc, self.cc_table.cpu().numpy()
 
     def replay_host(self, inputs, axis_name, iou_thr=0.25, ioa_thr=0.25):
         """Pure host part (native code, releases the GIL): safe to run on a worker thread."""
@@ -226,18 +275,18 @@ class PlanePost:
     def replay(self, axis_name, iou_thr=0.25, ioa_thr=0.25):
         return self.replay_host(self.replay_inputs(), axis_name, iou_thr, ioa_thr)
 
-    # ------------------------------------------------------------------ stage 4: relabel + runs
-    def relabel(self, lut, axis_name, shape3d, batch=64):
-        """Paint final labels (lut [N, stride] int32, 0 = dropped) into a (D,H,W) device volume."""
+    # ------------------------------------------------------------------ stage 4: paint
+    def relabel(self, lut, axis_name, shape3d):
+        """Paint final labels (lut [N, stride] int32, 0 = dropped) into a (D,H,W) device volume:
+        every voxel is written exactly once, from the runs."""
         D, Hv, Wv = shape3d
         vol = torch.empty(shape3d, dtype=torch.int32, device=self.dev)
-        lut_d = torch.from_numpy(np.ascontiguousarray(lut)).to(self.dev)
+        lut_d = torch.from_numpy(np.ascontiguousarray(lut, dtype=np.int32)).to(self.dev)
         strides = {"xy": (Hv * Wv, Wv, 1), "xz": (Wv, Hv * Wv, 1), "yz": (1, Hv * Wv, Wv)}[axis_name]
-        for s0 in range(0, self.N, batch):
-            s1 = min(self.N, s0 + batch)
-            call("be_relabel", ptr(self.cc[s0]), s1 - s0, self.h, self.w, s0, ptr(lut_d),
-                 lut_d.shape[1], ptr(vol), *strides, stream_ptr())
-            self.launches += 1
+        r = self.runs
+        call("be_runs_paint", ptr(r["row_ptr"]), ptr(r["yx"]), ptr(r["x1"]), ptr(r["cc"]), ptr(r["slice_off"]),
+             ptr(lut_d), int(lut_d.shape[1]), 0, 0, self.N, self.h, self.w, ptr(vol), *strides, stream_ptr())
+        self.launches += 1
         self._lut_d = lut_d
         return vol
 

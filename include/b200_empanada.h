@@ -112,6 +112,7 @@ int be_centers(const float* ctr, int B, int h4, int w4, float thr, int k, int* c
  * get_panoptic_seg / merge_semantic_and_instance (engines.py:278-298, postprocess.py:224-296) */
 int be_group_pixels(const float* off, const int* centers, int cap, const int* counts, int B, int h4,
                     int w4, float step, int* cells4, be_stream st);
+int be_rank_ids(int* present, int B, int cap, int label_divisor, int class_id, be_stream st);
 int be_merge_pan(const uint8_t* hard, const int* cells4, int B, int H, int W, int h, int w,
                  int scale, int cap, int label_divisor, int class_id, int void_label, int* present,
                  int* pan, be_stream st);
@@ -143,6 +144,37 @@ int be_runs_write(const int* img, long long n, long long seg_len, const long lon
 int be_sort_runs(const unsigned long long* keys_in, unsigned long long* keys_out, const int* idx_in,
                  int* idx_out, int n, void* temp, size_t temp_bytes, size_t* temp_needed,
                  be_stream st);
+/* ---- pieces (3), (5), (6b) on ROW RUNS (csrc/run_kernels.cu), the batched plane path: grouping
+ * only where a thing pixel exists + presence flags (postprocess.py:119-169,224-296); maximal row
+ * runs of equal panoptic value inside a class range, straight from the mask + cell ids (the
+ * pan_seg of engines.py:278-298 restricted as in rle.py:60-66 never reaches HBM); 8-connected
+ * equal-value components in raster order as a union-find over runs (rle.py:18-24); area / bbox per
+ * component (rle.py:75-83); adjacent-slice overlaps (array_utils.py:375-407); and the relabelled
+ * volume written once from the runs (patterns.py:204-213). Run arrays are sized by the caller from
+ * stats[0] (total runs) after be_rowruns_count. */
+int be_group_flags(const uint8_t* hard, const float* off, const int* centers, int cap,
+                   const int* counts, int B, int H, int W, int scale, int* cells, int* present,
+                   be_stream st);
+int be_rowruns_count(const uint8_t* hard, const int* cells, const int* newid, int B, int H, int W,
+                     int h, int w, int scale, int cap, int void_label, int lo, int hi, int* counts,
+                     int* n_runs, int* slice_off, int* stats, int* row_ptr, be_stream st);
+int be_rowruns_write(const uint8_t* hard, const int* cells, const int* newid, int B, int H, int W,
+                     int h, int w, int scale, int cap, int void_label, int lo, int hi, int* counts,
+                     const int* slice_off, int* row_ptr, int* run_yx, int* run_x1, int* run_val,
+                     int* L, be_stream st);
+int be_runs_cc(const int* row_ptr, const int* run_yx, const int* run_x1, const int* run_val,
+               const int* slice_off, int B, int h, int max_runs, int* L, int* run_cc, int* n_cc,
+               be_stream st);
+int be_runs_stats(const int* run_yx, const int* run_x1, const int* run_cc, const int* slice_off,
+                  int B, int max_runs, int cap, int* table, be_stream st);
+int be_runs_overlap(const int* row_ptr, const int* run_yx, const int* run_x1, const int* run_cc,
+                    const int* slice_off, int B, int h, int max_runs, int key_s0,
+                    unsigned long long* keys, int* vals, unsigned long long cap, int* overflow,
+                    be_stream st);
+int be_runs_paint(const int* row_ptr, const int* run_yx, const int* run_x1, const int* run_cc,
+                  const int* slice_off, const int* lut, int lut_stride, int add, int b0, int nb, int h,
+                  int w, int* dst, long long stride_s, long long stride_y, long long stride_x,
+                  be_stream st);
 /* ---- piece (6): merge_objects_from_trackers (consensus.py:233-287,449-460), fill
  * (array_utils.py:754-765), filters on the painted volume */
 int be_plane_pairs(const int* va, const int* vb, const int* vc, const int* la, const int* lb,
