@@ -51,6 +51,16 @@ _SIGNATURES = {
     "be_vote_paint": ([P, P, P, P, P, P, I, I, I, LL, I, P, P, I, P, P, P, P, I, P, P], I),
     "be_label_hist": ([P, LL, I, I, P, P], I),
     "be_lut_inplace": ([P, LL, P, I, P], I),
+    # consensus_runs.cu
+    "be_triple_count": ([P, P, P, P, P, P, I, I, I, LL, I, P, P], I),
+    "be_triple_write": ([P, P, P, P, P, P, I, I, I, LL, I, P, P, P, P, P, P], I),
+    "be_triple_pairs": ([P, P, P, LL, P, P, ULL, P, P], I),
+    "be_triple_stats": ([P, P, P, LL, P, P, I, P, P, P, ULL, P, P], I),
+    "be_triple_rec_count": ([P, P, P, LL, P, P, I, P, P, P, P], I),
+    "be_triple_rec_write": ([P, P, P, LL, I, LL, P, P, I, P, P, P, P, P, P, P], I),
+    "be_sort_records": ([P, P, P, P, LL, P, SZ, POINTER(SZ), P], I),
+    "be_join_flags": ([P, P, LL, P, P, P, SZ, POINTER(SZ), P], I),
+    "be_join_write": ([P, P, P, P, LL, P, P, P, P], I),
     # match_replay.cpp (host)
     "be_match_replay": ([I, P, P, I, P, P, LL, I, I, D, D, I, P, I, P, P, P, I, P], I),
 }

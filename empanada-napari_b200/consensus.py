@@ -24,6 +24,9 @@ MIN_OVERLAP = 100
 MIN_IOU = 1e-2
 LAST_PROFILE = {}
 LAST_LAUNCHES = 0  # kernels launched by the last merge_objects_from_trackers call
+# initial capacities of the growable device tables (None: sized from the node count); every table
+# regrows on overflow, tests start them tiny to exercise that
+CAPS = {"pairs": None, "votes": 1 << 16, "side": 1 << 20}
 
 
 def merge_boxes(box1, box2):
@@ -181,76 +184,153 @@ def extract_runs(vol):
     return labels, starts, lens
 
 
+# ------------------------------------------------------------------------- triple runs (device)
+def _scan_i32_to_i64(counts, n):
+    """Exclusive scan of counts[0:n] (int32, device) into int64 offsets[0:n+1] (offsets[n] = total;
+    counts must have n + 1 readable entries) on the library's scan."""
+    dev = counts.device
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    need = _lib.SZ(0)
+    _lib.lib().be_scan_i32_to_i64(None, None, n, None, 0, need, None)
+    temp = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
+    call("be_scan_i32_to_i64", ptr(counts), ptr(offsets), n, ptr(temp), temp.numel(), None, stream_ptr())
+    return offsets
+
+
+class TripleRuns:
+    """Maximal x-runs of identical (xy, xz, yz) node triples of three dense label volumes
+    (csrc/consensus_runs.cu): two dense passes build them, everything afterwards is per run."""
+
+    def __init__(self, vols, luts, shape3d, flat0=0):
+        self.dev = next(v for v in vols if v is not None).device
+        D, H, W = shape3d
+        self.rows, self.W, self.flat0 = D * H, W, flat0
+        n = D * H * W
+        self.vargs = [ptr(v) for v in vols] + [ptr(l) for l in luts] + [int(l.numel()) if l is not None else 0 for l in luts]
+        chunks = (n + 1023) // 1024
+        st = stream_ptr()
+        counts = torch.zeros(2 * (chunks + 1), dtype=torch.int32, device=self.dev)
+        call("be_triple_count", *self.vargs, n, W, ptr(counts), st)
+        offs = torch.cat([_scan_i32_to_i64(counts[:chunks + 1], chunks), _scan_i32_to_i64(counts[chunks + 1:], chunks)])
+        self.n = int(offs[chunks].item())
+        R = max(self.n, 1)
+        self.row_ptr = torch.empty(self.rows + 1, dtype=torch.int32, device=self.dev)
+        self.row_ptr[self.rows] = self.n
+        self.yx = torch.empty((R, 2), dtype=torch.int32, device=self.dev)
+        self.x1 = torch.empty(R, dtype=torch.int32, device=self.dev)
+        self.abc = torch.empty((R, 4), dtype=torch.int32, device=self.dev)
+        call("be_triple_write", *self.vargs, n, W, ptr(offs), ptr(self.row_ptr), ptr(self.yx), ptr(self.x1),
+             ptr(self.abc), st)
+        self.launches = 4
+        self.rargs = (ptr(self.yx), ptr(self.x1), ptr(self.abc), self.n)
+
+    def _hash_pass(self, name, cap, *mid):
+        """Runs `name` with a growing (key, count) table until nothing overflows."""
+        while True:
+            keys, vals = _hash_table(cap, self.dev)
+            overflow = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            call(name, *self.rargs, *mid, ptr(keys), ptr(vals), cap, ptr(overflow), stream_ptr())
+            self.launches += 3
+            ov = int(overflow.item())
+            if ov == 2:
+                raise _lib.B200EmpanadaError("a voxel is claimed by more than 32 consensus clusters")
+            if ov == 0:
+                return keys, vals, cap
+            cap *= 4
+
+    def pairs(self, cap):
+        keys, vals, cap = self._hash_pass("be_triple_pairs", cap)
+        return _hash_items(keys, vals, cap, self.dev)
+
+    def stats(self, memb_off_d, memb_list_d, vote_thr, n_cands, cap):
+        csize_d = torch.zeros(n_cands + 1, dtype=torch.int32, device=self.dev)
+        keys, vals, cap = None, None, cap
+        while True:       # sizes accumulate inside the pass: start from zero on every attempt
+            csize_d.zero_()
+            ktab, vtab = _hash_table(cap, self.dev)
+            overflow = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            call("be_triple_stats", *self.rargs, ptr(memb_off_d), ptr(memb_list_d), int(vote_thr), ptr(csize_d),
+                 ptr(ktab), ptr(vtab), cap, ptr(overflow), stream_ptr())
+            self.launches += 3
+            ov = int(overflow.item())
+            if ov == 2:
+                raise _lib.B200EmpanadaError("a voxel is claimed by more than 32 consensus clusters")
+            if ov == 0:
+                break
+            cap *= 4
+        ca, cb, cinter = _hash_items(ktab, vtab, cap, self.dev)
+        return csize_d.cpu().numpy().astype(np.int64), ca, cb, cinter
+
+    def final_sizes(self, memb_off_d, memb_list_d, vote_thr, cid_final_d, n_final):
+        """Voxels claimed by every final instance (overlapped voxels count for each claimant) and
+        the per-run number of claiming instances."""
+        self.rec_count = torch.zeros(self.n + 1, dtype=torch.int32, device=self.dev)
+        fsize = torch.zeros(n_final + 1, dtype=torch.int32, device=self.dev)
+        call("be_triple_rec_count", *self.rargs, ptr(memb_off_d), ptr(memb_list_d), int(vote_thr),
+             ptr(cid_final_d), ptr(self.rec_count), ptr(fsize), stream_ptr())
+        self.launches += 1
+        return fsize.cpu().numpy().astype(np.int64)
+
+    def records(self, memb_off_d, memb_list_d, vote_thr, cid_final_d, keep_d):
+        """(run_val: painted id per run, joined per-instance ranges (id, start, length) sorted by
+        (id, start))."""
+        dev, st = self.dev, stream_ptr()
+        rec_off = _scan_i32_to_i64(self.rec_count, self.n)
+        n_rec = int(rec_off[self.n].item())
+        run_val = torch.zeros(max(self.n, 1), dtype=torch.int32, device=dev)
+        key = torch.empty(max(n_rec, 1), dtype=torch.int64, device=dev)
+        ln = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
+        call("be_triple_rec_write", *self.rargs, self.W, int(self.flat0), ptr(memb_off_d), ptr(memb_list_d),
+             int(vote_thr), ptr(cid_final_d), ptr(rec_off), ptr(keep_d), ptr(key), ptr(ln), ptr(run_val), st)
+        self.launches += 2
+        self.run_val = run_val
+        self.rec_key, self.rec_len, self.n_rec = key, ln, n_rec
+        return run_val
+
+    def joined_ranges(self):
+        """Host arrays (ids int32, starts int64, lengths int64) of the joined ranges."""
+        dev, st, n = self.dev, stream_ptr(), self.n_rec
+        if n == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        key2, len2 = torch.empty_like(self.rec_key), torch.empty_like(self.rec_len)
+        need = _lib.SZ(0)
+        _lib.lib().be_sort_records(None, None, None, None, n, None, 0, need, None)
+        temp = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
+        call("be_sort_records", ptr(self.rec_key), ptr(key2), ptr(self.rec_len), ptr(len2), n, ptr(temp),
+             temp.numel(), None, st)
+        head = torch.empty(n, dtype=torch.int32, device=dev)
+        rank = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.lib().be_join_flags(None, None, n, None, None, None, 0, need, None)
+        temp2 = torch.empty(max(int(need.value), 1), dtype=torch.uint8, device=dev)
+        call("be_join_flags", ptr(key2), ptr(len2), n, ptr(head), ptr(rank), ptr(temp2), temp2.numel(), None, st)
+        m = int(rank[n - 1].item())
+        out_start = torch.empty(m, dtype=torch.int64, device=dev)
+        out_len = torch.zeros(m, dtype=torch.int64, device=dev)
+        out_id = torch.empty(m, dtype=torch.int32, device=dev)
+        call("be_join_write", ptr(key2), ptr(len2), ptr(head), ptr(rank), n, ptr(out_start), ptr(out_len),
+             ptr(out_id), st)
+        self.launches += 8
+        return out_id.cpu().numpy(), out_start.cpu().numpy(), out_len.cpu().numpy()
+
+    def paint(self, out):
+        """Writes every voxel of `out` (rows x W int32, contiguous) from run_val."""
+        slice_off = torch.tensor([0, self.n], dtype=torch.int32, device=self.dev)
+        call("be_runs_paint", ptr(self.row_ptr), ptr(self.yx), ptr(self.x1), ptr(self.run_val), ptr(slice_off),
+             None, 0, 0, 0, 1, self.rows, self.W, ptr(out), 0, self.W, 1, stream_ptr())
+        self.launches += 1
+        return out
+
+
 # ------------------------------------------------------------------------- consensus
-def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75, bypass=False,
-                                min_size=None, min_extent=None, on_volume_ready=None):
-    """consensus.py:348-469 followed by the two tracker filters (inference.py:149-150).
-    Returns (device int32 volume with the final ids painted, instances dict)."""
-    global LAST_LAUNCHES, LAST_PROFILE
-    import os as _os, time as _time
-    _prof_on = _os.environ.get("B200_EMPANADA_PROFILE") == "1"
-    LAST_PROFILE = {}
-    _t0 = [_time.perf_counter()]
-
-    def _mark(name):
-        if _prof_on:
-            torch.cuda.synchronize()
-            t1 = _time.perf_counter()
-            LAST_PROFILE[name] = t1 - _t0[0]
-            _t0[0] = t1
-    LAST_LAUNCHES = 12  # hash clear/compact x2, pairs, vote stats, vote paint, hist, lut, runs x2
-    dev = torch.device("cuda", torch.cuda.current_device())
-    shape3d = tuple(int(s) for s in trackers[0].shape3d)
-    n_vox = int(np.prod(shape3d))
-    W = shape3d[2]
-    n_votes = len(trackers)
-    if n_votes > 3:
-        raise _lib.B200EmpanadaError("consensus kernels take at most three planes")
-    min_cluster = 1 if bypass else (n_votes // 2) + 1
-    if pixel_vote_thr < min_cluster:
-        cluster_iou_thr = 0
-
-    # nodes in tracker order / dict order (consensus.py:400-406)
-    node_sizes, node_boxes, luts, vols = [], [], [], []
-    nid = 0
-    for tr in trackers:
-        labels = [int(l) for l in tr.instances.keys()]
-        lut = np.zeros((max(labels) + 1) if labels else 1, dtype=np.int32)
-        known = getattr(tr, "_b200_sizes", None)
-        for l in labels:
-            nid += 1
-            lut[l] = nid
-            node_sizes.append(int(known[l]) if known is not None else int(np.sum(tr.instances[l]["runs"])))
-            node_boxes.append(tuple(int(v) for v in tr.instances[l]["box"]))
-        luts.append(torch.from_numpy(lut).to(dev))
-        vols.append(dense_volume(tr, dev))
-    n_nodes = nid
-    empty_vol = torch.zeros(shape3d, dtype=torch.int32, device=dev)
-    if n_nodes == 0:
-        return empty_vol, {}
-    while len(vols) < 3:
-        vols.append(None)
-        luts.append(None)
-    vargs = [ptr(v) for v in vols] + [ptr(l) for l in luts] + [int(l.numel()) if l is not None else 0 for l in luts]
-
-    # pass 1: overlaps between instances of different planes
-    cap = _next_pow2(max(1 << 16, 16 * n_nodes))
-    while True:
-        keys, vals = _hash_table(cap, dev)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        call("be_plane_pairs", *vargs, n_vox, W, ptr(keys), ptr(vals), cap, ptr(overflow), stream_ptr())
-        if int(overflow.item()) == 0:
-            break
-        cap *= 4
-    pa, pb, inter = _hash_items(keys, vals, cap, dev)
-    _mark('plane pairs kernel')
+def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_thr, min_cluster):
+    """Host graph logic of consensus.py:400-447: instance graph from the pair table, connected
+    components in networkx order, IoU sub-clustering, cluster merging. Returns the candidate list
+    [(component index, member nodes, merged box)]."""
     order = np.lexsort((pb, pa))
-    sizes = np.array(node_sizes, dtype=np.int64)
     ea, eb, eit = pa[order] - 1, pb[order] - 1, inter[order]
     eiou = eit / (sizes[ea] + sizes[eb] - eit)          # float64, as `intersection / union`
     pos = eiou > 0
     ea, eb, eit, eiou = ea[pos], eb[pos], eit[pos], eiou[pos]
-    _mark('host build nx graph')
     # Connected components of the instance graph. networkx yields them in order of their first
     # node in insertion order (0..n-1), i.e. by smallest node id; scipy's labelling is renumbered
     # to that order. Member order inside a component never reaches the output (boxes are
@@ -270,6 +350,7 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     node_start = np.concatenate([[0], np.cumsum(comp_size)])
     edge_order = np.argsort(comp_of[ea], kind="stable")   # edges grouped by component, lexsorted inside
     edge_start = np.concatenate([[0], np.cumsum(np.bincount(comp_of[ea], minlength=n_comp))])
+    boxes = np.asarray(node_boxes, dtype=np.int64).reshape(-1, 6)
     cands = []  # (component index, member node list, merged box)
     for ci in np.flatnonzero(comp_size >= min_cluster):
         members = node_order[node_start[ci]:node_start[ci + 1]]
@@ -285,46 +366,16 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
         for cluster in clusters:
             if len(cluster) < min_cluster:
                 continue
-            box = node_boxes[cluster[0]]
-            for m in cluster[1:]:
-                box = merge_boxes(box, node_boxes[m])
+            b = boxes[cluster]
+            box = tuple(int(v) for v in np.concatenate([b[:, :3].min(0), b[:, 3:].max(0)]))
             cands.append((int(ci), cluster, box))
-    _mark('host graph clustering')
-    if not cands:
-        return empty_vol, {}
+    return cands
 
-    # membership lists: node (1-based) -> candidate ids (1-based)
-    memb = [[] for _ in range(n_nodes + 2)]
-    for cid, (_, cluster, _) in enumerate(cands, start=1):
-        for m in cluster:
-            memb[m + 1].append(cid)
-    memb_off = np.zeros(n_nodes + 3, dtype=np.int32)
-    memb_off[1:] = np.cumsum([len(m) for m in memb])
-    memb_list = np.array([c for m in memb for c in m] or [0], dtype=np.int32)
-    memb_off_d = torch.from_numpy(memb_off).to(dev)
-    memb_list_d = torch.from_numpy(memb_list).to(dev)
 
-    # pass 2: voxels claimed by each candidate, overlaps between candidates
-    csize_d = torch.zeros(len(cands) + 1, dtype=torch.int32, device=dev)
-    cap2 = 1 << 16
-    while True:
-        csize_d.zero_()
-        keys, vals = _hash_table(cap2, dev)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        call("be_vote_stats", *vargs, n_vox, W, ptr(memb_off_d), ptr(memb_list_d),
-             int(pixel_vote_thr), ptr(csize_d), ptr(keys), ptr(vals), cap2, ptr(overflow), stream_ptr())
-        ov = int(overflow.item())
-        if ov == 2:
-            raise _lib.B200EmpanadaError("a voxel is claimed by more than 32 consensus clusters")
-        if ov == 0:
-            break
-        cap2 *= 4
-    csize = csize_d.cpu().numpy().astype(np.int64)
-    _mark('vote stats kernel')
-    ca, cb, cinter = _hash_items(keys, vals, cap2, dev)
-    cpair = {(int(a), int(b)): int(v) for a, b, v in zip(ca, cb, cinter)}
-
-    # merge_overlapping per component, final ids in discovery order
+def merge_overlapping_candidates(cands, csize, cpair):
+    """merge_overlapping per component (consensus.py:144-195,461-466): candidates of one component
+    whose voted voxel sets overlap (IoU > 0.01 or > 100 voxels) become one instance; final ids
+    1..n in discovery order. Returns (cid -> final id [n_cands + 1], {final id: box})."""
     cid_final = np.zeros(len(cands) + 1, dtype=np.int32)
     final_boxes = {}
     next_id = 1
@@ -353,39 +404,42 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
                     box = cands[cid - 1][2] if box is None else merge_boxes(box, cands[cid - 1][2])
             final_boxes[next_id] = tuple(int(v) for v in box)
             next_id += 1
-    n_final = next_id - 1
-    if n_final == 0:
-        return empty_vol, {}
+    return cid_final, final_boxes
 
-    # pass 3: paint (max final id wins, as the reference's in-order fill) + multi-claim side list
-    out = torch.empty(shape3d, dtype=torch.int32, device=dev)
-    cid_final_d = torch.from_numpy(cid_final).to(dev)
-    side_cap = 1 << 20
-    while True:
-        side_vox = torch.empty(side_cap, dtype=torch.int64, device=dev)
-        side_id = torch.empty(side_cap, dtype=torch.int32, device=dev)
-        side_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        call("be_vote_paint", *vargs, n_vox, W, ptr(memb_off_d), ptr(memb_list_d),
-             int(pixel_vote_thr), ptr(cid_final_d), ptr(out), ptr(side_vox), ptr(side_id),
-             side_cap, ptr(side_count), stream_ptr())
-        n_side = int(side_count.item())
-        if n_side <= side_cap:
-            break
-        side_cap = _next_pow2(n_side)
-    _mark('host merge_overlapping + paint kernel')
-    hist = torch.zeros(n_final + 1, dtype=torch.int32, device=dev)
-    call("be_label_hist", ptr(out), n_vox, W, n_final + 1, ptr(hist), stream_ptr())
-    fsize = hist.cpu().numpy().astype(np.int64)
-    flat = out.view(-1)
-    side_vox, side_id = side_vox[:n_side], side_id[:n_side]
-    if n_side:
-        hidden = side_id != flat[side_vox]  # claimed by id but painted with a larger id
-        hv, hi = side_vox[hidden].cpu().numpy(), side_id[hidden].cpu().numpy()
-        np.add.at(fsize, hi, 1)
-    else:
-        hv, hi = np.zeros(0, np.int64), np.zeros(0, np.int32)
 
-    # filters (filters.py:22-56) on the tables
+def membership_tables(cands, n_nodes, dev):
+    """node (1-based) -> candidate ids (1-based) as CSR device arrays."""
+    memb = [[] for _ in range(n_nodes + 2)]
+    for cid, (_, cluster, _) in enumerate(cands, start=1):
+        for m in cluster:
+            memb[m + 1].append(cid)
+    memb_off = np.zeros(n_nodes + 3, dtype=np.int32)
+    memb_off[1:] = np.cumsum([len(m) for m in memb])
+    memb_list = np.array([c for m in memb for c in m] or [0], dtype=np.int32)
+    return torch.from_numpy(memb_off).to(dev), torch.from_numpy(memb_list).to(dev)
+
+
+def tracker_nodes(trackers, dev):
+    """Nodes in tracker order / dict order (consensus.py:400-406): per-plane label -> node LUTs,
+    node sizes and boxes, device label volumes."""
+    node_sizes, node_boxes, luts, vols = [], [], [], []
+    nid = 0
+    for tr in trackers:
+        labels = [int(l) for l in tr.instances.keys()]
+        lut = np.zeros((max(labels) + 1) if labels else 1, dtype=np.int32)
+        known = getattr(tr, "_b200_sizes", None)
+        for l in labels:
+            nid += 1
+            lut[l] = nid
+            node_sizes.append(int(known[l]) if known is not None else int(np.sum(tr.instances[l]["runs"])))
+            node_boxes.append(tuple(int(v) for v in tr.instances[l]["box"]))
+        luts.append(torch.from_numpy(lut).to(dev))
+        vols.append(dense_volume(tr, dev))
+    return nid, node_sizes, node_boxes, luts, vols
+
+
+def keep_mask(final_boxes, fsize, n_final, min_size, min_extent):
+    """filters.remove_small_objects / remove_pancakes (filters.py:22-56) on the tables."""
     keep = np.ones(n_final + 1, dtype=bool)
     keep[0] = False
     for fid in range(1, n_final + 1):
@@ -394,53 +448,92 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
             keep[fid] = False
         if min_extent is not None and any(s < min_extent for s in (b[3] - b[0], b[4] - b[1], b[5] - b[2])):
             keep[fid] = False
-    keep_lut = np.where(keep, np.arange(n_final + 1), 0).astype(np.int32)
-    if not keep.all():
-        call("be_lut_inplace", ptr(out), n_vox, ptr(torch.from_numpy(keep_lut).to(dev)), n_final + 1, stream_ptr())
-        if n_side:  # voxels whose painted instance was dropped fall back to a surviving claim
-            sid = torch.from_numpy(keep_lut).to(dev)[side_id.long()]
-            flat.scatter_reduce_(0, side_vox, sid, reduce="amax", include_self=True)
+    return keep
 
-    # the painted volume is final from here on: let the caller start its device->host copy while
-    # the run-length tables are extracted
-    if on_volume_ready is not None:
-        on_volume_ready(out)
-    # instances: runs of the painted volume (+ hidden voxels of overlapped instances)
-    _mark('hist + filters')
-    labels, starts, lens = extract_runs(out)
-    order = torch.argsort(labels.long(), stable=True)
-    lab_s = labels[order].cpu().numpy()
-    st_s = starts[order].cpu().numpy()
-    ln_s = lens[order].long().cpu().numpy()
-    bounds = np.searchsorted(lab_s, np.arange(1, n_final + 2))
-    if len(hv):
-        # voxels claimed by an instance but painted with another id (after the fix-up above):
-        # one gather for all of them, then grouped by instance
-        still = out.view(-1)[torch.from_numpy(hv).to(dev)].cpu().numpy() != hi
-        hv, hi = hv[still], hi[still]
-        o = np.argsort(hi, kind="stable")
-        hv, hi = hv[o], hi[o]
-    hb = np.searchsorted(hi, np.arange(1, n_final + 2))
+
+def instances_from_ranges(ids, starts, lens, final_boxes, keep, n_final):
+    """{id: {'box', 'starts', 'runs'}} from joined ranges sorted by (id, start)."""
+    bounds = np.searchsorted(ids, np.arange(1, n_final + 2))
     instances = {}
     for fid in range(1, n_final + 1):
         if not keep[fid]:
             continue
         a, b = bounds[fid - 1], bounds[fid]
-        s, r = st_s[a:b], ln_s[a:b]
-        extra = hv[hb[fid - 1]:hb[fid]]
-        if len(extra):
-            # join touching / overlapping ranges (array_utils.py:659-752 `_join_ranges`)
-            rng = np.concatenate([np.stack([s, s + r], 1), np.stack([extra, extra + 1], 1)])
-            rng = rng[np.argsort(rng[:, 0], kind="stable")]
-            st_, en_ = rng[:, 0], rng[:, 1]
-            reach = np.maximum.accumulate(en_)
-            head = np.ones(len(st_), dtype=bool)
-            head[1:] = st_[1:] > reach[:-1]
-            hidx = np.flatnonzero(head)
-            s = st_[hidx]
-            r = np.maximum.reduceat(en_, hidx) - s
-        instances[fid] = {"box": final_boxes[fid], "starts": s, "runs": r}
-    _mark('runs + instances dict')
+        instances[fid] = {"box": final_boxes[fid], "starts": starts[a:b], "runs": lens[a:b]}
+    return instances
+
+
+def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75, bypass=False,
+                                min_size=None, min_extent=None, on_volume_ready=None):
+    """consensus.py:348-469 followed by the two tracker filters (inference.py:149-150).
+    Returns (device int32 volume with the final ids painted, instances dict)."""
+    global LAST_LAUNCHES, LAST_PROFILE
+    import os as _os, time as _time
+    _prof_on = _os.environ.get("B200_EMPANADA_PROFILE") == "1"
+    LAST_PROFILE = {}
+    _t0 = [_time.perf_counter()]
+
+    def _mark(name):
+        if _prof_on:
+            torch.cuda.synchronize()
+            t1 = _time.perf_counter()
+            LAST_PROFILE[name] = t1 - _t0[0]
+            _t0[0] = t1
+    LAST_LAUNCHES = 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shape3d = tuple(int(s) for s in trackers[0].shape3d)
+    n_votes = len(trackers)
+    if n_votes > 3:
+        raise _lib.B200EmpanadaError("consensus kernels take at most three planes")
+    min_cluster = 1 if bypass else (n_votes // 2) + 1
+    if pixel_vote_thr < min_cluster:
+        cluster_iou_thr = 0
+
+    n_nodes, node_sizes, node_boxes, luts, vols = tracker_nodes(trackers, dev)
+    if n_nodes == 0:
+        return torch.zeros(shape3d, dtype=torch.int32, device=dev), {}
+    while len(vols) < 3:
+        vols.append(None)
+        luts.append(None)
+
+    # triple runs + overlaps between instances of different planes
+    runs = TripleRuns(vols, luts, shape3d)
+    _mark('triple runs (2 dense passes)')
+    pa, pb, inter = runs.pairs(_next_pow2(CAPS["pairs"] or max(1 << 16, 16 * n_nodes)))
+    _mark('pairs kernel')
+    sizes = np.array(node_sizes, dtype=np.int64)
+    cands = cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_thr, min_cluster)
+    _mark('host graph clustering')
+    out = torch.empty(shape3d, dtype=torch.int32, device=dev)
+    if not cands:
+        LAST_LAUNCHES = runs.launches
+        return out.zero_(), {}
+
+    # voxels claimed by each candidate, overlaps between candidates
+    memb_off_d, memb_list_d = membership_tables(cands, n_nodes, dev)
+    csize, ca, cb, cinter = runs.stats(memb_off_d, memb_list_d, pixel_vote_thr, len(cands), _next_pow2(CAPS["votes"]))
+    cpair = {(int(a), int(b)): int(v) for a, b, v in zip(ca, cb, cinter)}
+    _mark('vote stats kernel')
+    cid_final, final_boxes = merge_overlapping_candidates(cands, csize, cpair)
+    n_final = len(final_boxes)
+    if n_final == 0:
+        LAST_LAUNCHES = runs.launches
+        return out.zero_(), {}
+    cid_final_d = torch.from_numpy(cid_final).to(dev)
+    fsize = runs.final_sizes(memb_off_d, memb_list_d, pixel_vote_thr, cid_final_d, n_final)
+    keep = keep_mask(final_boxes, fsize, n_final, min_size, min_extent)
+    _mark('host merge_overlapping + sizes + filters')
+    runs.records(memb_off_d, memb_list_d, pixel_vote_thr, cid_final_d, torch.from_numpy(keep.astype(np.int32)).to(dev))
+    runs.paint(out)
+    _mark('records + paint kernels')
+    # the painted volume is final from here on: let the caller start its device->host copy while
+    # the run-length tables are sorted and joined
+    if on_volume_ready is not None:
+        on_volume_ready(out)
+    ids, starts, lens = runs.joined_ranges()
+    instances = instances_from_ranges(ids, starts, lens, final_boxes, keep, n_final)
+    _mark('sort + join + instances dict')
+    LAST_LAUNCHES = runs.launches
     return out, instances
 
 

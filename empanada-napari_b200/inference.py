@@ -266,7 +266,8 @@ class Engine3d:
                          label_divisor=e.label_divisor, void_label=e.void_label,
                          nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
                          confidence_thr=e.confidence_thr, device=self.device,
-                         scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap)
+                         scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap,
+                         **getattr(self, "_post_kwargs", {}))
 
     def _finish_plane(self, post, axis_name, shape3d, prof=None, defer=False):
         """Everything after the head maps are in: median tail, components, tracker replay,

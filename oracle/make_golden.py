@@ -309,9 +309,65 @@ def gen_model_bifpn_tiny():
     print("bifpn tiny", {k: tuple(v.shape) for k, v in o.items()})
 
 
+def gen_eval_cases():
+    """Reference `Evaluator` (evaluation/evaluator.py:24-122) with f1_50 / f1_75 / iou on pairs of
+    tracker JSONs written by the reference InstanceTracker: ground truth = exact ellipsoid labels,
+    prediction = the same labels eroded / shifted / with objects dropped and merged."""
+    import json
+    import tempfile
+    from empanada.evaluation.evaluator import Evaluator
+    from empanada.evaluation.instance_metrics import f1_50, f1_75
+    from empanada.evaluation.semantic_metrics import iou
+    from empanada.inference.tracker import InstanceTracker
+    from empanada.array_utils import rle_encode
+
+    def tracker_json(lab, path):
+        tr = InstanceTracker(1, 1000, lab.shape, "xy")
+        flat = lab.ravel()
+        for l in np.unique(flat):
+            if l == 0:
+                continue
+            idx = np.flatnonzero(flat == l)
+            starts, runs = rle_encode(idx)
+            zz, yy, xx = np.unravel_index(idx, lab.shape)
+            tr.instances[int(l)] = {"box": (int(zz.min()), int(yy.min()), int(xx.min()), int(zz.max()) + 1,
+                                            int(yy.max()) + 1, int(xx.max()) + 1), "starts": starts, "runs": runs}
+        tr.finished = True
+        tr.write_to_json(path)
+
+    cases = []
+    ev = Evaluator(semantic_metrics={"iou": iou}, instance_metrics={"f1_50": f1_50, "f1_75": f1_75})
+    with tempfile.TemporaryDirectory() as tmp:
+        for ci, (seed, shape, mode) in enumerate([(3, (24, 40, 36), "same"), (4, (28, 44, 40), "shift"),
+                                                  (5, (20, 48, 48), "drop"), (6, (24, 40, 40), "merge")]):
+            _, lab, _ = syn.make_volume(shape, seed=seed, scale=1.0)
+            pred = lab.copy()
+            if mode == "shift":
+                pred = np.roll(pred, 2, axis=2)
+                pred[:, :, :2] = 0
+            elif mode == "drop":
+                ids = np.unique(pred)[1:]
+                pred[np.isin(pred, ids[::3])] = 0
+            elif mode == "merge":
+                ids = np.unique(pred)[1:]
+                pred[pred == ids[1]] = ids[0]
+                pred[:, ::2, :][pred[:, ::2, :] == ids[2]] = 0
+            gp, pp = os.path.join(tmp, f"gt{ci}.json"), os.path.join(tmp, f"pr{ci}.json")
+            tracker_json(lab, gp)
+            tracker_json(pred, pp)
+            res = ev(gp, pp)
+            cases.append({"gt": json.load(open(gp)), "pred": json.load(open(pp)),
+                          "results": {k: float(v) for k, v in res.items()}})
+    with open(os.path.join(GOLD, "eval_cases.json"), "w") as f:
+        json.dump(cases, f)
+    print("eval cases:", [c["results"] for c in cases])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes"]
+    if "eval" in which:
+        gen_eval_cases()
     if "post" in which:
         gen_post_cases()
     if "post_fine" in which:

@@ -1,0 +1,183 @@
+"""-m gpu: bit-exact CUDA-vs-oracle parity at the benchmark's scale and on the configurations the
+small fixtures do not reach:
+
+* 256^3 volume from the BENCHMARK generator (>= 300 instances per plane; tracker labels beyond
+  label_divisor), with every growable table started far too small so that the regrow paths run
+  (centre slots, overlap hash tables, consensus hash tables, multi-claim side list);
+* an anisotropic NucleoNet / DropNet-like stack (padding factor 512, the shipped configs'
+  value: empanada_napari/configs/NucleoNet_base_v2.yaml:31);
+* Engine2d label ids (force_connected numbering) against oracle.pipeline.engine2d_infer;
+* the widget's call sequence, including the `tracker.instances.keys()` reads between planes
+  (empanada_napari/_volume_inference.py:331-346);
+* end-to-end agreement (network's own heads, bf16 vs fp32) scored with the reference Evaluator
+  (oracle/evaluation.py <- empanada/evaluation/evaluator.py:24-122) on >= 100 instances.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_instances_equal
+
+pytestmark = pytest.mark.gpu
+
+NORMS = {"mean": 0.57571, "std": 0.12765}
+
+
+def _cfg(pf=16):
+    return {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": pf,
+            "norms": NORMS, "model": None}
+
+
+def _device_heads_engine(heads, cfg, **kw):
+    from empanada_napari_b200.inference import Engine3d
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    cfg = dict(cfg)
+    cfg["model"] = SyntheticHeadsModel(lambda a, s0, s1: tuple(t[s0:s1] for t in heads[a]))
+    return Engine3d(cfg, **kw), cfg
+
+
+def _compare_with_oracle(vol, heads_np, cfg, got, kw, vote_kw, tracker_consensus):
+    from oracle import consensus as ocons, pipeline
+    want = {}
+    for a, name in enumerate(("xy", "xz", "yz")):
+        sem, ctr, off = heads_np[a]
+        _, want[name] = pipeline.infer_on_axis(vol, name, lambda i, x: (sem[i][None], ctr[i], off[i]), cfg,
+                                               save_panoptic=False, **kw)
+        assert_instances_equal(got[name][0].instances, want[name][0].instances)
+    (v, _, inst), = list(tracker_consensus(got, None, cfg, dtype=np.int32, **vote_kw))
+    (ov, _, oinst), = list(ocons.tracker_consensus(want, cfg, dtype=np.int32, **vote_kw))
+    assert_instances_equal(inst, oinst)
+    assert np.array_equal(v, ov)
+    return want, inst
+
+
+def test_bench_generator_256_bit_exact_with_regrowth():
+    import torch
+    import bench
+    from empanada_napari_b200 import consensus
+    from empanada_napari_b200.inference import tracker_consensus
+    S = 256
+    dev = torch.device("cuda:0")
+    vol_d, lab_d, n_obj = bench.synth_on_device(S, dev)
+    heads = {a: bench.analytic_heads_on_device(lab_d, a, n_obj) for a in range(3)}
+    kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5)
+    eng, cfg = _device_heads_engine(heads, _cfg(), batch_size=16, **kw)
+    # start every growable table far too small
+    eng.engine.center_cap = 8
+    eng._post_kwargs = dict(hash_cap=256)
+    old = dict(consensus.CAPS)
+    consensus.CAPS.update(pairs=256, votes=64, side=16)
+    try:
+        got = {}
+        for name in ("xy", "xz", "yz"):
+            _, got[name] = eng.infer_on_axis(vol_d, name)
+            n_inst = len(got[name][0].instances.keys())      # what the widget reads between planes
+            assert n_inst >= 300, (name, n_inst)
+            assert max(got[name][0].instances.keys()) >= 2000   # ids ran past label_divisor
+        assert eng.engine.center_cap > 8
+        vol = vol_d.cpu().numpy()
+        heads_np = {a: tuple(t.cpu().numpy() for t in heads[a]) for a in range(3)}
+        _, inst = _compare_with_oracle(vol, heads_np, cfg, got, kw,
+                                       dict(pixel_vote_thr=2, min_size=500, min_extent=5), tracker_consensus)
+        assert len(inst) >= 300
+    finally:
+        consensus.CAPS.clear()
+        consensus.CAPS.update(old)
+
+
+@pytest.mark.parametrize("shape,pf,ks,nms", [((48, 256, 192), 512, 3, 3), ((20, 150, 70), 128, 5, 7)])
+def test_anisotropic_stack_large_padding_factor(shape, pf, ks, nms):
+    """C5-like: anisotropic volume, every plane padded to the configs' padding factor."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import tracker_consensus
+    vol, lab, _ = syn.make_volume(shape, seed=31, scale=1.0)
+    dev = torch.device("cuda:0")
+    heads_np = {}
+    for a in range(3):
+        hs = [syn.analytic_heads(np.take(lab, i, axis=a), pad_to=pf) for i in range(shape[a])]
+        heads_np[a] = (np.stack([h[0][0] for h in hs]), np.stack([h[1] for h in hs]), np.stack([h[2] for h in hs]))
+    heads = {a: tuple(torch.from_numpy(t).to(dev) for t in heads_np[a]) for a in range(3)}
+    kw = dict(median_kernel_size=ks, nms_kernel=nms, confidence_thr=0.5, min_size=50, min_extent=3)
+    eng, cfg = _device_heads_engine(heads, _cfg(pf), batch_size=6, **kw)
+    got = {name: eng.infer_on_axis(vol, name)[1] for name in ("xy", "xz", "yz")}
+    _, inst = _compare_with_oracle(vol, heads_np, cfg, got, kw, dict(pixel_vote_thr=2, min_size=50, min_extent=3),
+                                   tracker_consensus)
+    assert len(inst) >= 10
+
+
+@pytest.mark.parametrize("fine", [False, True])
+def test_engine2d_labels_exact(fine):
+    """Engine2d.infer label ids (per-class connected-component renumbering of force_connected,
+    inference.py:263-279) equal to the oracle's on identical head maps."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import Engine2d, upsample_instance_heads
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    from oracle import pipeline
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(17)
+    _, lab, _ = syn.make_volume((3, 250, 230), seed=23, scale=1.0)
+    for i in range(3):
+        sem, ctr, off = syn.analytic_heads(lab[i], pad_to=16)
+        sem = (sem + rng.normal(0, 1.5, sem.shape)).astype(np.float32)     # noisy mask: fragments + holes
+        off = (off + rng.normal(0, 1.0, off.shape)).astype(np.float32)
+        d = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in (sem, ctr[None], off[None])]
+        cfg = _cfg()
+        cfg["model"] = SyntheticHeadsModel(lambda a, s0, s1, d=d: (d[0], d[1], d[2]))
+        eng = Engine2d(cfg, confidence_thr=0.5, nms_threshold=0.1, nms_kernel=7, fine_boundaries=fine)
+        img = np.full(lab[i].shape, 100, dtype=np.uint8)
+        out = eng.infer(img)
+        if fine:
+            c, o = upsample_instance_heads(d[1], d[2])
+            ctr_o, off_o = c[0].cpu().numpy(), o[0].cpu().numpy()
+        else:
+            ctr_o, off_o = ctr, off
+        want = pipeline.engine2d_infer(img, lambda k, x: (sem, ctr_o, off_o), cfg, confidence_thr=0.5,
+                                       nms_threshold=0.1, nms_kernel=7, fine_boundaries=fine)
+        assert out.dtype == np.int32 and out.shape == img.shape
+        assert len(np.unique(out)) > 10
+        assert np.array_equal(out, want), i
+
+
+def test_end_to_end_evaluator_f1_on_many_instances(tmp_path):
+    """Whole path with the network's OWN heads (bf16 tcgen05 forward + CUDA post-processing +
+    consensus) against the fp32 oracle network + oracle pipeline on the same volume, scored with
+    the reference's Evaluator (tracker JSONs in, f1_50 / f1_75 / iou out). BASELINE.md section 4:
+    instance F1 and IoU agreement >= 0.99 on >= 100 instances."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import Engine3d, tracker_consensus
+    from empanada_napari_b200.tracking import InstanceTracker
+    from oracle import consensus as ocons, model as omodel, pipeline
+    from oracle.evaluation import Evaluator, f1_50, f1_75, iou
+    sd = syn.make_pdl_state_dict(0)
+    cfg = _cfg()
+    cfg["model"] = sd
+    shape = (96, 176, 176)
+    vol, _, _ = syn.make_volume(shape, seed=9, scale=1.0)
+    kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.45, min_size=8, min_extent=1)
+    eng = Engine3d(cfg, batch_size=8, **kw)
+    got = {ax: eng.infer_on_axis(vol, ax)[1] for ax in ("xy", "xz", "yz")}
+
+    def heads_fn(i, x):
+        o = omodel.pdl_forward(sd, torch.from_numpy(x[None, None]), 2, False)
+        return o["sem_logits"][0].numpy(), o["ctr_hmp"][0, 0].numpy(), o["offsets"][0].numpy()
+
+    want = {ax: pipeline.infer_on_axis(vol, ax, heads_fn, cfg, save_panoptic=False, **kw)[1] for ax in ("xy", "xz", "yz")}
+    vote = dict(pixel_vote_thr=2, min_size=8, min_extent=1, dtype=np.int32)
+    (v, _, inst), = list(tracker_consensus(got, None, cfg, **vote))
+    (ov, _, oinst), = list(ocons.tracker_consensus(want, cfg, **vote))
+    tr = InstanceTracker(1, 1000, shape, "xy")
+    tr.instances = inst
+    otr = InstanceTracker(1, 1000, shape, "xy")     # JSON writer of tracker.py:125-147
+    otr.instances = oinst
+    gp, pp = str(tmp_path / "oracle.json"), str(tmp_path / "b200.json")
+    otr.write_to_json(gp)
+    tr.write_to_json(pp)
+    res = Evaluator(semantic_metrics={"iou": iou}, instance_metrics={"f1_50": f1_50, "f1_75": f1_75})(gp, pp)
+    print("instances", len(inst), len(oinst), res)
+    assert len(oinst) >= 100 and len(inst) >= 100
+    assert res["f1_50"] >= 0.99 and res["f1_75"] >= 0.99 and res["iou"] >= 0.99, res

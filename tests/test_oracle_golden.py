@@ -149,3 +149,21 @@ def test_bifpn_restatement_matches_reference_fixture():
     out = model.bifpn_forward(syn.make_bifpn_state_dict(0), torch.from_numpy(x), 2, False)
     for k in ("sem_logits", "ctr_hmp", "offsets"):
         assert np.allclose(out[k].numpy(), z[k], atol=2e-4, rtol=1e-4), k
+
+
+def test_evaluator_against_reference_fixture(tmp_path):
+    """oracle.evaluation.Evaluator reproduces the reference Evaluator's f1_50 / f1_75 / iou on the
+    tracker JSON pairs of tests/golden/eval_cases.json (generated by oracle/make_golden.py eval)."""
+    import json
+    from oracle.evaluation import Evaluator, f1_50, f1_75, iou
+    cases = json.load(open(os.path.join(GOLDEN, "eval_cases.json")))
+    ev = Evaluator(semantic_metrics={"iou": iou}, instance_metrics={"f1_50": f1_50, "f1_75": f1_75})
+    assert len(cases) >= 4
+    for i, c in enumerate(cases):
+        gp, pp = tmp_path / f"gt{i}.json", tmp_path / f"pr{i}.json"
+        gp.write_text(json.dumps(c["gt"]))
+        pp.write_text(json.dumps(c["pred"]))
+        got = ev(str(gp), str(pp))
+        assert set(got) == set(c["results"])
+        for k, v in c["results"].items():
+            assert float(got[k]) == v, (i, k, got[k], v)
