@@ -34,6 +34,26 @@ class SyntheticHeadsModel:
         return self.heads_fn(axis, s0, s1)
 
 
+class HostHeadsModel:
+    """Picklable variant of `SyntheticHeadsModel` for multi-process tests: `heads[axis]` =
+    (sem_logits (N,H,W), ctr_hmp (N,h4,w4), offsets (N,2,h4,w4)) numpy arrays, uploaded to the
+    current device on first use."""
+
+    def __init__(self, heads):
+        self.heads = heads
+        self.launches = 0
+        self._dev = None
+
+    def __getstate__(self):
+        return {"heads": self.heads, "launches": 0, "_dev": None}
+
+    def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
+        if self._dev is None:
+            self._dev = {a: tuple(torch.from_numpy(t).to(vol_d.device) for t in h) for a, h in self.heads.items()}
+        sem, ctr, off = self._dev[axis]
+        return sem[s0:s1], ctr[s0:s1], off[s0:s1]
+
+
 def load_state_dict_any(path):
     """state_dict of a TorchScript archive (the reference's deployment format) or a plain
     `torch.save(state_dict)` file."""

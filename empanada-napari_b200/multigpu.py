@@ -1,15 +1,17 @@
-"""Multi-GPU stack inference: one process per GPU (torchrun / torch.distributed, NCCL over
-NVLink). Replaces the reference's `MultiGPUEngine3d` (empanada_napari/multigpu.py:121-260), which
+"""Multi-GPU stack inference: one process per GPU (torch.distributed, NCCL over NVLink).
+Replaces the reference's `MultiGPUEngine3d` (empanada_napari/multigpu.py:121-260), which
 round-robins slices over ranks and all_gathers full-resolution `sem` and `instance_cells` on
 every step (patterns.py:226-240, multigpu.py:90-91).
 
-Here each rank runs the network on a CONTIGUOUS slice range of every plane and the head maps are
-gathered once per plane to that plane's leader rank (`dist.gather`), which runs the sequential
-part (recursive median, tracker replay) and the remaining post-processing; the three planes have
-different leaders, so their post-processing runs concurrently, and rank 0 receives the finished
-label volumes for the consensus. Round-1 scope: the conv stack (90 % of the single-GPU time) is
-what is sharded by slice; sharding the post-processing by slice range with halo exchange is the
-next step.
+* `ShardedEngine3d` (the engine under torchrun, and what `MultiGPUEngine3d` runs on every rank):
+  the WHOLE per-plane path - network, median queue, centres, grouping, components, overlap
+  tables, painting - sharded by contiguous slice range; NVLink carries the median-queue wavefront,
+  one component slice per shard boundary, the sparse tables to the plane's leader and the label
+  table back.
+* `MultiGPUEngine3d`: the widget-facing front end, constructed in one process with the reference's
+  keywords; it starts the other ranks itself.
+* `DistributedEngine3d`: the earlier scheme (only the network sharded, head maps gathered to the
+  plane leaders), kept selectable with B200_EMPANADA_MULTIGPU=gather.
 """
 import os
 import time
@@ -400,3 +402,159 @@ def tracking_replay(merged, cls, div, axis_name, iou_thr, ioa_thr, min_size, min
 def _lib_error(msg):
     from ._lib import B200EmpanadaError
     return B200EmpanadaError(msg)
+
+
+# ------------------------------------------------------------------------------------------
+# One-process front end: what the widget constructs (empanada_napari/_volume_inference.py:17,
+# empanada_napari/multigpu.py:121-260)
+# ------------------------------------------------------------------------------------------
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker_main(rank, world, port, model_config, engine_kwargs, cmd_q, err_q):
+    """Rank r > 0 of a `MultiGPUEngine3d`: a persistent process bound to GPU r that mirrors every
+    call of the parent (rank 0) on its own `ShardedEngine3d`."""
+    import traceback
+    try:
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=dev)
+        eng = ShardedEngine3d(model_config, **engine_kwargs)
+        vol_version, vol_d = None, None
+        while True:
+            cmd = cmd_q.get()
+            if cmd[0] == "close":
+                break
+            if cmd[0] == "update_params":
+                eng.update_params(*cmd[1])
+            elif cmd[0] == "infer":
+                _, axis_name, shape, dtype_name, version = cmd
+                if version != vol_version:
+                    vol_d = None
+                    vol_d = torch.empty(shape, dtype=getattr(torch, dtype_name), device=dev)
+                    dist.broadcast(vol_d, src=0)
+                    vol_version = version
+                _, trackers = eng.infer_on_axis(vol_d, axis_name)
+                eng.finalize({axis_name: trackers})
+            elif cmd[0] == "release":
+                vol_version, vol_d = None, None
+        dist.destroy_process_group()
+    except BaseException:
+        err_q.put((rank, traceback.format_exc()))
+        raise
+
+
+class MultiGPUEngine3d:
+    r"""Drop-in for `empanada_napari.multigpu.MultiGPUEngine3d` (multigpu.py:121-260): constructed
+    in ONE process with the reference's keywords, raises below two GPUs, runs one process per GPU
+    and returns `(stack, trackers)` from `infer_on_axis`.
+
+    The calling process is rank 0 (GPU 0); ranks 1..G-1 are persistent worker processes started
+    once in the constructor (the reference re-spawns and re-loads the model for every plane,
+    multigpu.py:216-220). Each call runs `ShardedEngine3d` on every rank: the whole per-plane path
+    sharded by slice range, the uint8 volume uploaded once by rank 0 and broadcast over NVLink."""
+
+    def __init__(self, model_config, inference_scale=1, label_divisor=1000, median_kernel_size=5,
+                 stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3,
+                 force_connected=True, min_size=500, min_extent=4, fine_boundaries=False,
+                 semantic_only=False, store_url=None, chunk_size=(256, 256, 256), save_panoptic=False,
+                 world_size=None, batch_size=None):
+        import torch.multiprocessing as mp
+        if not torch.cuda.device_count() > 1:
+            raise Exception("MultiGPU inference requires multiple GPUs! Run torch.cuda.device_count()")
+        if dist.is_initialized():
+            raise _lib_error("MultiGPUEngine3d starts its own process group; under torchrun use ShardedEngine3d")
+        self.world = int(world_size or torch.cuda.device_count())
+        if not 2 <= self.world <= torch.cuda.device_count():
+            raise _lib_error(f"world_size must be between 2 and {torch.cuda.device_count()}")
+        self.labels = model_config["labels"]
+        self.config = model_config
+        self.axes = {"xy": 0, "xz": 1, "yz": 2}
+        self.min_size, self.min_extent = min_size, min_extent
+        self.save_panoptic, self.chunk_size = save_panoptic, chunk_size
+        self.zarr_store = None
+        self.dtype = np.int32
+        kwargs = dict(inference_scale=inference_scale, label_divisor=label_divisor,
+                      median_kernel_size=median_kernel_size, stuff_area=stuff_area, void_label=void_label,
+                      nms_threshold=nms_threshold, nms_kernel=nms_kernel, confidence_thr=confidence_thr,
+                      force_connected=force_connected, min_size=min_size, min_extent=min_extent,
+                      fine_boundaries=fine_boundaries, semantic_only=semantic_only, store_url=store_url,
+                      chunk_size=chunk_size, save_panoptic=False, batch_size=batch_size)
+        port = _free_port()
+        ctx = mp.get_context("spawn")
+        self._err_q = ctx.Queue()
+        self._cmd_qs, self._procs = [], []
+        for r in range(1, self.world):
+            q = ctx.Queue()
+            p = ctx.Process(target=_worker_main, args=(r, self.world, port, model_config, kwargs, q, self._err_q),
+                            daemon=True)
+            p.start()
+            self._cmd_qs.append(q)
+            self._procs.append(p)
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=self.world,
+                                device_id=torch.device("cuda", 0))
+        self._engine = ShardedEngine3d(model_config, **kwargs)
+        self.engine = self._engine.engine
+        self._version = 0
+        self._uploaded = None
+
+    def _send(self, *cmd):
+        if not self._err_q.empty():
+            rank, tb = self._err_q.get()
+            raise _lib_error(f"worker rank {rank} failed:\n{tb}")
+        for q in self._cmd_qs:
+            q.put(cmd)
+
+    def create_trackers(self, shape3d, axis_name):
+        return self._engine.create_trackers(shape3d, axis_name)
+
+    def update_params(self, *args):
+        """Same positional arguments as `Engine3d.update_params` (inference.py:414-432)."""
+        self._send("update_params", args)
+        self._engine.update_params(*args)
+
+    def infer_on_axis(self, volume, axis_name):
+        eng = self._engine
+        vol_d = eng._cache.get(volume, eng.device)
+        if vol_d is not self._uploaded:          # a new device copy: every rank needs it
+            self._uploaded = vol_d
+            self._version += 1
+            fresh = True
+        else:
+            fresh = False
+        self._send("infer", axis_name, tuple(vol_d.shape), str(vol_d.dtype).replace("torch.", ""), self._version)
+        if fresh:
+            dist.broadcast(vol_d, src=0)
+        _, trackers = eng.infer_on_axis(vol_d, axis_name)
+        trackers = eng.finalize({axis_name: trackers})[axis_name]
+        stack = trackers[0]._b200_dense.cpu().numpy() if self.save_panoptic else None
+        return stack, trackers
+
+    def release(self):
+        self._send("release")
+        self._engine.release()
+        self._uploaded = None
+
+    def close(self):
+        """Stops the worker processes (also done when the object is collected)."""
+        if getattr(self, "_procs", None):
+            try:
+                for q in self._cmd_qs:
+                    q.put(("close",))
+                for p in self._procs:
+                    p.join(timeout=30)
+                dist.destroy_process_group()
+            finally:
+                self._procs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

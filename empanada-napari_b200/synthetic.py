@@ -25,6 +25,32 @@ def make_ellipsoids(shape, n_objects=None, seed=0, scale=None):
     return np.concatenate([centers, radii], axis=1).astype(np.float32)  # (n, 6): cz cy cx rz ry rx
 
 
+def make_separated_ellipsoids(shape, n_objects, seed=0, rmin=5.0, rmax=9.0, gap=5.0):
+    """Ellipsoid table (as `make_ellipsoids`) whose objects keep at least `gap` voxels between
+    their bounding spheres and stay inside the volume: every object is one well-separated
+    instance (used by the end-to-end agreement tests)."""
+    d, h, w = shape
+    rng = np.random.default_rng(seed)
+    out = []
+    tries = 0
+    while len(out) < n_objects and tries < 200 * n_objects:
+        tries += 1
+        r = rng.uniform(rmin, rmax, size=3)
+        c = rng.uniform(r + 1.0, np.array([d, h, w]) - r - 1.0)
+        if all(np.linalg.norm(c - o[:3]) >= r.max() + o[3:].max() + gap for o in out):
+            out.append(np.concatenate([c, r]))
+    return np.array(out, dtype=np.float32)
+
+
+def make_separated_volume(shape, n_objects, seed=0, **kw):
+    """(uint8 volume, int32 labels, ellipsoid table) of `make_separated_ellipsoids`."""
+    ell = make_separated_ellipsoids(shape, n_objects, seed, **kw)
+    lab = label_volume(shape, ell)
+    rng = np.random.default_rng(seed + 1)
+    img = np.where(lab > 0, 70.0, 170.0) + rng.normal(0.0, 8.0, size=shape)
+    return np.clip(img, 0, 255).astype(np.uint8), lab, ell
+
+
 def label_volume(shape, ell):
     """Dense int32 ground truth: voxel -> 1-based index of the LAST ellipsoid containing it."""
     d, h, w = shape

@@ -75,8 +75,10 @@ def pdl_head(sd, p, x):
     return _conv(sd, p + ".head.1", x)
 
 
-def point_rend(sd, coarse, features, render_steps, num_points=8192):
-    """models/point_rend.py:241-269 (eval branch)."""
+def point_rend(sd, coarse, features, render_steps, num_points=8192, collect=None):
+    """models/point_rend.py:241-269 (eval branch). `collect` (a list) receives, per render step,
+    (predictor input (R,C,k), point indices (R,k), H, W): used by oracle/probe.py to fit the
+    predictor layer."""
     sem = coarse.clone()
     nfc = 0
     # fused exports (PDL) nest conv+relu one level deeper than unfused ones (BiFPN)
@@ -106,6 +108,8 @@ def point_rend(sd, coarse, features, render_steps, num_points=8192):
             pre = fc_fmt.format(l)
             x = F.relu(F.conv1d(x, sd[pre + ".weight"], sd[pre + ".bias"]))
             x = torch.cat([x, cpts], dim=1)
+        if collect is not None:
+            collect.append((x, idx, sem.shape[2], sem.shape[3]))
         logits = F.conv1d(x, sd["semantic_pr.point_head.predictor.weight"],
                           sd["semantic_pr.point_head.predictor.bias"])
         N, C, H, W = sem.shape

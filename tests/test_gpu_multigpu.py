@@ -25,3 +25,26 @@ def test_distributed_engine_equals_single_gpu(engine, ks, fine):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "MULTIGPU_CHECK" in r.stdout and " PASS" in r.stdout
+
+
+def test_multigpu_engine_front_end():
+    """`MultiGPUEngine3d` as the widget constructs it (one process, reference keywords, worker
+    processes started by the engine): same stacks, trackers and consensus as `Engine3d`."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_multigpu_front.py")],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "MULTIGPU_FRONT PASS" in r.stdout
+
+
+def test_multigpu_engine_needs_two_gpus():
+    """multigpu.py:143-144: plain `Exception` below two GPUs."""
+    import torch
+    from empanada_napari_b200.multigpu import MultiGPUEngine3d
+    if torch.cuda.device_count() > 1:
+        pytest.skip("box has several GPUs")
+    with pytest.raises(Exception, match="MultiGPU inference requires multiple GPUs"):
+        MultiGPUEngine3d({"labels": [1], "thing_list": [1], "class_names": {1: "mito"}, "padding_factor": 16,
+                          "norms": {"mean": 0.5, "std": 0.1}, "model": {}})
