@@ -436,7 +436,8 @@ def main():
               "l2": "inputs larger than L2 (1 GiB volume, >4 GiB of heads per plane)",
               "parallelism": (f"every plane sharded by slice range x{world} (network + post-processing; median "
                               f"wavefront, boundary-overlap and table exchange over NCCL); tracker replay on one "
-                              f"leader rank per plane; consensus on rank 0") if world > 1 else "single GPU"}
+                              f"leader rank per plane, overlapped with the next plane; consensus sharded by z-slab "
+                              f"(slab all-to-all, sparse tables to rank 0), painted slabs gathered to rank 0") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -503,14 +504,21 @@ def main():
                 # the widget's call sequence reports the instance count of every plane before it
                 # starts the next one (empanada_napari/_volume_inference.py:339-346)
                 counts[name] = len(trackers[name][0].instances.keys())
-        if world > 1:  # deferred post-processing on the plane leaders, results to rank 0
-            trackers = eng.finalize(trackers)
+        sharded = world > 1 and hasattr(eng, "sharded_consensus")
+        if world > 1:  # label tables from the plane leaders; every rank paints its own slabs
+            trackers = eng.finalize(trackers, gather_dense=not sharded)
             n_l += eng.last_stats.get("kernel_launches", 0)
             if rank == 0:
                 for name in trackers:
                     counts[name] = len(trackers[name][0].instances.keys())
         out = None
-        if rank == 0:
+        if sharded:    # every rank votes on its own z-slab; graph decisions on rank 0
+            vol, _, inst = eng.sharded_consensus(trackers, cfg, pixel_vote_thr=2, min_size=500, min_extent=5)
+            n_l += eng.consensus_launches
+            if rank == 0:
+                from empanada_napari_b200.inference import _PINNED
+                out = (_PINNED.to_host(vol, np.int32) if to_host else vol, inst)
+        elif rank == 0:
             for vol, cname, inst in tracker_consensus(trackers, None, cfg, pixel_vote_thr=2, min_size=500,
                                                       min_extent=5, dtype=np.int32, to_host=to_host):
                 out = (vol, inst)

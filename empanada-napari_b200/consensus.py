@@ -407,8 +407,8 @@ def merge_overlapping_candidates(cands, csize, cpair):
     return cid_final, final_boxes
 
 
-def membership_tables(cands, n_nodes, dev):
-    """node (1-based) -> candidate ids (1-based) as CSR device arrays."""
+def membership_tables(cands, n_nodes):
+    """node (1-based) -> candidate ids (1-based) as CSR host arrays."""
     memb = [[] for _ in range(n_nodes + 2)]
     for cid, (_, cluster, _) in enumerate(cands, start=1):
         for m in cluster:
@@ -416,7 +416,7 @@ def membership_tables(cands, n_nodes, dev):
     memb_off = np.zeros(n_nodes + 3, dtype=np.int32)
     memb_off[1:] = np.cumsum([len(m) for m in memb])
     memb_list = np.array([c for m in memb for c in m] or [0], dtype=np.int32)
-    return torch.from_numpy(memb_off).to(dev), torch.from_numpy(memb_list).to(dev)
+    return memb_off, memb_list
 
 
 def tracker_nodes(trackers, dev):
@@ -436,6 +436,23 @@ def tracker_nodes(trackers, dev):
         luts.append(torch.from_numpy(lut).to(dev))
         vols.append(dense_volume(tr, dev))
     return nid, node_sizes, node_boxes, luts, vols
+
+
+def tracker_node_tables(trackers):
+    """`tracker_nodes` without the device volumes (host tables only): (n_nodes, sizes, boxes,
+    per-plane label -> node LUTs as numpy arrays). Trackers must carry `_b200_sizes`."""
+    node_sizes, node_boxes, luts = [], [], []
+    nid = 0
+    for tr in trackers:
+        labels = [int(l) for l in tr.instances.keys()]
+        lut = np.zeros((max(labels) + 1) if labels else 1, dtype=np.int32)
+        for l in labels:
+            nid += 1
+            lut[l] = nid
+            node_sizes.append(int(tr._b200_sizes[l]))
+            node_boxes.append(tuple(int(v) for v in tr.instances[l]["box"]))
+        luts.append(lut)
+    return nid, node_sizes, node_boxes, luts
 
 
 def keep_mask(final_boxes, fsize, n_final, min_size, min_extent):
@@ -463,10 +480,150 @@ def instances_from_ranges(ids, starts, lens, final_boxes, keep, n_final):
     return instances
 
 
+class ConsensusShard:
+    """Device side of the consensus for one z-slab [z0, z0 + dz) of the volume: the three
+    planes' label slabs (dz, H, W) + label -> node tables. Every method is one phase of
+    `consensus_driver`; arguments and results are small host tables (picklable), so the same
+    driver runs over in-process shards (single GPU) or one shard per rank (multigpu.py)."""
+
+    def __init__(self, vols, luts, z0=0):
+        vols, luts = list(vols), list(luts)
+        while len(vols) < 3:
+            vols.append(None)
+            luts.append(None)
+        first = next(v for v in vols if v is not None)
+        self.dev = first.device
+        self.shape = tuple(int(x) for x in first.shape)
+        self.z0 = int(z0)
+        self.vols, self.luts = vols, luts
+        self.runs = None
+        self.painted = None
+
+    def _lut_tensors(self, luts):
+        return [None if l is None else (l if isinstance(l, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(l, dtype=np.int32)).to(self.dev))
+                for l in luts]
+
+    def pairs(self, cap, luts=None):
+        """Triple runs of the slab + overlap table between nodes of different planes."""
+        if luts is not None:
+            self.luts = luts
+        self.luts = self._lut_tensors(self.luts)
+        D, H, W = self.shape
+        self.runs = TripleRuns(self.vols, self.luts, self.shape, flat0=self.z0 * H * W)
+        return self.runs.pairs(cap)
+
+    def stats(self, memb_off, memb_list, vote_thr, n_cands, cap):
+        self.memb = (torch.from_numpy(memb_off).to(self.dev), torch.from_numpy(memb_list).to(self.dev))
+        self.vote_thr = int(vote_thr)
+        return self.runs.stats(self.memb[0], self.memb[1], vote_thr, n_cands, cap)
+
+    def final_sizes(self, cid_final, n_final):
+        self.cid_final = torch.from_numpy(cid_final).to(self.dev)
+        return self.runs.final_sizes(self.memb[0], self.memb[1], self.vote_thr, self.cid_final, n_final)
+
+    def paint(self, keep, on_volume_ready=None):
+        """Paints the slab (kept in `self.painted`) and returns the joined ranges (ids, starts,
+        lengths) of the slab, sorted by (id, start), starts as GLOBAL flat indices."""
+        keep_d = torch.from_numpy(np.ascontiguousarray(keep, dtype=np.int32)).to(self.dev)
+        self.runs.records(self.memb[0], self.memb[1], self.vote_thr, self.cid_final, keep_d)
+        self.painted = self.runs.paint(torch.empty(self.shape, dtype=torch.int32, device=self.dev))
+        if on_volume_ready is not None:
+            on_volume_ready(self.painted)
+        return self.runs.joined_ranges()
+
+    def zero(self):
+        self.painted = torch.zeros(self.shape, dtype=torch.int32, device=self.dev)
+
+    @property
+    def launches(self):
+        return self.runs.launches if self.runs is not None else 0
+
+
+def _sum_by_pair(tables):
+    """[(a, b, count)] per shard -> one table with the counts of equal (a, b) summed."""
+    a = np.concatenate([t[0] for t in tables]).astype(np.int64)
+    b = np.concatenate([t[1] for t in tables]).astype(np.int64)
+    v = np.concatenate([t[2] for t in tables]).astype(np.int64)
+    if len(tables) == 1 or a.size == 0:
+        return a, b, v
+    key = (a << 32) | b
+    uk, inv = np.unique(key, return_inverse=True)
+    return uk >> 32, uk & 0xFFFFFFFF, np.bincount(inv, weights=v, minlength=len(uk)).astype(np.int64)
+
+
+def join_shard_ranges(parts, n_final):
+    """Per-shard joined ranges (ids ascending, starts ascending per id; shards in ascending z
+    order) -> per-id (starts, lengths) over the whole volume. Ranges that meet at a shard
+    boundary (the flat index runs on from the last voxel of one slab into the first voxel of the
+    next) are joined, as they are when the volume is processed in one piece."""
+    bounds = [np.searchsorted(ids, np.arange(1, n_final + 2)) for ids, _, _ in parts]
+    out = {}
+    for fid in range(1, n_final + 1):
+        ss, ll = [], []
+        for (ids, starts, lens), bd in zip(parts, bounds):
+            a, b = bd[fid - 1], bd[fid]
+            if b > a:
+                if ss and ss[-1][-1] + ll[-1][-1] == starts[a]:
+                    ll[-1] = ll[-1].copy()
+                    ll[-1][-1] += lens[a]
+                    a += 1
+                    if b == a:
+                        continue
+                ss.append(starts[a:b])
+                ll.append(lens[a:b])
+        if ss:
+            out[fid] = (ss[0], ll[0]) if len(ss) == 1 else (np.concatenate(ss), np.concatenate(ll))
+    return out
+
+
+def consensus_driver(each, n_shards, n_nodes, node_sizes, node_boxes, luts, pixel_vote_thr, cluster_iou_thr,
+                     min_cluster, min_size, min_extent, mark=lambda name: None, on_volume_ready=None):
+    """Host side of consensus.py:348-469 (+ the two tracker filters, inference.py:149-150) over
+    `n_shards` z-slabs. `each(method, *args)` runs `ConsensusShard.method(*args)` on every shard
+    and returns the list of results in ascending z order. Returns the instances dict; the painted
+    slabs stay on the shards (`ConsensusShard.painted`)."""
+    tables = each("pairs", _next_pow2(CAPS["pairs"] or max(1 << 16, 16 * n_nodes)), luts)
+    pa, pb, inter = _sum_by_pair(tables)
+    mark('triple runs + pairs kernel')
+    sizes = np.array(node_sizes, dtype=np.int64)
+    cands = cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_thr, min_cluster)
+    mark('host graph clustering')
+    if not cands:
+        each("zero")
+        return {}
+    memb_off, memb_list = membership_tables(cands, n_nodes)
+    res = each("stats", memb_off, memb_list, pixel_vote_thr, len(cands), _next_pow2(CAPS["votes"]))
+    csize = np.sum([r[0] for r in res], axis=0)
+    ca, cb, cinter = _sum_by_pair([r[1:] for r in res])
+    cpair = {(int(a), int(b)): int(v) for a, b, v in zip(ca, cb, cinter)}
+    mark('vote stats kernel')
+    cid_final, final_boxes = merge_overlapping_candidates(cands, csize, cpair)
+    n_final = len(final_boxes)
+    if n_final == 0:
+        each("zero")
+        return {}
+    fsize = np.sum(each("final_sizes", cid_final, n_final), axis=0)
+    keep = keep_mask(final_boxes, fsize, n_final, min_size, min_extent)
+    mark('host merge_overlapping + sizes + filters')
+    parts = each("paint", keep.astype(np.int32), on_volume_ready) if on_volume_ready is not None else each("paint", keep.astype(np.int32))
+    mark('records + paint + sort + join kernels')
+    if n_shards == 1:
+        ids, starts, lens = parts[0]
+        instances = instances_from_ranges(ids, starts, lens, final_boxes, keep, n_final)
+    else:
+        joined = join_shard_ranges(parts, n_final)
+        instances = {fid: {"box": final_boxes[fid], "starts": joined[fid][0], "runs": joined[fid][1]}
+                     for fid in range(1, n_final + 1) if keep[fid] and fid in joined}
+    mark('instances dict')
+    return instances
+
+
 def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75, bypass=False,
-                                min_size=None, min_extent=None, on_volume_ready=None):
+                                min_size=None, min_extent=None, on_volume_ready=None, z_shards=1):
     """consensus.py:348-469 followed by the two tracker filters (inference.py:149-150).
-    Returns (device int32 volume with the final ids painted, instances dict)."""
+    Returns (device int32 volume with the final ids painted, instances dict). `z_shards` > 1
+    processes the volume as that many z-slabs through the sharded driver (the code path of the
+    multi-GPU engines, exercised on one GPU by the tests)."""
     global LAST_LAUNCHES, LAST_PROFILE
     import os as _os, time as _time
     _prof_on = _os.environ.get("B200_EMPANADA_PROFILE") == "1"
@@ -492,48 +649,26 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     n_nodes, node_sizes, node_boxes, luts, vols = tracker_nodes(trackers, dev)
     if n_nodes == 0:
         return torch.zeros(shape3d, dtype=torch.int32, device=dev), {}
-    while len(vols) < 3:
-        vols.append(None)
-        luts.append(None)
+    D = shape3d[0]
+    z_shards = max(1, min(int(z_shards), D))
+    if z_shards == 1:
+        shards = [ConsensusShard(vols, luts)]
+    else:
+        cuts = [round(i * D / z_shards) for i in range(z_shards + 1)]
+        shards = [ConsensusShard([v[a:b] for v in vols], luts, z0=a) for a, b in zip(cuts[:-1], cuts[1:])]
 
-    # triple runs + overlaps between instances of different planes
-    runs = TripleRuns(vols, luts, shape3d)
-    _mark('triple runs (2 dense passes)')
-    pa, pb, inter = runs.pairs(_next_pow2(CAPS["pairs"] or max(1 << 16, 16 * n_nodes)))
-    _mark('pairs kernel')
-    sizes = np.array(node_sizes, dtype=np.int64)
-    cands = cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_thr, min_cluster)
-    _mark('host graph clustering')
-    out = torch.empty(shape3d, dtype=torch.int32, device=dev)
-    if not cands:
-        LAST_LAUNCHES = runs.launches
-        return out.zero_(), {}
+    def each(method, *args):
+        return [getattr(sh, method)(*args) for sh in shards]
 
-    # voxels claimed by each candidate, overlaps between candidates
-    memb_off_d, memb_list_d = membership_tables(cands, n_nodes, dev)
-    csize, ca, cb, cinter = runs.stats(memb_off_d, memb_list_d, pixel_vote_thr, len(cands), _next_pow2(CAPS["votes"]))
-    cpair = {(int(a), int(b)): int(v) for a, b, v in zip(ca, cb, cinter)}
-    _mark('vote stats kernel')
-    cid_final, final_boxes = merge_overlapping_candidates(cands, csize, cpair)
-    n_final = len(final_boxes)
-    if n_final == 0:
-        LAST_LAUNCHES = runs.launches
-        return out.zero_(), {}
-    cid_final_d = torch.from_numpy(cid_final).to(dev)
-    fsize = runs.final_sizes(memb_off_d, memb_list_d, pixel_vote_thr, cid_final_d, n_final)
-    keep = keep_mask(final_boxes, fsize, n_final, min_size, min_extent)
-    _mark('host merge_overlapping + sizes + filters')
-    runs.records(memb_off_d, memb_list_d, pixel_vote_thr, cid_final_d, torch.from_numpy(keep.astype(np.int32)).to(dev))
-    runs.paint(out)
-    _mark('records + paint kernels')
-    # the painted volume is final from here on: let the caller start its device->host copy while
-    # the run-length tables are sorted and joined
+    hook = on_volume_ready if z_shards == 1 else None
+    instances = consensus_driver(each, len(shards), n_nodes, node_sizes, node_boxes, None, pixel_vote_thr,
+                                 cluster_iou_thr, min_cluster, min_size, min_extent, _mark, hook)
+    LAST_LAUNCHES = sum(sh.launches for sh in shards)
+    if z_shards == 1:
+        return shards[0].painted, instances
+    out = torch.cat([sh.painted for sh in shards])
     if on_volume_ready is not None:
         on_volume_ready(out)
-    ids, starts, lens = runs.joined_ranges()
-    instances = instances_from_ranges(ids, starts, lens, final_boxes, keep, n_final)
-    _mark('sort + join + instances dict')
-    LAST_LAUNCHES = runs.launches
     return out, instances
 
 

@@ -140,10 +140,13 @@ class _VolumeCache:
         host = self.ref() if self.ref is not None else None
         if host is not volume or sig != self.sig or self.dev is None:
             self.dev = None
-            self.dev = _as_device_volume(volume, device)
+            self.dev = self._upload(volume, device)
             import weakref
             self.ref, self.sig = weakref.ref(volume), sig
         return self.dev
+
+    def _upload(self, volume, device):
+        return _as_device_volume(volume, device)
 
     def clear(self):
         self.ref, self.sig, self.dev = None, None, None
@@ -539,6 +542,18 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
         if class_id not in thing_list:
             _unsupported("semantic (stuff) class consensus")
         out = InstanceTracker(class_id, class_trackers[0].label_divisor, shape3d, "xy")
+        front = getattr(getattr(class_trackers[0], "_b200_sharded", None), "front", None)
+        if (front is not None and len(class_trackers) == 3 and set(trackers.keys()) == {"xy", "xz", "yz"}
+                and all(getattr(t, "_b200_sharded", None) is class_trackers[0]._b200_sharded
+                        and getattr(t, "_b200_dense", None) is None for t in class_trackers)):
+            # trackers of a MultiGPUEngine3d whose label volumes are still sharded over the GPUs:
+            # every rank votes on its own z-slab (multigpu.ShardedEngine3d.sharded_consensus)
+            vol_d, _, instances = front.consensus(trackers, model_config, pixel_vote_thr=pixel_vote_thr,
+                                                  cluster_iou_thr=cluster_iou_thr, allow_one_view=allow_one_view,
+                                                  min_size=min_size, min_extent=min_extent)
+            out.instances = instances
+            yield (_PINNED.to_host(vol_d, dtype) if to_host else vol_d), class_name, out.instances
+            continue
         pending = []
         # the device->host copy of the painted volume overlaps the extraction of the RLE tables
         hook = (lambda v: pending.append(_PINNED.start(v, dtype))) if to_host else None

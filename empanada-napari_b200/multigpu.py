@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .inference import Engine3d, upsample_instance_heads
+from .inference import Engine3d, _VolumeCache, _as_device_volume, upsample_instance_heads
 
 _PROFILE = os.environ.get("B200_EMPANADA_PROFILE") == "1"
 
@@ -190,6 +190,31 @@ class DistributedEngine3d(Engine3d):
         return trackers
 
 
+class _ReplicatedVolumeCache(_VolumeCache):
+    """Upload of a host volume that EVERY rank holds (one process per GPU under torchrun): each
+    rank copies 1/G of it over its own PCIe link and NCCL all-gathers the pieces over NVLink,
+    instead of G full pageable host->device copies competing for host memory bandwidth."""
+
+    def __init__(self, group, rank, world):
+        super().__init__()
+        self.group, self.rank, self.world = group, rank, world
+
+    def _upload(self, volume, device):
+        G, r = self.world, self.rank
+        D = volume.shape[0]
+        per = -(-D // G)
+        if not np.issubdtype(volume.dtype, np.integer):
+            return _as_device_volume(volume, device)      # raises the reference's error
+        tdtype = torch.from_numpy(np.zeros(1, dtype=volume.dtype)).dtype
+        full = torch.empty((per * G,) + tuple(volume.shape[1:]), dtype=tdtype, device=device)
+        piece = torch.zeros((per,) + tuple(volume.shape[1:]), dtype=tdtype, device=device)
+        lo, hi = min(D, r * per), min(D, (r + 1) * per)
+        if hi > lo:
+            piece[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(volume[lo:hi])))
+        dist.all_gather_into_tensor(full, piece, group=self.group)
+        return full[:D]
+
+
 def owned_ranges(n, world, mid):
     """Slice-sharded planes: rank r runs the network on F_r = slice_ranges(n, world)[r] and OWNS
     (emits, labels, paints) E_r = F_r shifted down by the median latency `mid` - pushing slice t
@@ -231,9 +256,13 @@ class ShardedEngine3d(Engine3d):
       recursion makes this a wavefront, but only the cheap median kernel is serialised;
     * one component-label slice per shard boundary for the cross-boundary overlap table;
     * the sparse per-slice tables (component areas / boxes, overlap pairs) gathered to the plane's
-      leader, which replays the sequential tracker and broadcasts the (slice, component) -> label
-      table; each rank paints its own slab;
-    * the painted slabs, gathered to rank 0 for the consensus.
+      leader, which replays the sequential tracker on a worker thread WHILE the next plane's
+      forward pass runs, and broadcasts the (slice, component) -> label table; each rank paints
+      its own slab;
+    * for the consensus (`sharded_consensus`): one all-to-all that turns the y-slabs of the xz
+      plane and the x-slabs of the yz plane into z-slabs, then only sparse tables (pair counts,
+      cluster membership, sizes, run-length ranges) between the ranks and rank 0;
+    * optionally (`finalize(gather_dense=True)`) the painted slabs, gathered to rank 0.
 
     Rank r also runs the network on the `mid` slices before its range so that it holds the
     instance heads of every slice it owns (no halo exchange for them). Every rank must call
@@ -241,17 +270,45 @@ class ShardedEngine3d(Engine3d):
     Raises when a shard would be shorter than the median kernel (use fewer ranks, or
     `DistributedEngine3d`, for very short stacks)."""
 
-    def __init__(self, *args, group=None, **kwargs):
+    def __init__(self, *args, group=None, replicated_input=True, **kwargs):
         super().__init__(*args, **kwargs)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self._pending = {}
+        self._slabs = {}
+        self.front = None        # the MultiGPUEngine3d that drives this engine, if any
+        if replicated_input:     # host volumes are passed to every rank (torchrun)
+            self._cache = _ReplicatedVolumeCache(group, self.rank, self.world)
 
     def leader_of(self, axis_name):
         return (self.axes[axis_name] + 1) % self.world
 
+    def gather_plane(self, name):
+        """Collective: the painted slabs of plane `name` assembled on rank 0 (None elsewhere)."""
+        G, r = self.world, self.rank
+        slab, E, shape3d = self._slabs[name]
+        ax = self.axes[name]
+        if r != 0:
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, slab.contiguous(), 0, group=self.group)]):
+                req.wait()
+            return None
+        dense = torch.empty(shape3d, dtype=torch.int32, device=self.device)
+        dense.narrow(ax, E[0][0], E[0][1] - E[0][0]).copy_(slab)
+        tmps, ops = [], []
+        for src in range(1, G):
+            shp = list(shape3d)
+            shp[ax] = E[src][1] - E[src][0]
+            tmps.append(torch.empty(shp, dtype=torch.int32, device=self.device))
+            ops.append(dist.P2POp(dist.irecv, tmps[-1], src, group=self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for src in range(1, G):
+            dense.narrow(ax, E[src][0], E[src][1] - E[src][0]).copy_(tmps[src - 1])
+        return dense
+
     def infer_on_axis(self, volume, axis_name):
+        from .inference import _Async
         self._check_supported()
         axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
         ks = self.median_kernel_size
@@ -314,40 +371,40 @@ class ShardedEngine3d(Engine3d):
             post.pair_keys = np.concatenate([post.pair_keys, bk])
             post.pair_vals = np.concatenate([post.pair_vals, bv])
         tm.mark("components + tables + boundary overlap")
+        # sparse tables -> the plane's leader, whose tracker replay runs on a worker thread while
+        # every rank goes on with the next plane
+        leader = self.leader_of(axis_name)
+        n_cc, table = post.replay_inputs()
+        parts = [None] * G if r == leader else None
+        dist.gather_object((n_cc, table, post.pair_keys, post.pair_vals), parts, dst=leader, group=self.group)
+        job = None
+        if r == leader:
+            merged = merge_shard_tables(parts, E)
+            job = _Async(tracking_replay, merged, post.cls, post.div, axis_name, self.merge_iou_thr,
+                         self.merge_ioa_thr, self.min_size, self.min_extent)
+        tm.mark("gather tables")
         if _PROFILE:
             print(f"[rank {self.rank}] {axis_name} " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
-        self._pending[axis_name] = (post, shape3d, (F, E))
+        self._pending[axis_name] = (post, shape3d, (F, E), job)
         self.last_stats = {"kernel_launches": getattr(self.model, "launches", 0) - launches0 + post.launches}
         return None, self.create_trackers(shape3d, axis_name)
 
-    def finalize(self, trackers):
-        """Collective: gathers the sparse tables of every plane to its leader, replays the tracker
-        there (the leaders of different planes work concurrently), broadcasts the label tables,
-        paints the local slabs and assembles the dense label volumes on rank 0. Returns the
-        trackers dict (complete on rank 0)."""
+    def finalize(self, trackers, gather_dense=True):
+        """Collective: the plane leaders' label tables are broadcast and every rank paints its
+        own slab of every plane (kept in `self._slabs` for `sharded_consensus`). With
+        `gather_dense` the slabs are also assembled into dense label volumes on rank 0, as the
+        single-GPU engine leaves them (`tracker_consensus`, per-plane RLE); without it rank 0's
+        trackers carry only the instance tables (boxes, sizes). Returns the trackers dict
+        (complete on rank 0)."""
         from .postproc import LazyPlane
-        from .inference import _Async
         tm = _Timer()
         G, r = self.world, self.rank
         names = list(self._pending.keys())
-        jobs = {}
-        for name in names:                      # (1) sparse tables -> leader
-            post, shape3d, (F, E) = self._pending[name]
-            leader = self.leader_of(name)
-            n_cc, table = post.replay_inputs()
-            obj = (n_cc, table, post.pair_keys, post.pair_vals)
-            parts = [None] * G if r == leader else None
-            dist.gather_object(obj, parts, dst=leader, group=self.group)
-            if r == leader:                     # (2) tracker replay on a worker thread
-                merged = merge_shard_tables(parts, E)
-                jobs[name] = _Async(tracking_replay, merged, post.cls, post.div, name, self.merge_iou_thr,
-                                    self.merge_ioa_thr, self.min_size, self.min_extent)
-        tm.mark("gather tables")
         n_launch = 0
-        for name in names:                      # (3) label tables back, paint the local slab
-            post, shape3d, (F, E) = self._pending[name]
+        for name in names:
+            post, shape3d, (F, E), job = self._pending[name]
             leader = self.leader_of(name)
-            payload = [jobs[name].result() if r == leader else None]
+            payload = [job.result() if r == leader else None]
             dist.broadcast_object_list(payload, src=leader, group=self.group)
             lut_f, kept_labels, kept_boxes, kept_sizes = payload[0]
             e_lo, e_hi = E[r]
@@ -356,31 +413,162 @@ class ShardedEngine3d(Engine3d):
             n0 = post.launches
             slab = post.relabel(np.ascontiguousarray(lut_f[e_lo:e_hi]), name, local_shape)
             n_launch += post.launches - n0
+            self._slabs[name] = (slab, E, shape3d)
             ax = self.axes[name]
-            if r == 0:                          # (4) slabs -> rank 0
-                dense = torch.empty(shape3d, dtype=torch.int32, device=self.device)
-                dense.narrow(ax, e_lo, e_hi - e_lo).copy_(slab)
-                for src in range(1, G):
-                    a, b = E[src]
-                    shp = list(shape3d)
-                    shp[ax] = b - a
-                    tmp = torch.empty(shp, dtype=torch.int32, device=self.device)
-                    dist.recv(tmp, src=src, group=self.group)
-                    dense.narrow(ax, a, b - a).copy_(tmp)
+            dense = self.gather_plane(name) if gather_dense else None
+            if r == 0:
                 tr = trackers[name][0]
-                plane = LazyPlane(dense, name, kept_labels, kept_boxes)
+                if dense is not None:
+                    plane = LazyPlane(dense, name, kept_labels, kept_boxes)
+                    tr._b200_dense = dense
+                else:
+                    plane = ShardedPlane(self, tr, name, kept_labels, kept_boxes)
                 tr.instances = plane.attrs
-                tr._b200_dense = dense
                 tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, kept_sizes)}
+                tr._b200_sharded = self
                 tr.finish()
-            else:
-                dist.send(slab.contiguous(), dst=0, group=self.group)
         self._pending = {}
-        tm.mark("replay + broadcast + paint + slabs to rank 0")
+        tm.mark("replay + broadcast + paint" + (" + slabs to rank 0" if gather_dense else ""))
         if _PROFILE:
             print(f"[rank {self.rank}] finalize " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
         self.last_stats = {"kernel_launches": n_launch}
         return trackers
+
+    # ------------------------------------------------------------------ sharded consensus
+    def _z_slabs(self):
+        """All-to-all re-shard of the painted plane slabs into this rank's z-slab of all three
+        planes: z ranges = the xy plane's slice ownership (no exchange for xy); xz arrives as
+        (dz, Y_src, W) blocks, yz as (dz, H, X_src) blocks."""
+        G, r = self.world, self.rank
+        xy_slab, Ez, shape3d = self._slabs["xy"]
+        D, Hv, Wv = shape3d
+        z0, z1 = Ez[r]
+        out = [xy_slab]
+        for name, ax in (("xz", 1), ("yz", 2)):
+            slab, E, _ = self._slabs[name]
+            send = [slab[Ez[q][0]:Ez[q][1]] for q in range(G)]              # leading-dim slices: contiguous
+            recv = []
+            for src in range(G):
+                shp = [z1 - z0, Hv, Wv]
+                shp[ax] = E[src][1] - E[src][0]
+                recv.append(torch.empty(shp, dtype=torch.int32, device=self.device))
+            dist.all_to_all(recv, send, group=self.group)
+            full = torch.empty((z1 - z0, Hv, Wv), dtype=torch.int32, device=self.device)
+            for src in range(G):
+                full.narrow(ax, E[src][0], E[src][1] - E[src][0]).copy_(recv[src])
+            out.append(full)
+        return out, z0
+
+    def sharded_consensus(self, trackers, model_config, pixel_vote_thr=2, cluster_iou_thr=0.75,
+                          allow_one_view=False, min_size=200, min_extent=4, gather_volume=True):
+        """Collective form of `tracker_consensus` for ONE thing class over the slabs `finalize`
+        left on every rank: each rank votes on its own z-slab; rank 0 runs the graph decisions on
+        the summed sparse tables (consensus.consensus_driver). Returns on rank 0
+        (device volume or None, class_name, instances); (None, None, None) elsewhere."""
+        from . import consensus
+        G, r = self.world, self.rank
+        tm = _Timer()
+        vols, z0 = self._z_slabs()
+        tm.mark("consensus: slab all-to-all")
+        shard = consensus.ConsensusShard(vols, [None, None, None], z0=z0)
+        if r == 0:
+            class_id = model_config["thing_list"][0]
+            class_name = model_config["class_names"][class_id]
+            trs = [trackers[n][0] for n in ("xy", "xz", "yz")]
+            n_nodes, node_sizes, node_boxes, luts = consensus.tracker_node_tables(trs)
+            min_cluster = 1 if allow_one_view else 2
+            if pixel_vote_thr < min_cluster:
+                cluster_iou_thr = 0
+
+            def each(method, *args):
+                dist.broadcast_object_list([(method, args)], src=0, group=self.group)
+                res = [None] * G
+                dist.gather_object(_guarded(shard, method, args), res, dst=0, group=self.group)
+                for x in res:
+                    if isinstance(x, BaseException):
+                        dist.broadcast_object_list([("done", ())], src=0, group=self.group)
+                        raise x
+                return res
+            if n_nodes == 0:
+                each("zero")
+                instances = {}
+            else:
+                instances = consensus.consensus_driver(each, G, n_nodes, node_sizes, node_boxes, luts, pixel_vote_thr,
+                                                       cluster_iou_thr, min_cluster, min_size, min_extent, tm.mark)
+            dist.broadcast_object_list([("done", ())], src=0, group=self.group)
+        else:
+            while True:
+                cmd = [None]
+                dist.broadcast_object_list(cmd, src=0, group=self.group)
+                method, args = cmd[0]
+                if method == "done":
+                    break
+                dist.gather_object(_guarded(shard, method, args), None, dst=0, group=self.group)
+        self.consensus_launches = shard.launches
+        vol = None
+        if gather_volume:
+            vol = self._gather_z(shard.painted)
+            tm.mark("consensus: painted slabs to rank 0")
+        if _PROFILE:
+            print(f"[rank {self.rank}] consensus " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
+        self._last_painted = shard.painted
+        if r != 0:
+            return None, None, None
+        return vol, class_name, instances
+
+    def _gather_z(self, painted):
+        """Painted z-slabs -> the whole volume on rank 0 (None elsewhere)."""
+        G, r = self.world, self.rank
+        _, Ez, shape3d = self._slabs["xy"]
+        if r == 0:
+            vol = torch.empty(shape3d, dtype=torch.int32, device=self.device)
+            vol[Ez[0][0]:Ez[0][1]].copy_(painted)
+            ops = [dist.P2POp(dist.irecv, vol[Ez[src][0]:Ez[src][1]], src, group=self.group) for src in range(1, G)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            return vol
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, painted, 0, group=self.group)]):
+            req.wait()
+        return None
+
+
+def _guarded(shard, method, args):
+    """One shard call of the consensus driver; an exception travels to rank 0 as the result."""
+    try:
+        return getattr(shard, method)(*args)
+    except Exception as e:  # re-raised on rank 0
+        return e
+
+
+class ShardedPlane:
+    """Instance table of one plane on rank 0 when the dense label volume stays sharded over the
+    ranks (`finalize(gather_dense=False)`): boxes and sizes are known, the per-instance RLE is
+    fetched from the ranks on first use when a `MultiGPUEngine3d` front end drives them."""
+
+    def __init__(self, engine, tracker, axis_name, labels, boxes):
+        from .postproc import LazyAttrs
+        self.engine, self.tracker, self.axis_name = engine, tracker, axis_name
+        self.labels, self.boxes = labels, boxes
+        self.attrs = {int(l): LazyAttrs(tuple(int(v) for v in b), self) for l, b in zip(labels, boxes)}
+
+    def dense(self):
+        front = self.engine.front
+        if front is None:
+            raise _lib_error(f"the {self.axis_name} label volume is sharded over the ranks: call "
+                             "finalize(trackers, gather_dense=True) to read per-plane volumes or run-length tables")
+        vol = front.gather_plane(self.axis_name)
+        self.tracker._b200_dense = vol
+        return vol
+
+    def materialize(self):
+        from .postproc import instances_from_dense
+        full = instances_from_dense(self.dense(), self.axis_name, self.labels, self.boxes)
+        for l, a in full.items():
+            attrs = self.attrs.get(l)
+            if attrs is not None:
+                attrs._owner = None
+                dict.__setitem__(attrs, "starts", a["starts"])
+                dict.__setitem__(attrs, "runs", a["runs"])
 
 
 def tracking_replay(merged, cls, div, axis_name, iou_thr, ioa_thr, min_size, min_extent):
@@ -424,7 +612,7 @@ def _worker_main(rank, world, port, model_config, engine_kwargs, cmd_q, err_q):
         dev = torch.device("cuda", rank)
         dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                                 device_id=dev)
-        eng = ShardedEngine3d(model_config, **engine_kwargs)
+        eng = ShardedEngine3d(model_config, replicated_input=False, **engine_kwargs)
         vol_version, vol_d = None, None
         while True:
             cmd = cmd_q.get()
@@ -440,7 +628,11 @@ def _worker_main(rank, world, port, model_config, engine_kwargs, cmd_q, err_q):
                     dist.broadcast(vol_d, src=0)
                     vol_version = version
                 _, trackers = eng.infer_on_axis(vol_d, axis_name)
-                eng.finalize({axis_name: trackers})
+                eng.finalize({axis_name: trackers}, gather_dense=cmd[5])
+            elif cmd[0] == "gather_plane":
+                eng.gather_plane(cmd[1])
+            elif cmd[0] == "consensus":
+                eng.sharded_consensus(None, None, **cmd[1])
             elif cmd[0] == "release":
                 vol_version, vol_d = None, None
         dist.destroy_process_group()
@@ -499,10 +691,12 @@ class MultiGPUEngine3d:
         torch.cuda.set_device(0)
         dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=self.world,
                                 device_id=torch.device("cuda", 0))
-        self._engine = ShardedEngine3d(model_config, **kwargs)
+        self._engine = ShardedEngine3d(model_config, replicated_input=False, **kwargs)
+        self._engine.front = self
         self.engine = self._engine.engine
         self._version = 0
         self._uploaded = None
+        self._planes_version = {"xy": None, "xz": None, "yz": None}
 
     def _send(self, *cmd):
         if not self._err_q.empty():
@@ -528,13 +722,30 @@ class MultiGPUEngine3d:
             fresh = True
         else:
             fresh = False
-        self._send("infer", axis_name, tuple(vol_d.shape), str(vol_d.dtype).replace("torch.", ""), self._version)
+        # the dense plane volume comes to rank 0 only when the caller wants the stack; otherwise it
+        # stays sharded (fetched on demand if someone reads the per-plane run-length tables)
+        self._send("infer", axis_name, tuple(vol_d.shape), str(vol_d.dtype).replace("torch.", ""), self._version,
+                   bool(self.save_panoptic))
         if fresh:
             dist.broadcast(vol_d, src=0)
         _, trackers = eng.infer_on_axis(vol_d, axis_name)
-        trackers = eng.finalize({axis_name: trackers})[axis_name]
+        trackers = eng.finalize({axis_name: trackers}, gather_dense=bool(self.save_panoptic))[axis_name]
         stack = trackers[0]._b200_dense.cpu().numpy() if self.save_panoptic else None
+        self._planes_version[axis_name] = self._version
         return stack, trackers
+
+    def gather_plane(self, axis_name):
+        """Dense (D,H,W) label volume of a plane on GPU 0 (collective, driven from here)."""
+        self._send("gather_plane", axis_name)
+        return self._engine.gather_plane(axis_name)
+
+    def consensus(self, trackers, model_config, **params):
+        """`tracker_consensus` over the slabs the ranks still hold (called by
+        `inference.tracker_consensus` when it is handed this engine's trackers)."""
+        if len(set(self._planes_version.get(n) for n in ("xy", "xz", "yz"))) != 1 or None in self._planes_version.values():
+            raise _lib_error("the xy, xz and yz trackers must come from the same volume")
+        self._send("consensus", params)
+        return self._engine.sharded_consensus(trackers, model_config, **params)
 
     def release(self):
         self._send("release")

@@ -35,3 +35,36 @@ def test_component_subgraph_matches_networkx_view():
             assert [sorted(ref.nodes[x]["cluster"]) for x in ref.nodes] == [sorted(got.nodes[x]["cluster"]) for x in got.nodes]
             checked += 1
     assert checked > 500
+
+
+def test_join_shard_ranges_merges_runs_across_slab_boundaries():
+    """Per-slab joined ranges -> whole-volume ranges: a run that continues from the last voxel of
+    one z-slab into the first voxel of the next is one range, exactly as in a one-piece pass."""
+    from empanada_napari_b200.consensus import join_shard_ranges
+    rng = np.random.default_rng(5)
+    n, n_final, cut = 4000, 6, (1000, 2500)
+    vol = np.zeros(n, dtype=np.int32)
+    pos = 0
+    while pos < n:                                    # random runs, some crossing the cuts
+        ln = int(rng.integers(1, 60))
+        vol[pos:pos + ln] = rng.integers(0, n_final + 1)
+        pos += ln
+    vol[990:1010] = 3
+    vol[2499:2501] = 5
+
+    def ranges(a, off):
+        ids, starts, lens = [], [], []
+        for fid in range(1, n_final + 1):
+            m = np.r_[0, (a == fid).astype(np.int8), 0]
+            d = np.diff(m)
+            st, en = np.flatnonzero(d == 1), np.flatnonzero(d == -1)
+            ids += [fid] * len(st); starts += list(st + off); lens += list(en - st)
+        return np.array(ids, np.int32), np.array(starts, np.int64), np.array(lens, np.int64)
+
+    bounds = (0,) + cut + (n,)
+    parts = [ranges(vol[a:b], a) for a, b in zip(bounds[:-1], bounds[1:])]
+    got = join_shard_ranges(parts, n_final)
+    ids, starts, lens = ranges(vol, 0)
+    for fid in range(1, n_final + 1):
+        m = ids == fid
+        assert np.array_equal(got[fid][0], starts[m]) and np.array_equal(got[fid][1], lens[m]), fid

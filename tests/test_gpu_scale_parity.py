@@ -82,6 +82,14 @@ def test_bench_generator_256_bit_exact_with_regrowth():
         _, inst = _compare_with_oracle(vol, heads_np, cfg, got, kw,
                                        dict(pixel_vote_thr=2, min_size=500, min_extent=5), tracker_consensus)
         assert len(inst) >= 300
+        # the z-slab sharded consensus driver (the multi-GPU code path, multigpu.py) on the same
+        # trackers: identical volume and instances for any number of slabs
+        trs = [got[n][0] for n in ("xy", "xz", "yz")]
+        v1, i1 = consensus.merge_objects_from_trackers(trs, 2, 0.75, False, 500, 5)
+        for shards in (2, 5):
+            vs, is_ = consensus.merge_objects_from_trackers(trs, 2, 0.75, False, 500, 5, z_shards=shards)
+            assert torch.equal(v1, vs), shards
+            assert_instances_equal(is_, i1)
     finally:
         consensus.CAPS.clear()
         consensus.CAPS.update(old)

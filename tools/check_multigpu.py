@@ -63,6 +63,20 @@ if rank == 0:
                     and np.array_equal(outs[0][1][k]["runs"], outs[1][1][k]["runs"]) for k in outs[0][1]))
     print("consensus instances", len(outs[0][1]), "equal", same)
     ok &= same and len(outs[0][1]) > 0
+# the z-slab sharded consensus (every rank votes on its own slab) against the same reference
+if engine_cls is multigpu.ShardedEngine3d:
+    trackers = {}
+    for name in ("xy", "xz", "yz"):
+        _, trackers[name] = deng.infer_on_axis(vol, name)
+    trackers = deng.finalize(trackers, gather_dense=False)
+    v, _, inst = deng.sharded_consensus(trackers, cfg, pixel_vote_thr=2, min_size=30, min_extent=3)
+    if rank == 0:
+        rv, rinst = outs[1]
+        same = (np.array_equal(v.cpu().numpy(), rv) and list(inst.keys()) == list(rinst.keys())
+                and all(np.array_equal(inst[k]["starts"], rinst[k]["starts"]) and np.array_equal(inst[k]["runs"], rinst[k]["runs"])
+                        and tuple(inst[k]["box"]) == tuple(rinst[k]["box"]) for k in inst))
+        print("sharded consensus instances", len(inst), "equal", same)
+        ok &= bool(same)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
