@@ -27,7 +27,8 @@ _SIGNATURES = {
     "be_merge_pan": ([P, P, I, I, I, I, I, I, I, I, I, I, P, P, P], I),
     "be_rank_ids": ([P, I, I, I, I, P], I),
     # run_kernels.cu
-    "be_group_flags": ([P, P, P, I, P, I, I, I, I, P, P, P], I),
+    "be_group_flags": ([P, P, P, I, P, I, I, I, I, I, P, P, P], I),
+    "be_slice_area": ([P, I, I, I, P, P], I),
     "be_rowruns_count": ([P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P], I),
     "be_rowruns_write": ([P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P], I),
     "be_runs_cc": ([P, P, P, P, P, I, I, I, P, P, P, P], I),
@@ -45,6 +46,7 @@ _SIGNATURES = {
     "be_runs_write": ([P, LL, LL, P, P, P, P, LL, P], I),
     "be_sort_runs": ([P, P, P, P, I, P, SZ, POINTER(SZ), P], I),
     "be_up4": ([P, I, I, I, P, P], I),
+    "be_resize_linear_u8": ([P, LL, LL, LL, I, I, I, I, I, P, P], I),
     # consensus_kernels.cu
     "be_plane_pairs": ([P, P, P, P, P, P, I, I, I, LL, I, P, P, ULL, P, P], I),
     "be_vote_stats": ([P, P, P, P, P, P, I, I, I, LL, I, P, P, I, P, P, P, ULL, P, P], I),

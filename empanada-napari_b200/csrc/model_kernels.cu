@@ -645,6 +645,44 @@ __global__ void up2_kernel(const float* __restrict__ in, int B, int h, int w, fl
 // bilinear x4, align_corners=True on planar fp32 maps: `Interpolate2d(4, 'bilinear',
 // align_corners=True)` applied to ctr_hmp / offsets when `interpolate_ins` is set
 // (quantization/panoptic_deeplab.py:233-234, blocks.py:74-92). One thread = 4 output pixels of a row.
+// one output pixel per thread (see be_resize_linear_u8)
+__device__ __forceinline__ void resize_coef(int d, double scale, int n, int clamp_edges, int& s0, int& c0, int& c1) {
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int s = static_cast<int>(floorf(f));
+  f -= static_cast<float>(s);
+  if (clamp_edges) {   // the x pass resets the fraction at the borders; the y pass clips the rows
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n - 1) { f = 0.f; s = n - 1; }
+  }
+  s0 = s;
+  c0 = static_cast<int>(rintf((1.f - f) * 2048.f));
+  c1 = static_cast<int>(rintf(f * 2048.f));
+}
+__global__ void __launch_bounds__(128)
+resize_linear_u8_kernel(const uint8_t* __restrict__ vol, long long stride_s, long long stride_y,
+                        long long stride_x, int h, int w, int dh, int dw, double scale_y,
+                        double scale_x, int area2, uint8_t* __restrict__ out) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
+  if (dx >= dw) return;
+  const uint8_t* img = vol + static_cast<long long>(b) * stride_s;
+  auto at = [&](int y, int x) { return static_cast<int>(__ldg(img + y * stride_y + x * stride_x)); };
+  int v;
+  if (area2) {
+    v = (at(2 * dy, 2 * dx) + at(2 * dy, 2 * dx + 1) + at(2 * dy + 1, 2 * dx) + at(2 * dy + 1, 2 * dx + 1) + 2) >> 2;
+  } else {
+    int sx, a0, a1, sy, b0, b1;
+    resize_coef(dx, scale_x, w, 1, sx, a0, a1);
+    resize_coef(dy, scale_y, h, 0, sy, b0, b1);
+    const int x1 = min(sx + 1, w - 1);
+    const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
+    const int r0 = at(y0, sx) * a0 + at(y0, x1) * a1;
+    const int r1 = at(y1, sx) * a0 + at(y1, x1) * a1;
+    v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+  }
+  out[(static_cast<long long>(b) * dh + dy) * dw + dx] = static_cast<uint8_t>(v);
+}
+
 __global__ void up4_kernel(const float* __restrict__ in, int planes, int h, int w, float* __restrict__ out) {
   const int Ho = 4 * h, Wo = 4 * w;
   const int pl = blockIdx.z, oy = blockIdx.y;
@@ -950,6 +988,22 @@ int be_aspp_pool_bias(const __nv_bfloat16* in, int B, int HW, int C, const float
   mk::gemv_relu_kernel<<<dim3((Cmid + 7) / 8, B), 256, 0, st>>>(w_pool, pooled, C, Cmid, 1, nullptr, mid);
   mk::gemv_relu_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(w_proj_pool, mid, Cmid, N, 0, bias_proj, bias_out);
   return be_check_launch("aspp_pool_bias kernels");
+}
+// Down-sampling of the slices of a uint8 volume by `resize_by_factor` (empanada/data/utils/
+// transforms.py:9-21): cv2.resize(image, (ceil(w/f), ceil(h/f))) with OpenCV's default
+// INTER_LINEAR. OpenCV is a third-party dependency that is not vendored in the reference; this
+// restates the 8-bit path of its imgproc/resize.cpp: pixel-centre mapping, 11-bit fixed-point
+// coefficients (round-half-even), horizontal pass in int32, vertical pass
+// ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2)>>2; an exact 2x2 reduction takes the INTER_AREA
+// fast path (a+b+c+d+2)>>2, as OpenCV switches to it for INTER_LINEAR.
+int be_resize_linear_u8(const uint8_t* vol, long long stride_s, long long stride_y, long long stride_x,
+                        int N, int h, int w, int dh, int dw, uint8_t* out, cudaStream_t st) {
+  if (dh < 1 || dw < 1 || dh > h || dw > w) return be_set_error("resize: only down-sampling is built");
+  const double scale_x = 1.0 / (static_cast<double>(dw) / w), scale_y = 1.0 / (static_cast<double>(dh) / h);
+  const int area2 = (h == 2 * dh && w == 2 * dw) ? 1 : 0;
+  dim3 grid((dw + 127) / 128, dh, N);
+  mk::resize_linear_u8_kernel<<<grid, 128, 0, st>>>(vol, stride_s, stride_y, stride_x, h, w, dh, dw, scale_y, scale_x, area2, out);
+  return be_check_launch("resize_linear_u8_kernel");
 }
 int be_up4(const float* in, int planes, int h, int w, float* out, cudaStream_t st) {
   if (reinterpret_cast<uintptr_t>(out) & 15) return be_set_error("up4: output must be 16-byte aligned");

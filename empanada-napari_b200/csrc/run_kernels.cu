@@ -34,7 +34,7 @@ constexpr int GROUP_TILE = 1024;
 __global__ void __launch_bounds__(256)
 group_flags_kernel(const uint8_t* __restrict__ hard, const float* __restrict__ off,
                    const int* __restrict__ centers, int cap, const int* __restrict__ counts, int H,
-                   int W, int scale, int* __restrict__ cells, int* __restrict__ present) {
+                   int W, int scale, int gstep, int* __restrict__ cells, int* __restrict__ present) {
   const int b = blockIdx.y;
   const int h4 = H / scale, w4 = W / scale;
   const int n = h4 * w4;
@@ -61,7 +61,9 @@ group_flags_kernel(const uint8_t* __restrict__ hard, const float* __restrict__ o
   }
   if (!__syncthreads_or(fg)) return;
   __shared__ float cy[GROUP_TILE], cx[GROUP_TILE];
-  const float step = static_cast<float>(scale);
+  // `gstep`: grid step of the head maps in model pixels (4, or 1 with fine boundaries); `scale`:
+  // output pixels per cell (= gstep x upsampling, engines.py:263-275)
+  const float step = static_cast<float>(gstep);
   float ly = 0.f, lx = 0.f;
   if (fg) {
     const float* ob = off + static_cast<long long>(b) * 2 * n;
@@ -97,6 +99,24 @@ group_flags_kernel(const uint8_t* __restrict__ hard, const float* __restrict__ o
       present[static_cast<long long>(b) * (cap + 1) + id] = 1;
     }
   }
+}
+
+// ------------------------------------------------------------------ per-slice mask area
+__global__ void __launch_bounds__(256)
+slice_area_kernel(const uint8_t* __restrict__ hard, long long n16, int* __restrict__ area) {
+  const uint4* src = reinterpret_cast<const uint4*>(hard) + static_cast<long long>(blockIdx.y) * n16;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = (static_cast<long long>(blockIdx.x) * 4 + k) * 256 + threadIdx.x;
+    if (i < n16) {
+      const uint4 v = __ldg(src + i);
+      // bytes are 0 / 1: the popcount of the low bits is the number of set pixels
+      cnt += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(area + blockIdx.y, cnt);
 }
 
 // ------------------------------------------------------------------ row runs
@@ -526,13 +546,23 @@ paint_yz_kernel(const int* __restrict__ row_ptr, const int2* __restrict__ run_yx
 extern "C" {
 
 int be_group_flags(const uint8_t* hard, const float* off, const int* centers, int cap,
-                   const int* counts, int B, int H, int W, int scale, int* cells, int* present,
+                   const int* counts, int B, int H, int W, int scale, int step, int* cells, int* present,
                    cudaStream_t stream) {
-  if (scale < 1 || H % scale || W % scale || W % 4) return be_set_error("group_flags: bad geometry");
+  if (scale < 1 || step < 1 || H % scale || W % scale || W % 4) return be_set_error("group_flags: bad geometry");
   const int n = (H / scale) * (W / scale);
   dim3 grid((n + 255) / 256, B);
-  runs::group_flags_kernel<<<grid, 256, 0, stream>>>(hard, off, centers, cap, counts, H, W, scale, cells, present);
+  runs::group_flags_kernel<<<grid, 256, 0, stream>>>(hard, off, centers, cap, counts, H, W, scale, step, cells, present);
   return be_check_launch("group_flags_kernel");
+}
+
+// area[b] = number of set pixels of hard[b] (H x W uint8, H * W % 16 == 0): the stuff-area test of
+// merge_semantic_and_instance (postprocess.py:283-294) for semantic-only planes. area must be zero.
+int be_slice_area(const uint8_t* hard, int B, int H, int W, int* area, cudaStream_t stream) {
+  const long long n = 1LL * H * W;
+  if (n % 16 || (reinterpret_cast<uintptr_t>(hard) & 15)) return be_set_error("slice_area: H * W must be a multiple of 16");
+  dim3 grid(static_cast<unsigned>((n / 16 + 1023) / 1024), B);
+  runs::slice_area_kernel<<<grid, 256, 0, stream>>>(hard, n / 16, area);
+  return be_check_launch("slice_area_kernel");
 }
 
 // counts: workspace [2 * B * chunks] int32, chunks = ceil(h * ceil(w/4) / 256). Leaves the scanned

@@ -69,18 +69,14 @@ class PanopticDeepLabRenderEngine:
 
     def _check(self, upsampling):
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
-        if upsampling != 1:
-            _unsupported("inference_scale / upsampling > 1")
-        if len(self.thing_list) != 1:
-            _unsupported("multi-class / semantic-only models")
+        if len(self.thing_list) > 1:
+            _unsupported("multi-class models")
 
     def infer(self, image, render_steps=2):
         """model(image, render_steps, interpolate_ins=not coarse_boundaries) + logits_to_prob
         (engines.py:248-256). `image`: padded (1, 1, H, W) fp32 on the device."""
-        if render_steps != 2:
-            _unsupported("render_steps != 2 (inference_scale > 1)")
         x = image.reshape(1, image.shape[-2], image.shape[-1]).to(torch.float32).contiguous()
-        sem, ctr, off = self.model.forward_slices(x, 0, 0, 1, None, self.padding_factor)
+        sem, ctr, off = self.model.forward_slices(x, 0, 0, 1, None, self.padding_factor, render_steps=int(render_steps))
         sem, ctr, off = sem[None].clone(), ctr[None].clone(), off.clone()
         if not self.coarse_boundaries:
             from .inference import upsample_instance_heads
@@ -140,8 +136,19 @@ class PanopticDeepLabRenderEngine:
 
     def get_panoptic_seg(self, sem, instance_cells):
         """engines.py:277-293: sem (1, H, W) hardened, instance_cells (1, 1, H, W) -> (1, H, W) int64."""
-        if len(self.thing_list) != 1:
-            _unsupported("multi-class / semantic-only models")
+        if len(self.thing_list) > 1:
+            _unsupported("multi-class models")
+        if len(self.thing_list) == 0:
+            # no thing classes: every class of the hardened map is pasted as stuff where it
+            # covers at least `stuff_area` pixels (postprocess.py:283-294)
+            pan = torch.full_like(sem, self.void_label, dtype=torch.int64)
+            for class_id in torch.unique(sem).tolist():
+                mask = (sem == class_id).to(torch.uint8).contiguous()
+                area = torch.zeros(1, dtype=torch.int32, device=sem.device)
+                call("be_slice_area", ptr(mask), 1, mask.shape[-2], mask.shape[-1], ptr(area), stream_ptr())
+                if int(area.item()) >= self.stuff_area:
+                    pan[mask.bool()] = int(class_id) * self.label_divisor
+            return pan
         hard = (sem[0] == self.thing_list[0]).to(torch.uint8).contiguous()
         cells = instance_cells[0, 0].to(torch.int32).contiguous()
         return self._pan_from(hard, cells, 1).long()

@@ -81,6 +81,26 @@ def upsample_instance_heads(ctr, off):
     return ctr_f, off_f
 
 
+def downsample_slices(vol_d, axis, scale):
+    """`VolumeDataset.__getitem__` with scale > 1 (volume_dataset.py:37-53): every slice of the
+    plane through `resize_by_factor` (data/utils/transforms.py:9-21). Returns the (n, ceil(h/s),
+    ceil(w/s)) uint8 stack of down-sampled slices (slices along dim 0)."""
+    if vol_d.dtype != torch.uint8:
+        raise _lib.B200EmpanadaError("inference_scale > 1 is built for uint8 images (OpenCV's 8-bit resize arithmetic)")
+    D, Hv, Wv = (int(v) for v in vol_d.shape)
+    n, (h, w) = (D, Hv, Wv)[axis], [(Hv, Wv), (D, Wv), (D, Hv)][axis]
+    strides = [(Hv * Wv, Wv, 1), (Wv, Hv * Wv, 1), (1, Hv * Wv, Wv)][axis]
+    dh, dw = math.ceil(h / scale), math.ceil(w / scale)
+    out = torch.empty((n, dh, dw), dtype=torch.uint8, device=vol_d.device)
+    _lib.call("be_resize_linear_u8", _lib.ptr(vol_d), *strides, n, h, w, dh, dw, _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def check_scale(scale):
+    assert math.log(scale, 2).is_integer(), "Upsampling factor not log base 2!"
+    return int(scale)
+
+
 def auto_slice_batch(H, W, sms=148, requested=None, max_pixels=40 << 20):
     """Slices per launch list for padded H x W slices. The deep, compute-heavy layers run on the
     1/16-resolution map, whose 128-pixel tiles should fill the SMs in whole waves (at 1024^2: 32
@@ -244,32 +264,41 @@ class Engine3d:
     def create_trackers(self, shape3d, axis_name):
         return [InstanceTracker(label, self.label_divisor, shape3d, axis_name) for label in self.labels]
 
-    def _check_supported(self):
-        if self.inference_scale != 1:
-            _unsupported("inference_scale > 1")
+    def _check_supported(self, sharded=False):
+        if sharded and self.inference_scale != 1:
+            _unsupported("inference_scale > 1 in the slice-sharded multi-GPU engine")
         if self.label_erosion or self.label_dilation or self.fill_holes_in_segmentation:
             _unsupported("tracker morphology (erode / dilate / fill holes)")
-        if len(self.labels) != 1 or list(self.engine.thing_list) != list(self.labels):
-            _unsupported("multi-class / semantic-only models")
+        if len(self.labels) != 1 or list(self.engine.thing_list) not in ([], list(self.labels)):
+            _unsupported("multi-class models")
 
     def _plane_setup(self, volume, axis_name):
+        """(axis, device volume, shape3d, slices, slice size h x w, size H x W of the semantic
+        map the network emits for a slice, padding factor). With inference_scale s > 1 the network
+        sees ceil(h/s) x ceil(w/s) slices padded to the factor and PointRend renders log2(s) extra
+        steps, so its semantic map is s times the padded down-sampled size (engines.py:300-325)."""
         axis = self.axes[axis_name]
         vol_d = self._cache.get(volume, self.device)
         shape3d = tuple(int(s) for s in vol_d.shape)
         n = shape3d[axis]
         h, w = [s for i, s in enumerate(shape3d) if i != axis]
         pf = self.padding_factor
-        H = h + (pf - h % pf) % pf
-        W = w + (pf - w % pf) % pf
+        sc = check_scale(self.inference_scale)
+        dh, dw = math.ceil(h / sc), math.ceil(w / sc)
+        H = (dh + (pf - dh % pf) % pf) * sc
+        W = (dw + (pf - dw % pf) % pf) * sc
         return axis, vol_d, shape3d, n, h, w, H, W, pf
 
     def _make_post(self, n, h, w, H, W):
         e = self.engine
-        return PlanePost(n, h, w, H, W, ks=e.ks, thing_class=e.thing_list[0],
+        step = 4 if e.coarse_boundaries else 1
+        semantic = len(e.thing_list) == 0
+        return PlanePost(n, h, w, H, W, ks=e.ks, thing_class=self.labels[0] if semantic else e.thing_list[0],
                          label_divisor=e.label_divisor, void_label=e.void_label,
                          nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
                          confidence_thr=e.confidence_thr, device=self.device,
-                         scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap,
+                         scale=step * int(self.inference_scale), step=step, center_cap=e.center_cap,
+                         semantic=semantic, stuff_area=e.stuff_area,
                          **getattr(self, "_post_kwargs", {}))
 
     def _finish_plane(self, post, axis_name, shape3d, prof=None, defer=False):
@@ -282,6 +311,10 @@ class Engine3d:
         prof.mark("forward+median+centres+grouping")
         post.run_cc()
         prof.mark("merge+cc+tables+overlaps")
+        if post.semantic:       # stuff class: one label per plane, nothing to match
+            trackers = self.create_trackers(shape3d, axis_name)
+            self._fill_tracker(trackers[0], post, post.semantic_tables(axis_name), axis_name, shape3d, prof)
+            return trackers
         if defer:
             tr = tracking.PendingTracker(self.labels[0], self.label_divisor, shape3d, axis_name)
             inputs = post.replay_inputs()
@@ -346,9 +379,14 @@ class Engine3d:
     def _forward_all(self, post, vol_d, axis, n, norms, pf):
         """Model forward over every slice of the plane, heads pushed into the post-processor."""
         bs = self.slice_batch(post.H, post.W)
+        sc = int(self.inference_scale)
+        kw = {}
+        if sc > 1:   # down-sampled slices become an xy stack; PointRend renders back up
+            kw = {"render_steps": int(2 + math.log(sc, 2)), "plane_axis": axis}
+            vol_d, axis = downsample_slices(vol_d, axis, sc), 0
         for s0 in range(0, n, bs):
             s1 = min(n, s0 + bs)
-            sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf, **kw)
             if not self.engine.coarse_boundaries:
                 ctr, off = upsample_instance_heads(ctr, off)
             post.push_heads(sem, ctr, off, is_prob=False)
@@ -412,10 +450,8 @@ class Engine2d:
 
     def infer_batch(self, images):
         """images: uint8 array (n, h, w) -> int32 (n, h, w). One launch sequence for the batch."""
-        if self.inference_scale != 1:
-            _unsupported("inference_scale > 1")
-        if len(self.labels) != 1 or list(self.engine.thing_list) != list(self.labels):
-            _unsupported("multi-class / semantic-only models")
+        if len(self.labels) != 1 or list(self.engine.thing_list) not in ([], list(self.labels)):
+            _unsupported("multi-class models")
         if self.tile_size > 0 and any(s > self.tile_size for s in images.shape[1:]):
             _unsupported("tiled 2-D inference")
         dev = self.device
@@ -425,12 +461,20 @@ class Engine2d:
             vol_d = images.contiguous()
         else:
             vol_d = _as_device_volume(images, dev)
-        n, h, w = vol_d.shape
+        n, h, w = (int(v) for v in vol_d.shape)
         pf = self.padding_factor
-        H = h + (pf - h % pf) % pf
-        W = w + (pf - w % pf) % pf
+        sc = check_scale(self.inference_scale)
+        kw = {}
+        if sc > 1:   # resize_by_factor + log2(scale) extra PointRend steps (inference.py:319-325)
+            vol_d = downsample_slices(vol_d, 0, sc)
+            kw = {"render_steps": int(2 + math.log(sc, 2))}
+        dh, dw = int(vol_d.shape[1]), int(vol_d.shape[2])
+        H = (dh + (pf - dh % pf) % pf) * sc
+        W = (dw + (pf - dw % pf) % pf) * sc
         e = self.engine
-        cls = e.thing_list[0]
+        semantic = len(e.thing_list) == 0
+        cls = self.labels[0] if semantic else e.thing_list[0]
+        step = 4 if e.coarse_boundaries else 1
         # tiles per launch list: whole SM waves on the 1/16 map, activation buffers within ~25 GB
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         chunk = max(1, min(n, auto_slice_batch(H, W, sms)))
@@ -438,11 +482,11 @@ class Engine2d:
         while True:
             post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=e.label_divisor,
                              void_label=e.void_label, nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
-                             confidence_thr=e.confidence_thr, device=dev,
-                             scale=4 if e.coarse_boundaries else 1, center_cap=e.center_cap)
+                             confidence_thr=e.confidence_thr, device=dev, scale=step * sc, step=step,
+                             center_cap=e.center_cap, semantic=semantic, stuff_area=e.stuff_area)
             for s0 in range(0, n, chunk):
                 s1 = min(n, s0 + chunk)
-                sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf)
+                sem, ctr, off = self.model.forward_slices(vol_d, 0, s0, s1, self.model_config["norms"], pf, **kw)
                 if not e.coarse_boundaries:
                     ctr, off = upsample_instance_heads(ctr, off)
                 post.push_heads(sem, ctr, off, is_prob=False)
@@ -451,9 +495,14 @@ class Engine2d:
                 break
             except CenterOverflow as err:
                 e.center_cap = _next_pow2(err.needed)
-        # force_connected (inference.py:263-279): pan <- class*div + component id
         post.run_cc()
-        out = post.cc_images(0, n, add=cls * self.label_divisor)
+        if semantic:
+            # no thing classes: force_connected has nothing to relabel (inference.py:263-279)
+            lut = np.full((n, post.cc_cap + 1), cls * e.label_divisor, dtype=np.int32)
+            out = post.relabel(lut, "xy", (n, h, w))
+        else:
+            # force_connected: pan <- class*div + component id
+            out = post.cc_images(0, n, add=cls * self.label_divisor)
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
         return out
 

@@ -27,11 +27,12 @@ class SyntheticHeadsModel:
         self.inner = inner
         self.launches = 0
 
-    def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
+    def forward_slices(self, vol_d, axis, s0, s1, norms, pf, **kw):
         if self.inner is not None:
-            self.inner.forward_slices(vol_d, axis, s0, s1, norms, pf)
+            self.inner.forward_slices(vol_d, axis, s0, s1, norms, pf, **kw)
             self.launches = self.inner.launches
-        return self.heads_fn(axis, s0, s1)
+        # `plane_axis`: the plane the slices were taken from when they arrive as a re-sampled stack
+        return self.heads_fn(kw.get("plane_axis", axis), s0, s1)
 
 
 class HostHeadsModel:
@@ -47,10 +48,10 @@ class HostHeadsModel:
     def __getstate__(self):
         return {"heads": self.heads, "launches": 0, "_dev": None}
 
-    def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
+    def forward_slices(self, vol_d, axis, s0, s1, norms, pf, **kw):
         if self._dev is None:
             self._dev = {a: tuple(torch.from_numpy(t).to(vol_d.device) for t in h) for a, h in self.heads.items()}
-        sem, ctr, off = self._dev[axis]
+        sem, ctr, off = self._dev[kw.get("plane_axis", axis)]
         return sem[s0:s1], ctr[s0:s1], off[s0:s1]
 
 

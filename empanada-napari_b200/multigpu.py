@@ -309,7 +309,9 @@ class ShardedEngine3d(Engine3d):
 
     def infer_on_axis(self, volume, axis_name):
         from .inference import _Async
-        self._check_supported()
+        self._check_supported(sharded=True)
+        if len(self.engine.thing_list) == 0:
+            raise _lib_error("semantic-only inference is not built in the slice-sharded multi-GPU engine")
         axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
         ks = self.median_kernel_size
         mid = (ks - 1) // 2

@@ -426,9 +426,11 @@ class _NetModel:
             oldest = next(iter(self.plans))
             del self.plans[oldest]
 
-    def forward_slices(self, vol_d, axis, s0, s1, norms, pf):
+    def forward_slices(self, vol_d, axis, s0, s1, norms, pf, render_steps=None, plane_axis=None):
         """Slices [s0, s1) of the (D,H,W) integer device volume along `axis` -> (sem_logits (B,H,W),
-        ctr_hmp (B,H/4,W/4), offsets (B,2,H/4,W/4)) fp32 device tensors owned by the plan."""
+        ctr_hmp (B,H/4,W/4), offsets (B,2,H/4,W/4)) fp32 device tensors owned by the plan. With
+        `render_steps` = 2 + k PointRend steps the semantic map is (B, 2^k H, 2^k W)."""
+        render_steps = self.render_steps if render_steps is None else int(render_steps)
         D, Hv, Wv = vol_d.shape
         h, w = [(Hv, Wv), (D, Wv), (D, Hv)][axis]
         strides = [(Hv * Wv, Wv, 1), (Wv, Hv * Wv, 1), (1, Hv * Wv, Wv)][axis]
@@ -439,7 +441,7 @@ class _NetModel:
         B = s1 - s0
         elem = elem_code(vol_d.dtype)
         mean255, den = norm_constants(norms, vol_d.dtype)
-        shape_key = (h, w, H, Wd, float(mean255), float(den), elem)
+        shape_key = (h, w, H, Wd, float(mean255), float(den), elem, render_steps)
         key = (B,) + shape_key
         plan = self.plans.pop(key, None)
         skip = 0
@@ -453,7 +455,7 @@ class _NetModel:
         if plan is None:
             self._evict(0)
             with torch.cuda.device(self.dev):
-                plan = self.plan_cls(self.W, B, h, w, H, Wd, float(mean255), float(den), self.render_steps, elem=elem)
+                plan = self.plan_cls(self.W, B, h, w, H, Wd, float(mean255), float(den), render_steps, elem=elem)
             # small batches are launch bound (hundreds of kernels of a few microseconds): replay
             # them as one CUDA graph; large batches keep plain launches (kernels >> launch cost)
             if USE_GRAPHS and B * H * Wd <= GRAPH_MAX_PIXELS:

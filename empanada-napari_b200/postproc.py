@@ -44,7 +44,13 @@ class PlanePost:
 
     def __init__(self, n_slices, h, w, H, W, *, ks, thing_class, label_divisor, void_label=0,
                  nms_threshold=0.1, nms_kernel=3, confidence_thr=0.5, scale=4, device="cuda:0",
-                 center_cap=4096, cc_cap=None, keep_prob=False, hash_cap=None):
+                 center_cap=4096, cc_cap=None, keep_prob=False, hash_cap=None, step=None,
+                 semantic=False, stuff_area=64):
+        """`scale`: output pixels per head-grid cell (grid step x upsampling, engines.py:263-275);
+        `step`: grid step of the head maps in model pixels (4, or 1 with fine boundaries; default
+        = scale). `semantic`: the class is a stuff class (engine thing_list = [], 'semantic
+        only'): no instances, the whole mask of a slice is one segment if it covers at least
+        `stuff_area` pixels of the padded slice (postprocess.py:283-294)."""
         if ks % 2 != 1:
             raise AssertionError("Kernel size must be odd integer!")
         if n_slices < ks:
@@ -53,6 +59,8 @@ class PlanePost:
         self.ks, self.mid = ks, (ks - 1) // 2
         self.cls, self.div, self.void = thing_class, label_divisor, void_label
         self.thr, self.k, self.conf, self.scale = nms_threshold, nms_kernel, confidence_thr, scale
+        self.step = scale if step is None else step
+        self.semantic, self.stuff_area = semantic, stuff_area
         self.dev = torch.device(device)
         self.h4, self.w4 = H // scale, W // scale
         self.center_cap = center_cap
@@ -113,6 +121,8 @@ class PlanePost:
             self.launches += 1
 
     def check_centers(self):
+        if self.semantic:
+            return
         cmax = int(self.center_counts.max().item())
         if cmax > self.center_cap:
             raise CenterOverflow(cmax, self.center_cap)
@@ -129,10 +139,19 @@ class PlanePost:
         if self.cells4 is not None:
             return
         N, d = self.N, self.dev
+        if self.semantic:
+            # one "cell id" everywhere; it maps to class * divisor where the slice's mask is large enough
+            self.cells4 = torch.ones((N, self.h4, self.w4), dtype=torch.int32, device=d)
+            self.newid = torch.zeros((N, self.center_cap + 1), dtype=torch.int32, device=d)
+            area = torch.zeros(N, dtype=torch.int32, device=d)
+            call("be_slice_area", ptr(self.hard), N, self.H, self.W, ptr(area), stream_ptr())
+            self.newid[:, 1] = torch.where(area >= int(self.stuff_area), int(self.cls * self.div), int(self.void))
+            self.launches += 1
+            return
         self.cells4 = torch.zeros((N, self.h4, self.w4), dtype=torch.int32, device=d)
         self.newid = torch.zeros((N, self.center_cap + 1), dtype=torch.int32, device=d)
         call("be_group_flags", ptr(self.hard), ptr(self.off_all), ptr(self.centers), self.center_cap,
-             ptr(self.center_counts), N, self.H, self.W, self.scale, ptr(self.cells4), ptr(self.newid),
+             ptr(self.center_counts), N, self.H, self.W, self.scale, self.step, ptr(self.cells4), ptr(self.newid),
              stream_ptr())
         call("be_rank_ids", ptr(self.newid), N, self.center_cap, int(self.div), int(self.cls), stream_ptr())
         self.launches += 2
@@ -143,7 +162,7 @@ class PlanePost:
         s1 = self.N if s1 is None else s1
         out = torch.empty((s1 - s0, self.h4, self.w4), dtype=torch.int32, device=self.dev)
         call("be_group_pixels", ptr(self.off_all[s0]), ptr(self.centers[s0]), self.center_cap,
-             ptr(self.center_counts[s0:]), s1 - s0, self.h4, self.w4, float(self.scale), ptr(out), stream_ptr())
+             ptr(self.center_counts[s0:]), s1 - s0, self.h4, self.w4, float(self.step), ptr(out), stream_ptr())
         return out
 
     def pan_batch(self, s0, s1):
@@ -274,6 +293,27 @@ class PlanePost:
 
     def replay(self, axis_name, iou_thr=0.25, ioa_thr=0.25):
         return self.replay_host(self.replay_inputs(), axis_name, iou_thr, ioa_thr)
+
+    def semantic_tables(self, axis_name):
+        """Tracker tables of a stuff class, in the format of `replay`: no matching takes place
+        (patterns.py:55-66 only matches thing classes); every slice contributes its whole mask to
+        the single label class * divisor (rle.py:60-83 without connected components,
+        tracker.py:61-105)."""
+        n_cc, table = self.replay_inputs()
+        label = int(self.cls * self.div)
+        lut = np.zeros((self.N, table.shape[1] + 1), dtype=np.int32)
+        lut[:, 1:] = label
+        has = np.flatnonzero(n_cc > 0)
+        if has.size == 0:
+            return lut, np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros((0, 6), np.int32)
+        valid = np.arange(table.shape[1])[None, :] < n_cc[:, None]
+        size = int(table[..., 0][valid].sum())
+        big = np.iinfo(np.int32).max
+        y0 = int(np.where(valid, table[..., 1], big).min()); x0 = int(np.where(valid, table[..., 2], big).min())
+        y1 = int(np.where(valid, table[..., 3], -1).max()); x1 = int(np.where(valid, table[..., 4], -1).max())
+        i0, i1 = int(has[0]), int(has[-1]) + 1
+        box = {"xy": (i0, y0, x0, i1, y1, x1), "xz": (y0, i0, x0, y1, i1, x1), "yz": (y0, x0, i0, y1, x1, i1)}[axis_name]
+        return lut, np.array([label], np.int32), np.array([size], np.int64), np.array([box], np.int32)
 
     # ------------------------------------------------------------------ stage 4: paint
     def relabel(self, lut, axis_name, shape3d):

@@ -89,6 +89,12 @@ int be_op_aspp_pool_bias(void* list, const void* in, int B, int HW, int C, const
 /* Interpolate2d(4, bilinear, align_corners=True) of ctr_hmp / offsets for `interpolate_ins`
  * (fine boundaries; quantization/panoptic_deeplab.py:233-234): planar fp32 [planes][h][w] -> [planes][4h][4w] */
 int be_up4(const float* in, int planes, int h, int w, float* out, be_stream st);
+/* `resize_by_factor` (empanada/data/utils/transforms.py:9-21; volume_dataset.py:42-47): the N
+ * slices (h x w, uint8, element strides stride_y / stride_x, slice stride stride_s) of a volume
+ * down-sampled to dh x dw = ceil(h/f) x ceil(w/f) with OpenCV's 8-bit INTER_LINEAR arithmetic
+ * (third-party, restated; see csrc/model_kernels.cu). out: [N][dh][dw] uint8, contiguous. */
+int be_resize_linear_u8(const uint8_t* vol, long long stride_s, long long stride_y, long long stride_x,
+                        int N, int h, int w, int dh, int dw, uint8_t* out, be_stream st);
 int be_op_up2(void* list, const float* in, int B, int h, int w, float* out, be_stream st);
 int be_op_topk(void* list, const float* x, int B, int n, int k, unsigned* state, unsigned* hist,
                int* idx_out, be_stream st);                        /* point_rend.py:110-137 */
@@ -153,8 +159,11 @@ int be_sort_runs(const unsigned long long* keys_in, unsigned long long* keys_out
  * volume written once from the runs (patterns.py:204-213). Run arrays are sized by the caller from
  * stats[0] (total runs) after be_rowruns_count. */
 int be_group_flags(const uint8_t* hard, const float* off, const int* centers, int cap,
-                   const int* counts, int B, int H, int W, int scale, int* cells, int* present,
+                   const int* counts, int B, int H, int W, int scale, int step, int* cells, int* present,
                    be_stream st);
+/* set pixels per slice of the hardened mask: the stuff-area test of merge_semantic_and_instance
+ * (postprocess.py:283-294) for semantic-only planes (engines.py thing_list = []) */
+int be_slice_area(const uint8_t* hard, int B, int H, int W, int* area, be_stream st);
 int be_rowruns_count(const uint8_t* hard, const int* cells, const int* newid, int B, int H, int W,
                      int h, int w, int scale, int cap, int void_label, int lo, int hi, int* counts,
                      int* n_runs, int* slice_off, int* stats, int* row_ptr, be_stream st);

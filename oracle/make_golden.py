@@ -49,7 +49,9 @@ class FakeModel(torch.nn.Module):
     def forward(self, x, render_steps: int = 2, interpolate_ins: bool = False):
         sem, ctr, off = self.heads[self.i]
         self.i += 1
-        assert tuple(x.shape[-2:]) == tuple(sem.shape[-2:]), (x.shape, sem.shape)
+        up = 2 ** (render_steps - 2)    # PointRend renders `render_steps` doublings from the /4 map
+        assert tuple(v * up for v in x.shape[-2:]) == tuple(sem.shape[-2:]), (x.shape, sem.shape)
+        assert tuple(v // 4 for v in x.shape[-2:]) == tuple(ctr.shape[-2:]), (x.shape, ctr.shape)
         return {"sem_logits": torch.from_numpy(sem)[None], "ctr_hmp": torch.from_numpy(ctr)[None, None],
                 "offsets": torch.from_numpy(off)[None]}
 
@@ -159,20 +161,33 @@ def gen_median():
     print("median done")
 
 
+def scaled_heads(label_slice, scale, noise, rng):
+    """Heads of the model for a slice that was down-sampled by `scale` (inference_scale): centre
+    and offset maps on the /4 grid of the padded down-sampled slice, semantic logits rendered back
+    to `scale` times that size (the FakeModel asserts both shapes)."""
+    sem, _, _ = noisy_heads(label_slice, 16 * scale, noise, rng)
+    _, ctr, off = noisy_heads(label_slice[::scale, ::scale], 16, noise, rng)
+    return sem, ctr, off
+
+
 def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent, tag, pixel_vote_thr=2,
-                         allow_one_view=False):
+                         allow_one_view=False, semantic_only=False, inference_scale=1):
     """Engine3d.infer_on_axis x3 + tracker_consensus + stack_postprocessing, unmodified."""
     import empanada_napari.inference as inf
 
     vol, lab, ell = syn.make_volume(shape, seed=seed, n_objects=n_objects, scale=1.0)
     out = {"shape": np.array(shape), "seed": seed, "noise": noise, "ks": ks, "n_objects": n_objects,
            "min_size": min_size, "min_extent": min_extent, "pixel_vote_thr": pixel_vote_thr,
-           "allow_one_view": int(allow_one_view)}
+           "allow_one_view": int(allow_one_view), "semantic_only": int(semantic_only),
+           "inference_scale": int(inference_scale)}
     rng = np.random.default_rng(seed + 100)
     trackers = {}
     orig_loader = inf.load_model_to_device
     for axis_name, axis in (("xy", 0), ("xz", 1), ("yz", 2)):
-        heads = [noisy_heads(s, 16, noise, rng) for s in slices_of(lab, axis)]
+        if inference_scale > 1:
+            heads = [scaled_heads(s, inference_scale, noise, rng) for s in slices_of(lab, axis)]
+        else:
+            heads = [noisy_heads(s, 16, noise, rng) for s in slices_of(lab, axis)]
         out[f"{axis_name}_sem"] = np.stack([h[0] for h in heads]).astype(np.float16)  # +-4 +- noise: stored as f16
         out[f"{axis_name}_ctr"] = np.stack([h[1] for h in heads]).astype(np.float32)
         out[f"{axis_name}_off"] = np.stack([h[2] for h in heads]).astype(np.float32)
@@ -180,9 +195,9 @@ def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent
         heads = [(out[f"{axis_name}_sem"][i].astype(np.float32), h[1], h[2]) for i, h in enumerate(heads)]
         fake = FakeModel(heads)
         inf.load_model_to_device = lambda url, device: fake
-        eng = inf.Engine3d(MODEL_CONFIG, inference_scale=1, label_divisor=1000, median_kernel_size=ks,
+        eng = inf.Engine3d(MODEL_CONFIG, inference_scale=inference_scale, label_divisor=1000, median_kernel_size=ks,
                            nms_threshold=0.1, nms_kernel=3, confidence_thr=0.5, min_size=min_size,
-                           min_extent=min_extent, use_gpu=False, save_panoptic=True)
+                           min_extent=min_extent, use_gpu=False, save_panoptic=True, semantic_only=semantic_only)
         stack, trs = eng.infer_on_axis(vol, axis_name)
         trackers[axis_name] = trs
         out[f"{axis_name}_stack"] = stack.astype(np.int32)
@@ -250,6 +265,26 @@ def gen_post_cases_fine():
             out[f"c{i}_{k}"] = np.asarray(v)
     np.savez_compressed(os.path.join(GOLD, "post_cases_fine.npz"), **out)
     print("post_cases_fine", len(cases), [len(c["centers"]) for c in cases])
+
+
+def gen_resize_cases():
+    """`resize_by_factor` (data/utils/transforms.py:9-21) with the build container's opencv-python:
+    pins oracle/transforms.py and the CUDA kernel on OpenCV's 8-bit INTER_LINEAR arithmetic."""
+    import cv2
+    from empanada.data.utils import resize_by_factor
+    rng = np.random.default_rng(21)
+    out = {"cv2_version": cv2.__version__}
+    cases = [(64, 64, 2), (63, 64, 2), (64, 63, 2), (100, 75, 2), (128, 128, 4), (127, 130, 4), (33, 47, 4),
+             (257, 255, 2), (96, 80, 8), (50, 50, 1), (17, 23, 16), (200, 333, 2)]
+    for i, (h, w, f) in enumerate(cases):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if i % 3 == 0:     # smooth content as well as noise
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = ((np.sin(yy / 7.0) + np.cos(xx / 5.0) + 2) * 63).astype(np.uint8)
+        out[f"r{i}_img"], out[f"r{i}_f"], out[f"r{i}_out"] = img, f, resize_by_factor(img, f)
+    out["n"] = len(cases)
+    np.savez_compressed(os.path.join(GOLD, "resize_cases.npz"), **out)
+    print("resize cases", len(cases), "opencv", cv2.__version__)
 
 
 def gen_model_tiny():
@@ -365,7 +400,16 @@ def gen_eval_cases():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes"]
+    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2"]
+    if "resize" in which:
+        gen_resize_cases()
+    if "volumes2" in which:
+        run_reference_volume((26, 44, 40), seed=5, noise=0.5, ks=3, n_objects=10, min_size=20, min_extent=2,
+                             tag="semantic_only", semantic_only=True)
+        run_reference_volume((28, 50, 46), seed=6, noise=0.4, ks=3, n_objects=10, min_size=20, min_extent=2,
+                             tag="scale2", inference_scale=2)
+        run_reference_volume((32, 70, 61), seed=7, noise=0.3, ks=1, n_objects=8, min_size=20, min_extent=2,
+                             tag="scale4_semantic", inference_scale=4, semantic_only=True)
     if "eval" in which:
         gen_eval_cases()
     if "post" in which:

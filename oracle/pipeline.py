@@ -26,12 +26,17 @@ def take_slice(volume, idx, axis):
 def infer_on_axis(volume, axis_name, heads_fn, model_config, label_divisor=1000,
                   median_kernel_size=3, stuff_area=64, void_label=0, nms_threshold=0.1,
                   nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=4,
-                  save_panoptic=True, dtype=np.int32, fine_boundaries=False):
+                  save_panoptic=True, dtype=np.int32, fine_boundaries=False, semantic_only=False,
+                  inference_scale=1):
     """`fine_boundaries=True`: `heads_fn` returns FULL-resolution ctr_hmp / offsets (the model's
-    `interpolate_ins=True` output) and pixels are grouped with step 1 (engines.py:263-275)."""
+    `interpolate_ins=True` output) and pixels are grouped with step 1 (engines.py:263-275).
+    `semantic_only`: engine thing_list = [] (inference.py:365-368). `inference_scale` s: slices go
+    through `resize_by_factor` (volume_dataset.py:42-47) and `heads_fn` stands for the model with
+    2 + log2(s) render steps: sem_logits at s times the padded down-sampled size."""
+    from .transforms import resize_by_factor
     axis = AXES[axis_name]
     labels = model_config["labels"]
-    thing_list = model_config["thing_list"]
+    thing_list = [] if semantic_only else model_config["thing_list"]
     pf = model_config["padding_factor"]
     norms = model_config["norms"]
     eng = post.RenderEnginePost(thing_list, label_divisor, stuff_area, void_label, nms_threshold,
@@ -43,11 +48,12 @@ def infer_on_axis(volume, axis_name, heads_fn, model_config, label_divisor=1000,
     for i in range(n):
         img = take_slice(volume, i, axis)
         h, w = img.shape
+        img = resize_by_factor(img, inference_scale)
         x = post.factor_pad(post.normalize(img, norms["mean"], norms["std"]), pf)
         sem_logits, ctr, off = heads_fn(i, x)
         sem = post.sigmoid(sem_logits) if sem_logits.shape[0] == 1 else _softmax(sem_logits)
-        pan_segs.append(eng(sem, ctr, off, (h, w)))
-    pan_segs.extend(eng.end())
+        pan_segs.append(eng(sem, ctr, off, (h, w), inference_scale))
+    pan_segs.extend(eng.end(inference_scale))
     rle_stack = forward_matching(pan_segs, matchers, labels, label_divisor, thing_list)
     for index, rle_seg in backward_matching(rle_stack, matchers, n):
         for tr in trackers:
@@ -70,17 +76,20 @@ def _softmax(x):
 
 
 def engine2d_infer(image, heads_fn, model_config, label_divisor=1000, nms_threshold=0.1,
-                   nms_kernel=3, confidence_thr=0.3, stuff_area=64, void_label=0, fine_boundaries=False):
-    """Engine2d.infer, no tiling, inference_scale 1 (empanada_napari/inference.py:319-325,263-279)."""
-    thing_list = model_config["thing_list"]
+                   nms_kernel=3, confidence_thr=0.3, stuff_area=64, void_label=0, fine_boundaries=False,
+                   semantic_only=False, inference_scale=1):
+    """Engine2d.infer, no tiling (empanada_napari/inference.py:319-325,263-279)."""
+    from .transforms import resize_by_factor
+    thing_list = [] if semantic_only else model_config["thing_list"]
     norms = model_config["norms"]
     h, w = image.shape
+    image = resize_by_factor(image, inference_scale)
     x = post.factor_pad(post.normalize(image, norms["mean"], norms["std"]), model_config["padding_factor"])
     sem_logits, ctr, off = heads_fn(0, x)
     sem = post.sigmoid(sem_logits) if sem_logits.shape[0] == 1 else _softmax(sem_logits)
     eng = post.RenderEnginePost(thing_list, label_divisor, stuff_area, void_label, nms_threshold,
                                 nms_kernel, confidence_thr, None, not fine_boundaries)
-    pan = eng(sem, ctr, off, (h, w)).astype(np.int32)
+    pan = eng(sem, ctr, off, (h, w), inference_scale).astype(np.int32)
     for label in thing_list:
         lo = label * label_divisor
         hi = lo + label_divisor

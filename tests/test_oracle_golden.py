@@ -96,7 +96,20 @@ def test_median_queue_matches_reference():
         assert np.array_equal(np.stack(ys), z[f"m{i}_y"])
 
 
-@pytest.mark.parametrize("tag", ["clean", "noisy", "ks5_odd"])
+VOLUME_TAGS = ["clean", "noisy", "ks5_odd", "semantic_only", "scale2", "scale4_semantic"]
+
+
+def test_resize_by_factor_matches_opencv_fixture():
+    """oracle/transforms.py against `resize_by_factor` run with the real opencv-python
+    (tests/golden/resize_cases.npz, oracle/make_golden.py gen_resize_cases)."""
+    from oracle.transforms import resize_by_factor
+    z = np.load(os.path.join(GOLDEN, "resize_cases.npz"))
+    for i in range(int(z["n"])):
+        got = resize_by_factor(z[f"r{i}_img"], int(z[f"r{i}_f"]))
+        assert got.dtype == np.uint8 and np.array_equal(got, z[f"r{i}_out"]), i
+
+
+@pytest.mark.parametrize("tag", VOLUME_TAGS)
 def test_volume_pipeline_matches_reference(tag):
     import empanada_napari_b200.synthetic as syn
     z = np.load(os.path.join(GOLDEN, f"volume_{tag}.npz"))
@@ -108,7 +121,9 @@ def test_volume_pipeline_matches_reference(tag):
         stack, trs = pipeline.infer_on_axis(
             vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), MODEL_CONFIG,
             median_kernel_size=int(z["ks"]), nms_kernel=3, confidence_thr=0.5,
-            min_size=int(z["min_size"]), min_extent=int(z["min_extent"]))
+            min_size=int(z["min_size"]), min_extent=int(z["min_extent"]),
+            semantic_only=bool(z["semantic_only"]) if "semantic_only" in z else False,
+            inference_scale=int(z["inference_scale"]) if "inference_scale" in z else 1)
         assert_instances_equal(trs[0].instances, unpack_instances(z, f"{axis_name}_tr_"))
         assert np.array_equal(stack, z[f"{axis_name}_stack"])
         trackers[axis_name] = trs
