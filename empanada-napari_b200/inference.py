@@ -128,6 +128,52 @@ def _as_device_volume(array, device):
     return torch.from_numpy(np.ascontiguousarray(array)).to(device, non_blocking=False)
 
 
+def _is_lazy_array(volume):
+    """zarr.Array / dask array / any sliceable (D,H,W) array-like that is not a numpy array."""
+    return (not isinstance(volume, (np.ndarray, torch.Tensor)) and hasattr(volume, "shape")
+            and hasattr(volume, "dtype") and hasattr(volume, "__getitem__") and len(volume.shape) == 3)
+
+
+def _read_block(volume, z0, z1):
+    block = volume[z0:z1]
+    if hasattr(block, "compute"):        # dask (volume_dataset.py:40-43)
+        block = block.compute()
+    return np.ascontiguousarray(np.asarray(block))
+
+
+def stream_to_device(volume, device, slab_bytes=256 << 20):
+    """zarr / dask volumes (empanada_napari/inference.py:491-494, volume_dataset.py:37-43) are read
+    slab by slab - whole chunk rows of the store when it exposes `.chunks` - through a page-locked
+    staging buffer into ONE device-resident copy; the host never holds more than two slabs."""
+    D, H, W = (int(v) for v in volume.shape)
+    dtype = np.dtype(volume.dtype)
+    if np.issubdtype(dtype, np.floating):
+        raise Exception("Input image cannot be float type!")
+    if not np.issubdtype(dtype, np.integer):
+        raise Exception(f"Input image must have an integer dtype, got {dtype}")
+    tdtype = torch.from_numpy(np.zeros(1, dtype=dtype)).dtype
+    out = torch.empty((D, H, W), dtype=tdtype, device=device)
+    zc = None
+    chunks = getattr(volume, "chunks", None)
+    if chunks is not None:
+        zc = chunks[0][0] if isinstance(chunks[0], (tuple, list)) else chunks[0]   # dask: tuple of tuples
+    per = max(1, slab_bytes // max(1, H * W * dtype.itemsize))
+    step = max(int(zc), (per // int(zc)) * int(zc)) if zc else per
+    stage = [torch.empty((min(step, D), H, W), dtype=tdtype).pin_memory() for _ in range(2)]
+    events = [None, None]
+    for i, z0 in enumerate(range(0, D, step)):
+        z1 = min(D, z0 + step)
+        buf = stage[i % 2]
+        if events[i % 2] is not None:
+            events[i % 2].synchronize()      # the previous copy out of this buffer has finished
+        buf[:z1 - z0].numpy()[...] = _read_block(volume, z0, z1)
+        out[z0:z1].copy_(buf[:z1 - z0], non_blocking=True)
+        events[i % 2] = torch.cuda.Event()
+        events[i % 2].record()
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
 class _VolumeCache:
     """Keeps the input volume resident in HBM across the xy/xz/yz passes of ONE host array.
 
@@ -140,6 +186,7 @@ class _VolumeCache:
         self.ref = None
         self.sig = None
         self.dev = None
+        self.lazy = None      # strong reference to a zarr / dask volume whose copy is cached
 
     @staticmethod
     def _signature(volume):
@@ -154,8 +201,17 @@ class _VolumeCache:
             if not volume.is_cuda or volume.dtype.is_floating_point or volume.dtype == torch.bool:
                 raise _lib.B200EmpanadaError("device volumes must be CUDA tensors of an integer dtype")
             return volume.contiguous()
+        if _is_lazy_array(volume):
+            # a store on disk: identity + geometry (sampling its content would read chunks)
+            sig = ("lazy", id(volume), tuple(volume.shape), str(volume.dtype))
+            if self.lazy is not volume or sig != self.sig or self.dev is None:
+                self.dev = None
+                self.dev = stream_to_device(volume, device)
+                self.lazy, self.ref, self.sig = volume, None, sig
+            return self.dev
         if not isinstance(volume, np.ndarray):
-            raise _lib.B200EmpanadaError("internal: lazily loaded volumes are streamed, not cached")
+            raise _lib.B200EmpanadaError(f"unsupported volume type {type(volume)}")
+        self.lazy = None
         sig = self._signature(volume)
         host = self.ref() if self.ref is not None else None
         if host is not volume or sig != self.sig or self.dev is None:
@@ -169,7 +225,7 @@ class _VolumeCache:
         return _as_device_volume(volume, device)
 
     def clear(self):
-        self.ref, self.sig, self.dev = None, None, None
+        self.ref, self.sig, self.dev, self.lazy = None, None, None, None
 
 
 class Engine3d:
@@ -206,9 +262,7 @@ class Engine3d:
         self.fine_boundaries = fine_boundaries
         self.save_panoptic = save_panoptic
         self.chunk_size = chunk_size
-        self.zarr_store = None
-        if store_url is not None:
-            _unsupported("zarr output stores")
+        self.zarr_store = open_zarr_store(store_url, mode="w") if store_url is not None else None
         self.dtype = np.int32
         self.batch_size = batch_size
         self.lazy_rle = lazy_rle
@@ -258,8 +312,17 @@ class Engine3d:
         self.engine.reset()
         self.save_panoptic = save_panoptic
         self.chunk_size = chunk_size
-        if store_url is not None:
-            _unsupported("zarr output stores")
+        self.zarr_store = open_zarr_store(store_url, mode="w") if store_url is not None else None
+
+    def create_panoptic_stack(self, axis_name, shape3d, dense):
+        """inference.py:474-489 + fill_panoptic_volume (patterns.py:215-220): the plane's label
+        volume as a zarr array of the store, a numpy array, or None."""
+        if not self.save_panoptic:
+            return None
+        if self.zarr_store is not None:
+            stack = create_store_array(self.zarr_store, f"panoptic_{axis_name}", shape3d, self.dtype, self.chunk_size)
+            return fill_store_from_device(stack, dense)
+        return dense.cpu().numpy()
 
     def create_trackers(self, shape3d, axis_name):
         return [InstanceTracker(label, self.label_divisor, shape3d, axis_name) for label in self.labels]
@@ -372,7 +435,7 @@ class Engine3d:
                 # for the densest slice (rare: > 4096 centres in one slice)
                 self.engine.center_cap = _next_pow2(e.needed)
         self.last_profile = prof.t
-        stack = trackers[0]._b200_dense.cpu().numpy() if self.save_panoptic else None
+        stack = self.create_panoptic_stack(axis_name, shape3d, trackers[0]._b200_dense) if self.save_panoptic else None
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
         return stack, trackers
 
@@ -573,6 +636,64 @@ class _PinnedPool:
 _PINNED = _PinnedPool()
 
 
+def open_zarr_store(store_url, mode=None):
+    """`zarr.open(store_url[, mode='w'])` (empanada_napari/inference.py:72-75,397-400). zarr is the
+    reference's own third-party dependency; it is imported only when a store is asked for."""
+    try:
+        import zarr
+    except ImportError as e:
+        raise _lib.B200EmpanadaError(f"store_url={store_url!r} needs the zarr package: {e}")
+    return zarr.open(store_url, mode=mode) if mode is not None else zarr.open(store_url)
+
+
+def create_store_array(store, name, shape, dtype, chunks):
+    """`zarr_store.create_array(name, shape=..., dtype=..., chunks=..., overwrite=True)` (zarr >= 3,
+    inference.py:99-104) or `create_dataset` (zarr 2, multigpu.py:200-204)."""
+    make = getattr(store, "create_array", None) or store.create_dataset
+    return make(name, shape=tuple(int(s) for s in shape), dtype=dtype, chunks=tuple(int(c) for c in chunks),
+                overwrite=True)
+
+
+def fill_store_from_device(array, vol_d):
+    """`zarr_fill_instances` (zarr_utils.py:97-184) for a label volume that is already rasterised in
+    HBM: the reference splits every instance's runs by chunk and lets a 4-process pool decode them
+    into the chunks; here each chunk ROW (all chunks of one z range) comes off the GPU in one
+    page-locked copy, cast to the store's dtype, and every chunk is written exactly once with a
+    chunk-aligned assignment (no read-modify-write in the store)."""
+    D, H, W = (int(v) for v in array.shape)
+    dc, hc, wc = (int(c) for c in array.chunks)
+    if tuple(vol_d.shape) != (D, H, W):
+        raise _lib.B200EmpanadaError(f"store array {array.shape} does not match the label volume {tuple(vol_d.shape)}")
+    dtype = np.dtype(array.dtype)
+    stage = [torch.empty((min(dc, D), H, W), dtype=vol_d.dtype).pin_memory() for _ in range(2)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    pending = None
+
+    def start(i, z0):
+        z1 = min(D, z0 + dc)
+        with torch.cuda.stream(side):
+            stage[i % 2][:z1 - z0].copy_(vol_d[z0:z1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return (i, z0, z1, ev)
+
+    zs = list(range(0, D, dc))
+    if zs:
+        pending = start(0, zs[0])
+    for i, z0 in enumerate(zs):
+        _, _, z1, ev = pending
+        pending = start(i + 1, zs[i + 1]) if i + 1 < len(zs) else None   # next slab copies while this one is written
+        ev.synchronize()
+        slab = stage[i % 2][:z1 - z0].numpy()
+        for y0 in range(0, H, hc):
+            for x0 in range(0, W, wc):
+                y1, x1 = min(H, y0 + hc), min(W, x0 + wc)
+                array[z0:z1, y0:y1, x0:x1] = slab[:, y0:y1, x0:x1].astype(dtype, copy=False)
+    torch.cuda.current_stream().wait_stream(side)
+    return array
+
+
 def get_axis_trackers_by_class(trackers, class_id):
     """patterns.py:154-166."""
     return [t for axis_trackers in trackers.values() for t in axis_trackers if t.class_id == class_id]
@@ -581,9 +702,9 @@ def get_axis_trackers_by_class(trackers, class_id):
 def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pixel_vote_thr=2,
                       cluster_iou_thr=0.75, allow_one_view=False, min_size=200, min_extent=4,
                       dtype=np.uint32, chunk_size=(256, 256, 256), to_host=True):
-    r"""Orthoplane consensus (generator, as the reference): yields (volume, class_name, instances)."""
-    if store_url is not None:
-        _unsupported("zarr output stores")
+    r"""Orthoplane consensus (generator, as the reference): yields (volume, class_name, instances).
+    With `store_url` the volume is a zarr array of that store (chunks = chunk_size)."""
+    zarr_store = open_zarr_store(store_url) if store_url is not None else None
     thing_list = model_config["thing_list"]
     for class_id, class_name in model_config["class_names"].items():
         class_trackers = get_axis_trackers_by_class(trackers, class_id)
@@ -601,18 +722,24 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
                                                   cluster_iou_thr=cluster_iou_thr, allow_one_view=allow_one_view,
                                                   min_size=min_size, min_extent=min_extent)
             out.instances = instances
-            yield (_PINNED.to_host(vol_d, dtype) if to_host else vol_d), class_name, out.instances
+            if zarr_store is not None:
+                vol = fill_store_from_device(create_store_array(zarr_store, f"{class_name}", shape3d, dtype, chunk_size), vol_d)
+            else:
+                vol = _PINNED.to_host(vol_d, dtype) if to_host else vol_d
+            yield vol, class_name, out.instances
             continue
         pending = []
         # the device->host copy of the painted volume overlaps the extraction of the RLE tables
-        hook = (lambda v: pending.append(_PINNED.start(v, dtype))) if to_host else None
+        hook = (lambda v: pending.append(_PINNED.start(v, dtype))) if (to_host and zarr_store is None) else None
         vol_d, instances = consensus.merge_objects_from_trackers(
             class_trackers, pixel_vote_thr, cluster_iou_thr, allow_one_view, min_size, min_extent,
             on_volume_ready=hook)
         out.instances = instances
         tracker_consensus.last_launches = consensus.LAST_LAUNCHES
         # `to_host=False` (not in the reference signature) leaves the painted volume on the GPU
-        if not to_host:
+        if zarr_store is not None:
+            vol = fill_store_from_device(create_store_array(zarr_store, f"{class_name}", shape3d, dtype, chunk_size), vol_d)
+        elif not to_host:
             vol = vol_d
         elif pending and pending[0] is not None:
             vol = _PINNED.finish(pending[0])
@@ -623,9 +750,9 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
 
 def stack_postprocessing(trackers, store_url, model_config, label_divisor=1000, min_size=200,
                          min_extent=4, dtype=np.uint32, chunk_size=(256, 256, 256)):
-    r"""Relabel 1..n + filter + fill for single-plane stacks (generator, as the reference)."""
-    if store_url is not None:
-        _unsupported("zarr output stores")
+    r"""Relabel 1..n + filter + fill for single-plane stacks (generator, as the reference).
+    With `store_url` the volume is a zarr array of that store (chunks = chunk_size)."""
+    zarr_store = open_zarr_store(store_url) if store_url is not None else None
     thing_list = model_config["thing_list"]
     for class_id, class_name in model_config["class_names"].items():
         ct = get_axis_trackers_by_class(trackers, class_id)[0]
@@ -634,5 +761,10 @@ def stack_postprocessing(trackers, store_url, model_config, label_divisor=1000, 
         if class_id in thing_list:
             tracking.remove_small_objects(st, min_size=min_size)
             tracking.remove_pancakes(st, min_span=min_extent)
-        vol = consensus.fill_volume_device(ct, st.instances, dtype, to_host=_PINNED.to_host)
+        if zarr_store is not None:
+            class_dtype = dtype if class_id in thing_list else np.uint8
+            vol_d = consensus.fill_volume_device(ct, st.instances, dtype, to_host=lambda v, dt: v)
+            vol = fill_store_from_device(create_store_array(zarr_store, f"{class_name}", ct.shape3d, class_dtype, chunk_size), vol_d)
+        else:
+            vol = consensus.fill_volume_device(ct, st.instances, dtype, to_host=_PINNED.to_host)
         yield vol, class_name, st.instances
