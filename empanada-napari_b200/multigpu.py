@@ -598,6 +598,11 @@ def _lib_error(msg):
 # One-process front end: what the widget constructs (empanada_napari/_volume_inference.py:17,
 # empanada_napari/multigpu.py:121-260)
 # ------------------------------------------------------------------------------------------
+# a collective that a dead rank never joins must not hang the caller's thread for ever: the ranks
+# only meet inside one `infer_on_axis` / `consensus` call (seconds), idle waits are on queues
+_FRONT_TIMEOUT = __import__("datetime").timedelta(seconds=int(os.environ.get("B200_EMPANADA_NCCL_TIMEOUT", "300")))
+
+
 def _free_port():
     import socket
     with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
@@ -613,7 +618,7 @@ def _worker_main(rank, world, port, model_config, engine_kwargs, cmd_q, err_q):
         torch.cuda.set_device(rank)
         dev = torch.device("cuda", rank)
         dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
-                                device_id=dev)
+                                device_id=dev, timeout=_FRONT_TIMEOUT)
         eng = ShardedEngine3d(model_config, replicated_input=False, **engine_kwargs)
         vol_version, vol_d = None, None
         while True:
@@ -623,14 +628,14 @@ def _worker_main(rank, world, port, model_config, engine_kwargs, cmd_q, err_q):
             if cmd[0] == "update_params":
                 eng.update_params(*cmd[1])
             elif cmd[0] == "infer":
-                _, axis_name, shape, dtype_name, version = cmd
+                _, axis_name, shape, dtype_name, version, gather_dense = cmd
                 if version != vol_version:
                     vol_d = None
                     vol_d = torch.empty(shape, dtype=getattr(torch, dtype_name), device=dev)
                     dist.broadcast(vol_d, src=0)
                     vol_version = version
                 _, trackers = eng.infer_on_axis(vol_d, axis_name)
-                eng.finalize({axis_name: trackers}, gather_dense=cmd[5])
+                eng.finalize({axis_name: trackers}, gather_dense=gather_dense)
             elif cmd[0] == "gather_plane":
                 eng.gather_plane(cmd[1])
             elif cmd[0] == "consensus":
@@ -692,7 +697,7 @@ class MultiGPUEngine3d:
             self._procs.append(p)
         torch.cuda.set_device(0)
         dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=self.world,
-                                device_id=torch.device("cuda", 0))
+                                device_id=torch.device("cuda", 0), timeout=_FRONT_TIMEOUT)
         self._engine = ShardedEngine3d(model_config, replicated_input=False, **kwargs)
         self._engine.front = self
         self.engine = self._engine.engine
@@ -704,6 +709,9 @@ class MultiGPUEngine3d:
         if not self._err_q.empty():
             rank, tb = self._err_q.get()
             raise _lib_error(f"worker rank {rank} failed:\n{tb}")
+        dead = [i + 1 for i, p in enumerate(self._procs) if not p.is_alive()]
+        if dead:
+            raise _lib_error(f"worker rank(s) {dead} exited; create a new MultiGPUEngine3d")
         for q in self._cmd_qs:
             q.put(cmd)
 

@@ -22,7 +22,7 @@ def test_distributed_engine_equals_single_gpu(engine, ks, fine):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "check_multigpu.py")]
     env = dict(os.environ, CHECK_ENGINE=engine, CHECK_KS=ks, CHECK_FINE=fine, CHECK_WITH_NETWORK="0")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT, env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "MULTIGPU_CHECK" in r.stdout and " PASS" in r.stdout
 
@@ -34,7 +34,8 @@ def test_multigpu_engine_front_end():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least two GPUs")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_multigpu_front.py")],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       capture_output=True, text=True, timeout=420, cwd=ROOT,
+                       env=dict(os.environ, B200_EMPANADA_NCCL_TIMEOUT="120"))
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "MULTIGPU_FRONT PASS" in r.stdout
 
