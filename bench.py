@@ -513,11 +513,12 @@ def main():
                     counts[name] = len(trackers[name][0].instances.keys())
         out = None
         if sharded:    # every rank votes on its own z-slab; graph decisions on rank 0
-            vol, _, inst = eng.sharded_consensus(trackers, cfg, pixel_vote_thr=2, min_size=500, min_extent=5)
+            # to_host: every rank copies its own painted z-slab into one shared host volume
+            vol, _, inst = eng.sharded_consensus(trackers, cfg, pixel_vote_thr=2, min_size=500, min_extent=5,
+                                                 to_host=to_host, gather_volume=not to_host)
             n_l += eng.consensus_launches
             if rank == 0:
-                from empanada_napari_b200.inference import _PINNED
-                out = (_PINNED.to_host(vol, np.int32) if to_host else vol, inst)
+                out = (vol, inst)
         elif rank == 0:
             for vol, cname, inst in tracker_consensus(trackers, None, cfg, pixel_vote_thr=2, min_size=500,
                                                       min_extent=5, dtype=np.int32, to_host=to_host):

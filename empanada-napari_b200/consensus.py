@@ -121,6 +121,193 @@ def component_subgraph(members, edges, n_nodes):
     return sub
 
 
+# ------------------------------------------------------------------------- the same, without networkx
+class _Graph:
+    """Undirected graph with EXACTLY networkx.Graph's container semantics (dict of node ->
+    attribute dict, dict of node -> dict of neighbour -> shared edge attribute dict, all in
+    insertion order; `copy` re-inserts edges node by node as `Graph.copy` does), so that every
+    order-dependent step of create_graph_of_clusters / merge_clusters gives what networkx gives,
+    at a fraction of its per-call overhead. `tests/test_consensus_host.py` checks it against the
+    networkx versions above on thousands of random components."""
+    __slots__ = ("node", "adj")
+
+    def __init__(self):
+        self.node, self.adj = {}, {}
+
+    def add_node(self, n, attr=None):
+        if n not in self.node:
+            self.adj[n] = {}
+            self.node[n] = {}
+        if attr:
+            self.node[n].update(attr)
+
+    def add_edge(self, u, v, attr=None):
+        if u not in self.node:
+            self.adj[u] = {}
+            self.node[u] = {}
+        if v not in self.node:
+            self.adj[v] = {}
+            self.node[v] = {}
+        dd = self.adj[u].get(v, {})
+        if attr:
+            dd.update(attr)
+        self.adj[u][v] = dd
+        self.adj[v][u] = dd
+
+    def remove_edge(self, u, v):
+        del self.adj[u][v]
+        if u != v:
+            del self.adj[v][u]
+
+    def remove_node(self, n):
+        nbrs = list(self.adj[n])
+        del self.node[n]
+        for u in nbrs:
+            del self.adj[u][n]
+        del self.adj[n]
+
+    def copy(self):
+        g = _Graph()
+        for n, d in self.node.items():
+            g.add_node(n, d)
+        for u, nbrs in self.adj.items():
+            for v, dd in nbrs.items():
+                g.add_edge(u, v, dd)
+        return g
+
+    def edges(self):
+        seen = set()
+        for n, nbrs in self.adj.items():
+            for nbr, dd in nbrs.items():
+                if nbr not in seen:
+                    yield n, nbr, dd
+            seen.add(n)
+
+    def n_edges(self):
+        return sum(len(nbrs) + (n in nbrs) for n, nbrs in self.adj.items()) // 2
+
+    def degree(self, n):
+        nbrs = self.adj[n]
+        return len(nbrs) + (n in nbrs)
+
+    def has_edge(self, u, v):
+        return u in self.adj and v in self.adj[u]
+
+    def components(self):
+        """networkx.connected_components: sets built by `_plain_bfs`, in node order."""
+        seen = set()
+        n = len(self.adj)
+        for v in self.adj:
+            if v not in seen:
+                c = _plain_bfs(self.adj, n, v)
+                seen.update(c)
+                yield c
+
+
+def _plain_bfs(adj, n, source):
+    """networkx/algorithms/components/connected.py `_plain_bfs` (same insertions, same order:
+    the iteration order of the returned set is part of the contract)."""
+    seen = {source}
+    nextlevel = [source]
+    while nextlevel:
+        thislevel = nextlevel
+        nextlevel = []
+        for v in thislevel:
+            for w in adj[v]:
+                if w not in seen:
+                    seen.add(w)
+                    nextlevel.append(w)
+            if len(seen) == n:
+                return seen
+    return seen
+
+
+def _avg_edge_fast(G, c1, c2, key):
+    w = []
+    adj = G.adj
+    for a in c1:
+        na = adj[a]
+        for b in c2:
+            w.append(na[b][key] if b in na else 0)
+    return sum(w) / len(w)
+
+
+def create_graph_of_clusters_fast(G, cluster_iou_thr):
+    H = G.copy()
+    for (u, v, d) in list(G.edges()):
+        if d["iou"] <= cluster_iou_thr:
+            H.remove_edge(u, v)
+    CG = _Graph()
+    owner = {}
+    for i, cluster in enumerate(H.components()):
+        CG.add_node(i, {"cluster": cluster})
+        for n in cluster:
+            owner[n] = i
+    linked = set()
+    for u, v, _ in G.edges():
+        a, b = owner[u], owner[v]
+        if a != b:
+            linked.add((a, b) if a < b else (b, a))
+    for n1, n2 in sorted(linked):
+        c1, c2 = CG.node[n1]["cluster"], CG.node[n2]["cluster"]
+        iw = _avg_edge_fast(G, c1, c2, "iou")
+        ow = _avg_edge_fast(G, c1, c2, "overlap")
+        if iw > MIN_IOU or ow > MIN_OVERLAP:
+            CG.add_edge(n1, n2, {"iou": iw, "overlap": ow})
+    return CG
+
+
+def merge_clusters_fast(G):
+    H = G.copy()
+    node = H.node
+    while H.n_edges() > 0:
+        mc = max(node, key=H.degree)
+        nbrs = sorted(H.adj[mc], key=lambda x: len(node[x]["cluster"]), reverse=True)
+        if len(node[nbrs[0]]["cluster"]) > len(node[mc]["cluster"]):
+            for nb in nbrs:
+                node[nb]["cluster"] = node[nb]["cluster"].union(node[mc]["cluster"])
+                H.remove_edge(mc, nb)
+            H.remove_node(mc)
+        else:
+            for nb in nbrs:
+                node[mc]["cluster"] = node[mc]["cluster"].union(node[nb]["cluster"])
+                H.remove_edge(nb, mc)
+                for sn in list(H.adj[nb]):
+                    if not H.has_edge(mc, sn):
+                        H.add_edge(mc, nb, {"iou": H.adj[nb][sn]["iou"]})
+                H.remove_node(nb)
+    return H
+
+
+def component_subgraph_fast(members, edges, n_nodes):
+    """`component_subgraph` as a `_Graph` (no networkx objects)."""
+    adj = {m: {} for m in members}
+    for a, b, _, _ in edges:
+        adj[a][b] = None
+        adj[b][a] = None
+    comp_set = _plain_bfs(adj, n_nodes, members[0])
+    node_seq = list(set(v for v in comp_set)) if 2 * len(comp_set) < n_nodes else list(members)
+    sub = _Graph()
+    for n in node_seq:
+        sub.add_node(n)
+    for a, b, iou, overlap in edges:
+        sub.add_edge(a, b, {"iou": iou, "overlap": overlap})
+    return sub
+
+
+def component_clusters(members, edges, n_nodes, cluster_iou_thr):
+    """Clusters (lists of nodes, in the cluster graph's node order) of one connected component
+    whose edges do not all pass the IoU cut."""
+    cg = merge_clusters_fast(create_graph_of_clusters_fast(component_subgraph_fast(members, edges, n_nodes), cluster_iou_thr))
+    return [list(cg.node[n]["cluster"]) for n in cg.node]
+
+
+def component_clusters_nx(members, edges, n_nodes, cluster_iou_thr):
+    """The same through networkx (the reference's own dependency): the checker of the fast path."""
+    cg = merge_clusters(create_graph_of_clusters(component_subgraph(members, edges, n_nodes), cluster_iou_thr))
+    return [list(cg.nodes[n]["cluster"]) for n in cg.nodes]
+
+
 # ------------------------------------------------------------------------- device helpers
 def _hash_table(cap, dev):
     keys = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -141,16 +328,15 @@ def _hash_items(keys, vals, cap, dev):
     return (k >> np.uint64(32)).astype(np.int64), (k & np.uint64(0xFFFFFFFF)).astype(np.int64), v
 
 
-def dense_volume(tracker, dev):
-    """Device (D,H,W) int32 label volume of a tracker: the one `Engine3d.infer_on_axis` left on
-    the GPU, or a rasterisation of the RLE (trackers loaded from JSON)."""
-    vol = getattr(tracker, "_b200_dense", None)
-    if vol is not None:
-        return vol
-    shape3d = tuple(int(s) for s in tracker.shape3d)
+def rasterize_instances(instances, shape3d, dev):
+    """`numpy_fill_instances` (array_utils.py:754-765) on the device: every instance's runs
+    painted into a zero (D,H,W) int32 volume in dictionary order (later instances overwrite
+    earlier ones; runs are clipped to the volume, as numpy slicing clips them)."""
+    shape3d = tuple(int(s) for s in shape3d)
     vol = torch.zeros(shape3d, dtype=torch.int32, device=dev)
     flat = vol.view(-1)
-    for label, attrs in tracker.instances.items():
+    n = flat.numel()
+    for label, attrs in instances.items():
         starts = torch.from_numpy(np.asarray(attrs["starts"], dtype=np.int64)).to(dev)
         runs = torch.from_numpy(np.asarray(attrs["runs"], dtype=np.int64)).to(dev)
         if starts.numel() == 0:
@@ -158,8 +344,17 @@ def dense_volume(tracker, dev):
         total = int(runs.sum().item())
         rep = torch.repeat_interleave(starts - torch.cumsum(runs, 0) + runs, runs)
         idx = rep + torch.arange(total, device=dev)
-        flat[idx] = int(label)
+        flat[idx[idx < n]] = int(label)
     return vol
+
+
+def dense_volume(tracker, dev):
+    """Device (D,H,W) int32 label volume of a tracker: the one `Engine3d.infer_on_axis` left on
+    the GPU, or a rasterisation of the RLE (trackers loaded from JSON)."""
+    vol = getattr(tracker, "_b200_dense", None)
+    if vol is not None:
+        return vol
+    return rasterize_instances(tracker.instances, tracker.shape3d, dev)
 
 
 def extract_runs(vol):
@@ -351,6 +546,9 @@ def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_th
     edge_order = np.argsort(comp_of[ea], kind="stable")   # edges grouped by component, lexsorted inside
     edge_start = np.concatenate([[0], np.cumsum(np.bincount(comp_of[ea], minlength=n_comp))])
     boxes = np.asarray(node_boxes, dtype=np.int64).reshape(-1, 6)
+    # edges grouped by component as plain Python lists (one conversion for all components)
+    ea_l, eb_l = ea[edge_order].tolist(), eb[edge_order].tolist()
+    eiou_l, eit_l = eiou[edge_order].tolist(), eit[edge_order].tolist()
     cands = []  # (component index, member node list, merged box)
     for ci in np.flatnonzero(comp_size >= min_cluster):
         members = node_order[node_start[ci]:node_start[ci + 1]]
@@ -359,10 +557,9 @@ def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_th
             # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
             clusters = [members.tolist()]
         else:
-            eidx = edge_order[edge_start[ci]:edge_start[ci + 1]]
-            sub = component_subgraph(members.tolist(), [(int(ea[k]), int(eb[k]), float(eiou[k]), int(eit[k])) for k in eidx], n_nodes)
-            cg = merge_clusters(create_graph_of_clusters(sub, cluster_iou_thr))
-            clusters = [list(cg.nodes[node]["cluster"]) for node in cg.nodes]
+            e0, e1 = edge_start[ci], edge_start[ci + 1]
+            clusters = component_clusters(members.tolist(), list(zip(ea_l[e0:e1], eb_l[e0:e1], eiou_l[e0:e1], eit_l[e0:e1])),
+                                          n_nodes, cluster_iou_thr)
         for cluster in clusters:
             if len(cluster) < min_cluster:
                 continue

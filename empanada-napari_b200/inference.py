@@ -411,6 +411,16 @@ class Engine3d:
         # (tracker_consensus below never needs them); set lazy_rle=False for eager dictionaries
         plane = LazyPlane(dense, axis_name, kept_labels, boxes[keep])
         tr.instances = plane.attrs
+        if axis_name == "xz" and dense.shape[0] > 1 and bool(
+                ((dense[:-1, :, -1] == dense[1:, :, 0]) & (dense[1:, :, 0] != 0)).any()):
+            # An instance runs from the last pixel of one row of an xz slice into the first pixel
+            # of the next. The reference lifts such a 2-D run to 3-D unsplit (tracker.py:80-84), so
+            # its tail lands in the next y-row instead of the next z-row, and everything downstream
+            # (stacks, stack_postprocessing, consensus) sees those voxels there. Reproduce it: the
+            # run-length tables come from the true geometry, the label volume from the tables.
+            plane.materialize()
+            dense = consensus.rasterize_instances(tr.instances, shape3d, dense.device)
+            tr._b200_xz_wrap = True
         if not self.lazy_rle:
             plane.materialize()
         tr.finish()
@@ -718,12 +728,15 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
                         and getattr(t, "_b200_dense", None) is None for t in class_trackers)):
             # trackers of a MultiGPUEngine3d whose label volumes are still sharded over the GPUs:
             # every rank votes on its own z-slab (multigpu.ShardedEngine3d.sharded_consensus)
-            vol_d, _, instances = front.consensus(trackers, model_config, pixel_vote_thr=pixel_vote_thr,
+            direct = to_host and zarr_store is None and np.dtype(dtype).itemsize == 4 and np.dtype(dtype).kind in "iu"
+            vol_d, _, instances = front.consensus(trackers, model_config, to_host=direct, pixel_vote_thr=pixel_vote_thr,
                                                   cluster_iou_thr=cluster_iou_thr, allow_one_view=allow_one_view,
                                                   min_size=min_size, min_extent=min_extent)
             out.instances = instances
             if zarr_store is not None:
                 vol = fill_store_from_device(create_store_array(zarr_store, f"{class_name}", shape3d, dtype, chunk_size), vol_d)
+            elif direct:     # every GPU copied its own slab into shared host memory
+                vol = vol_d.view(dtype)
             else:
                 vol = _PINNED.to_host(vol_d, dtype) if to_host else vol_d
             yield vol, class_name, out.instances

@@ -190,6 +190,87 @@ class DistributedEngine3d(Engine3d):
         return trackers
 
 
+class _SharedHostVolume:
+    """A (D,H,W) int32 result volume in POSIX shared memory that every rank of one host maps: each
+    rank copies its own painted z-slab device->host over its own PCIe link (its range of the
+    mapping is page-locked once with cudaHostRegister), instead of funnelling the whole volume
+    through rank 0's GPU and one link. Rank 0 owns the segment and hands out a numpy view; the
+    segment is reused for the next result of the same shape once the caller has released the
+    previous array (as the single-GPU page-locked pool does)."""
+
+    def __init__(self, group, rank, world):
+        self.group, self.rank, self.world = group, rank, world
+        self.shm, self.name, self.shape = None, None, None
+        self.array = None        # rank 0: the numpy view handed to the caller
+        self.registered = None   # (address, bytes) of the page-locked range of this rank
+        self.serial = 0
+
+    def _unregister(self):
+        if self.registered is not None:
+            torch.cuda.cudart().cudaHostUnregister(self.registered[0])
+            self.registered = None
+
+    def close(self):
+        self._unregister()
+        self.array = None
+        if self.shm is not None:
+            try:
+                self.shm.close()
+                if self.rank == 0:
+                    self.shm.unlink()
+            except Exception:
+                pass
+            self.shm = None
+
+    def acquire(self, shape, z_range):
+        """Collective. Returns (torch int32 view of the whole volume, numpy view on rank 0)."""
+        import sys
+        from multiprocessing import shared_memory
+        shape = tuple(int(v) for v in shape)
+        nbytes = int(np.prod(shape)) * 4
+        name = [None]
+        if self.rank == 0:
+            busy = self.array is not None and sys.getrefcount(self.array) > 2
+            if self.shm is None or self.shape != shape or busy:
+                if busy:      # the caller still holds the previous result: leave that segment to it
+                    self._unregister()
+                    self.shm, self.array = None, None
+                else:
+                    self.close()
+                self.serial += 1
+                try:     # a too-small /dev/shm would only fail later, with SIGBUS on first touch
+                    st = os.statvfs("/dev/shm")
+                    room = st.f_bavail * st.f_frsize
+                except OSError:
+                    room = 0
+                if room > nbytes + (64 << 20):
+                    self.shm = shared_memory.SharedMemory(create=True, size=nbytes,
+                                                          name=f"b200emp_{os.getpid()}_{self.serial}")
+                    self.shape = shape
+            name[0] = self.shm.name if self.shm is not None else None
+        dist.broadcast_object_list(name, src=0, group=self.group)
+        if name[0] is None:      # no room in shared memory: the caller gathers through rank 0
+            return None, None
+        if self.rank != 0 and (self.shm is None or self.shm.name != name[0]):
+            self.close()
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            self.shape = shape
+        full = np.ndarray(shape, dtype=np.int32, buffer=self.shm.buf)
+        z0, z1 = z_range
+        if z1 > z0:
+            part = full[z0:z1]
+            addr, size = part.ctypes.data, part.nbytes
+            if self.registered != (addr, size):
+                self._unregister()
+                err = torch.cuda.cudart().cudaHostRegister(addr, size, 0)
+                if int(err) != 0:
+                    raise _lib_error(f"cudaHostRegister failed ({err})")
+                self.registered = (addr, size)
+        if self.rank == 0:
+            self.array = full
+        return torch.from_numpy(full), (full if self.rank == 0 else None)
+
+
 class _ReplicatedVolumeCache(_VolumeCache):
     """Upload of a host volume that EVERY rank holds (one process per GPU under torchrun): each
     rank copies 1/G of it over its own PCIe link and NCCL all-gathers the pieces over NVLink,
@@ -278,6 +359,7 @@ class ShardedEngine3d(Engine3d):
         self._pending = {}
         self._slabs = {}
         self.front = None        # the MultiGPUEngine3d that drives this engine, if any
+        self._host_out = _SharedHostVolume(group, self.rank, self.world)
         if replicated_input:     # host volumes are passed to every rank (torchrun)
             self._cache = _ReplicatedVolumeCache(group, self.rank, self.world)
 
@@ -462,11 +544,13 @@ class ShardedEngine3d(Engine3d):
         return out, z0
 
     def sharded_consensus(self, trackers, model_config, pixel_vote_thr=2, cluster_iou_thr=0.75,
-                          allow_one_view=False, min_size=200, min_extent=4, gather_volume=True):
+                          allow_one_view=False, min_size=200, min_extent=4, gather_volume=True, to_host=False):
         """Collective form of `tracker_consensus` for ONE thing class over the slabs `finalize`
         left on every rank: each rank votes on its own z-slab; rank 0 runs the graph decisions on
-        the summed sparse tables (consensus.consensus_driver). Returns on rank 0
-        (device volume or None, class_name, instances); (None, None, None) elsewhere."""
+        the summed sparse tables (consensus.consensus_driver). Returns on rank 0 (volume,
+        class_name, instances); (None, None, None) elsewhere. The volume is the device tensor
+        assembled on rank 0 (`gather_volume`), or with `to_host` a numpy int32 array in shared
+        host memory that every rank filled with its own slab in parallel."""
         from . import consensus
         G, r = self.world, self.rank
         tm = _Timer()
@@ -508,7 +592,22 @@ class ShardedEngine3d(Engine3d):
                 dist.gather_object(_guarded(shard, method, args), None, dst=0, group=self.group)
         self.consensus_launches = shard.launches
         vol = None
-        if gather_volume:
+        full_t = None
+        if to_host:
+            _, Ez, shape3d = self._slabs["xy"]
+            full_t, vol = self._host_out.acquire(shape3d, Ez[r])
+        if full_t is not None:
+            full_t[Ez[r][0]:Ez[r][1]].copy_(shard.painted, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)
+            tm.mark("consensus: painted slabs to shared host memory")
+        elif to_host:            # fallback: assemble on rank 0, one page-locked copy from there
+            from .inference import _PINNED
+            vol = self._gather_z(shard.painted)
+            if r == 0:
+                vol = _PINNED.to_host(vol, np.int32)
+            tm.mark("consensus: painted slabs to rank 0 + copy to the host")
+        elif gather_volume:
             vol = self._gather_z(shard.painted)
             tm.mark("consensus: painted slabs to rank 0")
         if _PROFILE:
@@ -642,6 +741,7 @@ def _worker_main(rank, world, port, model_config, engine_kwargs, cmd_q, err_q):
                 eng.sharded_consensus(None, None, **cmd[1])
             elif cmd[0] == "release":
                 vol_version, vol_d = None, None
+        eng._host_out.close()
         dist.destroy_process_group()
     except BaseException:
         err_q.put((rank, traceback.format_exc()))
@@ -749,11 +849,12 @@ class MultiGPUEngine3d:
         self._send("gather_plane", axis_name)
         return self._engine.gather_plane(axis_name)
 
-    def consensus(self, trackers, model_config, **params):
+    def consensus(self, trackers, model_config, to_host=False, **params):
         """`tracker_consensus` over the slabs the ranks still hold (called by
         `inference.tracker_consensus` when it is handed this engine's trackers)."""
         if len(set(self._planes_version.get(n) for n in ("xy", "xz", "yz"))) != 1 or None in self._planes_version.values():
             raise _lib_error("the xy, xz and yz trackers must come from the same volume")
+        params = dict(params, to_host=bool(to_host), gather_volume=not to_host)
         self._send("consensus", params)
         return self._engine.sharded_consensus(trackers, model_config, **params)
 
@@ -770,6 +871,7 @@ class MultiGPUEngine3d:
                     q.put(("close",))
                 for p in self._procs:
                     p.join(timeout=30)
+                self._engine._host_out.close()
                 dist.destroy_process_group()
             finally:
                 self._procs = []

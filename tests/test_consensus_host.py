@@ -68,3 +68,39 @@ def test_join_shard_ranges_merges_runs_across_slab_boundaries():
     for fid in range(1, n_final + 1):
         m = ids == fid
         assert np.array_equal(got[fid][0], starts[m]) and np.array_equal(got[fid][1], lens[m]), fid
+
+
+def test_networkx_free_clustering_equals_networkx():
+    """`component_clusters` (plain dict graphs with networkx's container semantics) against the
+    networkx path on the reference's subgraph VIEW: same clusters, same order, same member
+    iteration order (the float sums of `_avg_edge` run over it), for many thresholds and shapes."""
+    from empanada_napari_b200.consensus import component_clusters, create_graph_of_clusters, merge_clusters
+    rng = np.random.default_rng(7)
+    checked = 0
+    for trial in range(400):
+        n = int(rng.integers(4, 120))
+        m = int(rng.integers(3, 200))
+        ea, eb = rng.integers(0, n, m), rng.integers(0, n, m)
+        keep = ea < eb
+        key = np.unique(ea[keep] * 100000 + eb[keep])
+        ea, eb = key // 100000, key % 100000
+        # a mix of strong, weak and tiny overlaps so that every branch of the merge runs
+        iou = np.where(rng.random(len(ea)) < 0.5, rng.uniform(0.7, 1.0, len(ea)), rng.uniform(0.0, 0.05, len(ea)))
+        ov = np.where(rng.random(len(ea)) < 0.5, rng.integers(1, 90, len(ea)), rng.integers(90, 400, len(ea)))
+        thr = float(rng.choice([0.0, 0.5, 0.75, 0.9]))
+        G = nx.Graph()
+        for i in range(n):
+            G.add_node(i)
+        for a, b, i, o in zip(ea, eb, iou, ov):
+            G.add_edge(int(a), int(b), iou=float(i), overlap=int(o))
+        for comp in nx.connected_components(G):
+            if len(comp) < 2:
+                continue
+            view = G.subgraph(comp)
+            edges = [(int(ea[k]), int(eb[k]), float(iou[k]), int(ov[k])) for k in range(len(ea)) if int(ea[k]) in comp]
+            ref = merge_clusters(create_graph_of_clusters(view, thr))
+            want = [list(ref.nodes[x]["cluster"]) for x in ref.nodes]
+            got = component_clusters(sorted(comp), edges, n, thr)
+            assert got == want, (trial, sorted(comp))
+            checked += 1
+    assert checked > 1500

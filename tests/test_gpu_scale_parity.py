@@ -197,3 +197,46 @@ def test_end_to_end_evaluator_f1_on_many_instances(tmp_path):
     assert len(oinst) >= 100 and len(inst) >= 100
     assert fg_gt > 0.6                                # the probe-fitted model does segment the objects
     assert res["f1_50"] >= 0.99 and res["f1_75"] >= 0.99 and res["iou"] >= 0.99, res
+
+
+def test_xz_row_wrap_follows_the_reference():
+    """An object that spans the full width of consecutive rows of an xz slice: its 2-D runs wrap
+    from (z, W-1) into (z+1, 0), and the reference lifts them to 3-D unsplit (tracker.py:80-84),
+    which puts the wrapped tail in the next y-row. Trackers, the xz stack, stack_postprocessing
+    and the consensus must reproduce exactly that."""
+    import torch
+    import empanada_napari_b200.synthetic as syn
+    from empanada_napari_b200.inference import stack_postprocessing, tracker_consensus
+    from oracle import consensus as ocons
+    shape = (24, 40, 32)
+    vol, lab, _ = syn.make_volume(shape, seed=5, n_objects=6, scale=1.0)
+    lab[8:14, 10:22, :] = 99                      # a slab across the whole x extent, 6 deep in z
+    dev = torch.device("cuda:0")
+    heads_np = {}
+    for a in range(3):
+        hs = [syn.analytic_heads(np.take(lab, i, axis=a), pad_to=16) for i in range(shape[a])]
+        heads_np[a] = (np.stack([h[0][0] for h in hs]), np.stack([h[1] for h in hs]), np.stack([h[2] for h in hs]))
+    heads = {a: tuple(torch.from_numpy(t).to(dev) for t in heads_np[a]) for a in range(3)}
+    kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=20, min_extent=2)
+    eng, cfg = _device_heads_engine(heads, _cfg(), batch_size=6, save_panoptic=True, **kw)
+    got, stacks = {}, {}
+    for name in ("xy", "xz", "yz"):
+        stacks[name], got[name] = eng.infer_on_axis(vol, name)
+    assert getattr(got["xz"][0], "_b200_xz_wrap", False)          # the case is triggered
+    from oracle import pipeline
+    want = {}
+    for a, name in enumerate(("xy", "xz", "yz")):
+        sem, ctr, off = heads_np[a]
+        ostack, want[name] = pipeline.infer_on_axis(vol, name, lambda i, x: (sem[i][None], ctr[i], off[i]), cfg,
+                                                    save_panoptic=True, **kw)
+        assert_instances_equal(got[name][0].instances, want[name][0].instances)
+        assert np.array_equal(stacks[name], ostack), name
+    vote = dict(pixel_vote_thr=2, min_size=20, min_extent=2, dtype=np.int32)
+    (v, _, inst), = list(tracker_consensus(got, None, cfg, **vote))
+    (ov, _, oinst), = list(ocons.tracker_consensus(want, cfg, **vote))
+    assert_instances_equal(inst, oinst)
+    assert np.array_equal(v, ov)
+    (v, _, inst), = list(stack_postprocessing({"xz": got["xz"]}, None, cfg, min_size=20, min_extent=2, dtype=np.int32))
+    (ov, _, oinst), = list(ocons.stack_postprocessing({"xz": want["xz"]}, cfg, min_size=20, min_extent=2, dtype=np.int32))
+    assert_instances_equal(inst, oinst)
+    assert np.array_equal(v, ov)
