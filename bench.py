@@ -37,16 +37,19 @@ PDL_GFLOP_PER_PIXEL = 559.15e9 / (1024 * 1024)  # SURVEY.md section 8d (per plan
 
 # ------------------------------------------------------------------------------ synthetic data
 def synth_on_device(S, dev, seed=0):
-    """EM-like uint8 volume + int32 ground-truth labels, rasterised on the GPU (setup, untimed)."""
+    """EM-like uint8 volume + int32 ground-truth labels, rasterised on the GPU (setup, untimed).
+    S: edge of a cube, or a (D, H, W) shape."""
     import torch
     import empanada_napari_b200.synthetic as syn
-    ell = syn.make_ellipsoids((S, S, S), seed=seed)
-    lab = torch.zeros((S, S, S), dtype=torch.int32, device=dev)
-    ar = torch.arange(S, device=dev, dtype=torch.float32)
+    shape = (S, S, S) if isinstance(S, int) else tuple(int(v) for v in S)
+    D, Hs, Ws = shape
+    ell = syn.make_ellipsoids(shape, seed=seed)
+    lab = torch.zeros(shape, dtype=torch.int32, device=dev)
+    ar = torch.arange(max(shape), device=dev, dtype=torch.float32)
     for i, (cz, cy, cx, rz, ry, rx) in enumerate(ell.tolist(), start=1):
-        z0, z1 = max(0, int(cz - rz)), min(S, int(cz + rz) + 2)
-        y0, y1 = max(0, int(cy - ry)), min(S, int(cy + ry) + 2)
-        x0, x1 = max(0, int(cx - rx)), min(S, int(cx + rx) + 2)
+        z0, z1 = max(0, int(cz - rz)), min(D, int(cz + rz) + 2)
+        y0, y1 = max(0, int(cy - ry)), min(Hs, int(cy + ry) + 2)
+        x0, x1 = max(0, int(cx - rx)), min(Ws, int(cx + rx) + 2)
         if z0 >= z1 or y0 >= y1 or x0 >= x1:
             continue
         dz = ((ar[z0:z1] - cz) / rz) ** 2
@@ -56,8 +59,8 @@ def synth_on_device(S, dev, seed=0):
         sub = lab[z0:z1, y0:y1, x0:x1]
         sub[m] = i
     g = torch.Generator(device=dev).manual_seed(seed + 1)
-    vol = torch.empty((S, S, S), dtype=torch.uint8, device=dev)
-    for z in range(0, S, 64):
+    vol = torch.empty(shape, dtype=torch.uint8, device=dev)
+    for z in range(0, D, 64):
         blk = lab[z:z + 64]
         img = torch.where(blk > 0, 70.0, 170.0) + torch.randn(blk.shape, generator=g, device=dev) * 8.0
         vol[z:z + 64] = img.clamp_(0, 255).to(torch.uint8)
@@ -385,6 +388,48 @@ def bench_stack_512(pdl, dev, S=512, steps=2):
             "ms_per_step": ms, "voxels_per_s": float(S) ** 3 / (ms * 1e-3), "instances": len(out[1])}
 
 
+def bench_c5(pdl, dev, shape=(512, 2048, 2048), pf=512, steps=1):
+    """BASELINE config C5: NucleoNet + DropNet (both PanopticDeepLab-PointRend, padding factor
+    512, nms_kernel 7: empanada_napari/configs/NucleoNet_base_v2.yaml, DropNet_base_v1.yaml) 3-D
+    orthoplane inference + consensus on an anisotropic volume - two complete jobs on the same
+    volume, one per model - here on ONE GPU (device-resident volume, host label volumes out).
+    Both models are the same network graph; seeded random weights, analytic heads as in the main arm."""
+    import torch
+    from empanada_napari_b200.inference import Engine3d, tracker_consensus
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    vol_d, lab_d, n_obj = synth_on_device(shape, dev, seed=5)
+    heads = {a: analytic_heads_on_device(lab_d, a, n_obj, pf=pf) for a in range(3)}
+    del lab_d
+    engines = []
+    for name in ("nuclei", "lipid"):
+        cfg = {"class_names": {1: name}, "labels": [1], "thing_list": [1], "padding_factor": pf, "norms": NORMS,
+               "model": SyntheticHeadsModel(lambda a, s0, s1: tuple(t[s0:s1] for t in heads[a]), inner=pdl)}
+        engines.append((cfg, Engine3d(cfg, median_kernel_size=3, nms_kernel=7, confidence_thr=0.5, min_size=500, min_extent=5)))
+
+    def job():
+        counts = []
+        for cfg, eng in engines:
+            trackers = {ax: eng.infer_on_axis(vol_d, ax)[1] for ax in ("xy", "xz", "yz")}
+            for vol, _, inst in tracker_consensus(trackers, None, cfg, pixel_vote_thr=2, min_size=500, min_extent=5, dtype=np.int32):
+                counts.append(len(inst))
+            del vol, trackers
+        return counts
+
+    counts = job()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        counts = job()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    vox = float(np.prod(shape))
+    return {"workload": f"NucleoNet + DropNet class PDL 3D orthoplane + consensus, {shape[0]}x{shape[1]}x{shape[2]} volume, padding factor {pf}, two models, 1 GPU",
+            "ms_per_step": ms, "voxels_per_s": vox / (ms * 1e-3), "voxels_per_s_per_model": 2 * vox / (ms * 1e-3),
+            "consensus_instances": counts, "objects": int(n_obj)}
+
+
 def result_checksum(out, plane_counts):
     """Checksums of the job's result (consensus label volume + instance table); they must be
     identical for every GPU count (the sharded engine is bit-exact against the single-GPU one)."""
@@ -423,6 +468,7 @@ def main():
                     help="full-size slices per plane in one CPU sample step (>= the median kernel)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-2d", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the NucleoNet + DropNet anisotropic secondary figure")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -634,6 +680,12 @@ def main():
         torch.cuda.empty_cache()
         stack512 = bench_stack_512(pdl, dev)
 
+    c5 = None
+    if rank == 0 and world == 1 and not args.no_c5 and not args.no_2d and S >= 1024:
+        torch.cuda.empty_cache()
+        pdl.release_plans()
+        c5 = bench_c5(pdl, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = CpuSample(S, n=args.cpu_slices)
@@ -655,6 +707,7 @@ def main():
             "post_roofline": post_roof, "consensus_instances": n_instances, "checksum": checksum,
             "tiles_2d": tiles2d,
             "stack_xy_512": stack512,
+            "c5_nucleonet_dropnet": c5,
         }
         print(json.dumps(line))
     if world > 1:
