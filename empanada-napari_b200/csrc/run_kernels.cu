@@ -120,120 +120,119 @@ slice_area_kernel(const uint8_t* __restrict__ hard, long long n16, int* __restri
 }
 
 // ------------------------------------------------------------------ row runs
-struct Src {   // one plane's mask / cell ids / renumbering table
-  const uint8_t* hard; const int* cells; const int* newid;
-  int H, W, h, w, scale, cap, void_label, lo, hi;
-};
-__device__ __forceinline__ int cls_filter(int v, int lo, int hi) { return (v >= lo && v < hi && v != 0) ? v : 0; }
-__device__ __forceinline__ int pan_at(const Src& s, const uint8_t* hb, const int* cb, const int* nid, int y, int x) {
-  int v = s.void_label;
-  if (hb[static_cast<long long>(y) * s.W + x]) {
-    const int id = cb[(y / s.scale) * (s.W / s.scale) + x / s.scale];
-    if (id > 0) v = nid[id];
-  }
-  return cls_filter(v, s.lo, s.hi);
-}
-struct RowQuad { int v[4]; int head[4]; int tail[4]; };
-// four consecutive pixels (x0 .. x0+3, x0 % 4 == 0) of row y of slice b
-__device__ __forceinline__ bool load_rowquad(const Src& s, int b, int y, int x0, RowQuad& q) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { q.v[j] = 0; q.head[j] = 0; q.tail[j] = 0; }
-  const uint8_t* hb = s.hard + static_cast<long long>(b) * s.H * s.W;
-  const uint32_t hq = __ldg(reinterpret_cast<const uint32_t*>(hb + static_cast<long long>(y) * s.W + x0));
-  const int bg = cls_filter(s.void_label, s.lo, s.hi);
-  if (hq == 0 && bg == 0) return false;
-  const int w4 = s.W / s.scale;
-  const int* cb = s.cells + static_cast<long long>(b) * (s.H / s.scale) * w4;
-  const int* nid = s.newid + static_cast<long long>(b) * (s.cap + 1);
-  const int* crow = cb + (y / s.scale) * w4;
-  bool any = false;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (x0 + j >= s.w) continue;
-    int v = s.void_label;
-    if ((hq >> (8 * j)) & 0xff) {
-      const int id = crow[(x0 + j) / s.scale];
-      if (id > 0) v = nid[id];
-    }
-    q.v[j] = cls_filter(v, s.lo, s.hi);
-    any |= q.v[j] != 0;
-  }
-  if (!any) return false;
-  const int left = (x0 > 0 && q.v[0] != 0) ? pan_at(s, hb, cb, nid, y, x0 - 1) : 0;
-  const int right = (x0 + 4 < s.w && q.v[3] != 0) ? pan_at(s, hb, cb, nid, y, x0 + 4) : 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int x = x0 + j;
-    if (q.v[j] == 0) continue;
-    const int pv = (j == 0) ? left : q.v[j - 1];
-    const int nv = (j == 3) ? right : q.v[j + 1];
-    q.head[j] = (x == 0) || (pv != q.v[j]);
-    q.tail[j] = (x == s.w - 1) || (nv != q.v[j]);
-  }
-  return true;
+// The panoptic value of a pixel is  hard ? cellval[cell] : bg  (restricted to the class range):
+// `resolve_cells_kernel` first turns the per-cell centre ids into final values in place
+// (cell id -> per-class running counter, postprocess.py:273-288; void / out-of-range -> 0), so the
+// per-pixel passes below chase one pointer instead of two.
+__host__ __device__ __forceinline__ int cls_filter(int v, int lo, int hi) { return (v >= lo && v < hi && v != 0) ? v : 0; }
+__global__ void __launch_bounds__(256)
+resolve_cells_kernel(int* __restrict__ cells, const int* __restrict__ newid, long long per_slice, int cap,
+                     int void_label, int lo, int hi, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int id = cells[i];
+  const int v = id > 0 ? __ldg(newid + (i / per_slice) * (cap + 1) + id) : void_label;
+  cells[i] = cls_filter(v, lo, hi);
 }
 
-// One thread = one quad; quads are numbered row-major over the cropped slice (qpr per row).
-// PASS 0: heads / tails per 256-quad chunk. PASS 1: run records at
+struct Src {   // one plane's mask / resolved cell values
+  const uint8_t* hard; const int* cellval;
+  int H, W, h, w, scale, bg;
+};
+__device__ __forceinline__ int val_at(const Src& s, const uint8_t* hb, const int* cb, int y, int x) {
+  return hb[static_cast<long long>(y) * s.W + x] ? __ldg(cb + (y / s.scale) * (s.W / s.scale) + x / s.scale) : s.bg;
+}
+
+// One thread = 16 consecutive pixels of a row (one 16-byte load of the mask, one 16-byte load of
+// four cell values at scale 4); groups are numbered row-major over the cropped slice (gpr per row).
+// PASS 0: heads / tails per 256-group chunk. PASS 1: run records at
 // slice_off[b] + (scanned chunk offset) + (rank inside the chunk); k-th head and k-th tail of a
 // slice delimit the same run. Also emits row_ptr (slice-local index of the first run of a row).
 constexpr int RR_THREADS = 256;
+constexpr int RR_PX = 16;
 template <int PASS>
 __global__ void __launch_bounds__(RR_THREADS)
-rowruns_kernel(Src s, int qpr, int chunks, int* __restrict__ counts /*[2][B][chunks]*/, int B,
+rowruns_kernel(Src s, int gpr, int chunks, int* __restrict__ counts /*[2][B][chunks]*/, int B,
                const int* __restrict__ slice_off, int* __restrict__ row_ptr /*[B][h+1]*/,
                int2* __restrict__ run_yx, int* __restrict__ run_x1, int* __restrict__ run_val,
                int* __restrict__ L) {
   const int b = blockIdx.y, ch = blockIdx.x;
   const int g = ch * RR_THREADS + threadIdx.x;
-  const int y = g / qpr, qi = g - y * qpr;
+  const int y = g / gpr, gi = g - y * gpr;
+  const int x0 = RR_PX * gi;
   const bool valid = y < s.h;
-  RowQuad q;
-  bool any = false;
-  if (valid) any = load_rowquad(s, b, y, 4 * qi, q);
+  int v[RR_PX];
+#pragma unroll
+  for (int i = 0; i < RR_PX; ++i) v[i] = 0;
+  unsigned hm = 0, tm = 0;
+  if (valid) {
+    const uint8_t* hb = s.hard + static_cast<long long>(b) * s.H * s.W;
+    const int w4 = s.W / s.scale;
+    const int* cb = s.cellval + static_cast<long long>(b) * (s.H / s.scale) * w4;
+    const uint4 hq = __ldg(reinterpret_cast<const uint4*>(hb + static_cast<long long>(y) * s.W + x0));
+    const unsigned hw[4] = {hq.x, hq.y, hq.z, hq.w};
+    if ((hq.x | hq.y | hq.z | hq.w) != 0 || s.bg != 0) {
+      const int* crow = cb + (y / s.scale) * w4;
+      if (s.scale == 4) {
+        const int4 cv = __ldg(reinterpret_cast<const int4*>(crow + x0 / 4));
+        const int c4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[4 * k + j] = (x0 + 4 * k + j < s.w) ? (((hw[k] >> (8 * j)) & 0xffu) ? c4[k] : s.bg) : 0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < RR_PX; ++i)
+          if (x0 + i < s.w) v[i] = ((hw[i >> 2] >> (8 * (i & 3))) & 0xffu) ? __ldg(crow + (x0 + i) / s.scale) : s.bg;
+      }
+      const int left = (x0 > 0 && v[0] != 0) ? val_at(s, hb, cb, y, x0 - 1) : 0;
+      const int right = (x0 + RR_PX < s.w && v[RR_PX - 1] != 0) ? val_at(s, hb, cb, y, x0 + RR_PX) : 0;
+#pragma unroll
+      for (int i = 0; i < RR_PX; ++i) {
+        if (v[i] == 0) continue;
+        const int pv = (i == 0) ? left : v[i - 1];
+        const int nv = (i == RR_PX - 1) ? right : v[i + 1];
+        if (x0 + i == 0 || pv != v[i]) hm |= 1u << i;
+        if (x0 + i == s.w - 1 || nv != v[i]) tm |= 1u << i;
+      }
+    }
+  }
   const long long cidx = static_cast<long long>(b) * chunks + ch;
   int* counts_t = counts + static_cast<long long>(B) * chunks;
-  if (!__syncthreads_or(any)) {
+  if (!__syncthreads_or(hm != 0)) {
     if (PASS == 0) {
       if (threadIdx.x == 0) { counts[cidx] = 0; counts_t[cidx] = 0; }
-    } else if (valid && qi == 0) {
+    } else if (valid && gi == 0) {
       row_ptr[static_cast<long long>(b) * (s.h + 1) + y] = counts[cidx];
     }
     return;
   }
-  int nh = 0, nt = 0;
-  if (any) {
-    nh = q.head[0] + q.head[1] + q.head[2] + q.head[3];
-    nt = q.tail[0] + q.tail[1] + q.tail[2] + q.tail[3];
-  }
+  // heads in the low half, tails in the high half of one scanned word (<= 4096 each per chunk)
+  const int packed = __popc(hm) | (__popc(tm) << 16);
   typedef cub::BlockScan<int, RR_THREADS> Scan;
   __shared__ typename Scan::TempStorage tmp;
+  int ex, tot;
+  Scan(tmp).ExclusiveSum(packed, ex, tot);
   if (PASS == 0) {
-    int exh, toth, ext, tott;
-    Scan(tmp).ExclusiveSum(nh, exh, toth);
-    __syncthreads();
-    Scan(tmp).ExclusiveSum(nt, ext, tott);
-    if (threadIdx.x == 0) { counts[cidx] = toth; counts_t[cidx] = tott; }
+    if (threadIdx.x == 0) { counts[cidx] = tot & 0xffff; counts_t[cidx] = tot >> 16; }
     return;
   }
-  int exh, ext;
-  Scan(tmp).ExclusiveSum(nh, exh);
-  __syncthreads();
-  Scan(tmp).ExclusiveSum(nt, ext);
+  const int exh = ex & 0xffff, ext = ex >> 16;
   const int offh = counts[cidx], offt = counts_t[cidx];
-  if (valid && qi == 0) row_ptr[static_cast<long long>(b) * (s.h + 1) + y] = offh + exh;
+  if (valid && gi == 0) row_ptr[static_cast<long long>(b) * (s.h + 1) + y] = offh + exh;
   const int so = slice_off[b];
-  if (nh) {
+  if (hm) {
     int pos = so + offh + exh;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (q.head[j]) { run_yx[pos] = make_int2(y, 4 * qi + j); run_val[pos] = q.v[j]; L[pos] = pos; ++pos; }
+    for (int i = 0; i < RR_PX; ++i)
+      if ((hm >> i) & 1u) { run_yx[pos] = make_int2(y, x0 + i); run_val[pos] = v[i]; L[pos] = pos; ++pos; }
   }
-  if (nt) {
+  if (tm) {
     int pos = so + offt + ext;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (q.tail[j]) { run_x1[pos] = 4 * qi + j + 1; ++pos; }
+    for (int i = 0; i < RR_PX; ++i)
+      if ((tm >> i) & 1u) { run_x1[pos] = x0 + i + 1; ++pos; }
   }
 }
 
@@ -565,18 +564,25 @@ int be_slice_area(const uint8_t* hard, int B, int H, int W, int* area, cudaStrea
   return be_check_launch("slice_area_kernel");
 }
 
-// counts: workspace [2 * B * chunks] int32, chunks = ceil(h * ceil(w/4) / 256). Leaves the scanned
+// counts: workspace [2 * B * chunks] int32, chunks = ceil(h * ceil(w/16) / 256). Leaves the scanned
 // chunk offsets in `counts`, n_runs[B], slice_off[B+1], stats[2] = {total runs, max runs per slice}
 // and row_ptr[b][h] = n_runs[b]; the caller reads stats, allocates the run arrays and calls
 // be_rowruns_write with the same arguments.
-int be_rowruns_count(const uint8_t* hard, const int* cells, const int* newid, int B, int H, int W,
+int be_rowruns_count(const uint8_t* hard, int* cells, const int* newid, int B, int H, int W,
                      int h, int w, int scale, int cap, int void_label, int lo, int hi, int* counts,
                      int* n_runs, int* slice_off, int* stats, int* row_ptr, cudaStream_t stream) {
-  if (W % 4 || (reinterpret_cast<uintptr_t>(hard) & 3)) return be_set_error("rowruns: padded width must be a multiple of 4");
-  runs::Src s{hard, cells, newid, H, W, h, w, scale, cap, void_label, lo, hi};
-  const int qpr = (w + 3) / 4;
-  const int chunks = (h * qpr + runs::RR_THREADS - 1) / runs::RR_THREADS;
-  runs::rowruns_kernel<0><<<dim3(chunks, B), runs::RR_THREADS, 0, stream>>>(s, qpr, chunks, counts, B, nullptr, nullptr,
+  if (W % runs::RR_PX || (reinterpret_cast<uintptr_t>(hard) & 15) || scale < 1 || H % scale || W % scale)
+    return be_set_error("rowruns: padded width must be a multiple of 16 (and of the cell size)");
+  if (scale == 4 && ((reinterpret_cast<uintptr_t>(cells) & 15) || (W / 4) % 4))
+    return be_set_error("rowruns: cell rows must be 16-byte aligned");
+  // cells: centre ids -> final panoptic values, in place (be_rowruns_write expects them resolved)
+  const long long per_slice = 1LL * (H / scale) * (W / scale), total = per_slice * B;
+  runs::resolve_cells_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      cells, newid, per_slice, cap, void_label, lo, hi, total);
+  runs::Src s{hard, cells, H, W, h, w, scale, runs::cls_filter(void_label, lo, hi)};
+  const int gpr = (w + runs::RR_PX - 1) / runs::RR_PX;
+  const int chunks = (h * gpr + runs::RR_THREADS - 1) / runs::RR_THREADS;
+  runs::rowruns_kernel<0><<<dim3(chunks, B), runs::RR_THREADS, 0, stream>>>(s, gpr, chunks, counts, B, nullptr, nullptr,
                                                                           nullptr, nullptr, nullptr, nullptr);
   runs::rowruns_scan_kernel<<<B, 1024, 0, stream>>>(counts, B, chunks, n_runs, row_ptr, h);
   runs::slice_offsets_kernel<<<1, 1024, 0, stream>>>(n_runs, B, slice_off, stats);
@@ -587,11 +593,12 @@ int be_rowruns_write(const uint8_t* hard, const int* cells, const int* newid, in
                      int h, int w, int scale, int cap, int void_label, int lo, int hi, int* counts,
                      const int* slice_off, int* row_ptr, int* run_yx, int* run_x1, int* run_val,
                      int* L, cudaStream_t stream) {
-  runs::Src s{hard, cells, newid, H, W, h, w, scale, cap, void_label, lo, hi};
-  const int qpr = (w + 3) / 4;
-  const int chunks = (h * qpr + runs::RR_THREADS - 1) / runs::RR_THREADS;
+  (void)newid; (void)cap;
+  runs::Src s{hard, cells, H, W, h, w, scale, runs::cls_filter(void_label, lo, hi)};
+  const int gpr = (w + runs::RR_PX - 1) / runs::RR_PX;
+  const int chunks = (h * gpr + runs::RR_THREADS - 1) / runs::RR_THREADS;
   runs::rowruns_kernel<1><<<dim3(chunks, B), runs::RR_THREADS, 0, stream>>>(
-      s, qpr, chunks, counts, B, slice_off, row_ptr, reinterpret_cast<int2*>(run_yx), run_x1, run_val, L);
+      s, gpr, chunks, counts, B, slice_off, row_ptr, reinterpret_cast<int2*>(run_yx), run_x1, run_val, L);
   return be_check_launch("rowruns write kernel");
 }
 

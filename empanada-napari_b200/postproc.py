@@ -183,10 +183,12 @@ class PlanePost:
         neighbouring slices. (`batch` is accepted for compatibility; the run pipeline handles the
         whole plane in one launch sequence.)"""
         N, h, w, d = self.N, self.h, self.w, self.dev
+        if self.runs is not None:      # already done (the cell ids were consumed by the first call)
+            return
         self.group()
         st = stream_ptr()
-        qpr = (w + 3) // 4
-        chunks = (h * qpr + 255) // 256
+        gpr = (w + 15) // 16                 # one thread per 16 pixels of a row (csrc/run_kernels.cu)
+        chunks = (h * gpr + 255) // 256
         counts = torch.empty(2 * N * chunks, dtype=torch.int32, device=d)
         n_runs = torch.empty(N, dtype=torch.int32, device=d)
         slice_off = torch.empty(N + 1, dtype=torch.int32, device=d)

@@ -164,7 +164,10 @@ int be_group_flags(const uint8_t* hard, const float* off, const int* centers, in
 /* set pixels per slice of the hardened mask: the stuff-area test of merge_semantic_and_instance
  * (postprocess.py:283-294) for semantic-only planes (engines.py thing_list = []) */
 int be_slice_area(const uint8_t* hard, int B, int H, int W, int* area, be_stream st);
-int be_rowruns_count(const uint8_t* hard, const int* cells, const int* newid, int B, int H, int W,
+/* be_rowruns_count first resolves `cells` IN PLACE from centre ids to final panoptic values
+ * (newid lookup, void label, class range); be_rowruns_write takes the resolved array. W must be a
+ * multiple of 16. counts: workspace [2 * B * chunks], chunks = ceil(h * ceil(w/16) / 256). */
+int be_rowruns_count(const uint8_t* hard, int* cells, const int* newid, int B, int H, int W,
                      int h, int w, int scale, int cap, int void_label, int lo, int hi, int* counts,
                      int* n_runs, int* slice_off, int* stats, int* row_ptr, be_stream st);
 int be_rowruns_write(const uint8_t* hard, const int* cells, const int* newid, int B, int H, int W,
