@@ -550,22 +550,37 @@ def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_th
     ea_l, eb_l = ea[edge_order].tolist(), eb[edge_order].tolist()
     eiou_l, eit_l = eiou[edge_order].tolist(), eit[edge_order].tolist()
     cands = []  # (component index, member node list, merged box)
-    for ci in np.flatnonzero(comp_size >= min_cluster):
-        members = node_order[node_start[ci]:node_start[ci + 1]]
-        if comp_min_iou[ci] > cluster_iou_thr:
+    # merged boxes of WHOLE components in one shot (what the one-cluster components need)
+    sorted_boxes = boxes[node_order]
+    starts = node_start[:-1]
+    nonempty = comp_size > 0
+    comp_box = np.zeros((n_comp, 6), dtype=np.int64)
+    if nonempty.any():
+        comp_box[nonempty, :3] = np.minimum.reduceat(sorted_boxes[:, :3], starts[nonempty], axis=0)
+        comp_box[nonempty, 3:] = np.maximum.reduceat(sorted_boxes[:, 3:], starts[nonempty], axis=0)
+    comp_box_l = comp_box.tolist()
+    node_order_l = node_order.tolist()
+    node_start_l, edge_start_l = node_start.tolist(), edge_start.tolist()
+    one_cluster = (comp_min_iou > cluster_iou_thr).tolist()
+    boxes_l = None
+    for ci in np.flatnonzero(comp_size >= min_cluster).tolist():
+        members = node_order_l[node_start_l[ci]:node_start_l[ci + 1]]
+        if one_cluster[ci]:
             # every edge survives the IoU cut: the component is one cluster and the cluster graph
             # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
-            clusters = [members.tolist()]
-        else:
-            e0, e1 = edge_start[ci], edge_start[ci + 1]
-            clusters = component_clusters(members.tolist(), list(zip(ea_l[e0:e1], eb_l[e0:e1], eiou_l[e0:e1], eit_l[e0:e1])),
-                                          n_nodes, cluster_iou_thr)
+            cands.append((ci, members, tuple(comp_box_l[ci])))
+            continue
+        e0, e1 = edge_start_l[ci], edge_start_l[ci + 1]
+        clusters = component_clusters(members, list(zip(ea_l[e0:e1], eb_l[e0:e1], eiou_l[e0:e1], eit_l[e0:e1])),
+                                      n_nodes, cluster_iou_thr)
         for cluster in clusters:
             if len(cluster) < min_cluster:
                 continue
-            b = boxes[cluster]
-            box = tuple(int(v) for v in np.concatenate([b[:, :3].min(0), b[:, 3:].max(0)]))
-            cands.append((int(ci), cluster, box))
+            if boxes_l is None:
+                boxes_l = boxes.tolist()
+            bs = [boxes_l[m] for m in cluster]
+            box = tuple(min(b[k] for b in bs) if k < 3 else max(b[k] for b in bs) for k in range(6))
+            cands.append((ci, cluster, box))
     return cands
 
 

@@ -574,7 +574,7 @@ class ShardedEngine3d(Engine3d):
                     if isinstance(x, BaseException):
                         dist.broadcast_object_list([("done", ())], src=0, group=self.group)
                         raise x
-                return res
+                return [_import_arrays(x) for x in res]
             if n_nodes == 0:
                 each("zero")
                 instances = {}
@@ -583,13 +583,15 @@ class ShardedEngine3d(Engine3d):
                                                        cluster_iou_thr, min_cluster, min_size, min_extent, tm.mark)
             dist.broadcast_object_list([("done", ())], src=0, group=self.group)
         else:
+            exports = []      # shared-memory segments holding this rank's large results
             while True:
                 cmd = [None]
                 dist.broadcast_object_list(cmd, src=0, group=self.group)
                 method, args = cmd[0]
                 if method == "done":
                     break
-                dist.gather_object(_guarded(shard, method, args), None, dst=0, group=self.group)
+                dist.gather_object(_guarded(shard, method, args, exports), None, dst=0, group=self.group)
+            _release_exports(exports)
         self.consensus_launches = shard.launches
         vol = None
         full_t = None
@@ -633,12 +635,60 @@ class ShardedEngine3d(Engine3d):
         return None
 
 
-def _guarded(shard, method, args):
-    """One shard call of the consensus driver; an exception travels to rank 0 as the result."""
+def _guarded(shard, method, args, exports=None):
+    """One shard call of the consensus driver; an exception travels to rank 0 as the result.
+    `exports` (a list, non-root ranks): large numpy results go through a shared-memory segment of
+    this rank instead of the pickled object gather; the segment is appended for later clean-up."""
     try:
-        return getattr(shard, method)(*args)
+        res = getattr(shard, method)(*args)
     except Exception as e:  # re-raised on rank 0
         return e
+    if exports is not None and isinstance(res, tuple) and res and all(isinstance(a, np.ndarray) for a in res) \
+            and sum(a.nbytes for a in res) > (1 << 20):
+        try:
+            return _export_arrays(res, exports)
+        except Exception:
+            return res
+    return res
+
+
+def _export_arrays(arrays, exports):
+    from multiprocessing import shared_memory
+    total = sum(a.nbytes for a in arrays)
+    st = os.statvfs("/dev/shm")
+    if st.f_bavail * st.f_frsize < total + (64 << 20):
+        raise OSError("no room in /dev/shm")
+    shm = shared_memory.SharedMemory(create=True, size=total, name=f"b200emp_t{os.getpid()}_{len(exports)}_{time.monotonic_ns()}")
+    exports.append(shm)
+    meta, off = [], 0
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        np.ndarray(a.shape, a.dtype, buffer=shm.buf, offset=off)[...] = a
+        meta.append((a.shape, a.dtype.str, off))
+        off += a.nbytes
+    return ("__b200_shm__", shm.name, meta)
+
+
+def _import_arrays(res):
+    """Root side of `_export_arrays`: copies the arrays out of the peer's segment."""
+    if not (isinstance(res, tuple) and len(res) == 3 and res[0] == "__b200_shm__"):
+        return res
+    from multiprocessing import shared_memory
+    shm = shared_memory.SharedMemory(name=res[1])
+    try:
+        return tuple(np.array(np.ndarray(shape, np.dtype(dt), buffer=shm.buf, offset=off)) for shape, dt, off in res[2])
+    finally:
+        shm.close()
+
+
+def _release_exports(exports):
+    for shm in exports:
+        try:
+            shm.close()
+            shm.unlink()
+        except Exception:
+            pass
+    exports.clear()
 
 
 class ShardedPlane:
