@@ -253,7 +253,7 @@ class _SharedHostVolume:
             return None, None
         if self.rank != 0 and (self.shm is None or self.shm.name != name[0]):
             self.close()
-            self.shm = shared_memory.SharedMemory(name=name[0])
+            self.shm = _attach_shm(name[0])
             self.shape = shape
         full = np.ndarray(shape, dtype=np.int32, buffer=self.shm.buf)
         z0, z1 = z_range
@@ -652,6 +652,19 @@ def _guarded(shard, method, args, exports=None):
     return res
 
 
+def _attach_shm(name):
+    """Attach to a peer's segment without making this process's resource tracker its owner
+    (before Python 3.13 attaching registers the name, and the tracker would unlink it - with a
+    warning - when this process exits)."""
+    from multiprocessing import resource_tracker, shared_memory
+    shm = shared_memory.SharedMemory(name=name)
+    try:
+        resource_tracker.unregister(shm._name, "shared_memory")
+    except Exception:
+        pass
+    return shm
+
+
 def _export_arrays(arrays, exports):
     from multiprocessing import shared_memory
     total = sum(a.nbytes for a in arrays)
@@ -673,8 +686,7 @@ def _import_arrays(res):
     """Root side of `_export_arrays`: copies the arrays out of the peer's segment."""
     if not (isinstance(res, tuple) and len(res) == 3 and res[0] == "__b200_shm__"):
         return res
-    from multiprocessing import shared_memory
-    shm = shared_memory.SharedMemory(name=res[1])
+    shm = _attach_shm(res[1])
     try:
         return tuple(np.array(np.ndarray(shape, np.dtype(dt), buffer=shm.buf, offset=off)) for shape, dt, off in res[2])
     finally:
