@@ -536,7 +536,7 @@ def main():
     kw = dict(median_kernel_size=3, nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=5,
               batch_size=args.batch if args.batch > 0 else None)
     multi_cls = multigpu.DistributedEngine3d if os.environ.get("B200_EMPANADA_MULTIGPU") == "gather" else multigpu.ShardedEngine3d
-    eng = Engine3d(cfg, **kw) if world == 1 else multi_cls(cfg, **kw)
+    eng = Engine3d(cfg, **kw) if world == 1 else (multi_cls(cfg, gather_dense=False, **kw) if multi_cls is multigpu.ShardedEngine3d else multi_cls(cfg, **kw))
     vol_h = vol_d.cpu().numpy()
     launches = {"n": 0}
     counts = {}

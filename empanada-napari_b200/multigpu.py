@@ -351,11 +351,16 @@ class ShardedEngine3d(Engine3d):
     Raises when a shard would be shorter than the median kernel (use fewer ranks, or
     `DistributedEngine3d`, for very short stacks)."""
 
-    def __init__(self, *args, group=None, replicated_input=True, **kwargs):
+    def __init__(self, *args, group=None, replicated_input=True, gather_dense=True, **kwargs):
         super().__init__(*args, **kwargs)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        # gather_dense=False: the painted plane volumes stay sharded (sharded_consensus needs
+        # nothing else), and each plane is completed - label table broadcast, slabs painted - at
+        # the end of the NEXT plane's infer_on_axis, by when its tracker replay has long finished
+        self.gather_dense = gather_dense
+        self._finalize_launches = 0
         self._pending = {}
         self._slabs = {}
         self.front = None        # the MultiGPUEngine3d that drives this engine, if any
@@ -467,55 +472,65 @@ class ShardedEngine3d(Engine3d):
             job = _Async(tracking_replay, merged, post.cls, post.div, axis_name, self.merge_iou_thr,
                          self.merge_ioa_thr, self.min_size, self.min_extent)
         tm.mark("gather tables")
+        plane_trackers = self.create_trackers(shape3d, axis_name)
+        if not self.gather_dense:
+            for prev in list(self._pending.keys()):     # earlier planes: replay done behind this forward pass
+                self._finalize_plane(prev, False)
+            tm.mark("previous plane: broadcast + paint")
         if _PROFILE:
             print(f"[rank {self.rank}] {axis_name} " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
-        self._pending[axis_name] = (post, shape3d, (F, E), job)
+        self._pending[axis_name] = (post, shape3d, (F, E), job, plane_trackers)
         self.last_stats = {"kernel_launches": getattr(self.model, "launches", 0) - launches0 + post.launches}
-        return None, self.create_trackers(shape3d, axis_name)
+        return None, plane_trackers
 
-    def finalize(self, trackers, gather_dense=True):
+    def _finalize_plane(self, name, gather_dense):
+        """Collective: the leader's label table of plane `name` is broadcast, every rank paints
+        its slab, rank 0's tracker of the plane receives the instance table."""
+        from .postproc import LazyPlane
+        G, r = self.world, self.rank
+        post, shape3d, (F, E), job, plane_trackers = self._pending.pop(name)
+        leader = self.leader_of(name)
+        payload = [job.result() if r == leader else None]
+        dist.broadcast_object_list(payload, src=leader, group=self.group)
+        lut_f, kept_labels, kept_boxes, kept_sizes = payload[0]
+        e_lo, e_hi = E[r]
+        D, Hv, Wv = shape3d
+        local_shape = {"xy": (e_hi - e_lo, Hv, Wv), "xz": (D, e_hi - e_lo, Wv), "yz": (D, Hv, e_hi - e_lo)}[name]
+        n0 = post.launches
+        slab = post.relabel(np.ascontiguousarray(lut_f[e_lo:e_hi]), name, local_shape)
+        self._finalize_launches += post.launches - n0
+        self._slabs[name] = (slab, E, shape3d)
+        dense = self.gather_plane(name) if gather_dense else None
+        if r == 0:
+            tr = plane_trackers[0]
+            if dense is not None:
+                plane = LazyPlane(dense, name, kept_labels, kept_boxes)
+                tr._b200_dense = dense
+            else:
+                plane = ShardedPlane(self, tr, name, kept_labels, kept_boxes)
+            tr.instances = plane.attrs
+            tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, kept_sizes)}
+            tr._b200_sharded = self
+            tr.finish()
+
+    def finalize(self, trackers, gather_dense=None):
         """Collective: the plane leaders' label tables are broadcast and every rank paints its
         own slab of every plane (kept in `self._slabs` for `sharded_consensus`). With
-        `gather_dense` the slabs are also assembled into dense label volumes on rank 0, as the
-        single-GPU engine leaves them (`tracker_consensus`, per-plane RLE); without it rank 0's
-        trackers carry only the instance tables (boxes, sizes). Returns the trackers dict
-        (complete on rank 0)."""
-        from .postproc import LazyPlane
+        `gather_dense` (default: the constructor's value) the slabs are also assembled into dense
+        label volumes on rank 0, as the single-GPU engine leaves them (`tracker_consensus`,
+        per-plane RLE); without it rank 0's trackers carry only the instance tables (boxes, sizes).
+        Planes that were already completed at the end of a later `infer_on_axis` call (the engine
+        was constructed with `gather_dense=False`) are not touched again. Returns the trackers
+        dict (complete on rank 0; the tracker objects are the ones `infer_on_axis` returned)."""
         tm = _Timer()
-        G, r = self.world, self.rank
-        names = list(self._pending.keys())
-        n_launch = 0
-        for name in names:
-            post, shape3d, (F, E), job = self._pending[name]
-            leader = self.leader_of(name)
-            payload = [job.result() if r == leader else None]
-            dist.broadcast_object_list(payload, src=leader, group=self.group)
-            lut_f, kept_labels, kept_boxes, kept_sizes = payload[0]
-            e_lo, e_hi = E[r]
-            D, Hv, Wv = shape3d
-            local_shape = {"xy": (e_hi - e_lo, Hv, Wv), "xz": (D, e_hi - e_lo, Wv), "yz": (D, Hv, e_hi - e_lo)}[name]
-            n0 = post.launches
-            slab = post.relabel(np.ascontiguousarray(lut_f[e_lo:e_hi]), name, local_shape)
-            n_launch += post.launches - n0
-            self._slabs[name] = (slab, E, shape3d)
-            ax = self.axes[name]
-            dense = self.gather_plane(name) if gather_dense else None
-            if r == 0:
-                tr = trackers[name][0]
-                if dense is not None:
-                    plane = LazyPlane(dense, name, kept_labels, kept_boxes)
-                    tr._b200_dense = dense
-                else:
-                    plane = ShardedPlane(self, tr, name, kept_labels, kept_boxes)
-                tr.instances = plane.attrs
-                tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, kept_sizes)}
-                tr._b200_sharded = self
-                tr.finish()
-        self._pending = {}
+        gather_dense = self.gather_dense if gather_dense is None else gather_dense
+        for name in list(self._pending.keys()):
+            self._finalize_plane(name, gather_dense)
         tm.mark("replay + broadcast + paint" + (" + slabs to rank 0" if gather_dense else ""))
         if _PROFILE:
             print(f"[rank {self.rank}] finalize " + " ".join(f"{k}={v:.3f}" for k, v in tm.t.items()), flush=True)
-        self.last_stats = {"kernel_launches": n_launch}
+        self.last_stats = {"kernel_launches": self._finalize_launches}
+        self._finalize_launches = 0
         return trackers
 
     # ------------------------------------------------------------------ sharded consensus

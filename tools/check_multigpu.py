@@ -65,11 +65,20 @@ if rank == 0:
     ok &= same and len(outs[0][1]) > 0
 # the z-slab sharded consensus (every rank votes on its own slab) against the same reference
 if engine_cls is multigpu.ShardedEngine3d:
+    # gather_dense=False: planes stay sharded and are completed behind the next plane's forward pass
+    deng2 = multigpu.ShardedEngine3d(cfg, gather_dense=False, **kw)
     trackers = {}
     for name in ("xy", "xz", "yz"):
-        _, trackers[name] = deng.infer_on_axis(vol, name)
-    trackers = deng.finalize(trackers, gather_dense=False)
-    v, _, inst = deng.sharded_consensus(trackers, cfg, pixel_vote_thr=2, min_size=30, min_extent=3)
+        _, trackers[name] = deng2.infer_on_axis(vol, name)
+    trackers = deng2.finalize(trackers)
+    if rank == 0:
+        for name in ("xy", "xz", "yz"):
+            a, b = trackers[name][0], ref[name][0]
+            same = (list(a.instances.keys()) == list(b.instances.keys()) and a._b200_sizes == b._b200_sizes
+                    and all(tuple(a.instances[k]["box"]) == tuple(b.instances[k]["box"]) for k in a.instances))
+            print(name, "sharded tables equal", same)
+            ok &= bool(same)
+    v, _, inst = deng2.sharded_consensus(trackers, cfg, pixel_vote_thr=2, min_size=30, min_extent=3)
     if rank == 0:
         rv, rinst = outs[1]
         same = (np.array_equal(v.cpu().numpy(), rv) and list(inst.keys()) == list(rinst.keys())
