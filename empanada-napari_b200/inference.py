@@ -523,12 +523,11 @@ class Engine2d:
         self.engine.thing_list = [] if semantic_only else self.thing_list
         self.tile_size = tile_size
 
-    def infer_batch(self, images):
-        """images: uint8 array (n, h, w) -> int32 (n, h, w). One launch sequence for the batch."""
+    def _batch_post(self, images):
+        """Forward + per-slice post-processing + components of a batch of equally sized images:
+        returns the `PlanePost` (run_cc done), the class id and whether the class is stuff."""
         if len(self.labels) != 1 or list(self.engine.thing_list) not in ([], list(self.labels)):
             _unsupported("multi-class models")
-        if self.tile_size > 0 and any(s > self.tile_size for s in images.shape[1:]):
-            _unsupported("tiled 2-D inference")
         dev = self.device
         if isinstance(images, torch.Tensor):   # already resident (benchmarks / pipelines)
             if not images.is_cuda or images.dtype.is_floating_point or images.dtype == torch.bool:
@@ -553,7 +552,7 @@ class Engine2d:
         # tiles per launch list: whole SM waves on the 1/16 map, activation buffers within ~25 GB
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         chunk = max(1, min(n, auto_slice_batch(H, W, sms)))
-        launches0 = getattr(self.model, "launches", 0)
+        self._launches0 = getattr(self.model, "launches", 0)
         while True:
             post = PlanePost(n, h, w, H, W, ks=1, thing_class=cls, label_divisor=e.label_divisor,
                              void_label=e.void_label, nms_threshold=e.nms_threshold, nms_kernel=e.nms_kernel,
@@ -571,6 +570,14 @@ class Engine2d:
             except CenterOverflow as err:
                 e.center_cap = _next_pow2(err.needed)
         post.run_cc()
+        return post, cls, semantic
+
+    def infer_batch(self, images):
+        """images: integer array (n, h, w) -> int32 (n, h, w) device tensor. One launch sequence
+        for the batch (no tiling: every image is segmented whole)."""
+        post, cls, semantic = self._batch_post(images)
+        n, h, w = post.N, post.h, post.w
+        e = self.engine
         if semantic:
             # no thing classes: force_connected has nothing to relabel (inference.py:263-279)
             lut = np.full((n, post.cc_cap + 1), cls * e.label_divisor, dtype=np.int32)
@@ -578,8 +585,27 @@ class Engine2d:
         else:
             # force_connected: pan <- class*div + component id
             out = post.cc_images(0, n, add=cls * self.label_divisor)
-        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - launches0}
+        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - self._launches0}
         return out
+
+    def infer_tiled(self, image, layout=None):
+        """The tiled branch of `Engine2d.infer` (inference.py:283-318): tiles of `tile_size` with
+        at least min(128, 10 % of the tile) pixels of overlap, every tile segmented on its own
+        (run-length encoded with connected components, rle.py:26-86), objects that overlap across
+        tiles merged, single detections inside the overlap region dropped (consensus.py:524-626)
+        and the result rasterised. All tiles run as one batch. -> (h, w) int32 numpy array."""
+        from . import tiling
+        if image.ndim != 2:
+            raise ValueError("Engine2d.infer expects a 2-D image")
+        tiler = tiling.Tiler(image.shape, tile_size=self.tile_size,
+                             overlap_width=min(128, int(self.tile_size * 0.1)), layout=layout)
+        img_d = image if isinstance(image, torch.Tensor) else _as_device_volume(image, self.device)
+        tiles = torch.stack([img_d[y0:y1, x0:x1] for (y0, y1), (x0, x1) in zip(tiler.yranges, tiler.xranges)])
+        post, cls, semantic = self._batch_post(tiles)
+        out = tiling.merge_tiles(post, tiler, thing=not semantic, label_base=cls * self.engine.label_divisor)
+        self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - self._launches0,
+                           "tiles": len(tiler)}
+        return out.cpu().numpy().astype(np.int32)
 
     def infer_batch_host(self, images):
         """Host uint8 (n, h, w) in, host int32 (n, h, w) out (page-locked staging buffer)."""
@@ -588,6 +614,8 @@ class Engine2d:
     def infer(self, image):
         if image.ndim != 2:
             raise ValueError("Engine2d.infer expects a 2-D image")
+        if self.tile_size > 0 and any(s > self.tile_size for s in image.shape):
+            return self.infer_tiled(image)
         return self.infer_batch(image[None])[0].cpu().numpy().astype(np.int32)
 
 

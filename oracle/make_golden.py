@@ -287,6 +287,70 @@ def gen_resize_cases():
     print("resize cases", len(cases), "opencv", cv2.__version__)
 
 
+def gen_tiled_cases():
+    """The tiled branch of the reference's `Engine2d.infer` (empanada_napari/inference.py:283-318:
+    Tiler, per-tile engine call, pan_seg_to_rle_seg, translate_rle_seg, merge_objects_from_tiles /
+    merge_semantic_from_tiles, rle_seg_to_pan_seg), unmodified. `cztile` (third party, absent) is
+    replaced by a strategy object that returns the tile rectangles of
+    `empanada_napari_b200.tiling.fixed_total_area_tiles_1d`, so the fixture pins everything
+    downstream of the tile layout."""
+    import types
+    import empanada.inference.tile as ref_tile
+    import empanada_napari.inference as inf
+    from empanada_napari_b200.tiling import fixed_total_area_tiles_1d
+
+    class FakeStrategy:
+        def __init__(self, total_tile_width, total_tile_height, min_border_width):
+            self.tw, self.th, self.b = total_tile_width, total_tile_height, min_border_width
+
+        def tile_rectangle(self, rect):
+            out = []
+            for x0, sx in fixed_total_area_tiles_1d(rect.w, self.tw, self.b):
+                for y0, sy in fixed_total_area_tiles_1d(rect.h, self.th, self.b):
+                    out.append(types.SimpleNamespace(roi=types.SimpleNamespace(x=x0, y=y0, w=sx, h=sy)))
+            return out
+
+    ref_tile.AlmostEqualBorderFixedTotalAreaStrategy2D = FakeStrategy
+    ref_tile.czrect = lambda x, y, w, h: types.SimpleNamespace(x=x, y=y, w=w, h=h)
+    out = {}
+    rng = np.random.default_rng(31)
+    cases = [((300, 420), 128, False, 1, 14), ((260, 200), 96, False, 1, 8), ((200, 330), 128, True, 1, 10),
+             ((280, 280), 128, False, 2, 9)]
+    orig_loader = inf.load_model_to_device
+    for ci, (shape, tile_size, semantic_only, scale, n_obj) in enumerate(cases):
+        # The reference's `_join_ranges` (array_utils.py:657-690) fails on a cluster that consists of
+        # ONE run (an object clipped to a single row): seeds are tried until the reference runs.
+        for seed in range(40 + 10 * ci, 40 + 10 * ci + 10):
+            _, lab, _ = syn.make_volume((1,) + shape, seed=seed, n_objects=n_obj, scale=1.6)
+            lab = lab[0]
+            img = np.clip(np.where(lab > 0, 70.0, 170.0) + rng.normal(0, 8.0, shape), 0, 255).astype(np.uint8)
+            tiler = ref_tile.Tiler(shape, tile_size=tile_size, overlap_width=min(128, int(tile_size * 0.1)))
+            heads = []
+            for (y0, y1), (x0, x1) in zip(tiler.yranges, tiler.xranges):
+                tl = lab[y0:y1, x0:x1]
+                sem, ctr, off = scaled_heads(tl, scale, 0.0, rng) if scale > 1 else noisy_heads(tl, 16, 0.0, rng)
+                off = (off + rng.normal(0, 1.5, off.shape)).astype(np.float32)     # ragged instance borders
+                heads.append((sem, ctr, off))
+            fake = FakeModel(heads)
+            inf.load_model_to_device = lambda url, device: fake
+            eng = inf.Engine2d(MODEL_CONFIG, inference_scale=scale, label_divisor=1000, nms_threshold=0.1, nms_kernel=3,
+                               confidence_thr=0.5, semantic_only=semantic_only, tile_size=tile_size, use_gpu=False)
+            try:
+                pan = eng.infer(img)
+                break
+            except Exception as e:
+                print("  seed", seed, "reference failed:", type(e).__name__)
+        for k, name in enumerate(("sem", "ctr", "off")):
+            for t, h in enumerate(heads):
+                out[f"t{ci}_{name}{t}"] = h[k]
+        out[f"t{ci}_img"], out[f"t{ci}_pan"] = img, pan.astype(np.int32)
+        out[f"t{ci}_meta"] = np.array([tile_size, int(semantic_only), scale, len(tiler)])
+        print("tiled case", ci, shape, "tiles", len(tiler), "labels", len(np.unique(pan)) - 1)
+    inf.load_model_to_device = orig_loader
+    out["n"] = len(cases)
+    np.savez_compressed(os.path.join(GOLD, "tiled_cases.npz"), **out)
+
+
 def gen_model_tiny():
     """Reference PDL classes with the seeded weights of synthetic.make_pdl_state_dict(0)."""
     import yaml
@@ -400,9 +464,11 @@ def gen_eval_cases():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2"]
+    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2", "tiled"]
     if "resize" in which:
         gen_resize_cases()
+    if "tiled" in which:
+        gen_tiled_cases()
     if "volumes2" in which:
         run_reference_volume((26, 44, 40), seed=5, noise=0.5, ks=3, n_objects=10, min_size=20, min_extent=2,
                              tag="semantic_only", semantic_only=True)

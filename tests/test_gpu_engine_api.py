@@ -118,3 +118,30 @@ def test_render_engine3d_queue_protocol_vs_oracle():
             if a is not None:
                 assert a.dtype == torch.int64 and np.array_equal(a[0].cpu().numpy(), b)
         assert sum(a is None for a in got) == (ks - 1) // 2
+
+
+def test_tiled_inference_matches_reference_fixture():
+    """`Engine2d.infer` with tile_size > 0 on images larger than the tile (inference.py:283-318):
+    tests/golden/tiled_cases.npz holds the unmodified reference's output for the same tile layout
+    (oracle/make_golden.py gen_tiled_cases) - thing class with merging across tiles and the
+    overlap-region false-positive filter, semantic-only, and inference_scale 2."""
+    import torch
+    from empanada_napari_b200.inference import Engine2d
+    from empanada_napari_b200.model import SyntheticHeadsModel
+    z = np.load(os.path.join(GOLDEN, "tiled_cases.npz"))
+    dev = torch.device("cuda:0")
+    for ci in range(int(z["n"])):
+        tile_size, semantic_only, scale, n_tiles = (int(v) for v in z[f"t{ci}_meta"])
+        sem = torch.from_numpy(np.stack([z[f"t{ci}_sem{t}"][0] for t in range(n_tiles)])).to(dev)
+        ctr = torch.from_numpy(np.stack([z[f"t{ci}_ctr{t}"] for t in range(n_tiles)])).to(dev)
+        off = torch.from_numpy(np.stack([z[f"t{ci}_off{t}"] for t in range(n_tiles)])).to(dev)
+        cfg = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 16,
+               "norms": {"mean": 0.57571, "std": 0.12765},
+               "model": SyntheticHeadsModel(lambda a, s0, s1: (sem[s0:s1], ctr[s0:s1], off[s0:s1]))}
+        eng = Engine2d(cfg, inference_scale=scale, label_divisor=1000, nms_threshold=0.1, nms_kernel=3,
+                       confidence_thr=0.5, semantic_only=bool(semantic_only), tile_size=tile_size)
+        img = z[f"t{ci}_img"]
+        out = eng.infer(img)
+        assert eng.last_stats["tiles"] == n_tiles
+        assert out.dtype == np.int32 and out.shape == img.shape
+        assert np.array_equal(out, z[f"t{ci}_pan"]), ci
