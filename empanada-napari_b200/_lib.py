@@ -63,6 +63,11 @@ _SIGNATURES = {
     "be_sort_records": ([P, P, P, P, LL, P, SZ, POINTER(SZ), P], I),
     "be_join_flags": ([P, P, LL, P, P, P, SZ, POINTER(SZ), P], I),
     "be_join_write": ([P, P, P, P, LL, P, P, P, P], I),
+    # morph_kernels.cu
+    "be_morph3d": ([P, P, I, I, I, I, P], I),
+    "be_range_keep": ([P, LL, I, I, P], I),
+    "be_runs3d_cc": ([P, P, P, I, I, I, I, P, P, P, P], I),
+    "be_fill_holes": ([P, P, I, I, I, P, P, P, P], I),
     # match_replay.cpp (host)
     "be_match_replay": ([I, P, P, I, P, P, LL, I, I, D, D, I, P, I, P, P, P, I, P], I),
 }

@@ -330,8 +330,8 @@ class Engine3d:
     def _check_supported(self, sharded=False):
         if sharded and self.inference_scale != 1:
             _unsupported("inference_scale > 1 in the slice-sharded multi-GPU engine")
-        if self.label_erosion or self.label_dilation or self.fill_holes_in_segmentation:
-            _unsupported("tracker morphology (erode / dilate / fill holes)")
+        if sharded and (self.label_erosion or self.label_dilation or self.fill_holes_in_segmentation):
+            _unsupported("tracker morphology in the slice-sharded multi-GPU engine")
         if len(self.labels) != 1 or list(self.engine.thing_list) not in ([], list(self.labels)):
             _unsupported("multi-class models")
 
@@ -429,6 +429,11 @@ class Engine3d:
         prof.mark("runs + tracker dict")
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
         tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, sizes[keep])}
+        if self.label_erosion > 0 or self.label_dilation > 0 or self.fill_holes_in_segmentation:
+            from . import morphology       # filters.erode / dilate / fill_holes (inference.py:560-570)
+            morphology.apply_to_tracker(tr, dense, post.cls, self.label_divisor, not post.semantic,
+                                        self.label_erosion, self.label_dilation, self.fill_holes_in_segmentation)
+            prof.mark("tracker morphology")
 
     def infer_on_axis(self, volume, axis_name):
         self._check_supported()

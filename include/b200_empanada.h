@@ -204,6 +204,21 @@ int be_vote_paint(const int* va, const int* vb, const int* vc, const int* la, co
 int be_label_hist(const int* vol, long long n, int W, int nbins, int* hist, be_stream st);
 int be_lut_inplace(int* vol, long long n, const int* lut, int nlut, be_stream st);
 
+/* ---- tracker-level morphology (csrc/morph_kernels.cu; empanada/inference/filters.py:154-210 as
+ * applied by Engine3d.infer_on_axis, empanada_napari/inference.py:560-570). be_morph3d: one grey
+ * erosion (op 0) / dilation (op 1) pass with the 3-D cross on a (D,H,W) int32 label volume.
+ * be_range_keep: labels outside [lo, hi) -> 0 (filters.py:96-103). be_runs3d_cc: 26-connected
+ * equal-value components over the row runs of the volume (skimage.measure.label in 3-D,
+ * filters.py:15-20,105-107), root = raster-first run of the component. be_fill_holes: the
+ * per-slice, per-label bounding-box hole filling of filters.py:174-210 (scipy binary_fill_holes),
+ * labels ascending per slice in CSR form (slice_off [D+1], labels, boxes y0 x0 y1 x1). */
+int be_morph3d(const int* src, int* dst, int D, int H, int W, int op, be_stream st);
+int be_range_keep(int* vol, long long n, int lo, int hi, be_stream st);
+int be_runs3d_cc(const long long* run_start, const long long* run_end, const int* run_val, int n_runs,
+                 int D, int H, int W, int* row_ptr, int* L, int* root, be_stream st);
+int be_fill_holes(int* vol, uint8_t* scratch, int D, int H, int W, const int* slice_off,
+                  const int* labels, const int* boxes, be_stream st);
+
 #ifdef __cplusplus
 }
 #endif

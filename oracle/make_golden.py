@@ -171,7 +171,8 @@ def scaled_heads(label_slice, scale, noise, rng):
 
 
 def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent, tag, pixel_vote_thr=2,
-                         allow_one_view=False, semantic_only=False, inference_scale=1):
+                         allow_one_view=False, semantic_only=False, inference_scale=1, erosion=0, dilation=0,
+                         fill_holes=False):
     """Engine3d.infer_on_axis x3 + tracker_consensus + stack_postprocessing, unmodified."""
     import empanada_napari.inference as inf
 
@@ -179,7 +180,8 @@ def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent
     out = {"shape": np.array(shape), "seed": seed, "noise": noise, "ks": ks, "n_objects": n_objects,
            "min_size": min_size, "min_extent": min_extent, "pixel_vote_thr": pixel_vote_thr,
            "allow_one_view": int(allow_one_view), "semantic_only": int(semantic_only),
-           "inference_scale": int(inference_scale)}
+           "inference_scale": int(inference_scale), "erosion": int(erosion), "dilation": int(dilation),
+           "fill_holes": int(fill_holes)}
     rng = np.random.default_rng(seed + 100)
     trackers = {}
     orig_loader = inf.load_model_to_device
@@ -197,7 +199,8 @@ def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent
         inf.load_model_to_device = lambda url, device: fake
         eng = inf.Engine3d(MODEL_CONFIG, inference_scale=inference_scale, label_divisor=1000, median_kernel_size=ks,
                            nms_threshold=0.1, nms_kernel=3, confidence_thr=0.5, min_size=min_size,
-                           min_extent=min_extent, use_gpu=False, save_panoptic=True, semantic_only=semantic_only)
+                           min_extent=min_extent, use_gpu=False, save_panoptic=True, semantic_only=semantic_only,
+                           label_erosion=erosion, label_dilation=dilation, fill_holes_in_segmentation=fill_holes)
         stack, trs = eng.infer_on_axis(vol, axis_name)
         trackers[axis_name] = trs
         out[f"{axis_name}_stack"] = stack.astype(np.int32)
@@ -464,7 +467,7 @@ def gen_eval_cases():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2", "tiled"]
+    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2", "tiled", "morph"]
     if "resize" in which:
         gen_resize_cases()
     if "tiled" in which:
@@ -476,6 +479,13 @@ if __name__ == "__main__":
                              tag="scale2", inference_scale=2)
         run_reference_volume((32, 70, 61), seed=7, noise=0.3, ks=1, n_objects=8, min_size=20, min_extent=2,
                              tag="scale4_semantic", inference_scale=4, semantic_only=True)
+    if "morph" in which:
+        run_reference_volume((26, 44, 40), seed=8, noise=0.5, ks=3, n_objects=12, min_size=20, min_extent=2,
+                             tag="erode1", erosion=1)
+        run_reference_volume((24, 40, 36), seed=9, noise=0.5, ks=3, n_objects=12, min_size=20, min_extent=2,
+                             tag="dilate2_fill", dilation=2, fill_holes=True)
+        run_reference_volume((22, 48, 40), seed=10, noise=0.7, ks=1, n_objects=10, min_size=10, min_extent=2,
+                             tag="erode1_dilate1_fill", erosion=1, dilation=1, fill_holes=True)
     if "eval" in which:
         gen_eval_cases()
     if "post" in which:

@@ -27,7 +27,7 @@ def infer_on_axis(volume, axis_name, heads_fn, model_config, label_divisor=1000,
                   median_kernel_size=3, stuff_area=64, void_label=0, nms_threshold=0.1,
                   nms_kernel=3, confidence_thr=0.5, min_size=500, min_extent=4,
                   save_panoptic=True, dtype=np.int32, fine_boundaries=False, semantic_only=False,
-                  inference_scale=1):
+                  inference_scale=1, label_erosion=0, label_dilation=0, fill_holes_in_segmentation=False):
     """`fine_boundaries=True`: `heads_fn` returns FULL-resolution ctr_hmp / offsets (the model's
     `interpolate_ins=True` output) and pixels are grouped with step 1 (engines.py:263-275).
     `semantic_only`: engine thing_list = [] (inference.py:365-368). `inference_scale` s: slices go
@@ -62,6 +62,17 @@ def infer_on_axis(volume, axis_name, heads_fn, model_config, label_divisor=1000,
         tr.finish()
         remove_small_objects(tr, min_size=min_size)
         remove_pancakes(tr, min_span=min_extent)
+    # tracker morphology (empanada_napari/inference.py:560-570)
+    from . import tracking as _t
+    if label_erosion > 0:
+        for tr in trackers:
+            _t.erode(tr, volume.shape, labels, label_divisor, thing_list, iterations=label_erosion)
+    if label_dilation > 0:
+        for tr in trackers:
+            _t.dilate(tr, volume.shape, labels, label_divisor, thing_list, iterations=label_dilation)
+    if fill_holes_in_segmentation:
+        for tr in trackers:
+            _t.fill_holes_in_segmentation(tr, volume.shape, labels, label_divisor, thing_list)
     stack = None
     if save_panoptic:
         stack = np.zeros(volume.shape, dtype=dtype)

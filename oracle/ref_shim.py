@@ -4,9 +4,10 @@ TEST INFRASTRUCTURE ONLY. Used by `oracle/make_golden.py` (fixture generation) a
 pinning tests when /root/reference is present. Nothing in the product package imports this.
 
 The reference imports third-party packages that are absent from this image (scikit-image,
-zarr, dask, cztile, napari, ...). Only two functions of those are on the hot path:
-`skimage.measure.label` and `skimage.measure.regionprops` (call sites
-empanada/inference/rle.py:22,75). They are re-stated here from their documented behaviour
+zarr, dask, cztile, napari, ...). Only these are on the hot path: `skimage.measure.label` and `skimage.measure.regionprops` (call
+sites empanada/inference/rle.py:22,75, filters.py:18,109) and, for the tracker morphology options,
+`skimage.morphology.erosion` / `dilation` with their default footprint (filters.py:158,168 -
+re-stated as scipy's grey erosion / dilation with the cross, borders reflected). They are re-stated here from their documented behaviour
 (8-connected components of EQUAL-valued pixels, numbered in raster order of first pixel;
 regionprops ascending by label, half-open bbox, row-major coords). scikit-image itself is a
 lower-bounded, un-vendored dependency (setup.cfg:50) whose results are not pinned by any
@@ -64,6 +65,21 @@ def sk_label(seg, background=0, connectivity=None):
         m = lab > 0
         out[m] = lut[lab[m]]
     return out
+
+
+# ----------------------------------------------------------------------------- skimage.morphology
+def sk_erosion(image, footprint=None, out=None):
+    """skimage.morphology.erosion with its default footprint (the cross,
+    ndi.generate_binary_structure(ndim, 1)): scipy's grey erosion, borders reflected."""
+    from scipy import ndimage as ndi
+    fp = ndi.generate_binary_structure(np.asarray(image).ndim, 1) if footprint is None else footprint
+    return ndi.grey_erosion(image, footprint=fp)
+
+
+def sk_dilation(image, footprint=None, out=None):
+    from scipy import ndimage as ndi
+    fp = ndi.generate_binary_structure(np.asarray(image).ndim, 1) if footprint is None else footprint
+    return ndi.grey_dilation(image, footprint=fp)
 
 
 class _RegionProp:
@@ -127,7 +143,7 @@ def install():
         except Exception:
             sk = _stub("skimage")
             sk.measure = _stub("skimage.measure", label=sk_label, regionprops=sk_regionprops)
-            sk.morphology = _stub("skimage.morphology", erosion=_notimpl, dilation=_notimpl,
+            sk.morphology = _stub("skimage.morphology", erosion=sk_erosion, dilation=sk_dilation,
                                   remove_small_objects=_notimpl, binary_erosion=_notimpl,
                                   binary_dilation=_notimpl)
             sk.draw = _stub("skimage.draw")

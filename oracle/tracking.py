@@ -303,3 +303,84 @@ def instance_relabel(tracker):
         out[iid] = {"box": attrs["box"], "starts": cat[:, 0], "runs": cat[:, 1]}
         iid += 1
     return out
+
+
+# --------------------------------------------------------------------------- tracker morphology
+def rle_seg_to_pan_seg3d(tracker, shape):
+    """filters.py:120-152: every instance's runs painted in dictionary order (uint32 volume)."""
+    pan = np.zeros(shape, dtype=np.uint32).ravel()
+    for object_id, attrs in tracker.instances.items():
+        for s, r in zip(attrs["starts"], attrs["runs"]):
+            pan[s:s + r] = object_id
+    return pan.reshape(shape)
+
+
+def pan_seg_to_rle_seg3d(pan_seg, labels, label_divisor, thing_list, force_connected=True):
+    """filters.py:58-118 (n-dimensional form of rle.py:26-86; returns the flat instance dict)."""
+    instance_attrs = {}
+    for label in labels:
+        lo = label * label_divisor
+        hi = lo + label_divisor
+        ins = pan_seg.copy()
+        ins[np.logical_or(pan_seg < lo, pan_seg >= hi)] = 0
+        if force_connected and label in thing_list:
+            ins = connected_components(ins)
+            ins[ins > 0] += lo
+        flat = ins.ravel()
+        idx = np.flatnonzero(flat)
+        vals = flat[idx]
+        order = np.argsort(vals, kind="stable")
+        idx_s, vals_s = idx[order], vals[order]
+        bounds = np.flatnonzero(np.r_[True, vals_s[1:] != vals_s[:-1], True]) if len(vals_s) else np.zeros(1, int)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            coords = np.unravel_index(idx_s[a:b], ins.shape)
+            box = tuple(int(c.min()) for c in coords) + tuple(int(c.max()) + 1 for c in coords)
+            starts, runs = rle_encode(idx_s[a:b])
+            instance_attrs[int(vals_s[a])] = {"box": box, "starts": starts, "runs": runs}
+    return instance_attrs
+
+
+def _cross(ndim):
+    from scipy import ndimage as ndi
+    return ndi.generate_binary_structure(ndim, 1)
+
+
+def erode(tracker, shape, labels, label_divisor, thing_list, iterations=1):
+    """filters.py:154-163; skimage.morphology.erosion with the default footprint = grey erosion
+    with the cross, borders reflected (third party, re-stated: see oracle/ref_shim.py)."""
+    from scipy import ndimage as ndi
+    mask = rle_seg_to_pan_seg3d(tracker, shape)
+    for _ in range(iterations):
+        mask = ndi.grey_erosion(mask, footprint=_cross(mask.ndim))
+    tracker.instances = pan_seg_to_rle_seg3d(mask, labels, label_divisor, thing_list)
+    return tracker
+
+
+def dilate(tracker, shape, labels, label_divisor, thing_list, iterations=1):
+    """filters.py:165-172."""
+    from scipy import ndimage as ndi
+    mask = rle_seg_to_pan_seg3d(tracker, shape)
+    for _ in range(iterations):
+        mask = ndi.grey_dilation(mask, footprint=_cross(mask.ndim))
+    tracker.instances = pan_seg_to_rle_seg3d(mask, labels, label_divisor, thing_list)
+    return tracker
+
+
+def fill_holes_in_segmentation(tracker, shape, labels, label_divisor, thing_list):
+    """filters.py:174-210: slice by slice along axis 0, labels ascending, each inside its bounding
+    box of the unmodified slice; every non-zero pixel of the box and every hole takes the label."""
+    from scipy.ndimage import binary_fill_holes
+    mask3d = rle_seg_to_pan_seg3d(tracker, shape)
+    for z in range(mask3d.shape[0]):
+        mask = mask3d[z]
+        boxes = []
+        for l in np.unique(mask):
+            if l > 0:
+                yy, xx = np.nonzero(mask == l)
+                boxes.append((l, yy.min(), xx.min(), yy.max() + 1, xx.max() + 1))
+        for l, y0, x0, y1, x1 in boxes:
+            tmp = binary_fill_holes(mask[y0:y1, x0:x1].astype(bool))
+            mask[y0:y1, x0:x1] = tmp.astype(mask.dtype) * l
+        mask3d[z] = mask
+    tracker.instances = pan_seg_to_rle_seg3d(mask3d, labels, label_divisor, thing_list)
+    return tracker

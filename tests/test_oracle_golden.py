@@ -96,7 +96,8 @@ def test_median_queue_matches_reference():
         assert np.array_equal(np.stack(ys), z[f"m{i}_y"])
 
 
-VOLUME_TAGS = ["clean", "noisy", "ks5_odd", "semantic_only", "scale2", "scale4_semantic"]
+VOLUME_TAGS = ["clean", "noisy", "ks5_odd", "semantic_only", "scale2", "scale4_semantic", "erode1", "dilate2_fill",
+               "erode1_dilate1_fill"]
 
 
 def test_resize_by_factor_matches_opencv_fixture():
@@ -123,7 +124,10 @@ def test_volume_pipeline_matches_reference(tag):
             median_kernel_size=int(z["ks"]), nms_kernel=3, confidence_thr=0.5,
             min_size=int(z["min_size"]), min_extent=int(z["min_extent"]),
             semantic_only=bool(z["semantic_only"]) if "semantic_only" in z else False,
-            inference_scale=int(z["inference_scale"]) if "inference_scale" in z else 1)
+            inference_scale=int(z["inference_scale"]) if "inference_scale" in z else 1,
+            label_erosion=int(z["erosion"]) if "erosion" in z else 0,
+            label_dilation=int(z["dilation"]) if "dilation" in z else 0,
+            fill_holes_in_segmentation=bool(z["fill_holes"]) if "fill_holes" in z else False)
         assert_instances_equal(trs[0].instances, unpack_instances(z, f"{axis_name}_tr_"))
         assert np.array_equal(stack, z[f"{axis_name}_stack"])
         trackers[axis_name] = trs
