@@ -699,7 +699,7 @@ def _export_arrays(arrays, exports):
 
 def _import_arrays(res):
     """Root side of `_export_arrays`: copies the arrays out of the peer's segment."""
-    if not (isinstance(res, tuple) and len(res) == 3 and res[0] == "__b200_shm__"):
+    if not (isinstance(res, tuple) and len(res) == 3 and isinstance(res[0], str) and res[0] == "__b200_shm__"):
         return res
     shm = _attach_shm(res[1])
     try:
