@@ -446,9 +446,12 @@ class _NetModel:
         plan = self.plans.pop(key, None)
         skip = 0
         if plan is None:
-            # tail batch: replay a longer list of the same slice shape over [s1 - Bp, s1)
+            # tail batch: replay a longer list of the same slice shape over [s1 - Bp, s1) when that
+            # recomputes little (at most a third more slices); a short tail gets its own list -
+            # with G ranks a plane has G tails, and replaying the full list for each would waste
+            # up to a whole batch per rank (+15 % forward time at 8 ranks on 1024 slices)
             for k2 in list(self.plans.keys()):
-                if k2[1:] == shape_key and k2[0] > B and s1 - k2[0] >= 0:
+                if k2[1:] == shape_key and k2[0] > B and s1 - k2[0] >= 0 and 3 * (k2[0] - B) <= k2[0]:
                     key, plan = k2, self.plans.pop(k2)
                     skip = k2[0] - B
                     break
