@@ -244,7 +244,7 @@ class _SharedHostVolume:
                 except OSError:
                     room = 0
                 if room > nbytes + (64 << 20):
-                        self.shm = shared_memory.SharedMemory(create=True, size=nbytes,
+                    self.shm = shared_memory.SharedMemory(create=True, size=nbytes,
                                                           name=f"b200emp_{os.getpid()}_{id(self):x}_{self.serial}")
                     self.shape = shape
             name[0] = self.shm.name if self.shm is not None else None
