@@ -174,6 +174,40 @@ def stream_to_device(volume, device, slab_bytes=256 << 20):
     return out
 
 
+class _Upload:
+    """Progress of a chunked background host->device copy: `publish` (copy thread) announces that
+    slices [0, z) are enqueued behind `event`; `wait(z)` (consumer) blocks until that is so and
+    returns the event to order a stream after."""
+
+    def __init__(self, depth):
+        self.depth, self.done, self.event, self.error = depth, 0, None, None
+        self.cond = threading.Condition()
+        self.thread = None
+
+    def publish(self, z, event):
+        with self.cond:
+            self.done, self.event = z, event
+            self.cond.notify_all()
+
+    def fail(self, error):
+        with self.cond:
+            self.error = error
+            self.cond.notify_all()
+
+    def wait(self, z_end):
+        need = self.depth if z_end is None else min(int(z_end), self.depth)
+        with self.cond:
+            while self.done < need and self.error is None:
+                self.cond.wait()
+            if self.error is not None:
+                raise self.error
+            return self.event
+
+    def complete(self):
+        with self.cond:
+            return self.done >= self.depth
+
+
 class _VolumeCache:
     """Keeps the input volume resident in HBM across the xy/xz/yz passes of ONE host array.
 
@@ -187,6 +221,8 @@ class _VolumeCache:
         self.sig = None
         self.dev = None
         self.lazy = None      # strong reference to a zarr / dask volume whose copy is cached
+        self.upload = None    # chunked background copy in flight (`_Upload`)
+        self.streamed = os.environ.get("B200_EMPANADA_STREAMED_UPLOAD", "1") == "1"
 
     @staticmethod
     def _signature(volume):
@@ -222,9 +258,53 @@ class _VolumeCache:
         return self.dev
 
     def _upload(self, volume, device):
-        return _as_device_volume(volume, device)
+        """Host -> device copy of a numpy volume. Large volumes are copied by a background thread
+        in z-chunks on a side stream, so the first (xy) plane's forward pass starts on the first
+        chunk instead of waiting for the whole pageable copy (`ready` orders the consumers)."""
+        if (not self.streamed or volume.nbytes < (256 << 20) or not np.issubdtype(volume.dtype, np.integer)
+                or not volume.flags.c_contiguous):
+            return _as_device_volume(volume, device)
+        dev_t = torch.empty(volume.shape, dtype=torch.from_numpy(volume[:1, :1, :1]).dtype, device=device)
+        D = int(volume.shape[0])
+        step = max(1, (64 << 20) // max(1, volume[0].nbytes))
+        up = _Upload(D)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))   # the block may still be in use by queued work
+
+        def run():
+            try:
+                with torch.cuda.device(device), torch.cuda.stream(side):
+                    for z0 in range(0, D, step):
+                        z1 = min(D, z0 + step)
+                        dev_t[z0:z1].copy_(torch.from_numpy(volume[z0:z1]))
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        up.publish(z1, ev)
+            except BaseException as e:   # surfaced by the next `ready` call
+                up.fail(e)
+        up.thread = threading.Thread(target=run, daemon=True)
+        up.thread.start()
+        self.upload = up
+        return dev_t
+
+    def ready(self, z_end=None):
+        """Makes the current stream wait until slices [0, z_end) of the cached volume (everything
+        when None) have arrived. No-op when there is no copy in flight."""
+        up = self.upload
+        if up is None:
+            return
+        ev = up.wait(z_end)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        if up.complete():
+            up.thread.join()
+            self.upload = None
 
     def clear(self):
+        if self.upload is not None:
+            self.upload.wait(None)
+            self.upload.thread.join()
+            self.upload = None
         self.ref, self.sig, self.dev, self.lazy = None, None, None, None
 
 
@@ -461,11 +541,16 @@ class Engine3d:
         bs = self.slice_batch(post.H, post.W)
         sc = int(self.inference_scale)
         kw = {}
+        streamed_xy = axis == 0 and sc == 1        # z-slices can be consumed while the upload runs
+        if not streamed_xy:
+            self._cache.ready()
         if sc > 1:   # down-sampled slices become an xy stack; PointRend renders back up
             kw = {"render_steps": int(2 + math.log(sc, 2)), "plane_axis": axis}
             vol_d, axis = downsample_slices(vol_d, axis, sc), 0
         for s0 in range(0, n, bs):
             s1 = min(n, s0 + bs)
+            if streamed_xy:
+                self._cache.ready(s1)
             sem, ctr, off = self.model.forward_slices(vol_d, axis, s0, s1, norms, pf, **kw)
             if not self.engine.coarse_boundaries:
                 ctr, off = upsample_instance_heads(ctr, off)

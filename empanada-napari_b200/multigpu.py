@@ -96,6 +96,7 @@ class DistributedEngine3d(Engine3d):
     def infer_on_axis(self, volume, axis_name):
         self._check_supported()
         axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
+        self._cache.ready()
         leader = self.leader_of(axis_name)
         ranges = slice_ranges(n, self.world)
         lo, hi = ranges[self.rank]
@@ -400,6 +401,7 @@ class ShardedEngine3d(Engine3d):
         if len(self.engine.thing_list) == 0:
             raise _lib_error("semantic-only inference is not built in the slice-sharded multi-GPU engine")
         axis, vol_d, shape3d, n, h, w, H, W, pf = self._plane_setup(volume, axis_name)
+        self._cache.ready()
         ks = self.median_kernel_size
         mid = (ks - 1) // 2
         G, r = self.world, self.rank
@@ -914,6 +916,7 @@ class MultiGPUEngine3d:
         self._send("infer", axis_name, tuple(vol_d.shape), str(vol_d.dtype).replace("torch.", ""), self._version,
                    bool(self.save_panoptic))
         if fresh:
+            eng._cache.ready()           # the chunked upload has to be complete before it is broadcast
             dist.broadcast(vol_d, src=0)
         _, trackers = eng.infer_on_axis(vol_d, axis_name)
         trackers = eng.finalize({axis_name: trackers}, gather_dense=bool(self.save_panoptic))[axis_name]
