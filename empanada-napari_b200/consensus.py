@@ -620,14 +620,14 @@ def merge_overlapping_candidates(cands, csize, cpair):
 
 
 def membership_tables(cands, n_nodes):
-    """node (1-based) -> candidate ids (1-based) as CSR host arrays."""
-    memb = [[] for _ in range(n_nodes + 2)]
-    for cid, (_, cluster, _) in enumerate(cands, start=1):
-        for m in cluster:
-            memb[m + 1].append(cid)
+    """node (1-based) -> candidate ids (1-based) as CSR host arrays (ids ascending per node)."""
+    sizes = np.fromiter((len(c[1]) for c in cands), dtype=np.int64, count=len(cands))
+    nodes = np.fromiter((m for c in cands for m in c[1]), dtype=np.int64, count=int(sizes.sum())) + 1
+    cids = np.repeat(np.arange(1, len(cands) + 1, dtype=np.int64), sizes)
+    order = np.argsort(nodes, kind="stable")          # stable: candidate ids stay ascending per node
     memb_off = np.zeros(n_nodes + 3, dtype=np.int32)
-    memb_off[1:] = np.cumsum([len(m) for m in memb])
-    memb_list = np.array([c for m in memb for c in m] or [0], dtype=np.int32)
+    memb_off[1:] = np.cumsum(np.bincount(nodes, minlength=n_nodes + 2))
+    memb_list = cids[order].astype(np.int32) if len(cids) else np.array([0], dtype=np.int32)
     return memb_off, memb_list
 
 
@@ -671,12 +671,13 @@ def keep_mask(final_boxes, fsize, n_final, min_size, min_extent):
     """filters.remove_small_objects / remove_pancakes (filters.py:22-56) on the tables."""
     keep = np.ones(n_final + 1, dtype=bool)
     keep[0] = False
-    for fid in range(1, n_final + 1):
-        b = final_boxes[fid]
-        if min_size is not None and fsize[fid] < min_size:
-            keep[fid] = False
-        if min_extent is not None and any(s < min_extent for s in (b[3] - b[0], b[4] - b[1], b[5] - b[2])):
-            keep[fid] = False
+    if n_final == 0:
+        return keep
+    b = np.array([final_boxes[fid] for fid in range(1, n_final + 1)], dtype=np.int64).reshape(n_final, 6)
+    if min_size is not None:
+        keep[1:] &= np.asarray(fsize[1:n_final + 1]) >= min_size
+    if min_extent is not None:
+        keep[1:] &= ((b[:, 3:] - b[:, :3]) >= min_extent).all(axis=1)
     return keep
 
 
