@@ -780,6 +780,9 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if hasattr(eng, "close"):
+            out = None
+            eng.close()
         dist.destroy_process_group()
 
 

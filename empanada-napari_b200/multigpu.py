@@ -372,6 +372,10 @@ class ShardedEngine3d(Engine3d):
     def leader_of(self, axis_name):
         return (self.axes[axis_name] + 1) % self.world
 
+    def close(self):
+        """Releases the shared host result volume (rank 0 unlinks the segment)."""
+        self._host_out.close()
+
     def gather_plane(self, name):
         """Collective: the painted slabs of plane `name` assembled on rank 0 (None elsewhere)."""
         G, r = self.world, self.rank
