@@ -57,13 +57,22 @@ def random_stack(rng, n, h, w, mode):
             pan[4:10, w - 10 - off:w - 4 - off] = 1002
             if t % 2:
                 pan[4:10, 10 + off:w - 10 - off] = 1003
+        if mode == "lattice":    # a row of identical squares, shifted by half a period every slice:
+            # each square overlaps two squares of the neighbouring slice EQUALLY, so the IoU matrix
+            # has several optimal assignments (linear_sum_assignment tie order, matcher.py:213)
+            pan = np.zeros((h, w), dtype=np.int64)
+            period, side = 8, 6
+            shift = (period // 2) * (t % 2)
+            for j, x0 in enumerate(range(shift, w - side, period)):
+                pan[3:3 + side, x0:x0 + side] = 1001 + j
+                pan[h - 3 - side:h - 3, x0:x0 + side] = 1100 + j
         if mode == "noise":
             pan[rng.random((h, w)) < 0.08] = 0
         stack.append(pan)
     return stack
 
 
-@pytest.mark.parametrize("mode", ["plain", "flicker", "noise", "symmetric"])
+@pytest.mark.parametrize("mode", ["plain", "flicker", "noise", "symmetric", "lattice"])
 @pytest.mark.parametrize("axis_name", ["xy", "xz", "yz"])
 def test_replay_matches_oracle(mode, axis_name):
     from empanada_napari_b200 import tracking
