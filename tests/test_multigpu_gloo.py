@@ -46,3 +46,38 @@ def test_gather_two_ranks_gloo(tmp_path):
     mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
     out = np.load(tmp_path / "out.npy")
     assert np.array_equal(out, np.arange(n * 6, dtype=np.float32).reshape(n, 2, 3))
+
+
+def _export_child(q_out, q_in):
+    import numpy as np
+    from empanada_napari_b200 import multigpu as m
+    exports = []
+    arrays = (np.arange(400000, dtype=np.int32), np.arange(400000, dtype=np.int64) * 7, np.ones(400000, np.int64))
+    q_out.put(m._export_arrays(arrays, exports))
+    q_in.get()                   # the parent has read the segment
+    m._release_exports(exports)
+    q_out.put("released")
+
+
+def test_large_tables_cross_processes_through_shared_memory():
+    """The per-rank range tables of the sharded consensus travel as a shared-memory descriptor:
+    written by one process, read (copied out) by another, unlinked by the writer."""
+    import multiprocessing as mp
+    import numpy as np
+    from empanada_napari_b200 import multigpu as m
+    ctx = mp.get_context("spawn")
+    q_out, q_in = ctx.Queue(), ctx.Queue()
+    p = ctx.Process(target=_export_child, args=(q_out, q_in))
+    p.start()
+    desc = q_out.get(timeout=120)
+    assert desc[0] == "__b200_shm__"
+    got = m._import_arrays(desc)
+    assert np.array_equal(got[0], np.arange(400000, dtype=np.int32)) and got[0].dtype == np.int32
+    assert np.array_equal(got[1], np.arange(400000, dtype=np.int64) * 7) and np.all(got[2] == 1)
+    q_in.put("read")
+    assert q_out.get(timeout=60) == "released"
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    # tuples of plain arrays are passed through untouched
+    t = (np.arange(3), np.arange(3), np.arange(3))
+    assert m._import_arrays(t) is t
