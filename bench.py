@@ -701,14 +701,15 @@ def main():
         achieved = conv_fl / (conv_ms * 1e-3) * 1e-12
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture of the same launch list
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))
+            traffic_file = "r02_conv_traffic.json"
+            tr = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
             if S == 1024 and int(tr.get("batch_slices", 0)) == B:
                 traffic = float(tr["traffic_bytes_per_launch"])
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
+                "traffic_source": "profiles/r02_conv_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                 "per_launch": {"launches_per_batch": n_conv, "avg_ms": conv_ms / n_conv,
                                "flops_per_batch": conv_fl, "batch_slices": B},
