@@ -519,8 +519,9 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=0, help="slices per launch list (0 = engine default: whole SM waves)")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-slices", type=int, default=3,
-                    help="full-size slices per plane in one CPU sample step (>= the median kernel)")
+    ap.add_argument("--cpu-slices", type=int, default=0,
+                    help="full-size slices per plane in one CPU sample step (0: 3 for the cpu_baseline leg; for "
+                         "--impl reference the largest of 3 / 2 / 1 that keeps steps + warmup within ~200 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-2d", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the NucleoNet + DropNet anisotropic secondary figure")
@@ -545,7 +546,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = CpuSample(S, n=args.cpu_slices)
+        n_cpu = args.cpu_slices
+        if n_cpu <= 0:
+            # bounded run: one calibration step with a single slice per plane, then the largest
+            # sample whose steps + warmup stay within a few minutes on this host
+            probe = CpuSample(S, n=1)
+            t1 = probe.step()
+            t1 = min(t1, probe.step())
+            n_cpu = 1
+            for cand in (3, 2):
+                if (t1 * cand) * (args.steps + args.warmup) <= 200.0:
+                    n_cpu = cand
+                    break
+        sample = CpuSample(S, n=n_cpu)
         for _ in range(args.warmup):
             sample.step()
         times = [sample.step() for _ in range(args.steps)]
@@ -758,7 +771,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = CpuSample(S, n=args.cpu_slices)
+        sample = CpuSample(S, n=args.cpu_slices if args.cpu_slices > 0 else 3)
         dt = sample.step()
         cpu = {"value": sample.voxels() / dt, "unit": "voxels/s", "cores": sample.cores, "kind": "port",
                "sample": sample.describe() + f"; one step, {dt:.1f} s"}
