@@ -68,6 +68,9 @@ _SIGNATURES = {
     "be_range_keep": ([P, LL, I, I, P], I),
     "be_runs3d_cc": ([P, P, P, I, I, I, I, P, P, P, P], I),
     "be_fill_holes": ([P, P, I, I, I, P, P, P, P], I),
+    # cluster_graph.cpp (host)
+    "be_components_clusters": ([I, P, P, P, P, P, P, P, LL, D, D, D, I, P, P], I),
+    "be_components_clusters_fetch": ([P, P], I),
     # match_replay.cpp (host)
     "be_match_replay": ([I, P, P, I, P, P, LL, I, I, D, D, I, P, I, P, P, P, I, P], I),
 }

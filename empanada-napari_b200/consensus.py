@@ -27,6 +27,11 @@ LAST_LAUNCHES = 0  # kernels launched by the last merge_objects_from_trackers ca
 # initial capacities of the growable device tables (None: sized from the node count); every table
 # regrows on overflow, tests start them tiny to exercise that
 CAPS = {"pairs": None, "votes": 1 << 16, "side": 1 << 20}
+# cluster decisions of the non-trivial components in native code (0: the Python `_Graph` path)
+NATIVE_CLUSTERS = True
+# the reference averages edge weights with the builtin sum(), which is Neumaier-compensated on
+# floats from Python 3.12 on; the native path follows the running interpreter
+_COMPENSATED_SUM = __import__("sys").version_info >= (3, 12)
 
 
 def merge_boxes(box1, box2):
@@ -561,14 +566,59 @@ def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_th
     comp_box_l = comp_box.tolist()
     node_order_l = node_order.tolist()
     node_start_l, edge_start_l = node_start.tolist(), edge_start.tolist()
-    one_cluster = (comp_min_iou > cluster_iou_thr).tolist()
+    one_cluster_a = comp_min_iou > cluster_iou_thr
+    one_cluster = one_cluster_a.tolist()
+    eligible = comp_size >= min_cluster
+    # components with an edge at or below the IoU cut: create_graph_of_clusters + merge_clusters,
+    # natively and in one call (csrc/cluster_graph.cpp; `component_clusters` is the same in Python)
+    slow = np.flatnonzero(eligible & ~one_cluster_a)
+    slow_clusters = {}
+    if len(slow) and NATIVE_CLUSTERS:
+        n_nodes_c = comp_size[slow]
+        n_edges_c = (edge_start[1:] - edge_start[:-1])[slow]
+        noff = np.concatenate([[0], np.cumsum(n_nodes_c)]).astype(np.int32)
+        eoff = np.concatenate([[0], np.cumsum(n_edges_c)]).astype(np.int32)
+        nsel = np.repeat(node_start[slow] - noff[:-1], n_nodes_c) + np.arange(noff[-1])
+        esel = np.repeat(edge_start[slow] - eoff[:-1], n_edges_c) + np.arange(eoff[-1])
+        nodes_c = np.ascontiguousarray(node_order[nsel], dtype=np.int32)
+        eo = edge_order[esel]
+        ea_c = np.ascontiguousarray(ea[eo], dtype=np.int32)
+        eb_c = np.ascontiguousarray(eb[eo], dtype=np.int32)
+        ei_c = np.ascontiguousarray(eiou[eo], dtype=np.float64)
+        et_c = np.ascontiguousarray(eit[eo], dtype=np.int64)
+        ncl = np.zeros(len(slow), dtype=np.int32)
+        totals = np.zeros(2, dtype=np.int64)
+        call("be_components_clusters", len(slow), ptr(noff), ptr(nodes_c), ptr(eoff), ptr(ea_c), ptr(eb_c), ptr(ei_c),
+             ptr(et_c), int(n_nodes), float(cluster_iou_thr), float(MIN_IOU), float(MIN_OVERLAP),
+             1 if _COMPENSATED_SUM else 0, ptr(ncl), ptr(totals))
+        csz = np.zeros(max(1, int(totals[0])), dtype=np.int32)
+        cmem = np.zeros(max(1, int(totals[1])), dtype=np.int32)
+        call("be_components_clusters_fetch", ptr(csz), ptr(cmem))
+        n_cl = int(totals[0])
+        csz, cmem = csz[:n_cl], cmem[:int(totals[1])]
+        cstart = np.concatenate([[0], np.cumsum(csz)]).astype(np.int64)
+        cbox = np.zeros((n_cl, 6), dtype=np.int64)          # merged box of every cluster, in one shot
+        if n_cl:
+            mb = boxes[cmem]
+            cbox[:, :3] = np.minimum.reduceat(mb[:, :3], cstart[:-1], axis=0)
+            cbox[:, 3:] = np.maximum.reduceat(mb[:, 3:], cstart[:-1], axis=0)
+        csz_l, cmem_l, cbox_l, cstart_l = csz.tolist(), cmem.tolist(), cbox.tolist(), cstart.tolist()
+        cpos = 0
+        for c, k in zip(slow.tolist(), ncl.tolist()):
+            slow_clusters[c] = [(cmem_l[cstart_l[j]:cstart_l[j + 1]], tuple(cbox_l[j])) for j in range(cpos, cpos + k)]
+            cpos += k
     boxes_l = None
-    for ci in np.flatnonzero(comp_size >= min_cluster).tolist():
+    for ci in np.flatnonzero(eligible).tolist():
         members = node_order_l[node_start_l[ci]:node_start_l[ci + 1]]
         if one_cluster[ci]:
             # every edge survives the IoU cut: the component is one cluster and the cluster graph
             # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
             cands.append((ci, members, tuple(comp_box_l[ci])))
+            continue
+        if ci in slow_clusters:
+            for cluster, box in slow_clusters[ci]:
+                if len(cluster) >= min_cluster:
+                    cands.append((ci, cluster, box))
             continue
         e0, e1 = edge_start_l[ci], edge_start_l[ci + 1]
         clusters = component_clusters(members, list(zip(ea_l[e0:e1], eb_l[e0:e1], eiou_l[e0:e1], eit_l[e0:e1])),

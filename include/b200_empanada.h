@@ -219,6 +219,19 @@ int be_runs3d_cc(const long long* run_start, const long long* run_end, const int
 int be_fill_holes(int* vol, uint8_t* scratch, int D, int H, int W, const int* slice_off,
                   const int* labels, const int* boxes, be_stream st);
 
+/* ---- host: cluster decisions of the connected components of the consensus instance graph
+ * (csrc/cluster_graph.cpp; empanada/consensus.py:35-142 on graph.subgraph(comp)) for n_comp
+ * components in CSR layout: nodes ascending per component, edges (a, b, iou, overlap) in the
+ * instance graph's edge-insertion order. n_clusters [n_comp]; totals = {clusters, cluster members};
+ * the lists are fetched with be_components_clusters_fetch (cluster graph node order; clusters may
+ * share nodes). float_sum: 1 when the interpreter's builtin sum() is the compensated one of
+ * Python >= 3.12 (the reference averages edge weights with it). */
+int be_components_clusters(int n_comp, const int* node_off, const int* nodes, const int* edge_off,
+                           const int* ea, const int* eb, const double* eiou, const long long* eov,
+                           long long n_nodes_total, double cluster_iou_thr, double min_iou,
+                           double min_overlap, int float_sum, int* n_clusters, long long* totals);
+int be_components_clusters_fetch(int* cluster_sizes, int* members);
+
 #ifdef __cplusplus
 }
 #endif

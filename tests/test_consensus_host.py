@@ -104,3 +104,106 @@ def test_networkx_free_clustering_equals_networkx():
             assert got == want, (trial, sorted(comp))
             checked += 1
     assert checked > 1500
+
+
+def _random_tables(rng, n_obj, weak_links):
+    """Node sizes / boxes and a pair table shaped like three planes' instances of n_obj objects."""
+    sizes = rng.integers(2000, 200000, size=3 * n_obj).astype(np.int64)
+    boxes = [tuple(int(v) for v in np.r_[rng.integers(0, 900, 3), rng.integers(900, 1024, 3)]) for _ in range(3 * n_obj)]
+    pa, pb, inter = [], [], []
+    for i in range(n_obj):
+        ids = [p * n_obj + i + 1 for p in range(3)]
+        for a in range(3):
+            for b in range(a + 1, 3):
+                if rng.random() < 0.9:
+                    pa.append(ids[a]); pb.append(ids[b])
+                    inter.append(int(rng.uniform(0.05, 1.0) * min(sizes[ids[a] - 1], sizes[ids[b] - 1])))
+    for _ in range(weak_links):
+        i = int(rng.integers(0, n_obj - 1)); j = i + int(rng.integers(1, 3))
+        if j >= n_obj:
+            continue
+        a, b = rng.integers(0, 3, 2)
+        if a == b:
+            continue
+        x, y = sorted((a * n_obj + i + 1, b * n_obj + j + 1))
+        pa.append(x); pb.append(y); inter.append(int(rng.integers(1, 3000)))
+    pa, pb, inter = np.array(pa), np.array(pb), np.array(inter)
+    _, idx = np.unique((pa.astype(np.int64) << 32) | pb, return_index=True)
+    return sizes, boxes, pa[idx], pb[idx], inter[idx]
+
+
+def test_native_cluster_decisions_equal_python_graph():
+    """csrc/cluster_graph.cpp (CPython set iteration order, networkx container orders and the
+    interpreter's float summation re-stated natively) against the Python `_Graph` path, which the
+    test above ties to networkx: identical candidate lists for whole instance graphs."""
+    from empanada_napari_b200 import consensus as C
+    rng = np.random.default_rng(11)
+    total = 0
+    for trial in range(12):
+        n_obj = int(rng.integers(20, 400))
+        sizes, boxes, pa, pb, inter = _random_tables(rng, n_obj, weak_links=int(rng.integers(0, n_obj)))
+        for thr, min_cluster in ((0.75, 2), (0.0, 1), (0.5, 2)):
+            C.NATIVE_CLUSTERS = False
+            want = C.cluster_candidates(3 * n_obj, boxes, sizes, pa, pb, inter, thr, min_cluster)
+            C.NATIVE_CLUSTERS = True
+            got = C.cluster_candidates(3 * n_obj, boxes, sizes, pa, pb, inter, thr, min_cluster)
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert g[0] == w[0] and sorted(g[1]) == sorted(w[1]) and tuple(g[2]) == tuple(w[2])
+            total += len(want)
+    assert total > 3000
+
+
+def test_native_component_clusters_over_id_ranges():
+    """Single components with node ids from 0 to millions (set iteration order depends on the ids'
+    low bits, table growth and perturbation): native clusters == Python `component_clusters`,
+    including clusters that share nodes and components that ARE the whole graph."""
+    import sys
+    from empanada_napari_b200 import _lib, consensus as C
+    fs = 1 if sys.version_info >= (3, 12) else 0
+
+    def native(members, edges, n_nodes, thr):
+        mem = np.ascontiguousarray(members, dtype=np.int32)
+        ea = np.array([e[0] for e in edges], dtype=np.int32); eb = np.array([e[1] for e in edges], dtype=np.int32)
+        ei = np.array([e[2] for e in edges], dtype=np.float64); eo = np.array([e[3] for e in edges], dtype=np.int64)
+        noff, eoff = np.array([0, len(mem)], np.int32), np.array([0, len(ea)], np.int32)
+        ncl, tot = np.zeros(1, np.int32), np.zeros(2, np.int64)
+        _lib.call("be_components_clusters", 1, _lib.ptr(noff), _lib.ptr(mem), _lib.ptr(eoff), _lib.ptr(ea), _lib.ptr(eb),
+                  _lib.ptr(ei), _lib.ptr(eo), int(n_nodes), float(thr), C.MIN_IOU, float(C.MIN_OVERLAP), fs,
+                  _lib.ptr(ncl), _lib.ptr(tot))
+        sz, out = np.zeros(max(1, int(tot[0])), np.int32), np.zeros(max(1, int(tot[1])), np.int32)
+        _lib.call("be_components_clusters_fetch", _lib.ptr(sz), _lib.ptr(out))
+        res, pos = [], 0
+        for i in range(int(ncl[0])):
+            res.append(sorted(out[pos:pos + sz[i]].tolist()))
+            pos += sz[i]
+        return res
+
+    rng = np.random.default_rng(3)
+    checked = shared = 0
+    for trial in range(500):
+        n, m = int(rng.integers(4, 200)), int(rng.integers(3, 300))
+        base = int(rng.choice([0, 1000, 40000, 3000000]))
+        ids = np.sort(rng.choice(np.arange(base, base + 5 * n), size=n, replace=False))
+        a, b = rng.integers(0, n, m), rng.integers(0, n, m)
+        keep = a < b
+        key = np.unique(a[keep] * 100000 + b[keep])
+        a, b = key // 100000, key % 100000
+        iou = np.where(rng.random(len(a)) < 0.5, rng.uniform(0.7, 1.0, len(a)), rng.uniform(0.0, 0.05, len(a)))
+        ov = np.where(rng.random(len(a)) < 0.5, rng.integers(1, 90, len(a)), rng.integers(90, 400, len(a)))
+        thr = float(rng.choice([0.0, 0.5, 0.75, 0.9]))
+        whole = rng.random() < 0.2
+        G = nx.Graph()
+        G.add_nodes_from(range(n))
+        G.add_edges_from(zip(a.tolist(), b.tolist()))
+        for comp in nx.connected_components(G):
+            if len(comp) < 2 or (whole and len(comp) != n):
+                continue
+            n_total = n if whole else int(ids.max()) + 1 + int(rng.integers(0, 50))
+            members = ids[sorted(comp)].tolist()
+            edges = [(int(ids[a[k]]), int(ids[b[k]]), float(iou[k]), int(ov[k])) for k in range(len(a)) if int(a[k]) in comp]
+            want = [sorted(c) for c in C.component_clusters(members, edges, n_total, thr)]
+            assert native(members, edges, n_total, thr) == want, (trial, members[:6], thr)
+            checked += 1
+            shared += sum(len(c) for c in want) > len(members)
+    assert checked > 2000 and shared > 0
