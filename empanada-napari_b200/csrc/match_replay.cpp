@@ -15,7 +15,6 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
-#include <unordered_map>
 #include <vector>
 
 extern "C" int be_set_error(const char* msg);
@@ -38,9 +37,12 @@ struct SliceObjs {
 // cost is nr x nc row-major with nr <= nc. Returns col4row.
 static void lap_min(int nr, int nc, const std::vector<double>& cost, std::vector<int>& col4row) {
   const double INF = std::numeric_limits<double>::infinity();
-  std::vector<double> u(nr, 0.0), v(nc, 0.0), shortest(nc);
-  std::vector<int> path(nc, -1), row4col(nc, -1), remaining(nc);
-  std::vector<char> SR(nr), SC(nc);
+  static thread_local std::vector<double> u, v, shortest;
+  static thread_local std::vector<int> path, row4col, remaining;
+  static thread_local std::vector<char> SR, SC;
+  u.assign(nr, 0.0); v.assign(nc, 0.0); shortest.resize(nc);
+  path.assign(nc, -1); row4col.assign(nc, -1); remaining.resize(nc);
+  SR.resize(nr); SC.resize(nc);
   col4row.assign(nr, -1);
   for (int cur = 0; cur < nr; ++cur) {
     double min_val = 0.0;
@@ -87,79 +89,119 @@ static void lap_min(int nr, int nc, const std::vector<double>& cost, std::vector
 }
 
 struct Entry { int row, col; long long inter; };
+constexpr int kNoLabel = std::numeric_limits<int>::min();
 
 struct Scratch {
-  std::vector<Entry> agg;
+  std::vector<Entry> agg, bycol;
   std::vector<double> iou;
   std::vector<float> ioa;
-  std::vector<int> parent, matched_row, ioa_arg, order, rows, cols;
+  std::vector<int> parent, matched_row, ioa_arg, rows, cols, col_start, row_deg, col_deg, multi, root;
   std::vector<float> ioa_max;
-  std::vector<size_t> eorder;
   std::vector<double> dense, cost;
   std::vector<int> col4row;
-  std::vector<std::pair<int, int>> groups;  // (first index, start in order)
+  // merge_by_label
+  std::vector<int> gid, gcount, gstart, members, hkey, hval;
 };
 
 // One matcher step: relabel `match` objects against `target` objects.
 // entries: sparse intersections (row = target index, col = match index), duplicates allowed.
+// Everything here is linear in the number of entries for the common case (an object that
+// overlaps exactly one object of the neighbouring slice, and vice versa): entries are bucketed
+// by column, duplicates summed, and only the entries that share a row or a column with another
+// one go through the union-find / assignment machinery - an isolated positive entry is a
+// connected block of the IoU matrix by itself and always part of the optimum.
 static void match_step(const SliceObjs& target, const SliceObjs& match, std::vector<Entry>& entries,
                        double iou_thr, float ioa_thr, bool assign_new, int& next_label,
                        std::vector<int>& new_labels, Scratch& S) {
   const int n = target.size(), m = match.size();
   new_labels.assign(m, 0);
   S.matched_row.assign(m, -1);
-  // aggregate duplicate (row, col)
-  std::sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) {
-    return a.row != b.row ? a.row < b.row : a.col < b.col;
-  });
+  S.ioa_max.assign(m, 0.0f);
+  S.ioa_arg.assign(m, 0);
   std::vector<Entry>& agg = S.agg;
   agg.clear();
-  for (const Entry& e : entries) {
-    if (!agg.empty() && agg.back().row == e.row && agg.back().col == e.col) agg.back().inter += e.inter;
-    else agg.push_back(e);
-  }
-  S.iou.resize(agg.size());
-  S.ioa.resize(agg.size());
-  for (size_t k = 0; k < agg.size(); ++k) {
-    const long long inter = agg[k].inter;
-    const long long uni = target.area[agg[k].row] + match.area[agg[k].col] - inter;
-    S.iou[k] = static_cast<double>(inter) / static_cast<double>(uni);
-    S.ioa[k] = static_cast<float>(static_cast<double>(inter) / static_cast<double>(match.area[agg[k].col]));
-  }
-  if (n > 0 && m > 0 && !agg.empty()) {
-    // connected blocks of the bipartite graph (union-find over rows [0,n) and cols [n,n+m))
-    std::vector<int>& parent = S.parent;
-    parent.resize(n + m);
-    std::iota(parent.begin(), parent.end(), 0);
-    auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
-    for (const Entry& e : agg) {
-      const int a = find(e.row), b = find(n + e.col);
-      if (a != b) parent[std::max(a, b)] = std::min(a, b);
-    }
-    std::vector<size_t>& eo = S.eorder;
-    eo.resize(agg.size());
-    std::iota(eo.begin(), eo.end(), 0);
-    std::stable_sort(eo.begin(), eo.end(), [&](size_t a, size_t b) { return find(agg[a].row) < find(agg[b].row); });
-    size_t g0 = 0;
-    while (g0 < eo.size()) {
-      const int root = find(agg[eo[g0]].row);
-      size_t g1 = g0 + 1;
-      while (g1 < eo.size() && find(agg[eo[g1]].row) == root) ++g1;
-      if (g1 - g0 == 1) {  // isolated positive entry: always part of the optimum
-        const Entry& e = agg[eo[g0]];
-        if (S.iou[eo[g0]] >= iou_thr) S.matched_row[e.col] = e.row;
+  if (n > 0 && m > 0 && !entries.empty()) {
+    // stable counting sort by column, rows ascending inside a column, duplicates summed
+    std::vector<int>& cs = S.col_start;
+    cs.assign(m + 1, 0);
+    for (const Entry& e : entries) ++cs[e.col + 1];
+    for (int c = 0; c < m; ++c) cs[c + 1] += cs[c];
+    S.bycol.resize(entries.size());
+    S.col_deg.assign(m, 0);  // used as the fill cursor first
+    for (const Entry& e : entries) S.bycol[cs[e.col] + S.col_deg[e.col]++] = e;
+    S.row_deg.assign(n, 0);
+    for (int c = 0; c < m; ++c) {
+      Entry* b = S.bycol.data() + cs[c];
+      const int len = cs[c + 1] - cs[c];
+      if (len > 16) {
+        std::sort(b, b + len, [](const Entry& x, const Entry& y) { return x.row < y.row; });
       } else {
+        for (int i = 1; i < len; ++i) {
+          const Entry e = b[i];
+          int j = i - 1;
+          while (j >= 0 && b[j].row > e.row) { b[j + 1] = b[j]; --j; }
+          b[j + 1] = e;
+        }
+      }
+      int deg = 0;
+      for (int i = 0; i < len; ++i) {
+        if (deg > 0 && agg.back().row == b[i].row) agg.back().inter += b[i].inter;
+        else { agg.push_back(b[i]); ++deg; ++S.row_deg[b[i].row]; }
+      }
+      S.col_deg[c] = deg;
+    }
+    const size_t na = agg.size();
+    S.iou.resize(na);
+    S.ioa.resize(na);
+    S.multi.clear();
+    for (size_t k = 0; k < na; ++k) {
+      const Entry& e = agg[k];
+      const long long inter = e.inter;
+      const long long uni = target.area[e.row] + match.area[e.col] - inter;
+      S.iou[k] = static_cast<double>(inter) / static_cast<double>(uni);
+      S.ioa[k] = static_cast<float>(static_cast<double>(inter) / static_cast<double>(match.area[e.col]));
+      // per-column IoA maximum (float32 matrix semantics: zeros everywhere else, first max row
+      // wins - rows ascend inside a column, so ">" keeps the first one)
+      if (S.ioa[k] > S.ioa_max[e.col]) { S.ioa_max[e.col] = S.ioa[k]; S.ioa_arg[e.col] = e.row; }
+      if (S.row_deg[e.row] == 1 && S.col_deg[e.col] == 1) {
+        if (S.iou[k] >= iou_thr) S.matched_row[e.col] = e.row;
+      } else {
+        S.multi.push_back(static_cast<int>(k));
+      }
+    }
+    if (!S.multi.empty()) {
+      // connected blocks of the bipartite graph (union-find over rows [0,n) and cols [n,n+m))
+      std::vector<int>& parent = S.parent;
+      parent.resize(n + m);
+      for (int k : S.multi) { parent[agg[k].row] = agg[k].row; parent[n + agg[k].col] = n + agg[k].col; }
+      auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+      for (int k : S.multi) {
+        const int a = find(agg[k].row), b = find(n + agg[k].col);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+      }
+      S.root.resize(na);
+      for (int k : S.multi) S.root[k] = find(agg[k].row);
+      std::sort(S.multi.begin(), S.multi.end(), [&](int a, int b) {
+        return S.root[a] != S.root[b] ? S.root[a] < S.root[b] : a < b;
+      });
+      size_t g0 = 0;
+      const size_t ne = S.multi.size();
+      while (g0 < ne) {
+        const int root = S.root[S.multi[g0]];
+        size_t g1 = g0 + 1;
+        while (g1 < ne && S.root[S.multi[g1]] == root) ++g1;
         std::vector<int>&rows = S.rows, &cols = S.cols;
         rows.clear(); cols.clear();
-        for (size_t k = g0; k < g1; ++k) { rows.push_back(agg[eo[k]].row); cols.push_back(agg[eo[k]].col); }
+        for (size_t k = g0; k < g1; ++k) { rows.push_back(agg[S.multi[k]].row); cols.push_back(agg[S.multi[k]].col); }
         std::sort(rows.begin(), rows.end()); rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
         std::sort(cols.begin(), cols.end()); cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
         const int br = static_cast<int>(rows.size()), bc = static_cast<int>(cols.size());
         S.dense.assign(static_cast<size_t>(br) * bc, 0.0);
         for (size_t k = g0; k < g1; ++k) {
-          const int r = static_cast<int>(std::lower_bound(rows.begin(), rows.end(), agg[eo[k]].row) - rows.begin());
-          const int c = static_cast<int>(std::lower_bound(cols.begin(), cols.end(), agg[eo[k]].col) - cols.begin());
-          S.dense[static_cast<size_t>(r) * bc + c] = S.iou[eo[k]];
+          const Entry& e = agg[S.multi[k]];
+          const int r = static_cast<int>(std::lower_bound(rows.begin(), rows.end(), e.row) - rows.begin());
+          const int c = static_cast<int>(std::lower_bound(cols.begin(), cols.end(), e.col) - cols.begin());
+          S.dense[static_cast<size_t>(r) * bc + c] = S.iou[S.multi[k]];
         }
         // scipy: maximise == minimise(-cost); tall matrices are transposed first
         const bool transpose = bc < br;
@@ -176,17 +218,8 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
           const int r = transpose ? S.col4row[a] : a, c = transpose ? a : S.col4row[a];
           if (S.dense[static_cast<size_t>(r) * bc + c] >= iou_thr) S.matched_row[cols[c]] = rows[r];
         }
+        g0 = g1;
       }
-      g0 = g1;
-    }
-  }
-  // per-column IoA maximum (float32 matrix semantics: zeros everywhere else, first max row wins)
-  S.ioa_max.assign(m, 0.0f);
-  S.ioa_arg.assign(m, 0);
-  if (n > 0 && m > 0) {
-    for (size_t k = 0; k < agg.size(); ++k) {  // agg is sorted by row, so ">" keeps the first max
-      const int c = agg[k].col;
-      if (S.ioa[k] > S.ioa_max[c]) { S.ioa_max[c] = S.ioa[k]; S.ioa_arg[c] = agg[k].row; }
     }
   }
   for (int i = 0; i < m; ++i) {
@@ -202,38 +235,58 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
   }
 }
 
-// Objects with equal new label are merged; output order = first appearance (dict order).
+// Objects with equal new label are merged; output order = first appearance (dict order), members
+// of a merged object in index order. Labels are grouped through a small open-addressing table;
+// when every label is distinct (the common case) the slice is copied with its new labels.
 static void merge_by_label(const SliceObjs& match, const std::vector<int>& new_labels, SliceObjs& out,
                            Scratch& S) {
   const int m = match.size();
-  out.clear();
-  std::vector<int>& order = S.order;
-  order.resize(m);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return new_labels[a] < new_labels[b]; });
-  S.groups.clear();
-  for (int g0 = 0; g0 < m;) {
-    int g1 = g0 + 1;
-    while (g1 < m && new_labels[order[g1]] == new_labels[order[g0]]) ++g1;
-    S.groups.emplace_back(order[g0], g0);  // stable sort: order[g0] is the first appearance
-    g0 = g1;
+  int cap = 16;
+  while (cap < 2 * m) cap <<= 1;
+  S.hkey.assign(cap, kNoLabel);
+  S.hval.resize(cap);
+  S.gid.resize(m);
+  S.gcount.clear();
+  int ng = 0;
+  for (int i = 0; i < m; ++i) {
+    const int lab = new_labels[i];
+    unsigned h = (static_cast<unsigned>(lab) * 2654435761u) & (cap - 1);
+    while (S.hkey[h] != kNoLabel && S.hkey[h] != lab) h = (h + 1) & (cap - 1);
+    if (S.hkey[h] == kNoLabel) { S.hkey[h] = lab; S.hval[h] = ng++; S.gcount.push_back(0); }
+    S.gid[i] = S.hval[h];
+    ++S.gcount[S.gid[i]];
   }
-  std::sort(S.groups.begin(), S.groups.end());
-  for (const auto& gr : S.groups) {
-    const int lab = new_labels[gr.first];
+  if (ng == m) {  // nothing merges
+    out.label = new_labels;
+    out.area = match.area;
+    out.box = match.box;
+    out.cc_off = match.cc_off;
+    out.cc = match.cc;
+    return;
+  }
+  S.gstart.assign(ng + 1, 0);
+  for (int g = 0; g < ng; ++g) S.gstart[g + 1] = S.gstart[g] + S.gcount[g];
+  S.members.resize(m);
+  std::fill(S.gcount.begin(), S.gcount.end(), 0);
+  for (int i = 0; i < m; ++i) S.members[S.gstart[S.gid[i]] + S.gcount[S.gid[i]]++] = i;
+  out.label.resize(ng); out.area.resize(ng); out.box.resize(4 * ng); out.cc_off.resize(ng + 1);
+  out.cc.resize(match.cc.size());
+  out.cc_off[0] = 0;
+  int w = 0;
+  for (int g = 0; g < ng; ++g) {
     long long area = 0;
     int b0 = 0x7fffffff, b1 = 0x7fffffff, b2 = -1, b3 = -1;
-    for (int k = gr.second; k < m && new_labels[order[k]] == lab; ++k) {
-      const int i = order[k];
+    for (int k = S.gstart[g]; k < S.gstart[g + 1]; ++k) {
+      const int i = S.members[k];
       area += match.area[i];
       b0 = std::min(b0, match.box[4 * i]); b1 = std::min(b1, match.box[4 * i + 1]);
       b2 = std::max(b2, match.box[4 * i + 2]); b3 = std::max(b3, match.box[4 * i + 3]);
-      out.cc.insert(out.cc.end(), match.cc.begin() + match.cc_off[i], match.cc.begin() + match.cc_off[i + 1]);
+      for (int c = match.cc_off[i]; c < match.cc_off[i + 1]; ++c) out.cc[w++] = match.cc[c];
     }
-    out.label.push_back(lab);
-    out.area.push_back(area);
-    out.box.push_back(b0); out.box.push_back(b1); out.box.push_back(b2); out.box.push_back(b3);
-    out.cc_off.push_back(static_cast<int>(out.cc.size()));
+    out.label[g] = new_labels[S.members[S.gstart[g]]];
+    out.area[g] = area;
+    out.box[4 * g] = b0; out.box[4 * g + 1] = b1; out.box[4 * g + 2] = b2; out.box[4 * g + 3] = b3;
+    out.cc_off[g + 1] = w;
   }
 }
 
@@ -318,8 +371,8 @@ int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
   }
 
   // ---------------- backward pass (assign_new = False) + tracker
-  std::unordered_map<int, int> inst_pos;
-  inst_pos.reserve(4096);
+  // every label of the backward sweep was issued by the forward pass: base < label < next_label
+  std::vector<int> inst_pos(static_cast<size_t>(std::max(1, next_label - base_label)), -1);
   int ninst = 0;
   SliceObjs bwd_next, bwd_cur;
   std::vector<int> owner_next, owner_cur;
@@ -351,16 +404,17 @@ int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
       if (axis == 0) { b3[0] = s; b3[1] = ob[0]; b3[2] = ob[1]; b3[3] = s + 1; b3[4] = ob[2]; b3[5] = ob[3]; }
       else if (axis == 1) { b3[0] = ob[0]; b3[1] = s; b3[2] = ob[1]; b3[3] = ob[2]; b3[4] = s + 1; b3[5] = ob[3]; }
       else { b3[0] = ob[0]; b3[1] = ob[1]; b3[2] = s; b3[3] = ob[2]; b3[4] = ob[3]; b3[5] = s + 1; }
-      auto it = inst_pos.find(label);
-      if (it == inst_pos.end()) {
+      if (label <= base_label || label >= next_label) return be_set_error("tracker label outside the issued range");
+      int& pos = inst_pos[label - base_label];
+      if (pos < 0) {
         if (ninst >= max_inst) return be_set_error("instance table capacity exceeded; re-run with a larger max_inst");
-        inst_pos[label] = ninst;
+        pos = ninst;
         inst_labels[ninst] = label;
         inst_sizes[ninst] = bwd_cur.area[i];
         std::memcpy(inst_boxes + ninst * 6, b3, sizeof(b3));
         ++ninst;
       } else {
-        const int p = it->second;
+        const int p = pos;
         inst_sizes[p] += bwd_cur.area[i];
         int* bb = inst_boxes + p * 6;
         for (int d = 0; d < 3; ++d) { bb[d] = std::min(bb[d], b3[d]); bb[d + 3] = std::max(bb[d + 3], b3[d + 3]); }

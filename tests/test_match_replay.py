@@ -38,9 +38,11 @@ def random_stack(rng, n, h, w, mode):
     """Sequences of label images with persistent, splitting, merging and vanishing blobs."""
     stack = []
     yy, xx = np.mgrid[0:h, 0:w]
-    k = rng.integers(3, 9)
+    # "crowded": many small blobs that keep touching, splitting and merging, so that most IoU
+    # blocks hold several rows and columns (the assignment path) and labels merge in every slice
+    k = rng.integers(18, 32) if mode == "crowded" else rng.integers(3, 9)
     cy, cx = rng.uniform(0, h, k), rng.uniform(0, w, k)
-    r = rng.uniform(2, 7, k)
+    r = rng.uniform(1.5, 4.5, k) if mode == "crowded" else rng.uniform(2, 7, k)
     for t in range(n):
         cy += rng.normal(0, 1.2, k); cx += rng.normal(0, 1.2, k); r = np.clip(r + rng.normal(0, 0.6, k), 1.0, 9)
         pan = np.zeros((h, w), dtype=np.int64)
@@ -72,7 +74,7 @@ def random_stack(rng, n, h, w, mode):
     return stack
 
 
-@pytest.mark.parametrize("mode", ["plain", "flicker", "noise", "symmetric", "lattice"])
+@pytest.mark.parametrize("mode", ["plain", "flicker", "noise", "symmetric", "lattice", "crowded"])
 @pytest.mark.parametrize("axis_name", ["xy", "xz", "yz"])
 def test_replay_matches_oracle(mode, axis_name):
     from empanada_napari_b200 import tracking
