@@ -935,6 +935,40 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     return out, instances
 
 
+def merge_semantic_from_trackers(trackers, pixel_vote_thr=2, dev=None, runs_fn=None):
+    """`merge_semantic_from_trackers` (consensus.py:289-346) for a stuff class: every plane holds
+    at most one label, the consensus is the set of voxels that at least `pixel_vote_thr` planes
+    claim (`vote_by_ranges` on the sorted ranges = maximal flat-index runs of the voted mask;
+    `join_ranges` when the threshold is 1), its box the merge of the planes' boxes, its id 1.
+    Returns (device int32 volume holding 1 on the voted voxels, instances dict). `dev` / `runs_fn`
+    (default: the current CUDA device and the library's run extraction) exist for the host-side
+    unit test of the voting logic."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
+    runs_fn = extract_runs if runs_fn is None else runs_fn
+    shape3d = tuple(int(s) for s in trackers[0].shape3d)
+    boxes, vols = [], []
+    for tr in trackers:
+        assert len(tr.instances.keys()) <= 1, 'Semantic classes only have 1 label!'
+        for attrs in tr.instances.values():
+            boxes.append(tuple(int(v) for v in attrs["box"]))
+            vols.append(dense_volume(tr, dev))
+    if not boxes:
+        return torch.zeros(shape3d, dtype=torch.int32, device=dev), {}
+    box = boxes[0]
+    for b in boxes[1:]:
+        box = merge_boxes(box, b)
+    if pixel_vote_thr > 1 and len(vols) < pixel_vote_thr:
+        # `vote_by_ranges` hands back a 1-D empty array here and the reference fails on it
+        # (array_utils.py:631-635, consensus.py:340)
+        raise IndexError("too many indices for array: array is 1-dimensional, but 2 were indexed")
+    votes = torch.zeros(shape3d, dtype=torch.int32, device=dev)
+    for v in vols:
+        votes += (v != 0)
+    voted = (votes >= int(pixel_vote_thr)).to(torch.int32)
+    _, starts, lens = runs_fn(voted)
+    return voted, {1: {"box": box, "starts": starts.cpu().numpy(), "runs": lens.cpu().numpy().astype(np.int64)}}
+
+
 def instance_relabel(tracker):
     """empanada_napari/inference.py:31-54."""
     out = {}

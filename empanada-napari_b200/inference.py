@@ -839,9 +839,16 @@ def tracker_consensus(trackers, store_url, model_config, label_divisor=1000, pix
     for class_id, class_name in model_config["class_names"].items():
         class_trackers = get_axis_trackers_by_class(trackers, class_id)
         shape3d = class_trackers[0].shape3d
-        if class_id not in thing_list:
-            _unsupported("semantic (stuff) class consensus")
         out = InstanceTracker(class_id, class_trackers[0].label_divisor, shape3d, "xy")
+        if class_id not in thing_list:
+            # stuff class: a plain voxel vote, no size filters, uint8 in a store (inference.py:152-156)
+            vol_d, out.instances = consensus.merge_semantic_from_trackers(class_trackers, pixel_vote_thr)
+            if zarr_store is not None:
+                vol = fill_store_from_device(create_store_array(zarr_store, f"{class_name}", shape3d, np.uint8, chunk_size), vol_d)
+            else:
+                vol = _PINNED.to_host(vol_d, dtype) if to_host else vol_d
+            yield vol, class_name, out.instances
+            continue
         front = getattr(getattr(class_trackers[0], "_b200_sharded", None), "front", None)
         if (front is not None and len(class_trackers) == 3 and set(trackers.keys()) == {"xy", "xz", "yz"}
                 and all(getattr(t, "_b200_sharded", None) is class_trackers[0]._b200_sharded

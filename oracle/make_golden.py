@@ -172,16 +172,22 @@ def scaled_heads(label_slice, scale, noise, rng):
 
 def run_reference_volume(shape, seed, noise, ks, n_objects, min_size, min_extent, tag, pixel_vote_thr=2,
                          allow_one_view=False, semantic_only=False, inference_scale=1, erosion=0, dilation=0,
-                         fill_holes=False):
-    """Engine3d.infer_on_axis x3 + tracker_consensus + stack_postprocessing, unmodified."""
+                         fill_holes=False, stuff_config=False):
+    """Engine3d.infer_on_axis x3 + tracker_consensus + stack_postprocessing, unmodified.
+    `stuff_config`: the model config lists no thing class (`thing_list: []`), so the class is a
+    stuff class everywhere - one label per plane and `create_semantic_consensus` (a plain voxel
+    vote, consensus.py:289-346) instead of the instance consensus."""
     import empanada_napari.inference as inf
+    MODEL_CONFIG = dict(globals()["MODEL_CONFIG"])
+    if stuff_config:
+        MODEL_CONFIG["thing_list"] = []
 
     vol, lab, ell = syn.make_volume(shape, seed=seed, n_objects=n_objects, scale=1.0)
     out = {"shape": np.array(shape), "seed": seed, "noise": noise, "ks": ks, "n_objects": n_objects,
            "min_size": min_size, "min_extent": min_extent, "pixel_vote_thr": pixel_vote_thr,
            "allow_one_view": int(allow_one_view), "semantic_only": int(semantic_only),
            "inference_scale": int(inference_scale), "erosion": int(erosion), "dilation": int(dilation),
-           "fill_holes": int(fill_holes)}
+           "fill_holes": int(fill_holes), "stuff_config": int(stuff_config)}
     rng = np.random.default_rng(seed + 100)
     trackers = {}
     orig_loader = inf.load_model_to_device
@@ -467,7 +473,13 @@ def gen_eval_cases():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2", "tiled", "morph"]
+    which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2", "tiled", "morph",
+                             "stuff"]
+    if "stuff" in which:
+        run_reference_volume((24, 42, 38), seed=15, noise=0.5, ks=3, n_objects=10, min_size=20, min_extent=2,
+                             tag="stuff_class", stuff_config=True)
+        run_reference_volume((20, 36, 44), seed=16, noise=0.3, ks=1, n_objects=8, min_size=20, min_extent=2,
+                             tag="stuff_class_vote3", stuff_config=True, pixel_vote_thr=3)
     if "resize" in which:
         gen_resize_cases()
     if "tiled" in which:

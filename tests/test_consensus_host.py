@@ -3,6 +3,7 @@ the container orders of the reference's `graph.subgraph(comp)` (networkx view), 
 ids and merge decisions depend on them (empanada/consensus.py:35-142,427-431)."""
 import networkx as nx
 import numpy as np
+import pytest
 
 
 def test_component_subgraph_matches_networkx_view():
@@ -207,3 +208,51 @@ def test_native_component_clusters_over_id_ranges():
             checked += 1
             shared += sum(len(c) for c in want) > len(members)
     assert checked > 2000 and shared > 0
+
+
+def _numpy_runs(vol):
+    """Maximal flat-index runs of equal non-zero value (what `consensus.extract_runs` returns)."""
+    import torch
+    flat = vol.reshape(-1).numpy()
+    edges = np.flatnonzero(np.diff(np.concatenate([[0], flat, [0]])) != 0)
+    starts, ends = edges[:-1], edges[1:]
+    keep = flat[starts] != 0
+    starts, ends = starts[keep], ends[keep]
+    return (torch.from_numpy(flat[starts].astype(np.int32)), torch.from_numpy(starts.astype(np.int64)),
+            torch.from_numpy((ends - starts).astype(np.int32)))
+
+
+@pytest.mark.parametrize("tag", ["stuff_class", "stuff_class_vote3"])
+def test_semantic_consensus_vote_against_reference_fixture(tag):
+    """Stuff-class consensus (consensus.py:289-346): the voting / box logic of the product on the
+    reference's own per-plane trackers (rasterised on the CPU, numpy run extraction standing in for
+    the CUDA kernel) against the reference's consensus."""
+    import os
+    import torch
+    from conftest import GOLDEN, assert_instances_equal, unpack_instances
+    from empanada_napari_b200 import consensus
+    from empanada_napari_b200.tracking import InstanceTracker
+    z = np.load(os.path.join(GOLDEN, f"volume_{tag}.npz"))
+    shape = tuple(int(v) for v in z["shape"])
+    trackers = []
+    for axis_name in ("xy", "xz", "yz"):
+        tr = InstanceTracker(1, 1000, shape, axis_name)
+        tr.instances = unpack_instances(z, f"{axis_name}_tr_")
+        trackers.append(tr)
+    vol, inst = consensus.merge_semantic_from_trackers(trackers, int(z["pixel_vote_thr"]), dev=torch.device("cpu"),
+                                                       runs_fn=_numpy_runs)
+    assert_instances_equal(inst, unpack_instances(z, "consensus_"))
+    assert np.array_equal(vol.numpy(), z["consensus_vol"])
+    # threshold 1 = join_ranges (array_utils.py:690-697) against the oracle's restatement
+    from oracle import consensus as ocons
+    vol1, inst1 = consensus.merge_semantic_from_trackers(trackers, 1, dev=torch.device("cpu"), runs_fn=_numpy_runs)
+    assert_instances_equal(inst1, ocons.merge_semantic_from_trackers(trackers, 1))
+    # no plane found anything -> no instance, empty volume
+    empty = [InstanceTracker(1, 1000, shape, a) for a in ("xy", "xz", "yz")]
+    vol0, inst0 = consensus.merge_semantic_from_trackers(empty, 2, dev=torch.device("cpu"), runs_fn=_numpy_runs)
+    assert inst0 == {} and not vol0.any()
+    # fewer voting planes than the threshold: the reference fails on the empty 1-D vote result
+    with pytest.raises(IndexError):
+        consensus.merge_semantic_from_trackers(trackers[:1], 2, dev=torch.device("cpu"), runs_fn=_numpy_runs)
+    with pytest.raises(IndexError):
+        ocons.merge_semantic_from_trackers(trackers[:1], 2)

@@ -97,7 +97,7 @@ def test_median_queue_matches_reference():
 
 
 VOLUME_TAGS = ["clean", "noisy", "ks5_odd", "semantic_only", "scale2", "scale4_semantic", "erode1", "dilate2_fill",
-               "erode1_dilate1_fill"]
+               "erode1_dilate1_fill", "stuff_class", "stuff_class_vote3"]
 
 
 def test_resize_by_factor_matches_opencv_fixture():
@@ -117,10 +117,13 @@ def test_volume_pipeline_matches_reference(tag):
     shape = tuple(int(v) for v in z["shape"])
     vol, lab, _ = syn.make_volume(shape, seed=int(z["seed"]), n_objects=int(z["n_objects"]), scale=1.0)
     trackers = {}
+    cfg = dict(MODEL_CONFIG)
+    if "stuff_config" in z and int(z["stuff_config"]):   # the config itself lists no thing class
+        cfg["thing_list"] = []
     for axis_name in ("xy", "xz", "yz"):
         sem, ctr, off = z[f"{axis_name}_sem"].astype(np.float32), z[f"{axis_name}_ctr"], z[f"{axis_name}_off"]
         stack, trs = pipeline.infer_on_axis(
-            vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), MODEL_CONFIG,
+            vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), cfg,
             median_kernel_size=int(z["ks"]), nms_kernel=3, confidence_thr=0.5,
             min_size=int(z["min_size"]), min_extent=int(z["min_extent"]),
             semantic_only=bool(z["semantic_only"]) if "semantic_only" in z else False,
@@ -132,13 +135,13 @@ def test_volume_pipeline_matches_reference(tag):
         assert np.array_equal(stack, z[f"{axis_name}_stack"])
         trackers[axis_name] = trs
     for v, name, inst in consensus.tracker_consensus(
-            trackers, MODEL_CONFIG, pixel_vote_thr=int(z["pixel_vote_thr"]),
+            trackers, cfg, pixel_vote_thr=int(z["pixel_vote_thr"]),
             allow_one_view=bool(z["allow_one_view"]), min_size=int(z["min_size"]),
             min_extent=int(z["min_extent"]), dtype=np.int32):
         assert_instances_equal(inst, unpack_instances(z, "consensus_"))
         assert np.array_equal(v, z["consensus_vol"])
     for v, name, inst in consensus.stack_postprocessing(
-            {"xy": trackers["xy"]}, MODEL_CONFIG, min_size=int(z["min_size"]),
+            {"xy": trackers["xy"]}, cfg, min_size=int(z["min_size"]),
             min_extent=int(z["min_extent"]), dtype=np.int32):
         assert_instances_equal(inst, unpack_instances(z, "stackpost_"))
         assert np.array_equal(v, z["stackpost_vol"])
