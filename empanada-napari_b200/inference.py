@@ -17,7 +17,9 @@ from .model import load_model
 from .postproc import CenterOverflow, LazyPlane, PlanePost, _next_pow2
 from .tracking import InstanceTracker
 
-__all__ = ["Engine2d", "Engine3d", "tracker_consensus", "stack_postprocessing"]
+__all__ = ["Engine2d", "Engine3d", "tracker_consensus", "stack_postprocessing", "instance_relabel"]
+
+instance_relabel = consensus.instance_relabel      # empanada_napari/inference.py:31-54
 
 
 def _require_cuda():
@@ -394,14 +396,17 @@ class Engine3d:
         self.chunk_size = chunk_size
         self.zarr_store = open_zarr_store(store_url, mode="w") if store_url is not None else None
 
-    def create_panoptic_stack(self, axis_name, shape3d, dense):
+    def create_panoptic_stack(self, axis_name, shape3d, dense=None):
         """inference.py:474-489 + fill_panoptic_volume (patterns.py:215-220): the plane's label
-        volume as a zarr array of the store, a numpy array, or None."""
+        volume as a zarr array of the store, a numpy array, or None. Called as the reference calls
+        it (without `dense`) it returns the empty stack."""
         if not self.save_panoptic:
             return None
         if self.zarr_store is not None:
             stack = create_store_array(self.zarr_store, f"panoptic_{axis_name}", shape3d, self.dtype, self.chunk_size)
-            return fill_store_from_device(stack, dense)
+            return stack if dense is None else fill_store_from_device(stack, dense)
+        if dense is None:
+            return np.zeros(tuple(int(s) for s in shape3d), dtype=self.dtype)
         return dense.cpu().numpy()
 
     def create_trackers(self, shape3d, axis_name):
@@ -695,7 +700,7 @@ class Engine2d:
         out = tiling.merge_tiles(post, tiler, thing=not semantic, label_base=cls * self.engine.label_divisor)
         self.last_stats = {"kernel_launches": post.launches + getattr(self.model, "launches", 0) - self._launches0,
                            "tiles": len(tiler)}
-        return out.cpu().numpy().astype(np.int32)
+        return out.cpu().numpy().astype(np.int32, copy=False)
 
     def infer_batch_host(self, images):
         """Host uint8 (n, h, w) in, host int32 (n, h, w) out (page-locked staging buffer)."""
@@ -706,7 +711,7 @@ class Engine2d:
             raise ValueError("Engine2d.infer expects a 2-D image")
         if self.tile_size > 0 and any(s > self.tile_size for s in image.shape):
             return self.infer_tiled(image)
-        return self.infer_batch(image[None])[0].cpu().numpy().astype(np.int32)
+        return self.infer_batch(image[None])[0].cpu().numpy().astype(np.int32, copy=False)
 
 
 class _PinnedPool:
