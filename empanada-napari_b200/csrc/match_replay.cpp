@@ -35,11 +35,18 @@ struct SliceObjs {
 // Rectangular LAP, minimisation, shortest augmenting paths (Crouse, "On implementing 2D
 // rectangular assignment algorithms", 2016) - the algorithm behind scipy.optimize.linear_sum_assignment.
 // cost is nr x nc row-major with nr <= nc. Returns col4row.
-static void lap_min(int nr, int nc, const std::vector<double>& cost, std::vector<int>& col4row) {
+// The duals stay in the workspace: cost[i][j] - u[i] - v[j] >= 0, = 0 on the assignment.
+struct LapWork {
+  std::vector<double> u, v, shortest;
+  std::vector<int> path, row4col, remaining;
+  std::vector<char> SR, SC;
+};
+
+static void lap_min(int nr, int nc, const std::vector<double>& cost, std::vector<int>& col4row, LapWork& W) {
   const double INF = std::numeric_limits<double>::infinity();
-  static thread_local std::vector<double> u, v, shortest;
-  static thread_local std::vector<int> path, row4col, remaining;
-  static thread_local std::vector<char> SR, SC;
+  std::vector<double>&u = W.u, &v = W.v, &shortest = W.shortest;
+  std::vector<int>&path = W.path, &row4col = W.row4col, &remaining = W.remaining;
+  std::vector<char>&SR = W.SR, &SC = W.SC;
   u.assign(nr, 0.0); v.assign(nc, 0.0); shortest.resize(nc);
   path.assign(nc, -1); row4col.assign(nc, -1); remaining.resize(nc);
   SR.resize(nr); SC.resize(nc);
@@ -90,6 +97,7 @@ static void lap_min(int nr, int nc, const std::vector<double>& cost, std::vector
 
 struct Entry { int row, col; long long inter; };
 constexpr int kNoLabel = std::numeric_limits<int>::min();
+constexpr double kTieEps = 1e-12;  // reduced costs below this count as ties (IoUs are O(1))
 
 struct Scratch {
   std::vector<Entry> agg, bycol;
@@ -99,6 +107,7 @@ struct Scratch {
   std::vector<float> ioa_max;
   std::vector<double> dense, cost;
   std::vector<int> col4row;
+  LapWork lap;
   // merge_by_label
   std::vector<int> gid, gcount, gstart, members, hkey, hval;
 };
@@ -169,6 +178,7 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
         S.multi.push_back(static_cast<int>(k));
       }
     }
+    bool tie_risk = false;
     if (!S.multi.empty()) {
       // connected blocks of the bipartite graph (union-find over rows [0,n) and cols [n,n+m))
       std::vector<int>& parent = S.parent;
@@ -212,13 +222,42 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
             const double val = -S.dense[static_cast<size_t>(r) * bc + c];
             if (transpose) S.cost[static_cast<size_t>(c) * nc + r] = val; else S.cost[static_cast<size_t>(r) * nc + c] = val;
           }
-        lap_min(nr, nc, S.cost, S.col4row);
+        lap_min(nr, nc, S.cost, S.col4row, S.lap);
         for (int a = 0; a < nr; ++a) {
           if (S.col4row[a] < 0) continue;
           const int r = transpose ? S.col4row[a] : a, c = transpose ? a : S.col4row[a];
           if (S.dense[static_cast<size_t>(r) * bc + c] >= iou_thr) S.matched_row[cols[c]] = rows[r];
         }
+        // Is this optimum the only one? If every pair outside the assignment (zero entries of the
+        // block included) has a positive reduced cost, no other assignment of the block reaches
+        // the same total, and - cross-block entries being zero - SciPy's run on the full matrix
+        // must pick the same positive pairs. Otherwise the choice among equal optima depends on
+        // SciPy's scan order over the WHOLE matrix: replay that run literally (below).
+        for (int a = 0; a < nr && !tie_risk; ++a)
+          for (int j = 0; j < nc; ++j)
+            if (j != S.col4row[a] && S.cost[static_cast<size_t>(a) * nc + j] - S.lap.u[a] - S.lap.v[j] <= kTieEps) {
+              tie_risk = true;
+              break;
+            }
         g0 = g1;
+      }
+    }
+    if (tie_risk) {
+      // scipy.optimize.linear_sum_assignment(iou, maximize=True) on the full n x m matrix
+      // (matcher.py:213): negate, transpose when there are fewer columns than rows
+      const bool transpose = m < n;
+      const int nr = transpose ? m : n, nc = transpose ? n : m;
+      S.cost.assign(static_cast<size_t>(nr) * nc, 0.0);
+      for (size_t k = 0; k < na; ++k) {
+        const Entry& e = agg[k];
+        S.cost[transpose ? static_cast<size_t>(e.col) * nc + e.row : static_cast<size_t>(e.row) * nc + e.col] = -S.iou[k];
+      }
+      lap_min(nr, nc, S.cost, S.col4row, S.lap);
+      S.matched_row.assign(m, -1);
+      for (int a = 0; a < nr; ++a) {
+        if (S.col4row[a] < 0) continue;
+        const int r = transpose ? S.col4row[a] : a, c = transpose ? a : S.col4row[a];
+        if (-S.cost[static_cast<size_t>(a) * nc + S.col4row[a]] >= iou_thr) S.matched_row[c] = r;
       }
     }
   }
@@ -306,6 +345,9 @@ int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
                     int* lut, int lut_stride, int* inst_labels, long long* inst_sizes,
                     int* inst_boxes, int max_inst, int* n_inst) {
   if (n_slices <= 0) { *n_inst = 0; return 0; }
+  // With a threshold <= 0 the reference also keeps the ZERO-overlap pairs SciPy happens to assign;
+  // the sparse formulation has no such pairs (the engines fix both thresholds at 0.25).
+  if (!(iou_thr > 0.0)) return be_set_error("be_match_replay: iou_thr must be positive");
   for (int s = 0; s < n_slices; ++s)
     if (n_cc[s] > cap || n_cc[s] >= lut_stride || n_cc[s] >= (1 << 20))
       return be_set_error("component count exceeds table capacity; re-run with a larger cap");
