@@ -946,12 +946,13 @@ def merge_semantic_from_trackers(trackers, pixel_vote_thr=2, dev=None, runs_fn=N
     dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
     runs_fn = extract_runs if runs_fn is None else runs_fn
     shape3d = tuple(int(s) for s in trackers[0].shape3d)
-    boxes, vols = [], []
+    boxes, vols, voters = [], [], []
     for tr in trackers:
         assert len(tr.instances.keys()) <= 1, 'Semantic classes only have 1 label!'
         for attrs in tr.instances.values():
             boxes.append(tuple(int(v) for v in attrs["box"]))
-            vols.append(dense_volume(tr, dev))
+            vols.append(getattr(tr, "_b200_dense", None))
+            voters.append(tr)
     if not boxes:
         return torch.zeros(shape3d, dtype=torch.int32, device=dev), {}
     box = boxes[0]
@@ -961,12 +962,37 @@ def merge_semantic_from_trackers(trackers, pixel_vote_thr=2, dev=None, runs_fn=N
         # `vote_by_ranges` hands back a 1-D empty array here and the reference fails on it
         # (array_utils.py:631-635, consensus.py:340)
         raise IndexError("too many indices for array: array is 1-dimensional, but 2 were indexed")
-    votes = torch.zeros(shape3d, dtype=torch.int32, device=dev)
-    for v in vols:
-        votes += (v != 0)
+    # Votes per voxel. A plane's label volume gives one vote where it is set - except for a plane
+    # whose run-length table overlaps itself (the xz row-wrap quirk of tracker.py:80-84, DESIGN.md
+    # section 5; or any tracker that carries no label volume, e.g. one loaded from JSON): the
+    # reference votes on the RANGES, so a voxel covered by k ranges of one plane has k votes, and a
+    # range may even run past the end of the volume. Those planes are counted from their tables.
+    n = int(np.prod(shape3d))
+    from_tables = [getattr(tr, "_b200_dense", None) is None or getattr(tr, "_b200_xz_wrap", False) for tr in voters]
+    n_ext = n
+    for tr, ft in zip(voters, from_tables):
+        if ft:
+            for attrs in tr.instances.values():
+                if len(attrs["starts"]):
+                    n_ext = max(n_ext, int(np.max(np.asarray(attrs["starts"]) + np.asarray(attrs["runs"]))))
+    votes = torch.zeros(n_ext, dtype=torch.int32, device=dev)
+    for tr, ft, v in zip(voters, from_tables, vols):
+        if not ft:
+            votes[:n] += (v.reshape(-1) != 0)
+            continue
+        diff = torch.zeros(n_ext + 1, dtype=torch.int32, device=dev)
+        for attrs in tr.instances.values():
+            st = torch.from_numpy(np.ascontiguousarray(attrs["starts"], dtype=np.int64)).to(dev)
+            en = st + torch.from_numpy(np.ascontiguousarray(attrs["runs"], dtype=np.int64)).to(dev)
+            one = torch.ones(st.numel(), dtype=torch.int32, device=dev)
+            diff.index_add_(0, st, one)
+            diff.index_add_(0, en, -one)
+        votes += torch.cumsum(diff, 0)[:n_ext].to(torch.int32)
     voted = (votes >= int(pixel_vote_thr)).to(torch.int32)
-    _, starts, lens = runs_fn(voted)
-    return voted, {1: {"box": box, "starts": starts.cpu().numpy(), "runs": lens.cpu().numpy().astype(np.int64)}}
+    # ranges = maximal flat-index runs of the voted mask (over the extended index range when a
+    # table runs past the volume; the painted volume is clipped as numpy slicing clips the fill)
+    _, starts, lens = runs_fn(voted.view(shape3d) if n_ext == n else voted)
+    return voted[:n].view(shape3d), {1: {"box": box, "starts": starts.cpu().numpy(), "runs": lens.cpu().numpy().astype(np.int64)}}
 
 
 def instance_relabel(tracker):

@@ -256,3 +256,47 @@ def test_semantic_consensus_vote_against_reference_fixture(tag):
         consensus.merge_semantic_from_trackers(trackers[:1], 2, dev=torch.device("cpu"), runs_fn=_numpy_runs)
     with pytest.raises(IndexError):
         ocons.merge_semantic_from_trackers(trackers[:1], 2)
+
+
+def test_semantic_consensus_counts_self_overlapping_xz_runs_like_the_reference():
+    """A stuff class that spans the full width of xz slices: the reference lifts such 2-D runs to
+    3-D unsplit (tracker.py:80-84), the xz table then overlaps itself and `vote_by_ranges` counts
+    every covering range as a vote. The product votes from the table for such a plane (and from
+    the label volumes for the others, as on the GPU): identical to the oracle."""
+    import torch
+    from conftest import assert_instances_equal
+    from empanada_napari_b200 import consensus
+    from oracle import consensus as ocons, pipeline
+    from oracle.ranges import numpy_fill_instances
+    from test_gpu_post_parity import MODEL_CONFIG, random_engine_case
+    vol, heads, o = random_engine_case(6)            # stuff config, inference_scale 2
+    assert o["stuff_config"]
+    cfg = dict(MODEL_CONFIG, thing_list=[])
+    trackers = []
+    for a, axis_name in enumerate(("xy", "xz", "yz")):
+        sem, ctr, off = heads[a]
+        stack, trs = pipeline.infer_on_axis(
+            vol, axis_name, lambda i, x: (sem[i], ctr[i], off[i]), cfg, median_kernel_size=o["ks"],
+            nms_kernel=o["nms_kernel"], confidence_thr=o["conf"], min_size=o["min_size"],
+            min_extent=o["min_extent"], semantic_only=o["semantic_only"], inference_scale=o["scale"])
+        tr = trs[0]
+        # what Engine3d leaves on a tracker: the label volume; the xz plane is flagged when a run
+        # wraps around a row end and its volume is the rasterised table
+        tr._b200_dense = torch.from_numpy(stack.astype(np.int32))
+        covered = np.zeros(vol.size + 4096, np.int64)
+        for attrs in tr.instances.values():
+            for s, r in zip(attrs["starts"], attrs["runs"]):
+                covered[s:s + r] += 1
+        tr._b200_xz_wrap = bool(covered.max() > 1)
+        trackers.append(tr)
+    assert trackers[1]._b200_xz_wrap and not trackers[0]._b200_xz_wrap and not trackers[2]._b200_xz_wrap
+    for thr in (1, 2, 3):
+        want = ocons.merge_semantic_from_trackers(trackers, thr)
+        got_vol, got = consensus.merge_semantic_from_trackers(trackers, thr, dev=torch.device("cpu"), runs_fn=_numpy_runs)
+        assert_instances_equal(got, want)
+        want_vol = np.zeros(vol.shape, dtype=np.int32)
+        numpy_fill_instances(want_vol, want)
+        assert np.array_equal(got_vol.numpy(), want_vol)
+    # a plain dense vote would differ here (one vote per plane): the case is a real one
+    dense_votes = sum((t._b200_dense.numpy() != 0).astype(np.int32) for t in trackers)
+    assert int((dense_votes >= 2).sum()) != int(ocons.merge_semantic_from_trackers(trackers, 2)[1]["runs"].sum())
