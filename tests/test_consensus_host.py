@@ -268,7 +268,7 @@ def test_semantic_consensus_counts_self_overlapping_xz_runs_like_the_reference()
     from empanada_napari_b200 import consensus
     from oracle import consensus as ocons, pipeline
     from oracle.ranges import numpy_fill_instances
-    from test_gpu_post_parity import MODEL_CONFIG, random_engine_case
+    from test_gpu_z_random_options import MODEL_CONFIG, random_engine_case
     vol, heads, o = random_engine_case(6)            # stuff config, inference_scale 2
     assert o["stuff_config"]
     cfg = dict(MODEL_CONFIG, thing_list=[])
