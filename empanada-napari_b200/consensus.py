@@ -909,6 +909,11 @@ def merge_objects_from_trackers(trackers, pixel_vote_thr=2, cluster_iou_thr=0.75
     if pixel_vote_thr < min_cluster:
         cluster_iou_thr = 0
 
+    if any(getattr(tr, "_b200_xz_wrap", False) for tr in trackers):
+        import warnings
+        warnings.warn("an xz instance spans the full slice width: the reference lifts such runs unsplit "
+                      "(tracker.py:80-84) and counts their self-overlaps as extra votes; this consensus votes once "
+                      "per plane and may miss those voxels (DESIGN.md section 5)", RuntimeWarning, stacklevel=2)
     n_nodes, node_sizes, node_boxes, luts, vols = tracker_nodes(trackers, dev)
     if n_nodes == 0:
         return torch.zeros(shape3d, dtype=torch.int32, device=dev), {}
