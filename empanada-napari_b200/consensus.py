@@ -681,40 +681,37 @@ def membership_tables(cands, n_nodes):
     return memb_off, memb_list
 
 
-def tracker_nodes(trackers, dev):
-    """Nodes in tracker order / dict order (consensus.py:400-406): per-plane label -> node LUTs,
-    node sizes and boxes, device label volumes."""
-    node_sizes, node_boxes, luts, vols = [], [], [], []
-    nid = 0
-    for tr in trackers:
-        labels = [int(l) for l in tr.instances.keys()]
-        lut = np.zeros((max(labels) + 1) if labels else 1, dtype=np.int32)
-        known = getattr(tr, "_b200_sizes", None)
-        for l in labels:
-            nid += 1
-            lut[l] = nid
-            node_sizes.append(int(known[l]) if known is not None else int(np.sum(tr.instances[l]["runs"])))
-            node_boxes.append(tuple(int(v) for v in tr.instances[l]["box"]))
-        luts.append(torch.from_numpy(lut).to(dev))
-        vols.append(dense_volume(tr, dev))
-    return nid, node_sizes, node_boxes, luts, vols
-
-
-def tracker_node_tables(trackers):
-    """`tracker_nodes` without the device volumes (host tables only): (n_nodes, sizes, boxes,
-    per-plane label -> node LUTs as numpy arrays). Trackers must carry `_b200_sizes`."""
+def _node_tables(trackers):
+    """Nodes in tracker order / dict order (consensus.py:400-406): (n_nodes, sizes, boxes, per-plane
+    label -> node LUTs as numpy arrays). Sizes come from `_b200_sizes` when the engine left them
+    on the tracker, else from the run-length tables."""
     node_sizes, node_boxes, luts = [], [], []
     nid = 0
     for tr in trackers:
         labels = [int(l) for l in tr.instances.keys()]
         lut = np.zeros((max(labels) + 1) if labels else 1, dtype=np.int32)
-        for l in labels:
-            nid += 1
-            lut[l] = nid
-            node_sizes.append(int(tr._b200_sizes[l]))
-            node_boxes.append(tuple(int(v) for v in tr.instances[l]["box"]))
+        if labels:
+            lut[np.asarray(labels, dtype=np.int64)] = np.arange(nid + 1, nid + 1 + len(labels), dtype=np.int32)
+            nid += len(labels)
+            known = getattr(tr, "_b200_sizes", None)
+            if known is not None:
+                node_sizes.extend(int(known[l]) for l in labels)
+            else:
+                node_sizes.extend(int(np.sum(a["runs"])) for a in tr.instances.values())
+            node_boxes.extend(np.asarray([a["box"] for a in tr.instances.values()], dtype=np.int64).reshape(-1, 6).tolist())
         luts.append(lut)
-    return nid, node_sizes, node_boxes, luts
+    return nid, node_sizes, [tuple(b) for b in node_boxes], luts
+
+
+def tracker_nodes(trackers, dev):
+    """`_node_tables` + the LUTs and the label volumes on the device."""
+    nid, node_sizes, node_boxes, luts = _node_tables(trackers)
+    return nid, node_sizes, node_boxes, [torch.from_numpy(l).to(dev) for l in luts], [dense_volume(tr, dev) for tr in trackers]
+
+
+def tracker_node_tables(trackers):
+    """`tracker_nodes` without the device volumes (host tables only)."""
+    return _node_tables(trackers)
 
 
 def keep_mask(final_boxes, fsize, n_final, min_size, min_extent):

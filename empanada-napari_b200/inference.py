@@ -513,7 +513,7 @@ class Engine3d:
         tr.finish()
         prof.mark("runs + tracker dict")
         tr._b200_dense = dense  # device-resident label volume reused by tracker_consensus
-        tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, sizes[keep])}
+        tr._b200_sizes = dict(zip(kept_labels.tolist(), sizes[keep].tolist()))
         if self.label_erosion > 0 or self.label_dilation > 0 or self.fill_holes_in_segmentation:
             from . import morphology       # filters.erode / dilate / fill_holes (inference.py:560-570)
             morphology.apply_to_tracker(tr, dense, post.cls, self.label_divisor, not post.semantic,

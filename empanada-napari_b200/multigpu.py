@@ -515,7 +515,7 @@ class ShardedEngine3d(Engine3d):
             else:
                 plane = ShardedPlane(self, tr, name, kept_labels, kept_boxes)
             tr.instances = plane.attrs
-            tr._b200_sizes = {int(l): int(s) for l, s in zip(kept_labels, kept_sizes)}
+            tr._b200_sizes = dict(zip(np.asarray(kept_labels).tolist(), np.asarray(kept_sizes).tolist()))
             tr._b200_sharded = self
             tr.finish()
 
@@ -733,7 +733,7 @@ class ShardedPlane:
         from .postproc import LazyAttrs
         self.engine, self.tracker, self.axis_name = engine, tracker, axis_name
         self.labels, self.boxes = labels, boxes
-        self.attrs = {int(l): LazyAttrs(tuple(int(v) for v in b), self) for l, b in zip(labels, boxes)}
+        self.attrs = {l: LazyAttrs(tuple(b), self) for l, b in zip(np.asarray(labels).tolist(), np.asarray(boxes).tolist())}
 
     def dense(self):
         front = self.engine.front

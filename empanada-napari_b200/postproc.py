@@ -490,7 +490,7 @@ class LazyPlane:
 
     def __init__(self, dense, axis_name, labels, boxes):
         self.dense, self.axis_name, self.labels, self.boxes = dense, axis_name, labels, boxes
-        self.attrs = {int(l): LazyAttrs(tuple(int(v) for v in b), self) for l, b in zip(labels, boxes)}
+        self.attrs = {l: LazyAttrs(tuple(b), self) for l, b in zip(np.asarray(labels).tolist(), np.asarray(boxes).tolist())}
         self.done = False
 
     def materialize(self):
