@@ -134,6 +134,10 @@ int be_pair_overlap(const int* cc_plane, int h, int w, int s0, int s1, unsigned 
 int be_hash_compact(const unsigned long long* keys, const int* vals, unsigned long long cap,
                     unsigned long long* out_keys, int* out_vals, int out_cap, int* cursor,
                     be_stream st);
+/* be_match_replay: the Hungarian step (scipy.optimize.linear_sum_assignment, matcher.py:213) is
+ * solved per connected block of the sparse IoU matrix; a block whose optimum is not certified
+ * unique by its dual variables makes the step replay SciPy's run on the full matrix, so exact IoU
+ * ties resolve as in the reference. iou_thr must be > 0 (the engines use 0.25 as the reference). */
 int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
                     const unsigned long long* pair_keys, const int* pair_vals, long long n_pairs,
                     int class_id, int label_divisor, double iou_thr, double ioa_thr, int axis,
