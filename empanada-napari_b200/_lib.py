@@ -73,6 +73,7 @@ _SIGNATURES = {
     "be_components_clusters_fetch": ([P, P], I),
     # match_replay.cpp (host)
     "be_match_replay": ([I, P, P, I, P, P, LL, I, I, D, D, I, P, I, P, P, P, I, P], I),
+    "be_match_replay_stats": ([P], I),
 }
 
 

@@ -98,6 +98,9 @@ static void lap_min(int nr, int nc, const std::vector<double>& cost, std::vector
 struct Entry { int row, col; long long inter; };
 constexpr int kNoLabel = std::numeric_limits<int>::min();
 constexpr double kTieEps = 1e-12;  // reduced costs below this count as ties (IoUs are O(1))
+// diagnostics of the last be_match_replay call: matcher steps, steps with a multi-entry block,
+// steps replayed on the full matrix
+static long long g_stats[3] = {0, 0, 0};
 
 struct Scratch {
   std::vector<Entry> agg, bycol;
@@ -110,7 +113,56 @@ struct Scratch {
   LapWork lap;
   // merge_by_label
   std::vector<int> gid, gcount, gstart, members, hkey, hval;
+  // star blocks
+  std::vector<char> row_star, col_star;
+  std::vector<int> row_best, col_best;
+  std::vector<double> row_second, col_second;
+  // uniqueness test of a block optimum
+  std::vector<char> alt_adj, alt_free, alt_zero, alt_seen;
+  std::vector<int> alt_stack;
 };
+
+// Does the block have a second optimal assignment? By complementary slackness every optimal
+// assignment uses only TIGHT pairs (reduced cost cost[a][j] - u[a] - v[j] = 0) and covers every
+// column with v[j] < 0. Against the assignment found, another one differs by alternating cycles
+// (row a takes the column of row b, ... back to a) or by an alternating path that ends in a free
+// column and frees a column whose dual is zero. Rows are nodes; a -> b when (a, column of b) is
+// tight. Conservative under rounding: anything within kTieEps counts as tight / zero.
+static bool block_has_alternative(int nr, int nc, const std::vector<double>& cost, const std::vector<int>& col4row,
+                                  const LapWork& W, Scratch& S) {
+  S.alt_adj.assign(static_cast<size_t>(nr) * nr, 0);
+  S.alt_free.assign(nr, 0);
+  S.alt_zero.assign(nr, 0);
+  bool any_edge = false;
+  for (int a = 0; a < nr; ++a) {
+    S.alt_zero[a] = W.v[col4row[a]] >= -kTieEps;
+    for (int j = 0; j < nc; ++j) {
+      if (j == col4row[a] || cost[static_cast<size_t>(a) * nc + j] - W.u[a] - W.v[j] > kTieEps) continue;
+      const int b = W.row4col[j];
+      if (b < 0) { S.alt_free[a] = 1; if (S.alt_zero[a]) return true; }
+      else { S.alt_adj[static_cast<size_t>(a) * nr + b] = 1; any_edge = true; }
+    }
+  }
+  if (!any_edge) return false;
+  for (int start = 0; start < nr; ++start) {     // blocks are small: one search per row
+    S.alt_seen.assign(nr, 0);
+    S.alt_stack.clear();
+    S.alt_stack.push_back(start);
+    while (!S.alt_stack.empty()) {
+      const int a = S.alt_stack.back();
+      S.alt_stack.pop_back();
+      for (int b = 0; b < nr; ++b) {
+        if (!S.alt_adj[static_cast<size_t>(a) * nr + b]) continue;
+        if (b == start) return true;                              // alternating cycle
+        if (S.alt_seen[b]) continue;
+        S.alt_seen[b] = 1;
+        if (S.alt_zero[start] && S.alt_free[b]) return true;       // alternating path
+        S.alt_stack.push_back(b);
+      }
+    }
+  }
+  return false;
+}
 
 // One matcher step: relabel `match` objects against `target` objects.
 // entries: sparse intersections (row = target index, col = match index), duplicates allowed.
@@ -123,6 +175,7 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
                        double iou_thr, float ioa_thr, bool assign_new, int& next_label,
                        std::vector<int>& new_labels, Scratch& S) {
   const int n = target.size(), m = match.size();
+  ++g_stats[0];
   new_labels.assign(m, 0);
   S.matched_row.assign(m, -1);
   S.ioa_max.assign(m, 0.0f);
@@ -163,6 +216,23 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
     S.iou.resize(na);
     S.ioa.resize(na);
     S.multi.clear();
+    // Star blocks - one row against several columns that touch nothing else, or one column
+    // against several such rows (an object that splits in two, or two that merge) - are the
+    // bulk of the non-isolated entries: their assignment is the largest IoU of the star, unique
+    // exactly when the runner-up is smaller (the same dual certificate as for general blocks:
+    // u = -best, v = 0, reduced cost of the others = best - iou).
+    S.row_star.assign(n, 1);
+    S.col_star.assign(m, 1);
+    for (size_t k = 0; k < na; ++k) {
+      const Entry& e = agg[k];
+      if (S.col_deg[e.col] != 1) S.row_star[e.row] = 0;
+      if (S.row_deg[e.row] != 1) S.col_star[e.col] = 0;
+    }
+    S.row_best.assign(n, -1);
+    S.col_best.assign(m, -1);
+    S.row_second.assign(n, -1.0);
+    S.col_second.assign(m, -1.0);
+    bool tie_risk = false;
     for (size_t k = 0; k < na; ++k) {
       const Entry& e = agg[k];
       const long long inter = e.inter;
@@ -172,14 +242,37 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
       // per-column IoA maximum (float32 matrix semantics: zeros everywhere else, first max row
       // wins - rows ascend inside a column, so ">" keeps the first one)
       if (S.ioa[k] > S.ioa_max[e.col]) { S.ioa_max[e.col] = S.ioa[k]; S.ioa_arg[e.col] = e.row; }
-      if (S.row_deg[e.row] == 1 && S.col_deg[e.col] == 1) {
+      const int rd = S.row_deg[e.row], cd = S.col_deg[e.col];
+      if (rd == 1 && cd == 1) {
         if (S.iou[k] >= iou_thr) S.matched_row[e.col] = e.row;
+      } else if (cd > 1 && S.col_star[e.col]) {       // rd == 1 for every entry of this column
+        int& best = S.col_best[e.col];
+        double& second = S.col_second[e.col];
+        if (best < 0 || S.iou[k] > S.iou[best]) { if (best >= 0) second = std::max(second, S.iou[best]); best = static_cast<int>(k); }
+        else second = std::max(second, S.iou[k]);
+      } else if (rd > 1 && S.row_star[e.row]) {       // cd == 1 for every entry of this row
+        int& best = S.row_best[e.row];
+        double& second = S.row_second[e.row];
+        if (best < 0 || S.iou[k] > S.iou[best]) { if (best >= 0) second = std::max(second, S.iou[best]); best = static_cast<int>(k); }
+        else second = std::max(second, S.iou[k]);
       } else {
         S.multi.push_back(static_cast<int>(k));
       }
     }
-    bool tie_risk = false;
+    for (int c = 0; c < m; ++c) {
+      const int best = S.col_best[c];
+      if (best < 0) continue;
+      if (S.iou[best] - S.col_second[c] <= kTieEps) tie_risk = true;
+      else if (S.iou[best] >= iou_thr) S.matched_row[c] = agg[best].row;
+    }
+    for (int r = 0; r < n; ++r) {
+      const int best = S.row_best[r];
+      if (best < 0) continue;
+      if (S.iou[best] - S.row_second[r] <= kTieEps) tie_risk = true;
+      else if (S.iou[best] >= iou_thr) S.matched_row[agg[best].col] = r;
+    }
     if (!S.multi.empty()) {
+      ++g_stats[1];
       // connected blocks of the bipartite graph (union-find over rows [0,n) and cols [n,n+m))
       std::vector<int>& parent = S.parent;
       parent.resize(n + m);
@@ -228,21 +321,16 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
           const int r = transpose ? S.col4row[a] : a, c = transpose ? a : S.col4row[a];
           if (S.dense[static_cast<size_t>(r) * bc + c] >= iou_thr) S.matched_row[cols[c]] = rows[r];
         }
-        // Is this optimum the only one? If every pair outside the assignment (zero entries of the
-        // block included) has a positive reduced cost, no other assignment of the block reaches
-        // the same total, and - cross-block entries being zero - SciPy's run on the full matrix
-        // must pick the same positive pairs. Otherwise the choice among equal optima depends on
-        // SciPy's scan order over the WHOLE matrix: replay that run literally (below).
-        for (int a = 0; a < nr && !tie_risk; ++a)
-          for (int j = 0; j < nc; ++j)
-            if (j != S.col4row[a] && S.cost[static_cast<size_t>(a) * nc + j] - S.lap.u[a] - S.lap.v[j] <= kTieEps) {
-              tie_risk = true;
-              break;
-            }
+        // Is this optimum the only one? Cross-block entries being zero, SciPy's run on the full
+        // matrix must pick the same positive pairs when it is. Otherwise the choice among equal
+        // optima depends on SciPy's scan order over the WHOLE matrix: that run is replayed
+        // literally (below).
+        if (!tie_risk && block_has_alternative(nr, nc, S.cost, S.col4row, S.lap, S)) tie_risk = true;
         g0 = g1;
       }
     }
     if (tie_risk) {
+      ++g_stats[2];
       // scipy.optimize.linear_sum_assignment(iou, maximize=True) on the full n x m matrix
       // (matcher.py:213): negate, transpose when there are fewer columns than rows
       const bool transpose = m < n;
@@ -333,6 +421,13 @@ static void merge_by_label(const SliceObjs& match, const std::vector<int>& new_l
 
 extern "C" {
 
+// out[0..2]: matcher steps / steps with a multi-entry block / steps replayed on the full matrix,
+// of the last be_match_replay call of this process (diagnostics)
+int be_match_replay_stats(long long* out) {
+  for (int i = 0; i < 3; ++i) out[i] = g_stats[i];
+  return 0;
+}
+
 // n_cc        [n_slices]              components per slice
 // cc_table    [n_slices][cap][5]      area, y0, x0, y1, x1
 // pair_keys   slice(24)|prev_cc(20)|cur_cc(20), pair_vals = overlapping pixels (slice vs slice-1)
@@ -344,6 +439,7 @@ int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
                     int class_id, int label_divisor, double iou_thr, double ioa_thr, int axis,
                     int* lut, int lut_stride, int* inst_labels, long long* inst_sizes,
                     int* inst_boxes, int max_inst, int* n_inst) {
+  g_stats[0] = g_stats[1] = g_stats[2] = 0;
   if (n_slices <= 0) { *n_inst = 0; return 0; }
   // With a threshold <= 0 the reference also keeps the ZERO-overlap pairs SciPy happens to assign;
   // the sparse formulation has no such pairs (the engines fix both thresholds at 0.25).

@@ -143,6 +143,9 @@ int be_match_replay(int n_slices, const int* n_cc, const int* cc_table, int cap,
                     int class_id, int label_divisor, double iou_thr, double ioa_thr, int axis,
                     int* lut, int lut_stride, int* inst_labels, long long* inst_sizes,
                     int* inst_boxes, int max_inst, int* n_inst);            /* host function */
+/* diagnostics of the last be_match_replay call: out[0] matcher steps, out[1] steps with a
+ * multi-entry block, out[2] steps replayed on the full matrix */
+int be_match_replay_stats(long long* out);                                  /* host function */
 int be_relabel(const int* cc_batch, int B, int h, int w, int s0, const int* lut, int lut_stride,
                int* dst, long long stride_s, long long stride_y, long long stride_x, be_stream st);
 int be_runs_count(const int* img, long long n, long long seg_len, int* chunk_counts, be_stream st);
