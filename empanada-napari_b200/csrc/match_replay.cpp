@@ -192,6 +192,7 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
     S.col_deg.assign(m, 0);  // used as the fill cursor first
     for (const Entry& e : entries) S.bycol[cs[e.col] + S.col_deg[e.col]++] = e;
     S.row_deg.assign(n, 0);
+    bool shared = false;   // does any row or column hold more than one entry?
     for (int c = 0; c < m; ++c) {
       Entry* b = S.bycol.data() + cs[c];
       const int len = cs[c + 1] - cs[c];
@@ -208,9 +209,10 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
       int deg = 0;
       for (int i = 0; i < len; ++i) {
         if (deg > 0 && agg.back().row == b[i].row) agg.back().inter += b[i].inter;
-        else { agg.push_back(b[i]); ++deg; ++S.row_deg[b[i].row]; }
+        else { agg.push_back(b[i]); ++deg; if (++S.row_deg[b[i].row] > 1) shared = true; }
       }
       S.col_deg[c] = deg;
+      if (deg > 1) shared = true;
     }
     const size_t na = agg.size();
     S.iou.resize(na);
@@ -221,17 +223,19 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
     // bulk of the non-isolated entries: their assignment is the largest IoU of the star, unique
     // exactly when the runner-up is smaller (the same dual certificate as for general blocks:
     // u = -best, v = 0, reduced cost of the others = best - iou).
-    S.row_star.assign(n, 1);
-    S.col_star.assign(m, 1);
-    for (size_t k = 0; k < na; ++k) {
-      const Entry& e = agg[k];
-      if (S.col_deg[e.col] != 1) S.row_star[e.row] = 0;
-      if (S.row_deg[e.row] != 1) S.col_star[e.col] = 0;
+    if (shared) {
+      S.row_star.assign(n, 1);
+      S.col_star.assign(m, 1);
+      for (size_t k = 0; k < na; ++k) {
+        const Entry& e = agg[k];
+        if (S.col_deg[e.col] != 1) S.row_star[e.row] = 0;
+        if (S.row_deg[e.row] != 1) S.col_star[e.col] = 0;
+      }
+      S.row_best.assign(n, -1);
+      S.col_best.assign(m, -1);
+      S.row_second.assign(n, -1.0);
+      S.col_second.assign(m, -1.0);
     }
-    S.row_best.assign(n, -1);
-    S.col_best.assign(m, -1);
-    S.row_second.assign(n, -1.0);
-    S.col_second.assign(m, -1.0);
     bool tie_risk = false;
     for (size_t k = 0; k < na; ++k) {
       const Entry& e = agg[k];
@@ -259,13 +263,13 @@ static void match_step(const SliceObjs& target, const SliceObjs& match, std::vec
         S.multi.push_back(static_cast<int>(k));
       }
     }
-    for (int c = 0; c < m; ++c) {
+    for (int c = 0; shared && c < m; ++c) {
       const int best = S.col_best[c];
       if (best < 0) continue;
       if (S.iou[best] - S.col_second[c] <= kTieEps) tie_risk = true;
       else if (S.iou[best] >= iou_thr) S.matched_row[c] = agg[best].row;
     }
-    for (int r = 0; r < n; ++r) {
+    for (int r = 0; shared && r < n; ++r) {
       const int best = S.row_best[r];
       if (best < 0) continue;
       if (S.iou[best] - S.row_second[r] <= kTieEps) tie_risk = true;
