@@ -135,6 +135,19 @@ def _pair_counts(a, b):
         out_vals[:n].cpu().numpy().astype(np.int64)
 
 
+def _warn_if_runs_wrap(tiles):
+    """The reference run-length encodes every tile over its flat indices and translates only the
+    START of a run into the image frame (tile.py:126-166): a run that continues from the last
+    pixel of one tile row into the first pixel of the next (an object as wide as the tile) keeps
+    its length and is painted past the tile's right edge instead of into the next row. That
+    quirk is not reproduced here (every tile is painted where it is); say so when it applies."""
+    if tiles.shape[1] > 1 and bool(((tiles[:, :-1, -1] == tiles[:, 1:, 0]) & (tiles[:, 1:, 0] != 0)).any()):
+        import warnings
+        warnings.warn("an object spans the full width of a tile: the reference paints the wrapped part of such "
+                      "runs outside the tile (tile.py:126-166); this result keeps it inside (DESIGN.md section 7)",
+                      RuntimeWarning, stacklevel=3)
+
+
 def merge_tiles(post, tiler, thing, label_base, filter_overlap=True):
     """`merge_objects_from_tiles` (thing class) / `merge_semantic_from_tiles` (stuff class) on the
     batched tile post-processor `post` (run_cc done): returns the (h, w) int32 device image of the
@@ -151,6 +164,7 @@ def merge_tiles(post, tiler, thing, label_base, filter_overlap=True):
         lut = np.full((n, post.cc_cap + 1), label_base, dtype=np.int32)
         lut[:, 0] = 0
         tiles = post.relabel(lut, "xy", (n, post.h, post.w))
+        _warn_if_runs_wrap(tiles)
         for t in range(n):
             (y0, y1), (x0, x1) = tiler.yranges[t], tiler.xranges[t]
             torch.maximum(out[y0:y1, x0:x1], tiles[t], out=out[y0:y1, x0:x1])
@@ -200,6 +214,7 @@ def merge_tiles(post, tiler, thing, label_base, filter_overlap=True):
     for t in range(n):
         lut[t, 1:n_cc[t] + 1] = node_final[off[t]:off[t + 1]]
     tiles = post.relabel(lut, "xy", (n, post.h, post.w))
+    _warn_if_runs_wrap(cc)          # per-tile components: one run-length table each (rle.py:60-83)
     for t in range(n):
         (y0, y1), (x0, x1) = tiler.yranges[t], tiler.xranges[t]
         torch.maximum(out[y0:y1, x0:x1], tiles[t], out=out[y0:y1, x0:x1])
