@@ -5,7 +5,7 @@ reference and through `oracle.pipeline` / `oracle.consensus`; trackers, stacks, 
 and instance tables must be identical. The fixtures under tests/golden pin the oracle on a few
 cases; this widens the net (thousands of slices, many option combinations).
 
-    python -m oracle.fuzz_reference [first_seed] [n_cases]
+    python -m oracle.fuzz_reference [first_seed] [n_cases] [tiled]
 
 Needs /root/reference, so it is not part of the test suite (the GPU box has no reference).
 TEST INFRASTRUCTURE ONLY.
@@ -118,9 +118,89 @@ def one_case(seed):
     return "ok" if ref_err is None else f"ok (both raise {ref_err})", params
 
 
+def one_case_tiled(seed):
+    """Tiled `Engine2d.infer` (empanada_napari/inference.py:283-318) of the reference against
+    oracle/tiles.py; the tile layout is injected into both (cztile is absent)."""
+    import types
+    import empanada.inference.tile as ref_tile
+    import empanada_napari.inference as inf
+    from empanada_napari_b200.tiling import fixed_total_area_tiles_1d
+    from oracle import tiles as otiles
+
+    class FakeStrategy:
+        def __init__(self, total_tile_width, total_tile_height, min_border_width):
+            self.tw, self.th, self.b = total_tile_width, total_tile_height, min_border_width
+
+        def tile_rectangle(self, rect):
+            return [types.SimpleNamespace(roi=types.SimpleNamespace(x=x0, y=y0, w=sx, h=sy))
+                    for x0, sx in fixed_total_area_tiles_1d(rect.w, self.tw, self.b)
+                    for y0, sy in fixed_total_area_tiles_1d(rect.h, self.th, self.b)]
+
+    def layout(shape, tile, overlap):      # the rectangles FakeStrategy hands to the reference, same order
+        yr, xr = [], []
+        for x0, sx in fixed_total_area_tiles_1d(shape[1], tile[1], overlap):
+            for y0, sy in fixed_total_area_tiles_1d(shape[0], tile[0], overlap):
+                yr.append((y0, y0 + sy))
+                xr.append((x0, x0 + sx))
+        return yr, xr
+
+    ref_tile.AlmostEqualBorderFixedTotalAreaStrategy2D = FakeStrategy
+    ref_tile.czrect = lambda x, y, w, h: types.SimpleNamespace(x=x, y=y, w=w, h=h)
+    rng = np.random.default_rng(50000 + seed)
+    shape = (int(rng.integers(140, 330)), int(rng.integers(140, 330)))
+    tile_size = int(rng.choice([96, 128, 160]))
+    semantic_only = bool(rng.random() < 0.25)
+    scale = int(rng.choice([1, 1, 1, 2]))
+    wide = bool(rng.random() < 0.3)        # an object wider than a tile: its runs wrap around tile rows
+    params = dict(shape=shape, tile_size=tile_size, semantic_only=semantic_only, scale=scale, wide=wide)
+    _, lab, _ = syn.make_volume((1,) + shape, seed=50000 + seed, n_objects=int(rng.integers(4, 16)), scale=1.6)
+    lab = lab[0].copy()
+    if wide:
+        y0 = int(rng.integers(10, shape[0] - 30))
+        lab[y0:y0 + int(rng.integers(6, 20)), :] = int(lab.max()) + 1
+    img = np.clip(np.where(lab > 0, 70.0, 170.0) + rng.normal(0, 8.0, shape), 0, 255).astype(np.uint8)
+    yr, xr = layout(shape, (min(tile_size, shape[0]), min(tile_size, shape[1])), min(128, int(tile_size * 0.1)))
+    heads = []
+    for (y0, y1), (x0, x1) in zip(yr, xr):
+        tl = lab[y0:y1, x0:x1]
+        sem, ctr, off = scaled_heads(tl, scale, 0.0, rng) if scale > 1 else noisy_heads(tl, 16, 0.0, rng)
+        heads.append((sem, ctr, (off + rng.normal(0, 1.5, off.shape)).astype(np.float32)))
+    fake = FakeModel(heads)
+    orig_loader = inf.load_model_to_device
+    inf.load_model_to_device = lambda url, device: fake
+    try:
+        eng = inf.Engine2d(MODEL_CONFIG, inference_scale=scale, label_divisor=1000, nms_threshold=0.1, nms_kernel=3,
+                           confidence_thr=0.5, semantic_only=semantic_only, tile_size=tile_size, use_gpu=False)
+        try:
+            ref, ref_err = eng.infer(img).astype(np.int64), None
+        except Exception as e:
+            ref, ref_err = None, type(e).__name__
+    finally:
+        inf.load_model_to_device = orig_loader
+    try:
+        if any(s > tile_size for s in shape):
+            ora = otiles.engine2d_infer_tiled(img, lambda t, x: heads[t], MODEL_CONFIG, tile_size,
+                                              layout, nms_kernel=3,
+                                              confidence_thr=0.5, semantic_only=semantic_only, inference_scale=scale).astype(np.int64)
+        else:       # the image fits into one tile: the plain branch (inference.py:319-325)
+            ora = pipeline.engine2d_infer(img, lambda t, x: heads[0], MODEL_CONFIG, nms_kernel=3, confidence_thr=0.5,
+                                          semantic_only=semantic_only, inference_scale=scale).astype(np.int64)
+        ora_err = None
+    except Exception as e:
+        ora, ora_err = None, type(e).__name__
+    if ref_err != ora_err:
+        return f"tiled: error behaviour differs ({ref_err} vs {ora_err})", params
+    if ref_err is None and not np.array_equal(ref, ora):
+        return "tiled: label image differs", params
+    return ("ok" if ref_err is None else f"ok (both raise {ref_err})") + (" [wide object]" if wide else ""), params
+
+
 def main():
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    global one_case
+    if len(sys.argv) > 3 and sys.argv[3] == "tiled":
+        one_case = one_case_tiled
     t0 = time.time()
     tally = {}
     devnull = open(os.devnull, "w")

@@ -189,3 +189,19 @@ def test_evaluator_against_reference_fixture(tmp_path):
         assert set(got) == set(c["results"])
         for k, v in c["results"].items():
             assert float(got[k]) == v, (i, k, got[k], v)
+
+
+def test_tiled_inference_restatement_matches_reference_fixture():
+    """oracle/tiles.py (Tiler, overlap region, tile merge, tiled Engine2d.infer) against
+    tests/golden/tiled_cases.npz = the unmodified reference run with the same tile layout."""
+    from empanada_napari_b200.tiling import tile_rectangles
+    from oracle import tiles
+    z = np.load(os.path.join(GOLDEN, "tiled_cases.npz"))
+    layout = lambda shape, tile, ov: tile_rectangles(shape, tile, ov)      # noqa: E731 (cztile absent: the fixture's layout)
+    for ci in range(int(z["n"])):
+        tile_size, semantic_only, scale, n_tiles = (int(v) for v in z[f"t{ci}_meta"])
+        heads = [(z[f"t{ci}_sem{t}"], z[f"t{ci}_ctr{t}"], z[f"t{ci}_off{t}"]) for t in range(n_tiles)]
+        pan = tiles.engine2d_infer_tiled(z[f"t{ci}_img"], lambda t, x: heads[t], MODEL_CONFIG, tile_size, layout,
+                                         nms_kernel=3, confidence_thr=0.5, semantic_only=bool(semantic_only),
+                                         inference_scale=scale)
+        assert np.array_equal(pan.astype(np.int32), z[f"t{ci}_pan"]), ci
