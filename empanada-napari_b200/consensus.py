@@ -522,10 +522,42 @@ class TripleRuns:
 
 
 # ------------------------------------------------------------------------- consensus
+class Candidates:
+    """Candidate output instances in discovery order, as columns: `comp` (component index of the
+    instance graph), the member nodes of candidate i = `members[mstart[i]:mstart[i + 1]]` (0-based
+    node ids) and its merged box `boxes[i]`. Reads like the list of (component, members, box)
+    tuples it replaces (len, iteration, indexing)."""
+
+    def __init__(self, comp, mstart, members, boxes):
+        self.comp = np.asarray(comp, dtype=np.int64)
+        self.mstart = np.asarray(mstart, dtype=np.int64)
+        self.members = np.asarray(members, dtype=np.int64)
+        self.boxes = np.asarray(boxes, dtype=np.int64).reshape(-1, 6)
+
+    def __len__(self):
+        return len(self.comp)
+
+    def __getitem__(self, i):
+        return (int(self.comp[i]), self.members[self.mstart[i]:self.mstart[i + 1]].tolist(), tuple(self.boxes[i].tolist()))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _segment_boxes(boxes, starts):
+    """Merged box (min of the lower corner, max of the upper corner) of every segment of `boxes`
+    that begins at `starts` (non-empty segments, ascending)."""
+    out = np.zeros((len(starts), 6), dtype=np.int64)
+    if len(starts):
+        out[:, :3] = np.minimum.reduceat(boxes[:, :3], starts, axis=0)
+        out[:, 3:] = np.maximum.reduceat(boxes[:, 3:], starts, axis=0)
+    return out
+
+
 def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_thr, min_cluster):
     """Host graph logic of consensus.py:400-447: instance graph from the pair table, connected
-    components in networkx order, IoU sub-clustering, cluster merging. Returns the candidate list
-    [(component index, member nodes, merged box)]."""
+    components in networkx order, IoU sub-clustering, cluster merging. Returns the `Candidates`
+    (component index, member nodes, merged box) in the reference's discovery order."""
     order = np.lexsort((pb, pa))
     ea, eb, eit = pa[order] - 1, pb[order] - 1, inter[order]
     eiou = eit / (sizes[ea] + sizes[eb] - eit)          # float64, as `intersection / union`
@@ -551,28 +583,19 @@ def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_th
     edge_order = np.argsort(comp_of[ea], kind="stable")   # edges grouped by component, lexsorted inside
     edge_start = np.concatenate([[0], np.cumsum(np.bincount(comp_of[ea], minlength=n_comp))])
     boxes = np.asarray(node_boxes, dtype=np.int64).reshape(-1, 6)
-    # edges grouped by component as plain Python lists (one conversion for all components)
-    ea_l, eb_l = ea[edge_order].tolist(), eb[edge_order].tolist()
-    eiou_l, eit_l = eiou[edge_order].tolist(), eit[edge_order].tolist()
-    cands = []  # (component index, member node list, merged box)
-    # merged boxes of WHOLE components in one shot (what the one-cluster components need)
-    sorted_boxes = boxes[node_order]
-    starts = node_start[:-1]
-    nonempty = comp_size > 0
-    comp_box = np.zeros((n_comp, 6), dtype=np.int64)
-    if nonempty.any():
-        comp_box[nonempty, :3] = np.minimum.reduceat(sorted_boxes[:, :3], starts[nonempty], axis=0)
-        comp_box[nonempty, 3:] = np.maximum.reduceat(sorted_boxes[:, 3:], starts[nonempty], axis=0)
-    comp_box_l = comp_box.tolist()
-    node_order_l = node_order.tolist()
-    node_start_l, edge_start_l = node_start.tolist(), edge_start.tolist()
-    one_cluster_a = comp_min_iou > cluster_iou_thr
-    one_cluster = one_cluster_a.tolist()
+    one_cluster = comp_min_iou > cluster_iou_thr
     eligible = comp_size >= min_cluster
-    # components with an edge at or below the IoU cut: create_graph_of_clusters + merge_clusters,
+    # (a) every edge survives the IoU cut: the component is one cluster and the cluster graph has
+    # no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
+    one = np.flatnonzero(eligible & one_cluster)
+    one_box = _segment_boxes(boxes[node_order], node_start[:-1][comp_size > 0])
+    comp_box = np.zeros((n_comp, 6), dtype=np.int64)
+    comp_box[comp_size > 0] = one_box
+    # (b) components with an edge at or below the IoU cut: create_graph_of_clusters + merge_clusters,
     # natively and in one call (csrc/cluster_graph.cpp; `component_clusters` is the same in Python)
-    slow = np.flatnonzero(eligible & ~one_cluster_a)
-    slow_clusters = {}
+    slow = np.flatnonzero(eligible & ~one_cluster)
+    ncl = np.zeros(len(slow), dtype=np.int64)
+    csz, cmem = np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
     if len(slow) and NATIVE_CLUSTERS:
         n_nodes_c = comp_size[slow]
         n_edges_c = (edge_start[1:] - edge_start[:-1])[slow]
@@ -586,93 +609,87 @@ def cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_th
         eb_c = np.ascontiguousarray(eb[eo], dtype=np.int32)
         ei_c = np.ascontiguousarray(eiou[eo], dtype=np.float64)
         et_c = np.ascontiguousarray(eit[eo], dtype=np.int64)
-        ncl = np.zeros(len(slow), dtype=np.int32)
+        ncl32 = np.zeros(len(slow), dtype=np.int32)
         totals = np.zeros(2, dtype=np.int64)
         call("be_components_clusters", len(slow), ptr(noff), ptr(nodes_c), ptr(eoff), ptr(ea_c), ptr(eb_c), ptr(ei_c),
              ptr(et_c), int(n_nodes), float(cluster_iou_thr), float(MIN_IOU), float(MIN_OVERLAP),
-             1 if _COMPENSATED_SUM else 0, ptr(ncl), ptr(totals))
-        csz = np.zeros(max(1, int(totals[0])), dtype=np.int32)
-        cmem = np.zeros(max(1, int(totals[1])), dtype=np.int32)
-        call("be_components_clusters_fetch", ptr(csz), ptr(cmem))
-        n_cl = int(totals[0])
-        csz, cmem = csz[:n_cl], cmem[:int(totals[1])]
-        cstart = np.concatenate([[0], np.cumsum(csz)]).astype(np.int64)
-        cbox = np.zeros((n_cl, 6), dtype=np.int64)          # merged box of every cluster, in one shot
-        if n_cl:
-            mb = boxes[cmem]
-            cbox[:, :3] = np.minimum.reduceat(mb[:, :3], cstart[:-1], axis=0)
-            cbox[:, 3:] = np.maximum.reduceat(mb[:, 3:], cstart[:-1], axis=0)
-        csz_l, cmem_l, cbox_l, cstart_l = csz.tolist(), cmem.tolist(), cbox.tolist(), cstart.tolist()
-        cpos = 0
-        for c, k in zip(slow.tolist(), ncl.tolist()):
-            slow_clusters[c] = [(cmem_l[cstart_l[j]:cstart_l[j + 1]], tuple(cbox_l[j])) for j in range(cpos, cpos + k)]
-            cpos += k
-    boxes_l = None
-    for ci in np.flatnonzero(eligible).tolist():
-        members = node_order_l[node_start_l[ci]:node_start_l[ci + 1]]
-        if one_cluster[ci]:
-            # every edge survives the IoU cut: the component is one cluster and the cluster graph
-            # has no edges, so create_graph_of_clusters / merge_clusters reduce to the identity
-            cands.append((ci, members, tuple(comp_box_l[ci])))
-            continue
-        if ci in slow_clusters:
-            for cluster, box in slow_clusters[ci]:
-                if len(cluster) >= min_cluster:
-                    cands.append((ci, cluster, box))
-            continue
-        e0, e1 = edge_start_l[ci], edge_start_l[ci + 1]
-        clusters = component_clusters(members, list(zip(ea_l[e0:e1], eb_l[e0:e1], eiou_l[e0:e1], eit_l[e0:e1])),
-                                      n_nodes, cluster_iou_thr)
-        for cluster in clusters:
-            if len(cluster) < min_cluster:
-                continue
-            if boxes_l is None:
-                boxes_l = boxes.tolist()
-            bs = [boxes_l[m] for m in cluster]
-            box = tuple(min(b[k] for b in bs) if k < 3 else max(b[k] for b in bs) for k in range(6))
-            cands.append((ci, cluster, box))
-    return cands
+             1 if _COMPENSATED_SUM else 0, ptr(ncl32), ptr(totals))
+        csz32 = np.zeros(max(1, int(totals[0])), dtype=np.int32)
+        cmem32 = np.zeros(max(1, int(totals[1])), dtype=np.int32)
+        call("be_components_clusters_fetch", ptr(csz32), ptr(cmem32))
+        ncl = ncl32.astype(np.int64)
+        csz, cmem = csz32[:int(totals[0])].astype(np.int64), cmem32[:int(totals[1])].astype(np.int64)
+    elif len(slow):
+        ea_l, eb_l = ea[edge_order].tolist(), eb[edge_order].tolist()
+        eiou_l, eit_l = eiou[edge_order].tolist(), eit[edge_order].tolist()
+        node_order_l = node_order.tolist()
+        sz, mem = [], []
+        for k, ci in enumerate(slow.tolist()):
+            members = node_order_l[node_start[ci]:node_start[ci + 1]]
+            e0, e1 = int(edge_start[ci]), int(edge_start[ci + 1])
+            clusters = component_clusters(members, list(zip(ea_l[e0:e1], eb_l[e0:e1], eiou_l[e0:e1], eit_l[e0:e1])),
+                                          n_nodes, cluster_iou_thr)
+            ncl[k] = len(clusters)
+            for cluster in clusters:
+                sz.append(len(cluster))
+                mem.extend(cluster)
+        csz, cmem = np.array(sz, dtype=np.int64), np.array(mem, dtype=np.int64)
+    cstart = np.concatenate([[0], np.cumsum(csz)]).astype(np.int64)
+    big = csz >= min_cluster                               # `if len(cluster) < min_cluster: continue`
+    cl_comp = np.repeat(slow, ncl)[big]
+    cl_box = _segment_boxes(boxes[cmem], cstart[:-1])[big] if len(csz) else np.zeros((0, 6), dtype=np.int64)
+    # both kinds in discovery order: components ascending (a component is of one kind only),
+    # clusters of a component in the order the cluster graph yields them
+    comp_all = np.concatenate([one, cl_comp])
+    src_start = np.concatenate([node_start[one], len(node_order) + cstart[:-1][big]])
+    length = np.concatenate([comp_size[one], csz[big]])
+    box_all = np.concatenate([comp_box[one], cl_box])
+    sel = np.argsort(comp_all, kind="stable")
+    comp_all, src_start, length, box_all = comp_all[sel], src_start[sel], length[sel], box_all[sel]
+    mstart = np.concatenate([[0], np.cumsum(length)]).astype(np.int64)
+    src = np.concatenate([node_order, cmem])
+    gather = np.repeat(src_start - mstart[:-1], length) + np.arange(mstart[-1])
+    return Candidates(comp_all, mstart, src[gather] if len(gather) else np.zeros(0, np.int64), box_all)
 
 
-def merge_overlapping_candidates(cands, csize, cpair):
+def merge_overlapping_candidates(cands, csize, ca, cb, cinter):
     """merge_overlapping per component (consensus.py:144-195,461-466): candidates of one component
     whose voted voxel sets overlap (IoU > 0.01 or > 100 voxels) become one instance; final ids
-    1..n in discovery order. Returns (cid -> final id [n_cands + 1], {final id: box})."""
-    cid_final = np.zeros(len(cands) + 1, dtype=np.int32)
-    final_boxes = {}
-    next_id = 1
-    by_comp = {}
-    for cid, (ci, _, _) in enumerate(cands, start=1):
-        if csize[cid] > 0:  # `if len(voted_ranges) > 0`
-            by_comp.setdefault(ci, []).append(cid)
-    for ci in sorted(by_comp.keys()):
-        ids = by_comp[ci]
-        if len(ids) < 2:
-            groups = [set(ids)]
-        else:
-            mg = nx.Graph()
-            mg.add_nodes_from(ids)
-            for a, b in combinations(ids, 2):
-                it = cpair.get((min(a, b), max(a, b)), 0)
-                iou = it / (csize[a] + csize[b] - it)
-                if iou > MIN_IOU or it > MIN_OVERLAP:
-                    mg.add_edge(a, b)
-            groups = list(nx.connected_components(mg))
-        for grp in groups:
-            box = None
-            for cid in ids:  # dict order of cluster_instances
-                if cid in grp:
-                    cid_final[cid] = next_id
-                    box = cands[cid - 1][2] if box is None else merge_boxes(box, cands[cid - 1][2])
-            final_boxes[next_id] = tuple(int(v) for v in box)
-            next_id += 1
-    return cid_final, final_boxes
+    1..n in discovery order. `csize[cid]`: voted voxels of candidate cid (1-based); (ca, cb,
+    cinter): voxels claimed by both candidates of a pair. Returns (cid -> final id [n_cands + 1],
+    {final id: box}).
+
+    The reference walks the components in order and, inside one, networkx's connected components
+    of the overlap graph over the candidates that kept a voxel (`if len(voted_ranges) > 0`), i.e.
+    groups ordered by their smallest candidate id - candidate ids ascend with the component, so
+    the final ids are the ranks of the groups' smallest ids. Boxes are min / max merges."""
+    n = len(cands)
+    cid_final = np.zeros(n + 1, dtype=np.int32)
+    csize = np.asarray(csize, dtype=np.int64)
+    live = np.flatnonzero(csize[1:n + 1] > 0)              # 0-based candidate indices
+    if len(live) == 0:
+        return cid_final, {}
+    ca, cb, it = (np.asarray(v, dtype=np.int64) for v in (ca, cb, cinter))
+    ok = (ca >= 1) & (cb >= 1) & (ca <= n) & (cb <= n) & (it > 0)
+    ca, cb, it = ca[ok], cb[ok], it[ok]
+    iou = it / (csize[ca] + csize[cb] - it)
+    edge = ((iou > MIN_IOU) | (it > MIN_OVERLAP)) & (cands.comp[ca - 1] == cands.comp[cb - 1])
+    adj = coo_matrix((np.ones(int(edge.sum()), dtype=np.int8), (ca[edge] - 1, cb[edge] - 1)), shape=(n, n))
+    _, lab = connected_components(adj, directed=False)
+    gmin = np.full(int(lab.max()) + 1, n, dtype=np.int64)   # smallest live candidate of every group
+    np.minimum.at(gmin, lab[live], live)
+    heads = np.unique(gmin[lab[live]])                      # ascending = discovery order
+    fid = np.searchsorted(heads, gmin[lab[live]]) + 1
+    cid_final[live + 1] = fid
+    by_fid = np.argsort(fid, kind="stable")
+    fb = _segment_boxes(cands.boxes[live][by_fid], np.searchsorted(fid[by_fid], np.arange(1, len(heads) + 1)))
+    return cid_final, {i + 1: tuple(b) for i, b in enumerate(fb.tolist())}
 
 
 def membership_tables(cands, n_nodes):
     """node (1-based) -> candidate ids (1-based) as CSR host arrays (ids ascending per node)."""
-    sizes = np.fromiter((len(c[1]) for c in cands), dtype=np.int64, count=len(cands))
-    nodes = np.fromiter((m for c in cands for m in c[1]), dtype=np.int64, count=int(sizes.sum())) + 1
+    sizes = cands.mstart[1:] - cands.mstart[:-1]
+    nodes = cands.members + 1
     cids = np.repeat(np.arange(1, len(cands) + 1, dtype=np.int64), sizes)
     order = np.argsort(nodes, kind="stable")          # stable: candidate ids stay ascending per node
     memb_off = np.zeros(n_nodes + 3, dtype=np.int32)
@@ -682,8 +699,8 @@ def membership_tables(cands, n_nodes):
 
 
 def _node_tables(trackers):
-    """Nodes in tracker order / dict order (consensus.py:400-406): (n_nodes, sizes, boxes, per-plane
-    label -> node LUTs as numpy arrays). Sizes come from `_b200_sizes` when the engine left them
+    """Nodes in tracker order / dict order (consensus.py:400-406): (n_nodes, sizes, boxes as an
+    (n, 6) int64 array, per-plane label -> node LUTs as numpy arrays). Sizes come from `_b200_sizes` when the engine left them
     on the tracker, else from the run-length tables."""
     node_sizes, node_boxes, luts = [], [], []
     nid = 0
@@ -698,9 +715,10 @@ def _node_tables(trackers):
                 node_sizes.extend(int(known[l]) for l in labels)
             else:
                 node_sizes.extend(int(np.sum(a["runs"])) for a in tr.instances.values())
-            node_boxes.extend(np.asarray([a["box"] for a in tr.instances.values()], dtype=np.int64).reshape(-1, 6).tolist())
+            node_boxes.append(np.asarray([a["box"] for a in tr.instances.values()], dtype=np.int64).reshape(-1, 6))
         luts.append(lut)
-    return nid, node_sizes, [tuple(b) for b in node_boxes], luts
+    boxes = np.concatenate(node_boxes) if node_boxes else np.zeros((0, 6), dtype=np.int64)
+    return nid, node_sizes, boxes, luts
 
 
 def tracker_nodes(trackers, dev):
@@ -848,16 +866,15 @@ def consensus_driver(each, n_shards, n_nodes, node_sizes, node_boxes, luts, pixe
     sizes = np.array(node_sizes, dtype=np.int64)
     cands = cluster_candidates(n_nodes, node_boxes, sizes, pa, pb, inter, cluster_iou_thr, min_cluster)
     mark('host graph clustering')
-    if not cands:
+    if len(cands) == 0:
         each("zero")
         return {}
     memb_off, memb_list = membership_tables(cands, n_nodes)
     res = each("stats", memb_off, memb_list, pixel_vote_thr, len(cands), _next_pow2(CAPS["votes"]))
     csize = np.sum([r[0] for r in res], axis=0)
     ca, cb, cinter = _sum_by_pair([r[1:] for r in res])
-    cpair = {(int(a), int(b)): int(v) for a, b, v in zip(ca, cb, cinter)}
     mark('vote stats kernel')
-    cid_final, final_boxes = merge_overlapping_candidates(cands, csize, cpair)
+    cid_final, final_boxes = merge_overlapping_candidates(cands, csize, ca, cb, cinter)
     n_final = len(final_boxes)
     if n_final == 0:
         each("zero")
