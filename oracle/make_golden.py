@@ -296,7 +296,7 @@ def gen_resize_cases():
     print("resize cases", len(cases), "opencv", cv2.__version__)
 
 
-def gen_tiled_cases():
+def gen_tiled_cases(wide=False):
     """The tiled branch of the reference's `Engine2d.infer` (empanada_napari/inference.py:283-318:
     Tiler, per-tile engine call, pan_seg_to_rle_seg, translate_rle_seg, merge_objects_from_tiles /
     merge_semantic_from_tiles, rle_seg_to_pan_seg), unmodified. `cztile` (third party, absent) is
@@ -325,13 +325,22 @@ def gen_tiled_cases():
     rng = np.random.default_rng(31)
     cases = [((300, 420), 128, False, 1, 14), ((260, 200), 96, False, 1, 8), ((200, 330), 128, True, 1, 10),
              ((280, 280), 128, False, 2, 9)]
+    if wide:
+        # an object wider than a tile: its flat-index runs wrap around tile row ends and the
+        # reference translates only their starts (tile.py:126-166), painting the wrapped part
+        # outside the tile. Pins the oracle's restatement of that quirk (the CUDA path does not
+        # reproduce it and warns instead).
+        cases = [((240, 300), 96, False, 1, 8), ((220, 260), 128, True, 1, 7), ((260, 230), 96, False, 1, 10)]
     orig_loader = inf.load_model_to_device
     for ci, (shape, tile_size, semantic_only, scale, n_obj) in enumerate(cases):
         # The reference's `_join_ranges` (array_utils.py:657-690) fails on a cluster that consists of
         # ONE run (an object clipped to a single row): seeds are tried until the reference runs.
         for seed in range(40 + 10 * ci, 40 + 10 * ci + 10):
             _, lab, _ = syn.make_volume((1,) + shape, seed=seed, n_objects=n_obj, scale=1.6)
-            lab = lab[0]
+            lab = lab[0].copy()
+            if wide:
+                y0 = 30 + 17 * ci
+                lab[y0:y0 + 9 + 4 * ci, :] = int(lab.max()) + 1
             img = np.clip(np.where(lab > 0, 70.0, 170.0) + rng.normal(0, 8.0, shape), 0, 255).astype(np.uint8)
             tiler = ref_tile.Tiler(shape, tile_size=tile_size, overlap_width=min(128, int(tile_size * 0.1)))
             heads = []
@@ -357,7 +366,7 @@ def gen_tiled_cases():
         print("tiled case", ci, shape, "tiles", len(tiler), "labels", len(np.unique(pan)) - 1)
     inf.load_model_to_device = orig_loader
     out["n"] = len(cases)
-    np.savez_compressed(os.path.join(GOLD, "tiled_cases.npz"), **out)
+    np.savez_compressed(os.path.join(GOLD, "tiled_cases_wide.npz" if wide else "tiled_cases.npz"), **out)
 
 
 def gen_model_tiny():
@@ -474,7 +483,7 @@ def gen_eval_cases():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["post", "post_fine", "median", "model", "bifpn", "volumes", "resize", "volumes2", "tiled", "morph",
-                             "stuff"]
+                             "stuff", "tiled_wide"]
     if "stuff" in which:
         run_reference_volume((24, 42, 38), seed=15, noise=0.5, ks=3, n_objects=10, min_size=20, min_extent=2,
                              tag="stuff_class", stuff_config=True)
@@ -484,6 +493,8 @@ if __name__ == "__main__":
         gen_resize_cases()
     if "tiled" in which:
         gen_tiled_cases()
+    if "tiled_wide" in which:
+        gen_tiled_cases(wide=True)
     if "volumes2" in which:
         run_reference_volume((26, 44, 40), seed=5, noise=0.5, ks=3, n_objects=10, min_size=20, min_extent=2,
                              tag="semantic_only", semantic_only=True)

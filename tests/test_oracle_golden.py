@@ -191,12 +191,16 @@ def test_evaluator_against_reference_fixture(tmp_path):
             assert float(got[k]) == v, (i, k, got[k], v)
 
 
-def test_tiled_inference_restatement_matches_reference_fixture():
-    """oracle/tiles.py (Tiler, overlap region, tile merge, tiled Engine2d.infer) against
-    tests/golden/tiled_cases.npz = the unmodified reference run with the same tile layout."""
+@pytest.mark.parametrize("fixture", ["tiled_cases.npz", "tiled_cases_wide.npz"])
+def test_tiled_inference_restatement_matches_reference_fixture(fixture):
+    """oracle/tiles.py (Tiler, overlap region, tile merge, tiled Engine2d.infer) against the
+    unmodified reference run with the same tile layout. `tiled_cases_wide.npz`: an object wider
+    than a tile, whose runs wrap around tile row ends - the reference translates only their
+    starts (tile.py:126-166) and paints the wrapped part outside the tile; the fixture proves the
+    quirk is real (the painted image differs from a plain union of the tiles) and pins it."""
     from empanada_napari_b200.tiling import tile_rectangles
     from oracle import tiles
-    z = np.load(os.path.join(GOLDEN, "tiled_cases.npz"))
+    z = np.load(os.path.join(GOLDEN, fixture))
     layout = lambda shape, tile, ov: tile_rectangles(shape, tile, ov)      # noqa: E731 (cztile absent: the fixture's layout)
     for ci in range(int(z["n"])):
         tile_size, semantic_only, scale, n_tiles = (int(v) for v in z[f"t{ci}_meta"])
@@ -205,3 +209,10 @@ def test_tiled_inference_restatement_matches_reference_fixture():
                                          nms_kernel=3, confidence_thr=0.5, semantic_only=bool(semantic_only),
                                          inference_scale=scale)
         assert np.array_equal(pan.astype(np.int32), z[f"t{ci}_pan"]), ci
+        if fixture == "tiled_cases_wide.npz":      # the quirk is in the fixture: not a union of the tiles
+            yr, xr = layout(z[f"t{ci}_img"].shape, (tile_size, tile_size), min(128, int(tile_size * 0.1)))
+            eng = post.RenderEnginePost([] if semantic_only else [1], 1000, 64, 0, 0.1, 3, 0.5, None, True)
+            union = np.zeros(pan.shape, dtype=bool)
+            for t, ((y0, y1), (x0, x1)) in enumerate(zip(yr, xr)):
+                union[y0:y1, x0:x1] |= eng(post.sigmoid(heads[t][0]), heads[t][1], heads[t][2], (y1 - y0, x1 - x0), 1) > 0
+            assert int((union != (z[f"t{ci}_pan"] > 0)).sum()) > 500
