@@ -100,7 +100,7 @@ constexpr int kNoLabel = std::numeric_limits<int>::min();
 constexpr double kTieEps = 1e-12;  // reduced costs below this count as ties (IoUs are O(1))
 // diagnostics of the last be_match_replay call: matcher steps, steps with a multi-entry block,
 // steps replayed on the full matrix
-static long long g_stats[3] = {0, 0, 0};
+static thread_local long long g_stats[3] = {0, 0, 0};   // per calling thread: replays of two planes may overlap
 
 struct Scratch {
   std::vector<Entry> agg, bycol;
@@ -426,7 +426,7 @@ static void merge_by_label(const SliceObjs& match, const std::vector<int>& new_l
 extern "C" {
 
 // out[0..2]: matcher steps / steps with a multi-entry block / steps replayed on the full matrix,
-// of the last be_match_replay call of this process (diagnostics)
+// of the last be_match_replay call of the calling thread (diagnostics)
 int be_match_replay_stats(long long* out) {
   for (int i = 0; i < 3; ++i) out[i] = g_stats[i];
   return 0;
