@@ -32,3 +32,15 @@ def test_reference_arm_other_ranks_exit_without_work():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run(CMD, capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_b200_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without CUDA the product arm must fail, not print a number."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--size", "64"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode != 0
+    assert not any(l.startswith("{") for l in out.stdout.splitlines())
