@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -37,3 +39,23 @@ def test_no_cpu_fallback_message():
     with pytest.raises(_lib.B200EmpanadaError):
         Engine3d({"labels": [1], "class_names": {1: "m"}, "thing_list": [1], "padding_factor": 16,
                   "norms": {"mean": 0.5, "std": 0.1}, "model": None})
+
+
+def test_engines_raise_without_cuda_and_without_the_library(monkeypatch):
+    """No CPU fallback anywhere on the product path: without a CUDA device every engine raises,
+    and a missing shared library is an error, not a detour."""
+    import torch
+    from empanada_napari_b200 import _lib, inference
+    cfg = {"class_names": {1: "mito"}, "labels": [1], "thing_list": [1], "padding_factor": 16,
+           "norms": {"mean": 0.5, "std": 0.1}, "model": "does-not-matter"}
+    if not torch.cuda.is_available():
+        for make in (lambda: inference.Engine3d(cfg), lambda: inference.Engine2d(cfg)):
+            with pytest.raises(_lib.B200EmpanadaError, match="CUDA"):
+                make()
+    for make in (lambda: inference.Engine3d(cfg, use_gpu=False), lambda: inference.Engine2d(cfg, use_gpu=False)):
+        with pytest.raises(_lib.B200EmpanadaError):
+            make()
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libb200_empanada.so")
+    with pytest.raises(_lib.B200EmpanadaError, match="no CPU fallback"):
+        _lib.call("be_version")
