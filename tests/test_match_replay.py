@@ -254,3 +254,31 @@ def test_replay_vs_full_matrix_scipy_on_random_tables(seed):
         assert np.array_equal(lut, want_lut), ctx
         for i, lab in enumerate(labels.tolist()):
             assert int(sizes[i]) == want[lab][0] and tuple(boxes[i].tolist()) == tuple(want[lab][1]), ctx
+
+
+def test_replay_diagnostics_count_steps_and_full_matrix_replays():
+    """`be_match_replay_stats`: matcher steps = 2 (n - 1); a slice pair in which two objects tie
+    exactly for one target must be replayed on the full matrix, a tie-free one must not."""
+    import ctypes
+    from empanada_napari_b200 import _lib, tracking
+
+    def stats():
+        out = (ctypes.c_longlong * 3)()
+        _lib.lib().be_match_replay_stats(ctypes.cast(out, ctypes.c_void_p))
+        return list(out)
+
+    def tables(inter_b):
+        n_cc = np.array([1, 2], dtype=np.int32)
+        table = np.zeros((2, 2, 5), dtype=np.int32)
+        table[0, 0] = (10, 0, 0, 4, 4)
+        table[1, 0] = (6, 0, 0, 2, 3)
+        table[1, 1] = (6, 2, 0, 4, 3)
+        keys = np.array([(1 << 40) | (1 << 20) | 1, (1 << 40) | (1 << 20) | 2], dtype=np.uint64)
+        return n_cc, table, keys, np.array([3, inter_b], dtype=np.int32)
+
+    tracking.match_replay(*tables(3), 1, 1000, "xy")        # both candidates: IoU 3 / 13, an exact tie
+    steps, multi, full = stats()
+    assert steps == 2 and full >= 1
+    tracking.match_replay(*tables(2), 1, 1000, "xy")        # 3 / 13 against 2 / 14: unique optimum
+    steps, multi, full = stats()
+    assert steps == 2 and full == 0
